@@ -1,0 +1,128 @@
+// 2-bit seed codes shared by the host table builder and the device scan kernels.
+//
+// The matcher the reference runs (BNDMq, /root/reference/src/pattern_matching.rs:165-209, or
+// the aho-corasick DFA, src/cmd_extract.rs:260-265,332) is exact byte-string search. The device
+// replaces it by "seed and verify": every text position on a grid of stride D is turned into a
+// Q-base seed code; a seed that is in the query seed set is followed by an exact byte compare.
+// The only property the seed code needs is
+//     bytes that compare equal under the matcher  =>  equal 2-bit class,
+// which holds for  cls(c) = (c >> 1) & 3  both for exact compare and for ASCII case folding
+// (case is bit 5). A,C,G,T / a,c,g,t get the four distinct classes 0,1,3,2; every other byte
+// (N, IUPAC, amino acids ...) aliases onto one of them and is sorted out by the verify step, so
+// "N breaks the window" exactly as it does for the reference's byte compare.
+//
+// Texts are cut into UNITS of 16 bases (16 ASCII bytes, or 8 BAM bytes = 16 nibbles). Each unit
+// packs to one 32-bit word. Two packings exist:
+//   *_ord : base i of the unit sits at bits [31-2i, 30-2i] (base 0 most significant), so a seed
+//           starting at any offset o inside the unit is a funnel shift of (unit, next unit);
+//   *_perm: any fixed bit permutation, cheaper to compute; used when D == 16 (seed == unit).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MK_HD __host__ __device__ __forceinline__
+#else
+#define MK_HD inline
+#endif
+
+#define MK_UNIT_BASES 16
+
+// ---------------------------------------------------------------------------------------------
+// ASCII (1 byte / base). w0..w3 are the four little-endian 32-bit words of the 16-byte unit.
+// ---------------------------------------------------------------------------------------------
+
+// Permuted packing: 4 LOP + 3 IMAD + 1 SHF.  Bits of the result, per byte lane b (0..3) of the
+// word: [8b+0,8b+1] = cls(w0.byte b), [8b+2,8b+3] = cls(w1.byte b), [8b+4,8b+5] = cls(w2.byte b),
+// [8b+6,8b+7] = cls(w3.byte b).
+MK_HD uint32_t mk_pack_ascii_perm(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    const uint32_t K = 0x06060606u;
+    uint32_t a = w0 & K, b = w1 & K, c = w2 & K, e = w3 & K;
+    uint32_t ab = b * 4u + a;        // bits 1..4 of every byte
+    uint32_t ce = e * 4u + c;        // bits 1..4 of every byte
+    return ce * 8u + (ab >> 1);      // ab -> bits 0..3, ce -> bits 4..7
+}
+
+// Ordered packing: base i -> bits [31-2i, 30-2i].
+MK_HD uint32_t mk_pack4_ascii_top(uint32_t w) {
+    // cls of the 4 bytes gathered into the top byte, byte 0 (first base) most significant
+    return (((w >> 1) & 0x03030303u) * 0x40100401u) & 0xFF000000u;
+}
+MK_HD uint32_t mk_pack_ascii_ord(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    return mk_pack4_ascii_top(w0) | (mk_pack4_ascii_top(w1) >> 8) | (mk_pack4_ascii_top(w2) >> 16) |
+           (mk_pack4_ascii_top(w3) >> 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// BAM4 (2 bases / byte, first base in the high nibble; codes "=ACMGRSVTWYHKDBN",
+// /root/reference/src/cmd_tag.rs:395 decodes them through the bam crate). A unit is 8 bytes =
+// two little-endian words w0, w1. Nibble class: cls4(n) = ((n2|n3) << 1) | (n1|n3), which is
+// 0,1,2,3 for A(1),C(2),G(4),T(8). The host encodes query bytes to nibbles first, so text and
+// query always go through the same function.
+// ---------------------------------------------------------------------------------------------
+
+// per nibble: class in bits 1..2 of the nibble
+MK_HD uint32_t mk_cls4_mid(uint32_t w) {
+    uint32_t lo = (w | (w >> 2)) & 0x22222222u;   // bit1 = n1|n3
+    uint32_t hi = (w | (w >> 1)) & 0x44444444u;   // bit2 = n2|n3
+    return lo | hi;
+}
+MK_HD uint32_t mk_pack_bam_perm(uint32_t w0, uint32_t w1) {
+    return (mk_cls4_mid(w0) << 1) | (mk_cls4_mid(w1) >> 1);
+}
+
+MK_HD uint32_t mk_bswap32(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(w, 0, 0x0123);
+#else
+    return (w >> 24) | ((w >> 8) & 0xFF00u) | ((w << 8) & 0xFF0000u) | (w << 24);
+#endif
+}
+// 8 bases of one word -> 16 bits, first base most significant
+MK_HD uint32_t mk_pack8_bam_ord(uint32_t w) {
+    uint32_t c = mk_cls4_mid(mk_bswap32(w)) >> 1;       // class in bits 0..1 of every nibble
+    c = (c | (c >> 2)) & 0x0F0F0F0Fu;
+    c = (c | (c >> 4)) & 0x00FF00FFu;
+    c = (c | (c >> 8)) & 0x0000FFFFu;
+    return c;
+}
+MK_HD uint32_t mk_pack_bam_ord(uint32_t w0, uint32_t w1) {
+    return (mk_pack8_bam_ord(w0) << 16) | mk_pack8_bam_ord(w1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Seed extraction from ordered unit codes and the hashes of a seed code.
+// ---------------------------------------------------------------------------------------------
+
+// Seed of q bases starting at base offset o (0..15) of unit `cur`, `nxt` being the following unit.
+MK_HD uint32_t mk_seed_ord(uint32_t cur, uint32_t nxt, uint32_t o, uint32_t q) {
+#if defined(__CUDA_ARCH__)
+    uint32_t win = __funnelshift_l(nxt, cur, 2u * o);
+#else
+    uint32_t win = o ? ((cur << (2u * o)) | (nxt >> (32u - 2u * o))) : cur;
+#endif
+    return win >> (32u - 2u * q);
+}
+
+// First-level filter hashes (bit index into a 2^log2_bits bitmap) and cuckoo bucket hashes.
+MK_HD uint32_t mk_hash_f1(uint32_t code, uint32_t log2_bits) { return (code * 0x9E3779B1u) >> (32u - log2_bits); }
+MK_HD uint32_t mk_hash_f2(uint32_t code, uint32_t log2_bits) {
+    return ((code ^ (code >> 15)) * 0x85EBCA77u) >> (32u - log2_bits);
+}
+MK_HD uint32_t mk_mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
+MK_HD uint32_t mk_hash_b1(uint32_t code, uint32_t mask) { return mk_mix32(code) & mask; }
+MK_HD uint32_t mk_hash_b2(uint32_t code, uint32_t mask) { return mk_mix32(code ^ 0xA5A5F00Du) & mask; }
+
+// ASCII byte -> BAM nibble for query bytes (0xFF: the byte can never occur in decoded BAM text)
+MK_HD uint8_t mk_ascii_to_nibble(uint8_t c) {
+    switch (c) {
+        case '=': return 0;  case 'A': return 1;  case 'C': return 2;  case 'M': return 3;
+        case 'G': return 4;  case 'R': return 5;  case 'S': return 6;  case 'V': return 7;
+        case 'T': return 8;  case 'W': return 9;  case 'Y': return 10; case 'H': return 11;
+        case 'K': return 12; case 'D': return 13; case 'B': return 14; case 'N': return 15;
+        default: return 0xFF;
+    }
+}
+MK_HD uint8_t mk_fold(uint8_t c) { return (c >= 'A' && c <= 'Z') ? (uint8_t)(c | 0x20) : c; }

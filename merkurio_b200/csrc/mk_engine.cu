@@ -1,0 +1,511 @@
+// C ABI of the matching engine (include/merkurio_cuda.h): table upload, batch staging on CUDA
+// streams, kernel dispatch, overflow handling. No CPU matching path exists in this library.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "mk_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(MK_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    cudaError_t upload(const std::vector<T>& v) {
+        cudaError_t e = ensure(v.size() ? v.size() : 1);
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+};
+
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, n * sizeof(T), cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+};
+
+struct DeviceTables {
+    bool built = false;
+    mk::Tables host;
+    DevBuf<uint32_t> filter, postings, pat_off;
+    DevBuf<mk::SeedSlot> slots;
+    DevBuf<uint8_t> pat_bytes;
+    uint64_t bytes() const {
+        return host.slots.size() * sizeof(mk::SeedSlot) + host.postings.size() * 4 + host.pat_bytes.size() +
+               host.pat_off.size() * 4 + host.filter.size() * 4;
+    }
+};
+
+// Everything one in-flight batch needs on the device and for its results on the host.
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_scan = nullptr, ev_end = nullptr;
+    DevBuf<uint32_t> flags;                  // bitmap, 2 words per 64 records
+    DevBuf<mk::RawHit> raw_a, raw_b;
+    DevBuf<mk_hit> out;
+    DevBuf<uint32_t> heads, radix_table;
+    DevBuf<unsigned long long> counters;     // [0] hits appended, [1] distinct pairs
+    PinBuf<unsigned long long> h_counters;
+    PinBuf<uint64_t> h_flags;
+    PinBuf<mk_hit> h_hits;
+    uint64_t hit_cap = 0;
+    // description of the batch in flight
+    bool busy = false;
+    const void* d_seq = nullptr;
+    const unsigned long long* d_off = nullptr;
+    const uint32_t* d_lens = nullptr;
+    uint32_t n_records = 0;
+    uint64_t n_units = 0;
+    mk_encoding enc = MK_ENC_ASCII;
+    mk_mode mode = MK_MODE_FLAG;
+    bool fetch = true;
+    ~Workspace() {
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (ev_scan) cudaEventDestroy(ev_scan);
+        if (ev_end) cudaEventDestroy(ev_end);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+struct Slot {
+    Workspace ws;
+    PinBuf<uint8_t> h_seq;
+    PinBuf<uint64_t> h_off;
+    PinBuf<uint32_t> h_lens;
+    DevBuf<uint8_t> d_seq;
+    DevBuf<unsigned long long> d_off;
+    DevBuf<uint32_t> d_lens;
+};
+
+}  // namespace
+
+struct mk_engine {
+    int device = 0;
+    int sm_count = 0;
+    mk_config cfg{};
+    mk::PatternSet ps;
+    DeviceTables tables[2];
+    DevBuf<uint32_t> tie_rank;
+    std::vector<std::unique_ptr<Slot>> slots;
+    Workspace direct;  // mk_scan_device
+};
+
+namespace {
+
+using ScanKernel = void (*)(const mk::ScanParams);
+
+template <int ENC, int NHASH, bool SMEMF>
+ScanKernel pick_by_d(uint32_t d) {
+    switch (d) {
+        case 16: return mk::mk_scan_d16<ENC, NHASH, SMEMF, 4>;
+        case 8: return mk::mk_scan_ord<ENC, 8, NHASH, SMEMF, 4>;
+        case 4: return mk::mk_scan_ord<ENC, 4, NHASH, SMEMF, 4>;
+        case 2: return mk::mk_scan_ord<ENC, 2, NHASH, SMEMF, 2>;
+        default: return mk::mk_scan_ord<ENC, 1, NHASH, SMEMF, 2>;
+    }
+}
+int tile_vectors(uint32_t d) { return (d >= 4 ? 4 : 2) * 32; }
+
+ScanKernel pick_kernel(int enc, uint32_t d, uint32_t nhash, bool smemf) {
+    if (enc == MK_ENC_ASCII) {
+        if (smemf) return nhash == 2 ? pick_by_d<MK_ENC_ASCII, 2, true>(d) : pick_by_d<MK_ENC_ASCII, 1, true>(d);
+        return pick_by_d<MK_ENC_ASCII, 1, false>(d);
+    }
+    if (smemf) return nhash == 2 ? pick_by_d<MK_ENC_BAM4, 2, true>(d) : pick_by_d<MK_ENC_BAM4, 1, true>(d);
+    return pick_by_d<MK_ENC_BAM4, 1, false>(d);
+}
+
+int init_workspace(Workspace& ws) {
+    CU(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&ws.ev_begin));
+    CU(cudaEventCreate(&ws.ev_scan));
+    CU(cudaEventCreate(&ws.ev_end));
+    CU(ws.counters.ensure(2));
+    CU(ws.h_counters.ensure(2));
+    CU(ws.radix_table.ensure((size_t)256 * mk::kSortWarps));
+    return MK_OK;
+}
+
+int ensure_hit_capacity(Workspace& ws, uint64_t cap) {
+    if (cap <= ws.hit_cap) return MK_OK;
+    CU(ws.raw_a.ensure(cap));
+    CU(ws.raw_b.ensure(cap));
+    CU(ws.out.ensure(cap));
+    CU(ws.heads.ensure(cap));
+    ws.hit_cap = cap;
+    return MK_OK;
+}
+
+int ensure_tables(mk_engine* e, int enc) {
+    DeviceTables& dt = e->tables[enc];
+    if (dt.built) return MK_OK;
+    try {
+        dt.host = mk::build_tables(e->ps, enc);
+    } catch (const std::bad_alloc&) {
+        return fail(MK_ERR_NOMEM, "out of host memory while building the seed tables");
+    } catch (const std::exception& ex) {
+        return fail(MK_ERR_INVALID, "table build failed: %s", ex.what());
+    }
+    CU(dt.filter.upload(dt.host.filter));
+    CU(dt.postings.upload(dt.host.postings));
+    CU(dt.pat_off.upload(dt.host.pat_off));
+    CU(dt.slots.upload(dt.host.slots));
+    CU(dt.pat_bytes.upload(dt.host.pat_bytes));
+    ScanKernel k = pick_kernel(enc, dt.host.d, dt.host.filter_hashes, dt.host.filter_in_smem);
+    if (dt.host.filter_in_smem)
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dt.host.filter.size() * 4)));
+    dt.built = true;
+    return MK_OK;
+}
+
+// Enqueue the device work of one batch on ws.stream (no host synchronisation).
+int enqueue(mk_engine* e, Workspace& ws) {
+    DeviceTables& dt = e->tables[ws.enc];
+    const mk::Tables& t = dt.host;
+    const uint64_t seq_bytes = ws.enc == MK_ENC_ASCII ? ws.n_units : (ws.n_units + 1) / 2;
+    const size_t flag_words32 = ((size_t)ws.n_records + 63) / 64 * 2;
+
+    mk::ScanParams P{};
+    P.text = reinterpret_cast<const uint4*>(ws.d_seq);
+    P.n_units = ws.n_units;
+    P.n_vec = (seq_bytes + 15) / 16;
+    P.off = ws.d_off;
+    P.lens = ws.d_lens;
+    P.n_records = ws.n_records;
+    P.filter = dt.filter.p;
+    P.filter_log2_bits = t.filter_log2_bits;
+    P.slots = dt.slots.p;
+    P.bucket_mask = t.bucket_mask;
+    P.postings = dt.postings.p;
+    P.pat_bytes = dt.pat_bytes.p;
+    P.pat_off = dt.pat_off.p;
+    P.tie_rank = e->tie_rank.p;
+    P.q = t.q;
+    P.case_insensitive = e->ps.case_insensitive ? 1 : 0;
+    P.flags = ws.flags.p;
+    P.hits = ws.raw_a.p;
+    P.hit_capacity = ws.hit_cap;
+    P.hit_count = ws.counters.p;
+    P.mode = ws.mode;
+    P.len_bits = e->ps.len_bits;
+    P.tie_bits = e->ps.tie_bits;
+    P.pat_bits = mk::bits_for(e->ps.n ? e->ps.n - 1 : 0);
+    P.max_len = e->ps.max_len;
+
+    uint32_t key_bits;
+    if (ws.mode == MK_MODE_ALL_HITS) key_bits = mk::bits_for(ws.n_units) + P.len_bits + P.tie_bits;
+    else key_bits = mk::bits_for(ws.n_records) + P.pat_bits;
+    if (ws.mode != MK_MODE_FLAG && key_bits > 64)
+        return fail(MK_ERR_CAPACITY, "batch too large for the 64-bit hit sort key (%u bits)", key_bits);
+
+    CU(cudaMemsetAsync(ws.flags.p, 0, flag_words32 * 4, ws.stream));
+    CU(cudaMemsetAsync(ws.counters.p, 0, 2 * sizeof(unsigned long long), ws.stream));
+    CU(cudaEventRecord(ws.ev_begin, ws.stream));
+    if (P.n_vec > 0 && ws.n_records > 0) {
+        ScanKernel k = pick_kernel(ws.enc, t.d, t.filter_hashes, t.filter_in_smem);
+        uint64_t tiles = (P.n_vec + tile_vectors(t.d) - 1) / tile_vectors(t.d);
+        uint64_t want = (tiles + mk::kScanWarps - 1) / mk::kScanWarps;
+        int grid = (int)std::min<uint64_t>((uint64_t)e->sm_count, std::max<uint64_t>(want, 1));
+        size_t smem = t.filter_in_smem ? t.filter.size() * 4 : 0;
+        k<<<grid, mk::kScanThreads, smem, ws.stream>>>(P);
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(ws.ev_scan, ws.stream));
+    if (ws.mode != MK_MODE_FLAG) {
+        const unsigned long long* cnt = ws.counters.p;
+        mk::RawHit *src = ws.raw_a.p, *dst = ws.raw_b.p;
+        for (uint32_t shift = 0; shift < key_bits; shift += 8) {
+            mk::mk_radix_hist<<<mk::kSortBlocks, mk::kSortThreads, 0, ws.stream>>>(src, cnt, ws.hit_cap, shift, ws.radix_table.p);
+            mk::mk_radix_scan<<<1, 1024, 0, ws.stream>>>(cnt, ws.hit_cap, ws.radix_table.p);
+            mk::mk_radix_scatter<<<mk::kSortBlocks, mk::kSortThreads, 0, ws.stream>>>(src, dst, cnt, ws.hit_cap, shift,
+                                                                                    ws.radix_table.p);
+            std::swap(src, dst);
+        }
+        if (ws.mode == MK_MODE_ALL_HITS) {
+            mk::mk_finalize_hits<<<256, 256, 0, ws.stream>>>(src, ws.out.p, cnt, ws.hit_cap, ws.d_off, dt.pat_off.p,
+                                                            P.len_bits + P.tie_bits);
+        } else {
+            mk::mk_mark_heads<<<256, 256, 0, ws.stream>>>(src, cnt, ws.hit_cap, ws.heads.p);
+            mk::mk_scan_heads<<<1, 1024, 0, ws.stream>>>(cnt, ws.hit_cap, ws.heads.p, ws.counters.p + 1);
+            mk::mk_finalize_pairs<<<256, 256, 0, ws.stream>>>(src, ws.out.p, cnt, ws.hit_cap, ws.heads.p, dt.pat_off.p);
+        }
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(ws.ev_end, ws.stream));
+    CU(cudaMemcpyAsync(ws.h_counters.p, ws.counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ws.stream));
+    if (ws.fetch)
+        CU(cudaMemcpyAsync(ws.h_flags.p, ws.flags.p, flag_words32 * 4, cudaMemcpyDeviceToHost, ws.stream));
+    return MK_OK;
+}
+
+int begin_batch(mk_engine* e, Workspace& ws, const void* d_seq, const unsigned long long* d_off, const uint32_t* d_lens,
+                uint32_t n_records, uint64_t n_units, mk_encoding enc, mk_mode mode, bool fetch) {
+    if (enc != MK_ENC_ASCII && enc != MK_ENC_BAM4) return fail(MK_ERR_INVALID, "unknown encoding %d", (int)enc);
+    if (mode != MK_MODE_FLAG && mode != MK_MODE_PATTERN_SET && mode != MK_MODE_ALL_HITS)
+        return fail(MK_ERR_INVALID, "unknown mode %d", (int)mode);
+    int rc = ensure_tables(e, enc);
+    if (rc) return rc;
+    ws.d_seq = d_seq; ws.d_off = d_off; ws.d_lens = d_lens;
+    ws.n_records = n_records; ws.n_units = n_units; ws.enc = enc; ws.mode = mode; ws.fetch = fetch;
+    const size_t flag_words64 = ((size_t)n_records + 63) / 64;
+    CU(ws.flags.ensure(std::max<size_t>(flag_words64 * 2, 2)));
+    if (fetch) CU(ws.h_flags.ensure(std::max<size_t>(flag_words64, 1)));
+    if (mode != MK_MODE_FLAG) {
+        uint64_t cap = ws.hit_cap ? ws.hit_cap : (e->cfg.hit_capacity ? e->cfg.hit_capacity : (1ull << 20));
+        rc = ensure_hit_capacity(ws, cap);
+        if (rc) return rc;
+    }
+    rc = enqueue(e, ws);
+    if (rc) return rc;
+    ws.busy = true;
+    return MK_OK;
+}
+
+int finish_batch(mk_engine* e, Workspace& ws, mk_result* out) {
+    if (!ws.busy) return fail(MK_ERR_STATE, "no batch in flight");
+    uint32_t rescans = 0;
+    float ms_total = 0.f, ms_scan = 0.f;
+    for (;;) {
+        CU(cudaStreamSynchronize(ws.stream));
+        float a = 0.f, b = 0.f;
+        CU(cudaEventElapsedTime(&a, ws.ev_begin, ws.ev_end));
+        CU(cudaEventElapsedTime(&b, ws.ev_begin, ws.ev_scan));
+        ms_total += a; ms_scan += b;
+        if (ws.mode == MK_MODE_FLAG || ws.h_counters.p[0] <= ws.hit_cap) break;
+        // hit list overflowed: grow to the exact need and scan the batch again (never drop hits)
+        uint64_t need = ws.h_counters.p[0];
+        int rc = ensure_hit_capacity(ws, need + need / 8 + 1024);
+        if (rc) { ws.busy = false; return rc; }
+        ++rescans;
+        rc = enqueue(e, ws);
+        if (rc) { ws.busy = false; return rc; }
+    }
+    ws.busy = false;
+    uint64_t n_hits = 0;
+    if (ws.mode == MK_MODE_ALL_HITS) n_hits = ws.h_counters.p[0];
+    else if (ws.mode == MK_MODE_PATTERN_SET) n_hits = ws.h_counters.p[1];
+    if (ws.fetch && n_hits) {
+        CU(ws.h_hits.ensure(n_hits));
+        CU(cudaMemcpyAsync(ws.h_hits.p, ws.out.p, n_hits * sizeof(mk_hit), cudaMemcpyDeviceToHost, ws.stream));
+        CU(cudaStreamSynchronize(ws.stream));
+    }
+    if (out) {
+        out->record_flags = ws.fetch ? ws.h_flags.p : nullptr;
+        out->n_records = ws.n_records;
+        out->reserved = 0;
+        out->hits = (ws.fetch && n_hits) ? ws.h_hits.p : nullptr;
+        out->n_hits = n_hits;
+        out->bases_scanned = ws.n_units;
+        out->device_ns = (uint64_t)((double)ms_total * 1e6);
+        out->scan_ns = (uint64_t)((double)ms_scan * 1e6);
+        out->n_rescans = rescans;
+        out->reserved2 = 0;
+        out->d_record_flags = reinterpret_cast<const uint64_t*>(ws.flags.p);
+        out->d_hits = n_hits ? ws.out.p : nullptr;
+    }
+    return MK_OK;
+}
+
+int get_slot(mk_engine* e, uint32_t slot, Slot** out) {
+    if (!e) return fail(MK_ERR_INVALID, "null engine");
+    if (slot >= e->slots.size()) return fail(MK_ERR_STATE, "slot %u out of range (engine has %zu)", slot, e->slots.size());
+    *out = e->slots[slot].get();
+    return MK_OK;
+}
+
+int check_batch(mk_engine* e, uint32_t n_records, uint64_t n_units, mk_encoding enc) {
+    uint64_t bytes = enc == MK_ENC_ASCII ? n_units : (n_units + 1) / 2;
+    if (bytes > e->cfg.max_batch_bytes)
+        return fail(MK_ERR_CAPACITY, "batch of %llu bytes exceeds max_batch_bytes %llu", (unsigned long long)bytes,
+                    (unsigned long long)e->cfg.max_batch_bytes);
+    if (n_records > e->cfg.max_batch_records)
+        return fail(MK_ERR_CAPACITY, "batch of %u records exceeds max_batch_records %u", n_records, e->cfg.max_batch_records);
+    return MK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mk_last_error(void) { return g_err.c_str(); }
+const char* mk_version(void) { return "merkurio-b200 0.1.0 (sm_100a)"; }
+
+int mk_engine_create(const mk_patterns* patterns, const mk_config* config, mk_engine** out) {
+    if (!patterns || !config || !out) return fail(MK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (patterns->n == 0) return fail(MK_ERR_NO_PATTERNS, "No k-mers found in file or provided sequence.");
+    if (!patterns->bytes || !patterns->off) return fail(MK_ERR_INVALID, "null pattern storage");
+    if (patterns->n > mk::kMaxPatternId) return fail(MK_ERR_INVALID, "too many patterns (%u)", patterns->n);
+    for (uint32_t p = 0; p < patterns->n; ++p) {
+        if (patterns->off[p + 1] < patterns->off[p]) return fail(MK_ERR_INVALID, "pattern offsets must be non-decreasing");
+        if (patterns->off[p + 1] == patterns->off[p]) return fail(MK_ERR_EMPTY_PATTERN, "Pattern is empty.");
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(MK_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                    ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+    if (config->device < 0 || config->device >= ndev) return fail(MK_ERR_INVALID, "device %d out of range", config->device);
+    CU(cudaSetDevice(config->device));
+
+    std::unique_ptr<mk_engine> e(new (std::nothrow) mk_engine);
+    if (!e) return fail(MK_ERR_NOMEM, "out of memory");
+    e->device = config->device;
+    e->cfg = *config;
+    CU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device));
+    try {
+        e->ps = mk::make_pattern_set(patterns->bytes, patterns->off, patterns->n, config->case_insensitive != 0);
+    } catch (const std::bad_alloc&) {
+        return fail(MK_ERR_NOMEM, "out of host memory");
+    }
+    CU(e->tie_rank.upload(e->ps.tie_rank));
+    int rc = init_workspace(e->direct);
+    if (rc) return rc;
+    for (uint32_t s = 0; s < config->n_slots; ++s) {
+        std::unique_ptr<Slot> sl(new (std::nothrow) Slot);
+        if (!sl) return fail(MK_ERR_NOMEM, "out of memory");
+        rc = init_workspace(sl->ws);
+        if (rc) return rc;
+        size_t seq_cap = ((size_t)config->max_batch_bytes + 15) / 16 * 16 + 16;
+        CU(sl->h_seq.ensure(seq_cap));
+        CU(sl->d_seq.ensure(seq_cap));
+        CU(sl->h_off.ensure((size_t)config->max_batch_records + 1));
+        CU(sl->d_off.ensure((size_t)config->max_batch_records + 1));
+        CU(sl->h_lens.ensure(std::max<size_t>(config->max_batch_records, 1)));
+        CU(sl->d_lens.ensure(std::max<size_t>(config->max_batch_records, 1)));
+        e->slots.push_back(std::move(sl));
+    }
+    *out = e.release();
+    return MK_OK;
+}
+
+void mk_engine_destroy(mk_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    delete e;
+}
+
+int mk_engine_get_info(mk_engine* e, mk_engine_info* out) {
+    if (!e || !out) return fail(MK_ERR_INVALID, "null argument");
+    *out = mk_engine_info{};
+    out->n_patterns = e->ps.n;
+    out->min_len = e->ps.min_len;
+    out->max_len = e->ps.max_len;
+    out->sm_count = (uint32_t)e->sm_count;
+    for (int enc = 0; enc < 2; ++enc) {
+        const DeviceTables& dt = e->tables[enc];
+        if (!dt.built) continue;
+        out->seed_q[enc] = dt.host.q;
+        out->seed_d[enc] = dt.host.d;
+        out->n_seeds[enc] = dt.host.n_seeds;
+        out->filter_log2_bits[enc] = dt.host.filter_log2_bits;
+        out->filter_hashes[enc] = dt.host.filter_hashes;
+        out->filter_in_smem[enc] = dt.host.filter_in_smem ? 1 : 0;
+        out->table_bytes[enc] = dt.bytes();
+    }
+    return MK_OK;
+}
+
+int mk_slot_buffers(mk_engine* e, uint32_t slot, uint8_t** seq_pinned, uint64_t** off_pinned, uint32_t** lens_pinned) {
+    Slot* s = nullptr;
+    int rc = get_slot(e, slot, &s);
+    if (rc) return rc;
+    if (seq_pinned) *seq_pinned = s->h_seq.p;
+    if (off_pinned) *off_pinned = s->h_off.p;
+    if (lens_pinned) *lens_pinned = s->h_lens.p;
+    return MK_OK;
+}
+
+int mk_scan_host(mk_engine* e, uint32_t slot, const uint8_t* h_seq, const uint64_t* h_off, const uint32_t* h_lens,
+                 uint32_t n_records, uint64_t n_units, mk_encoding enc, mk_mode mode) {
+    Slot* s = nullptr;
+    int rc = get_slot(e, slot, &s);
+    if (rc) return rc;
+    if (s->ws.busy) return fail(MK_ERR_STATE, "slot %u still has a batch in flight", slot);
+    if (!h_seq || !h_off) return fail(MK_ERR_INVALID, "null batch buffers");
+    rc = check_batch(e, n_records, n_units, enc);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->device));
+    uint64_t bytes = enc == MK_ENC_ASCII ? n_units : (n_units + 1) / 2;
+    cudaStream_t st = s->ws.stream;
+    if (bytes) CU(cudaMemcpyAsync(s->d_seq.p, h_seq, bytes, cudaMemcpyHostToDevice, st));
+    // the last vector is read whole: clear its tail so that the scan input is deterministic
+    if (bytes % 16) CU(cudaMemsetAsync(s->d_seq.p + bytes, 0, 16 - bytes % 16, st));
+    CU(cudaMemcpyAsync(s->d_off.p, h_off, ((size_t)n_records + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (h_lens && n_records) CU(cudaMemcpyAsync(s->d_lens.p, h_lens, (size_t)n_records * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    return begin_batch(e, s->ws, s->d_seq.p, s->d_off.p, h_lens ? s->d_lens.p : nullptr, n_records, n_units, enc, mode, true);
+}
+
+int mk_scan_submit(mk_engine* e, uint32_t slot, uint32_t n_records, uint64_t n_units, int use_lens, mk_encoding enc,
+                   mk_mode mode) {
+    Slot* s = nullptr;
+    int rc = get_slot(e, slot, &s);
+    if (rc) return rc;
+    return mk_scan_host(e, slot, s->h_seq.p, s->h_off.p, use_lens ? s->h_lens.p : nullptr, n_records, n_units, enc, mode);
+}
+
+int mk_scan_wait(mk_engine* e, uint32_t slot, mk_result* out) {
+    Slot* s = nullptr;
+    int rc = get_slot(e, slot, &s);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->device));
+    return finish_batch(e, s->ws, out);
+}
+
+int mk_scan_device(mk_engine* e, const void* d_seq, const uint64_t* d_off, const uint32_t* d_lens, uint32_t n_records,
+                   uint64_t n_units, mk_encoding enc, mk_mode mode, int fetch, mk_result* out) {
+    if (!e) return fail(MK_ERR_INVALID, "null engine");
+    if ((!d_seq && n_units) || !d_off) return fail(MK_ERR_INVALID, "null device buffers");
+    if (reinterpret_cast<uintptr_t>(d_seq) % 16) return fail(MK_ERR_INVALID, "d_seq must be 16-byte aligned");
+    CU(cudaSetDevice(e->device));
+    int rc = begin_batch(e, e->direct, d_seq, reinterpret_cast<const unsigned long long*>(d_off), d_lens, n_records, n_units,
+                         enc, mode, fetch != 0);
+    if (rc) return rc;
+    return finish_batch(e, e->direct, out);
+}
+
+}  // extern "C"

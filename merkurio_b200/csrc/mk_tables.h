@@ -1,0 +1,279 @@
+// Host-side construction of the device query tables (the role src/pattern_preprocessing.rs:24-43
+// generate_masks and the AhoCorasick build at src/cmd_extract.rs:259-277 play in the reference).
+//
+// Input: the sorted unique pattern list (src/helpers.rs:76-133). Output, per text encoding:
+//   * seed geometry (q, d): every d-th text base starts a q-base seed; d + q - 1 <= min pattern
+//     length, so each occurrence of each pattern contains exactly one grid seed among its first d
+//     offsets;
+//   * a cuckoo hash table  seed code -> postings  (4-slot buckets of {code, first posting}; one
+//     bucket = one 32-byte L2 sector) and the postings (pattern id, seed offset j in the pattern);
+//   * the first-level filter bitmap probed for every seed (staged in shared memory when the seed
+//     set is small enough to leave it selective, else left L2-resident);
+//   * the pattern bytes used by the exact verify step (case-folded under -I).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mk_codes.h"
+
+namespace mk {
+
+constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
+constexpr uint32_t kBucketSlots = 4;
+constexpr uint32_t kSmemFilterLog2Bits = 20;  // 128 KiB bitmap staged per CTA
+constexpr uint32_t kMaxPatternId = (1u << 27) - 1;
+
+struct SeedSlot {
+    uint32_t code;
+    uint32_t first;  // index of the first posting, kEmptySlot if the slot is free
+};
+
+// posting = pattern_id << 5 | j << 1 | last_of_list
+inline uint32_t make_posting(uint32_t pid, uint32_t j, bool last) { return (pid << 5) | (j << 1) | (last ? 1u : 0u); }
+
+struct Tables {
+    int enc = 0;
+    uint32_t q = 0, d = 0;
+    bool perm = false;  // D == 16: permuted unit packing
+    uint32_t n_seeds = 0;
+    // first-level filter
+    uint32_t filter_log2_bits = 0, filter_hashes = 1;
+    bool filter_in_smem = true;
+    std::vector<uint32_t> filter;
+    // cuckoo table
+    uint32_t bucket_mask = 0;
+    std::vector<SeedSlot> slots;  // (bucket_mask + 1) * kBucketSlots
+    std::vector<uint32_t> postings;
+    // verify data
+    std::vector<uint8_t> pat_bytes;   // compare form of every pattern (folded under -I / nibble codes for BAM4)
+    std::vector<uint32_t> pat_off;    // n + 1
+    std::vector<uint8_t> pat_live;    // 0: pattern can never match in this encoding
+};
+
+struct PatternSet {
+    std::vector<uint8_t> bytes;
+    std::vector<uint32_t> off;  // n + 1
+    uint32_t n = 0, min_len = 0, max_len = 0;
+    bool case_insensitive = false;
+    // sort-key geometry (shared by both encodings)
+    uint32_t len_bits = 0, tie_bits = 0;
+    std::vector<uint32_t> tie_rank;  // rank inside the class of fold-equal patterns
+    uint32_t len(uint32_t p) const { return off[p + 1] - off[p]; }
+    const uint8_t* ptr(uint32_t p) const { return bytes.data() + off[p]; }
+};
+
+inline uint32_t bits_for(uint64_t v) {
+    uint32_t b = 0;
+    while (v) { ++b; v >>= 1; }
+    return b;
+}
+
+// Seed geometry from the shortest pattern: the largest stride whose seed is still selective.
+inline void choose_geometry(uint32_t min_len, uint32_t* q, uint32_t* d) {
+    const uint32_t strides[5] = {16, 8, 4, 2, 1};
+    for (uint32_t s : strides) {
+        if (min_len < s) continue;
+        uint32_t qq = std::min<uint32_t>(16, min_len - s + 1);
+        if (qq >= 12 || s == 1) { *q = qq; *d = s; return; }
+    }
+    *q = 1; *d = 1;
+}
+
+inline PatternSet make_pattern_set(const uint8_t* bytes, const uint32_t* off, uint32_t n, bool case_insensitive) {
+    PatternSet ps;
+    ps.n = n;
+    ps.case_insensitive = case_insensitive;
+    ps.off.assign(off, off + n + 1);
+    ps.bytes.assign(bytes + off[0], bytes + off[n]);
+    for (auto& o : ps.off) o -= off[0];
+    ps.min_len = UINT32_MAX;
+    for (uint32_t p = 0; p < n; ++p) {
+        ps.min_len = std::min(ps.min_len, ps.len(p));
+        ps.max_len = std::max(ps.max_len, ps.len(p));
+    }
+    ps.len_bits = bits_for(ps.max_len);
+    // Patterns equal up to ASCII case share every span under -I; they are reported in ascending
+    // pattern index (the order aho-corasick 1.1.3 appends pattern ids to a trie state).
+    ps.tie_rank.assign(n, 0);
+    uint32_t max_rank = 0;
+    if (case_insensitive) {
+        std::vector<uint32_t> idx(n);
+        for (uint32_t i = 0; i < n; ++i) idx[i] = i;
+        auto folded_less = [&](uint32_t a, uint32_t b) {
+            uint32_t la = ps.len(a), lb = ps.len(b);
+            const uint8_t *pa = ps.ptr(a), *pb = ps.ptr(b);
+            for (uint32_t i = 0; i < std::min(la, lb); ++i) {
+                uint8_t ca = mk_fold(pa[i]), cb = mk_fold(pb[i]);
+                if (ca != cb) return ca < cb;
+            }
+            if (la != lb) return la < lb;
+            return a < b;
+        };
+        auto folded_eq = [&](uint32_t a, uint32_t b) {
+            if (ps.len(a) != ps.len(b)) return false;
+            for (uint32_t i = 0; i < ps.len(a); ++i)
+                if (mk_fold(ps.ptr(a)[i]) != mk_fold(ps.ptr(b)[i])) return false;
+            return true;
+        };
+        std::sort(idx.begin(), idx.end(), folded_less);
+        for (uint32_t i = 1; i < n; ++i)
+            if (folded_eq(idx[i - 1], idx[i])) {
+                ps.tie_rank[idx[i]] = ps.tie_rank[idx[i - 1]] + 1;
+                max_rank = std::max(max_rank, ps.tie_rank[idx[i]]);
+            }
+    }
+    ps.tie_bits = bits_for(max_rank);
+    return ps;
+}
+
+// class of one compare-form symbol (ASCII byte or BAM nibble)
+inline uint32_t sym_class(int enc, uint8_t s) {
+    if (enc == 0) return (s >> 1) & 3u;
+    uint32_t n = s & 0xF;
+    return ((((n >> 2) | (n >> 3)) & 1u) << 1) | (((n >> 1) | (n >> 3)) & 1u);
+}
+
+// seed code of q symbols starting at sym[0] (ordered packing, as mk_seed_ord yields it)
+inline uint32_t seed_code_ord(int enc, const uint8_t* sym, uint32_t q) {
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < q; ++i) c = (c << 2) | sym_class(enc, sym[i]);
+    return c;
+}
+// seed code of exactly 16 symbols with the permuted packing of the device fast path
+inline uint32_t seed_code_perm(int enc, const uint8_t* sym) {
+    if (enc == 0) {
+        uint32_t w[4];
+        std::memcpy(w, sym, 16);
+        return mk_pack_ascii_perm(w[0], w[1], w[2], w[3]);
+    }
+    uint8_t b[8];
+    for (int i = 0; i < 8; ++i) b[i] = (uint8_t)((sym[2 * i] << 4) | (sym[2 * i + 1] & 0xF));
+    uint32_t w[2];
+    std::memcpy(w, b, 8);
+    return mk_pack_bam_perm(w[0], w[1]);
+}
+
+inline bool cuckoo_build(const std::vector<std::pair<uint32_t, uint32_t>>& keys /*code, first*/, uint32_t log2_buckets,
+                         std::vector<SeedSlot>* out, uint32_t* mask_out) {
+    uint32_t nb = 1u << log2_buckets, mask = nb - 1;
+    std::vector<SeedSlot> slots((size_t)nb * kBucketSlots, SeedSlot{0, kEmptySlot});
+    std::mt19937 rng(0x5EEDu + log2_buckets);
+    for (auto kv : keys) {
+        SeedSlot cur{kv.first, kv.second};
+        bool placed = false;
+        uint32_t from = UINT32_MAX;
+        for (int kick = 0; kick < 500 && !placed; ++kick) {
+            uint32_t cand[2] = {mk_hash_b1(cur.code, mask), mk_hash_b2(cur.code, mask)};
+            for (int h = 0; h < 2 && !placed; ++h)
+                for (uint32_t s = 0; s < kBucketSlots && !placed; ++s) {
+                    SeedSlot& sl = slots[(size_t)cand[h] * kBucketSlots + s];
+                    if (sl.first == kEmptySlot) { sl = cur; placed = true; }
+                }
+            if (placed) break;
+            // evict a random slot, preferring the bucket the item did not just come from
+            uint32_t b = (cand[0] == from) ? cand[1] : (cand[1] == from) ? cand[0] : cand[rng() & 1];
+            std::swap(cur, slots[(size_t)b * kBucketSlots + rng() % kBucketSlots]);
+            from = b;
+        }
+        if (!placed) return false;
+    }
+    *out = std::move(slots);
+    *mask_out = mask;
+    return true;
+}
+
+inline Tables build_tables(const PatternSet& ps, int enc) {
+    Tables t;
+    t.enc = enc;
+    const uint32_t n = ps.n;
+    // compare form of the patterns
+    t.pat_off = ps.off;
+    t.pat_bytes.resize(ps.bytes.size());
+    t.pat_live.assign(n, 1);
+    for (uint32_t p = 0; p < n; ++p) {
+        for (uint32_t i = ps.off[p]; i < ps.off[p + 1]; ++i) {
+            uint8_t c = ps.bytes[i];
+            if (enc == 0) {
+                t.pat_bytes[i] = ps.case_insensitive ? mk_fold(c) : c;
+            } else {
+                // decoded BAM text is upper-case "=ACMGRSVTWYHKDBN"; under -I lower-case query letters match it
+                if (ps.case_insensitive && c >= 'a' && c <= 'z') c = (uint8_t)(c - 0x20);
+                uint8_t nib = mk_ascii_to_nibble(c);
+                if (nib == 0xFF) { t.pat_live[p] = 0; nib = 0; }
+                t.pat_bytes[i] = nib;
+            }
+        }
+    }
+    choose_geometry(ps.min_len, &t.q, &t.d);
+    t.perm = (t.d == 16);
+
+    // (code, pattern, j) triples
+    struct Trip { uint32_t code, pid, j; };
+    std::vector<Trip> trips;
+    trips.reserve((size_t)n * t.d);
+    for (uint32_t p = 0; p < n; ++p) {
+        if (!t.pat_live[p]) continue;
+        const uint8_t* sym = t.pat_bytes.data() + t.pat_off[p];
+        for (uint32_t j = 0; j < t.d; ++j) {
+            uint32_t code = t.perm ? seed_code_perm(enc, sym + j) : seed_code_ord(enc, sym + j, t.q);
+            trips.push_back({code, p, j});
+        }
+    }
+    std::sort(trips.begin(), trips.end(), [](const Trip& a, const Trip& b) {
+        if (a.code != b.code) return a.code < b.code;
+        if (a.pid != b.pid) return a.pid < b.pid;
+        return a.j < b.j;
+    });
+    std::vector<std::pair<uint32_t, uint32_t>> keys;
+    t.postings.resize(trips.size());
+    for (size_t i = 0; i < trips.size(); ++i) {
+        bool first = (i == 0) || trips[i - 1].code != trips[i].code;
+        bool last = (i + 1 == trips.size()) || trips[i + 1].code != trips[i].code;
+        if (first) keys.emplace_back(trips[i].code, (uint32_t)i);
+        t.postings[i] = make_posting(trips[i].pid, trips[i].j, last);
+    }
+    if (t.postings.empty()) t.postings.push_back(make_posting(0, 0, true));  // keep device pointers non-null
+    t.n_seeds = (uint32_t)keys.size();
+
+    // cuckoo table at <= 50 % load, grown until the insertion succeeds
+    uint32_t lb = 1;
+    while (((uint64_t)kBucketSlots << lb) < (uint64_t)keys.size() * 2) ++lb;
+    while (!cuckoo_build(keys, lb, &t.slots, &t.bucket_mask)) {
+        if (++lb > 28) throw std::runtime_error("seed table does not fit");
+    }
+
+    // first-level filter
+    double nn = (double)t.n_seeds, m = std::ldexp(1.0, kSmemFilterLog2Bits);
+    double p1 = 1.0 - std::exp(-nn / m);
+    double p2 = std::pow(1.0 - std::exp(-2.0 * nn / m), 2.0);
+    if (std::min(p1, p2) <= 0.30) {
+        t.filter_in_smem = true;
+        t.filter_log2_bits = kSmemFilterLog2Bits;
+        t.filter_hashes = (p2 < p1) ? 2 : 1;
+    } else {
+        // too many seeds for shared memory: L2-resident bitmap, ~32 bits per seed, one hash
+        t.filter_in_smem = false;
+        t.filter_hashes = 1;
+        uint32_t b = kSmemFilterLog2Bits + 1;
+        while (b < 30 && std::ldexp(1.0, b) < nn * 32.0) ++b;
+        t.filter_log2_bits = b;
+    }
+    t.filter.assign((size_t)1 << (t.filter_log2_bits - 5), 0);
+    for (auto& kv : keys) {
+        uint32_t h = mk_hash_f1(kv.first, t.filter_log2_bits);
+        t.filter[h >> 5] |= 1u << (h & 31);
+        if (t.filter_hashes == 2) {
+            h = mk_hash_f2(kv.first, t.filter_log2_bits);
+            t.filter[h >> 5] |= 1u << (h & 31);
+        }
+    }
+    return t;
+}
+
+}  // namespace mk
