@@ -1,0 +1,311 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/merkurio_cuda.h), against the
+CPU oracle on the same seeded inputs. Bar: bit-exact hit lists, in the reference's report order."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from merkurio_b200 import capi
+from oracle import refmodel as rm
+
+NIB = rm.NIBBLE_CHARS
+
+
+def pack_records(records):
+    off = np.zeros(len(records) + 1, dtype=np.uint64)
+    if records:
+        off[1:] = np.cumsum([len(r) for r in records])
+    seq = np.frombuffer(b"".join(records), dtype=np.uint8).copy() if off[-1] else np.zeros(0, dtype=np.uint8)
+    return seq, off
+
+
+def oracle_hits(patterns, records, case_insensitive=False):
+    ac = rm.AhoCorasick(patterns, case_insensitive)
+    seq, off = pack_records(records)
+    rec, st, pat = ac.batch_hits(seq if seq.size else np.zeros(1, np.uint8), off)
+    return rec, st, pat
+
+
+def check_batch(patterns, records, case_insensitive=False, hit_capacity=0, engine=None):
+    """ALL_HITS, PATTERN_SET and FLAG of one batch against the oracle."""
+    patterns = sorted(set(patterns))
+    rec, st, pat = oracle_hits(patterns, records, case_insensitive)
+    seq, off = pack_records(records)
+    own = engine is None
+    if own:
+        engine = capi.Engine(patterns, case_insensitive=case_insensitive, max_batch_bytes=max(int(seq.size), 16) + 64,
+                             max_batch_records=max(len(records), 1), hit_capacity=hit_capacity)
+    try:
+        r = engine.scan(seq, off, capi.MK_MODE_ALL_HITS)
+        assert r.n_hits == len(rec), (r.n_hits, len(rec))
+        np.testing.assert_array_equal(r.hits["record"], rec)
+        np.testing.assert_array_equal(r.hits["start"], st)
+        np.testing.assert_array_equal(r.hits["pattern"], pat)
+        np.testing.assert_array_equal(r.hits["len"], np.array([len(patterns[p]) for p in pat], dtype=np.uint32))
+        want_flag = np.unique(rec)
+        np.testing.assert_array_equal(r.flagged_records(), want_flag)
+        f = engine.scan(seq, off, capi.MK_MODE_FLAG)
+        np.testing.assert_array_equal(f.flagged_records(), want_flag)
+        assert f.n_hits == 0
+        p = engine.scan(seq, off, capi.MK_MODE_PATTERN_SET)
+        pairs = sorted(set(zip(rec.tolist(), pat.tolist())))
+        assert list(zip(p.hits["record"].tolist(), p.hits["pattern"].tolist())) == pairs
+        np.testing.assert_array_equal(p.flagged_records(), want_flag)
+        return r
+    finally:
+        if own:
+            engine.close()
+
+
+def rand_seq(rng, n, alphabet=b"ACGT"):
+    return bytes(rng.choice(np.frombuffer(alphabet, dtype=np.uint8), size=n).tobytes())
+
+
+def planted_records(rng, patterns, n_records, min_len, max_len, alphabet=b"ACGT", plant_p=0.3, noise=b"N"):
+    recs = []
+    for _ in range(n_records):
+        n = int(rng.integers(min_len, max_len + 1))
+        r = bytearray(rand_seq(rng, n, alphabet))
+        if n and rng.random() < plant_p:
+            for _k in range(int(rng.integers(1, 4))):
+                p = patterns[int(rng.integers(len(patterns)))]
+                if len(p) <= n:
+                    s = int(rng.integers(0, n - len(p) + 1))
+                    r[s:s + len(p)] = p
+        if n and rng.random() < 0.2:
+            s = int(rng.integers(0, n))
+            e = min(n, s + int(rng.integers(1, 6)))
+            r[s:e] = noise * (e - s)
+        recs.append(bytes(r))
+    return recs
+
+
+# ------------------------------------------------------------------------------------------------
+def test_version_and_info():
+    assert "sm_100a" in capi.version()
+    with capi.Engine([b"A" * 31, b"C" * 40]) as e:
+        e.scan(np.frombuffer(b"ACGT" * 16, dtype=np.uint8), np.array([0, 64], dtype=np.uint64))
+        info = e.info()
+        assert info.n_patterns == 2 and info.min_len == 31 and info.max_len == 40
+        assert info.seed_q[0] == 16 and info.seed_d[0] == 16 and info.sm_count > 0
+
+
+def test_reference_toy_vectors():
+    # src/pattern_matching.rs:353-392 through the device
+    r = check_batch([b"abc"], [b"abcabcabc", b"xabcabcabcx", b"ab", b""])
+    assert r.hits["start"].tolist() == [0, 3, 6, 1, 4, 7]
+    # self-overlap and substring patterns
+    r = check_batch([b"AAA"], [b"AAAAA"])
+    assert r.hits["start"].tolist() == [0, 1, 2]
+    r = check_batch([b"CTC", b"TC", b"C"], [b"GGCTCGG"])
+    assert [(h["pattern"], h["start"]) for h in r.hits] == [(0, 2), (1, 2), (2, 3), (0, 4)]
+
+
+def test_golden_fixture_texts(ref_tree):
+    fx = ref_tree / "tests" / "fixtures" / "input"
+    recs = [r.seq for r in rm.parse_fastx((fx / "simple.fasta").read_bytes())]
+    check_batch([b"ACG", b"CGT"], recs)
+    recs = [r.seq for r in rm.parse_fastx((fx / "fixed-width.faa").read_bytes())]
+    r = check_batch([b"DKAT"], recs)
+    assert r.hits["start"].tolist() == [79, 272]
+    _, sam = rm.parse_bam((fx / "simple.bam").read_bytes())
+    pats = rm.parse_pattern_list(None, ["CTC", "AC", "CT", "AA", "T", "A", "C", "G", "GA", "AG"], True, False, False, False)
+    r = check_batch([p.encode() for p in pats], [s.seq for s in sam])
+    assert r.n_hits == 96  # tests/fixtures/extract/log.json
+
+
+def test_cfg1_example_minimal(ref_tree):
+    recs = [r.seq for r in rm.parse_fastx((ref_tree / "example-minimal" / "sample.fasta").read_bytes())]
+    r = check_batch([b"AAC", b"GTT"], recs)
+    assert r.n_hits == 74 and sum(len(x) for x in recs) == 1795
+
+
+def test_example_workflow_reads(ref_tree):
+    ew = ref_tree / "example-workflow"
+    pats = rm.parse_pattern_list(ew / "data" / "significant_kmers.txt", None, True, False, False, False)
+    r1 = [r.seq for r in rm.parse_fastx((ew / "data" / "mutant_R1.fastq").read_bytes())]
+    r2 = [r.seq for r in rm.parse_fastx((ew / "data" / "mutant_R2.fastq").read_bytes())]
+    a = check_batch([p.encode() for p in pats], r1)
+    b = check_batch([p.encode() for p in pats], r2)
+    assert a.n_hits + b.n_hits == 36 and len(a.flagged_records()) == 9 and len(b.flagged_records()) == 15
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 11, 12, 13, 14, 15, 16, 17, 18, 19, 21, 22, 23, 27, 30, 31, 32, 33, 47, 63, 64, 65, 100])
+def test_random_single_length(k):
+    rng = np.random.default_rng(1000 + k)
+    n_pat = 3 if k < 4 else 40
+    pats = sorted({rand_seq(rng, k) for _ in range(n_pat)})
+    recs = planted_records(rng, pats, 300, 0, 220, plant_p=0.4 if k > 3 else 0.0)
+    check_batch(pats, recs)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_mixed_lengths(seed):
+    rng = np.random.default_rng(7 + seed)
+    lo = [1, 4, 12, 17, 21, 31][seed]
+    pats = sorted({rand_seq(rng, int(rng.integers(lo, lo + 45))) for _ in range(60)})
+    # suffix/prefix-related patterns: two patterns ending at the same position
+    pats = sorted(set(pats) | {p[3:] for p in pats[:10] if len(p) - 3 >= lo} | {p[:-2] for p in pats[10:20] if len(p) - 2 >= lo})
+    recs = planted_records(rng, pats, 400, 0, 400, plant_p=0.5)
+    check_batch(pats, recs)
+
+
+def test_non_acgt_queries_and_text():
+    rng = np.random.default_rng(5)
+    base = [rand_seq(rng, 31) for _ in range(30)]
+    pats = []
+    for p in base:
+        b = bytearray(p)
+        b[int(rng.integers(31))] = ord("N")
+        pats.append(bytes(b))
+    pats += [b"MKVLAAGIVGLCAKENYVDQWERTPLSHFM", b"acgtacgtacgtacgtacgtacgtacgtacg", b"ACGTNNNNNNNNNNNNNNNNNNNNNNNACGT"]
+    pats = sorted(set(pats + base[:5]))
+    recs = planted_records(rng, pats, 300, 20, 300, alphabet=b"ACGTNacgt", plant_p=0.6)
+    # the same windows with one byte changed to N / lower case must not hit
+    broken = []
+    for p in base[:10]:
+        b = bytearray(b"GG" + p + b"GG")
+        b[2 + 7] = ord("N")
+        broken.append(bytes(b))
+        broken.append((b"GG" + p + b"GG").lower())
+    check_batch(pats, recs + broken)
+
+
+def test_case_modes():
+    rng = np.random.default_rng(11)
+    pats = sorted({rand_seq(rng, 24) for _ in range(20)})
+    recs = planted_records(rng, pats, 200, 10, 200, plant_p=0.6)
+    recs = [r.lower() if i % 3 == 0 else (r.swapcase() if i % 3 == 1 else r) for i, r in enumerate(recs)]
+    check_batch(pats, recs, case_insensitive=False)
+    check_batch(pats, recs, case_insensitive=True)
+    # -L style: lower-case queries against upper-case reads -> no hits unless -I
+    low = sorted(p.lower() for p in pats)
+    up = [r.upper() for r in recs]
+    r = check_batch(low, up, case_insensitive=False)
+    assert r.n_hits == 0
+    r = check_batch(low, up, case_insensitive=True)
+    assert r.n_hits > 0
+    # patterns equal up to case share their spans under -I: ascending pattern index
+    r = check_batch([b"ACGTACGTACGTAC", b"acgtacgtacgtac", b"AcGtAcGtAcGtAc"], [b"TTACGTACGTACGTACTT"], case_insensitive=True)
+    assert r.hits["pattern"].tolist() == [0, 1, 2]
+
+
+def test_record_boundaries_and_ragged_layout():
+    rng = np.random.default_rng(3)
+    p = rand_seq(rng, 31)
+    # a hit may not straddle two records; hits at offset 0 and at len-k
+    recs = [p[:15], p[15:], p, b"", b"", p + p, b"A", p[:-1], b"G" + p, p + b"G", b""]
+    r = check_batch([p], recs)
+    assert r.hits["record"].tolist() == [2, 5, 5, 8, 9]
+    # odd record lengths shift every later record off the 16-byte grid
+    recs = planted_records(rng, [p], 500, 0, 97, plant_p=0.7)
+    check_batch([p], recs)
+
+
+def test_long_record_every_alignment():
+    rng = np.random.default_rng(17)
+    pats = sorted({rand_seq(rng, int(k)) for k in (21, 31, 33, 40, 64, 65)})
+    big = bytearray(rand_seq(rng, 1 << 20))
+    pos = 1000
+    for i in range(600):
+        p = pats[i % len(pats)]
+        big[pos:pos + len(p)] = p
+        pos += 1600 + (i % 67)  # walks through every residue mod 16/32/512/2048
+    check_batch(pats, [bytes(big[:300000]), bytes(big[300000:])])
+
+
+def test_hit_overflow_rescan():
+    rng = np.random.default_rng(23)
+    recs = [rand_seq(rng, 150) for _ in range(200)]
+    r = check_batch([b"A", b"AC"], recs, hit_capacity=64)
+    assert r.n_rescans >= 1 and r.n_hits > 64
+
+
+def test_many_patterns_l2_filter():
+    # enough seeds to push the first-level filter out of shared memory
+    rng = np.random.default_rng(29)
+    genome = rand_seq(rng, 400000)
+    starts = rng.integers(0, len(genome) - 70, size=60000)
+    pats = sorted({genome[s:s + int(k)] for s, k in zip(starts, rng.integers(21, 64, size=len(starts)))})
+    with capi.Engine(pats, max_batch_bytes=len(genome) + 64, max_batch_records=4) as e:
+        check_batch(pats, [genome[:150000], genome[150000:]], engine=e)
+        assert e.info().filter_in_smem[0] == 0
+
+
+def test_bam4_encoding():
+    rng = np.random.default_rng(31)
+    pats = sorted({rand_seq(rng, int(k)) for k in rng.integers(16, 50, size=40)} | {b"ACGTNNACGTACGTAAGGCTNAC", b"acgtacgtacgtacgtacgt"})
+    recs = planted_records(rng, [p for p in pats if p.isupper()], 300, 0, 180, alphabet=b"ACGTNRY", plant_p=0.6)
+    ac = rm.AhoCorasick(pats, False)
+    # pack as BAM: 2 bases / byte, records byte aligned, explicit lengths
+    nib = np.full(256, 15, dtype=np.uint8)
+    for i, c in enumerate(NIB):
+        nib[c] = i
+    chunks, off, lens, pos = [], [0], [], 0
+    for r in recs:
+        codes = nib[np.frombuffer(r, dtype=np.uint8)] if r else np.zeros(0, np.uint8)
+        if len(codes) % 2:
+            codes = np.append(codes, 0)
+        chunks.append((codes[0::2] << 4 | codes[1::2]).astype(np.uint8))
+        lens.append(len(r))
+        pos += len(codes)
+        off.append(pos)
+    packed = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
+    off = np.array(off, dtype=np.uint64)
+    lens = np.array(lens, dtype=np.uint32)
+    seq, aoff = pack_records(recs)
+    rec, st, pat = ac.batch_hits(seq, aoff)
+    with capi.Engine(pats, max_batch_bytes=int(packed.size) + 64, max_batch_records=len(recs)) as e:
+        r = e.scan(packed, off, capi.MK_MODE_ALL_HITS, enc=capi.MK_ENC_BAM4, lens=lens, n_units=int(off[-1]))
+        np.testing.assert_array_equal(r.hits["record"], rec)
+        np.testing.assert_array_equal(r.hits["start"], st)
+        np.testing.assert_array_equal(r.hits["pattern"], pat)
+        p = e.scan(packed, off, capi.MK_MODE_PATTERN_SET, enc=capi.MK_ENC_BAM4, lens=lens, n_units=int(off[-1]))
+        assert list(zip(p.hits["record"].tolist(), p.hits["pattern"].tolist())) == sorted(set(zip(rec.tolist(), pat.tolist())))
+
+
+def test_double_buffered_slots_match_single_batch():
+    rng = np.random.default_rng(37)
+    pats = sorted({rand_seq(rng, 31) for _ in range(100)})
+    recs = planted_records(rng, pats, 4000, 150, 150, plant_p=0.05)
+    whole = oracle_hits(pats, recs)
+    with capi.Engine(pats, n_slots=2, max_batch_bytes=1000 * 150, max_batch_records=1000) as e:
+        got = []
+        pending = []
+        for b in range(4):
+            part = recs[b * 1000:(b + 1) * 1000]
+            seq, off = pack_records(part)
+            slot = b % 2
+            if len(pending) == 2:
+                s0, b0 = pending.pop(0)
+                r = e.wait(s0)
+                got.append((b0, r.hits.copy()))
+            a, o, _ = e.slot_arrays(slot)
+            a[: seq.size] = seq
+            o[: off.size] = off
+            e.submit(slot, len(part), int(seq.size), capi.MK_ENC_ASCII, capi.MK_MODE_ALL_HITS)
+            pending.append((slot, b))
+        for s0, b0 in pending:
+            got.append((b0, e.wait(s0).hits.copy()))
+    rec = np.concatenate([h["record"] + 1000 * b for b, h in got])
+    st = np.concatenate([h["start"] for b, h in got])
+    pat = np.concatenate([h["pattern"] for b, h in got])
+    np.testing.assert_array_equal(rec, whole[0])
+    np.testing.assert_array_equal(st, whole[1])
+    np.testing.assert_array_equal(pat, whole[2])
+
+
+def test_errors_across_the_boundary():
+    with pytest.raises(capi.MkError) as ei:
+        capi.Engine([])
+    assert ei.value.code == -3 and "No k-mers found" in ei.value.message
+    with pytest.raises(capi.MkError) as ei:
+        capi.Engine([b"ACGT", b""])
+    assert ei.value.code == -2 and "Pattern is empty" in ei.value.message
+    with capi.Engine([b"ACGT"], n_slots=1, max_batch_bytes=64, max_batch_records=4) as e:
+        with pytest.raises(capi.MkError) as ei:
+            e.scan(np.zeros(1000, np.uint8), np.array([0, 1000], dtype=np.uint64))
+        assert ei.value.code == -6
+        with pytest.raises(capi.MkError) as ei:
+            e.wait(0)
+        assert ei.value.code == -7
