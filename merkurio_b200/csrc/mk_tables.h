@@ -80,7 +80,8 @@ inline void choose_geometry(uint32_t min_len, uint32_t* q, uint32_t* d) {
     for (uint32_t s : strides) {
         if (min_len < s) continue;
         uint32_t qq = std::min<uint32_t>(16, min_len - s + 1);
-        if (qq >= 12 || s == 1) { *q = qq; *d = s; return; }
+        // stride 16 uses the permuted whole-unit packing, which needs the full 16-base seed
+        if (s == 16 ? qq == 16 : (qq >= 12 || s == 1)) { *q = qq; *d = s; return; }
     }
     *q = 1; *d = 1;
 }
