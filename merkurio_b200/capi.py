@@ -110,8 +110,10 @@ class ScanResult:
         if r.record_flags and nw:
             a = np.ctypeslib.as_array(C.cast(r.record_flags, C.POINTER(C.c_uint64)), shape=(nw,))
             self.flags = a.copy() if copy else a
+        elif r.record_flags:
+            self.flags = np.zeros(0, dtype=np.uint64)
         else:
-            self.flags = np.zeros(nw, dtype=np.uint64)
+            self.flags = None  # not fetched (device-resident scan without fetch)
         if r.hits and r.n_hits:
             buf = (C.c_uint8 * (self.n_hits * 16)).from_address(r.hits)
             a = np.frombuffer(buf, dtype=HIT_DTYPE)

@@ -103,11 +103,18 @@ MK_HD uint32_t mk_seed_ord(uint32_t cur, uint32_t nxt, uint32_t o, uint32_t q) {
     return win >> (32u - 2u * q);
 }
 
-// First-level filter hashes (bit index into a 2^log2_bits bitmap) and cuckoo bucket hashes.
-MK_HD uint32_t mk_hash_f1(uint32_t code, uint32_t log2_bits) { return (code * 0x9E3779B1u) >> (32u - log2_bits); }
-MK_HD uint32_t mk_hash_f2(uint32_t code, uint32_t log2_bits) {
-    return ((code ^ (code >> 15)) * 0x85EBCA77u) >> (32u - log2_bits);
+// First-level filter. Shared-memory flavour: a blocked Bloom filter of 2^15 32-bit words; a seed
+// selects one word with the top 15 bits of code * MK_BLOOM_MUL and two bit positions inside it from
+// bits 7..11 and 12..16 of the same product (one LDS per probe). Global flavour (seed sets too large
+// for shared memory): a plain bitmap of 2^log2_bits bits indexed by mk_hash_f1.
+#define MK_BLOOM_MUL 0x9E3779B1u
+#define MK_BLOOM_LOG2_WORDS 15
+MK_HD uint32_t mk_bloom_word(uint32_t code) { return (code * MK_BLOOM_MUL) >> (32 - MK_BLOOM_LOG2_WORDS); }
+MK_HD uint32_t mk_bloom_mask(uint32_t code) {
+    uint32_t h = code * MK_BLOOM_MUL;
+    return (1u << ((h >> 7) & 31)) | (1u << ((h >> 12) & 31));
 }
+MK_HD uint32_t mk_hash_f1(uint32_t code, uint32_t log2_bits) { return (code * 0x9E3779B1u) >> (32u - log2_bits); }
 MK_HD uint32_t mk_mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
     return x;

@@ -4,12 +4,14 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <new>
 #include <string>
 #include <vector>
 
-#include "mk_kernels.cuh"
+#include "mk_scan.cuh"
+#include "mk_sort.cuh"
 
 namespace {
 
@@ -137,25 +139,35 @@ namespace {
 
 using ScanKernel = void (*)(const mk::ScanParams);
 
-template <int ENC, int NHASH, bool SMEMF>
+// Launch shape of the stride-16 scan: U 16-byte vectors per lane and tile (two tiles in flight).
+// MK_TUNE_U overrides the default (used by scripts/tune_scan.py only).
+int scan_tune_u() {
+    int u = 2;
+    if (const char* s = std::getenv("MK_TUNE_U")) u = std::atoi(s);
+    return (u == 2 || u == 4 || u == 8) ? u : 2;
+}
+
+template <int ENC, int FMODE>
 ScanKernel pick_by_d(uint32_t d) {
     switch (d) {
-        case 16: return mk::mk_scan_d16<ENC, NHASH, SMEMF, 4>;
-        case 8: return mk::mk_scan_ord<ENC, 8, NHASH, SMEMF, 4>;
-        case 4: return mk::mk_scan_ord<ENC, 4, NHASH, SMEMF, 4>;
-        case 2: return mk::mk_scan_ord<ENC, 2, NHASH, SMEMF, 2>;
-        default: return mk::mk_scan_ord<ENC, 1, NHASH, SMEMF, 2>;
+        case 16:
+            switch (scan_tune_u()) {
+                default: return mk::mk_scan_d16<ENC, FMODE, 2>;
+                case 8: return mk::mk_scan_d16<ENC, FMODE, 8>;
+                case 4: return mk::mk_scan_d16<ENC, FMODE, 4>;
+            }
+        case 8: return mk::mk_scan_ord<ENC, 8, FMODE, 4>;
+        case 4: return mk::mk_scan_ord<ENC, 4, FMODE, 4>;
+        case 2: return mk::mk_scan_ord<ENC, 2, FMODE, 2>;
+        default: return mk::mk_scan_ord<ENC, 1, FMODE, 2>;
     }
 }
-int tile_vectors(uint32_t d) { return (d >= 4 ? 4 : 2) * 32; }
+int tile_vectors(uint32_t d) { return (d == 16 ? scan_tune_u() : d >= 4 ? 4 : 2) * 32; }
 
-ScanKernel pick_kernel(int enc, uint32_t d, uint32_t nhash, bool smemf) {
-    if (enc == MK_ENC_ASCII) {
-        if (smemf) return nhash == 2 ? pick_by_d<MK_ENC_ASCII, 2, true>(d) : pick_by_d<MK_ENC_ASCII, 1, true>(d);
-        return pick_by_d<MK_ENC_ASCII, 1, false>(d);
-    }
-    if (smemf) return nhash == 2 ? pick_by_d<MK_ENC_BAM4, 2, true>(d) : pick_by_d<MK_ENC_BAM4, 1, true>(d);
-    return pick_by_d<MK_ENC_BAM4, 1, false>(d);
+ScanKernel pick_kernel(int enc, uint32_t d, bool smemf) {
+    if (enc == MK_ENC_ASCII)
+        return smemf ? pick_by_d<MK_ENC_ASCII, mk::kFilterSmem>(d) : pick_by_d<MK_ENC_ASCII, mk::kFilterGlobal>(d);
+    return smemf ? pick_by_d<MK_ENC_BAM4, mk::kFilterSmem>(d) : pick_by_d<MK_ENC_BAM4, mk::kFilterGlobal>(d);
 }
 
 int init_workspace(Workspace& ws) {
@@ -194,7 +206,7 @@ int ensure_tables(mk_engine* e, int enc) {
     CU(dt.pat_off.upload(dt.host.pat_off));
     CU(dt.slots.upload(dt.host.slots));
     CU(dt.pat_bytes.upload(dt.host.pat_bytes));
-    ScanKernel k = pick_kernel(enc, dt.host.d, dt.host.filter_hashes, dt.host.filter_in_smem);
+    ScanKernel k = pick_kernel(enc, dt.host.d, dt.host.filter_in_smem);
     if (dt.host.filter_in_smem)
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dt.host.filter.size() * 4)));
     dt.built = true;
@@ -211,7 +223,8 @@ int enqueue(mk_engine* e, Workspace& ws) {
     mk::ScanParams P{};
     P.text = reinterpret_cast<const uint4*>(ws.d_seq);
     P.n_units = ws.n_units;
-    P.n_vec = (seq_bytes + 15) / 16;
+    if ((seq_bytes + 15) / 16 > 0xFFFFFFF0ull) return fail(MK_ERR_CAPACITY, "batch larger than 64 GiB of sequence");
+    P.n_vec = (uint32_t)((seq_bytes + 15) / 16);
     P.off = ws.d_off;
     P.lens = ws.d_lens;
     P.n_records = ws.n_records;
@@ -245,7 +258,7 @@ int enqueue(mk_engine* e, Workspace& ws) {
     CU(cudaMemsetAsync(ws.counters.p, 0, 2 * sizeof(unsigned long long), ws.stream));
     CU(cudaEventRecord(ws.ev_begin, ws.stream));
     if (P.n_vec > 0 && ws.n_records > 0) {
-        ScanKernel k = pick_kernel(ws.enc, t.d, t.filter_hashes, t.filter_in_smem);
+        ScanKernel k = pick_kernel(ws.enc, t.d, t.filter_in_smem);
         uint64_t tiles = (P.n_vec + tile_vectors(t.d) - 1) / tile_vectors(t.d);
         uint64_t want = (tiles + mk::kScanWarps - 1) / mk::kScanWarps;
         int grid = (int)std::min<uint64_t>((uint64_t)e->sm_count, std::max<uint64_t>(want, 1));

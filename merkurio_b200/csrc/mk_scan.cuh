@@ -1,0 +1,362 @@
+// Device scan of the matching engine (sm_100a): replaces BNDMq::find_iter / find_match
+// (/root/reference/src/pattern_matching.rs:128-209) and AhoCorasick::find_overlapping_iter
+// (src/cmd_extract.rs:332,480,507, src/cmd_tag.rs:393-396).
+//
+// HBM-bound by design: every text byte is read exactly once with coalesced 16-byte loads (read-only
+// path, no L1 allocation, evict-first in L2), packed to 2-bit classes in registers, and one seed per
+// D bases is probed in a blocked Bloom filter staged in shared memory (one LDS per seed). The rare
+// survivors go through the L2-resident cuckoo seed table and an exact byte compare against the
+// pattern bytes, which is what makes the result identical to the reference's byte matchers.
+#pragma once
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/merkurio_cuda.h"
+#include "mk_codes.h"
+#include "mk_tables.h"
+
+namespace mk {
+
+struct RawHit {
+    unsigned long long key;
+    uint32_t record;
+    uint32_t pattern;
+};
+static_assert(sizeof(RawHit) == 16, "RawHit must be 16 bytes");
+
+struct ScanParams {
+    // text
+    const uint4* text;   // raw sequence bytes, 16-byte aligned
+    uint64_t n_units;    // bases in the batch
+    uint32_t n_vec;      // 16-byte vectors that cover them
+    uint32_t n_records;
+    const unsigned long long* off;  // n_records + 1 unit offsets
+    const uint32_t* lens;           // optional record lengths
+    // tables
+    const uint32_t* filter;
+    uint32_t filter_log2_bits;
+    uint32_t bucket_mask;
+    const SeedSlot* slots;
+    const uint32_t* postings;
+    const uint8_t* pat_bytes;
+    const uint32_t* pat_off;
+    const uint32_t* tie_rank;
+    uint32_t q;
+    int case_insensitive;
+    // outputs
+    uint32_t* flags;                // 1 bit / record
+    RawHit* hits;
+    unsigned long long hit_capacity;
+    unsigned long long* hit_count;
+    int mode;
+    uint32_t len_bits, tie_bits, pat_bits, max_len;
+};
+
+constexpr int kScanThreads = 1024;
+constexpr int kScanWarps = kScanThreads / 32;
+
+// First-level filter flavours
+constexpr int kFilterSmem = 0;    // blocked Bloom in shared memory: 2 bits inside one 32-bit word
+constexpr int kFilterGlobal = 1;  // plain 1-hash bitmap left in global memory (L2-resident)
+
+__device__ __forceinline__ uint64_t make_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4* p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+
+// One probe of the first-level filter. kFilterSmem: `f` is the shared-memory copy.
+template <int FMODE>
+__device__ __forceinline__ uint32_t filter_probe(const uint32_t* __restrict__ f, uint32_t code, uint32_t lb) {
+    if (FMODE == kFilterSmem) {
+        uint32_t h = code * MK_BLOOM_MUL;
+        uint32_t w = f[h >> (32 - (kSmemFilterLog2Bits - 5))];
+        // shifts by a register use its low 5 bits (SHF.R.W), so the bit positions need no masking
+        return (w >> ((h >> 7) & 31)) & (w >> ((h >> 12) & 31)) & 1u;
+    } else {
+        uint32_t h = mk_hash_f1(code, lb);
+        return (__ldg(f + (h >> 5)) >> (h & 31)) & 1u;
+    }
+}
+
+// last record r with off[r] <= s  (records of length 0 are skipped by construction)
+__device__ __forceinline__ uint32_t find_record(const unsigned long long* __restrict__ off, uint32_t n, uint64_t s) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (off[mid] <= s) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <int ENC>
+__device__ __forceinline__ uint8_t text_symbol(const uint8_t* __restrict__ t, uint64_t pos, int ci) {
+    if (ENC == MK_ENC_ASCII) {
+        uint8_t c = t[pos];
+        return ci ? mk_fold(c) : c;
+    }
+    uint8_t b = t[pos >> 1];
+    return (pos & 1) ? (b & 0xF) : (b >> 4);
+}
+
+// Slow path: a seed at base position `pos` passed the first-level filter.
+template <int ENC>
+__device__ __noinline__ void verify_seed(const ScanParams& P, uint64_t pos, uint32_t code) {
+    // cuckoo lookup: two 32-byte buckets
+    uint32_t first = kEmptySlot;
+#pragma unroll
+    for (int h = 0; h < 2 && first == kEmptySlot; ++h) {
+        uint32_t b = h == 0 ? mk_hash_b1(code, P.bucket_mask) : mk_hash_b2(code, P.bucket_mask);
+        const uint4* bp = reinterpret_cast<const uint4*>(P.slots + (size_t)b * kBucketSlots);
+        uint4 lo = __ldg(bp), hi = __ldg(bp + 1);
+        if (lo.x == code && lo.y != kEmptySlot) first = lo.y;
+        else if (lo.z == code && lo.w != kEmptySlot) first = lo.w;
+        else if (hi.x == code && hi.y != kEmptySlot) first = hi.y;
+        else if (hi.z == code && hi.w != kEmptySlot) first = hi.w;
+    }
+    if (first == kEmptySlot) return;
+
+    const uint8_t* text = reinterpret_cast<const uint8_t*>(P.text);
+    for (uint32_t i = first;; ++i) {
+        uint32_t e = __ldg(P.postings + i);
+        uint32_t pid = e >> 5, j = (e >> 1) & 15u;
+        if (pos >= j) {
+            uint64_t s = pos - j;
+            uint32_t po = __ldg(P.pat_off + pid);
+            uint32_t L = __ldg(P.pat_off + pid + 1) - po;
+            if (s + L <= P.n_units) {
+                const uint8_t* pat = P.pat_bytes + po;
+                bool eq = true;
+                for (uint32_t k = 0; k < L; ++k) {
+                    if (text_symbol<ENC>(text, s + k, P.case_insensitive) != __ldg(pat + k)) { eq = false; break; }
+                }
+                if (eq && s >= P.off[0]) {
+                    uint32_t r = find_record(P.off, P.n_records, s);
+                    uint64_t rend = P.lens ? P.off[r] + P.lens[r] : P.off[r + 1];
+                    if (s + L <= rend) {
+                        atomicOr(P.flags + (r >> 5), 1u << (r & 31));
+                        if (P.mode != MK_MODE_FLAG) {
+                            // warp-aggregated append: one atomic per group of lanes that got here together
+                            cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
+                            unsigned long long base = 0;
+                            if (g.thread_rank() == 0) base = atomicAdd(P.hit_count, (unsigned long long)g.size());
+                            base = g.shfl(base, 0);
+                            unsigned long long slot = base + g.thread_rank();
+                            if (slot < P.hit_capacity) {
+                                RawHit hrec;
+                                if (P.mode == MK_MODE_ALL_HITS)
+                                    hrec.key = ((((unsigned long long)(s + L) << P.len_bits) | (P.max_len - L)) << P.tie_bits) |
+                                               __ldg(P.tie_rank + pid);
+                                else
+                                    hrec.key = ((unsigned long long)r << P.pat_bits) | pid;
+                                hrec.record = r;
+                                hrec.pattern = pid;
+                                P.hits[slot] = hrec;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (e & 1u) break;
+    }
+}
+
+template <int FMODE>
+__device__ __forceinline__ void stage_filter(const ScanParams& P, uint32_t* s_filter) {
+    if (FMODE != kFilterSmem) return;
+    constexpr uint32_t n16 = 1u << (kSmemFilterLog2Bits - 7);  // uint4 count
+    const uint4* src = reinterpret_cast<const uint4*>(P.filter);
+    uint4* dst = reinterpret_cast<uint4*>(s_filter);
+    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// D == 16: the seed is the 16-base unit itself; no lane needs its neighbour.
+// ASCII: one seed per 16-byte vector. BAM4: two seeds per vector.
+//
+// Work split: a tile is U rows of 512 contiguous bytes (lane l owns vector l of every row); warp w of
+// the grid takes tiles w, w + W, w + 2W, ... The loop is unrolled twice over two register buffers so
+// that the loads of the next tile are in flight while the current one is processed (2*U loads per
+// lane) and no register copies are needed. Only full tiles run through the loop; the ragged last
+// tile is handled once, with bounds checks, after it.
+// ---------------------------------------------------------------------------------------------
+// Candidate queue of one warp (shared memory). Seeds that pass the first-level filter are rare and
+// scattered over the lanes; verifying them where they occur would stall the whole warp on two
+// dependent L2 reads for one or two active lanes. Instead they are compacted (ballot + popc) into
+// this queue and verified 32 at a time, one candidate per lane, with all lookups in flight together.
+constexpr int kQueueCap = 64;
+struct WarpQueue {
+    uint2* slot;     // kQueueCap entries of {unit index, seed code}
+    uint32_t count;  // warp-uniform
+};
+
+template <int ENC>
+__device__ __forceinline__ void queue_drain32(const ScanParams& P, WarpQueue& wq, uint32_t lane) {
+    wq.count -= 32;
+    uint2 e = wq.slot[wq.count + lane];
+    __syncwarp();
+    verify_seed<ENC>(P, (uint64_t)e.x * MK_UNIT_BASES, e.y);
+    __syncwarp();
+}
+template <int ENC>
+__device__ __forceinline__ void queue_flush(const ScanParams& P, WarpQueue& wq, uint32_t lane) {
+    __syncwarp();
+    if (lane < wq.count) {
+        uint2 e = wq.slot[lane];
+        verify_seed<ENC>(P, (uint64_t)e.x * MK_UNIT_BASES, e.y);
+    }
+    wq.count = 0;
+    __syncwarp();
+}
+// push the lanes whose `mine` is set; unit/code are per lane
+template <int ENC>
+__device__ __forceinline__ void queue_push(const ScanParams& P, WarpQueue& wq, uint32_t lane, bool mine, uint32_t unit,
+                                           uint32_t code) {
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+    if (m) {
+        if (mine) wq.slot[wq.count + __popc(m & ((1u << lane) - 1u))] = make_uint2(unit, code);
+        wq.count += __popc(m);
+        __syncwarp();
+        if (wq.count >= 32) queue_drain32<ENC>(P, wq, lane);
+    }
+}
+
+template <int ENC, int FMODE, int U>
+__device__ __forceinline__ void process_tile(const ScanParams& P, const uint32_t* __restrict__ filt, uint32_t lb,
+                                             const uint4 (&v)[U], uint32_t v0, WarpQueue& wq, uint32_t lane) {
+    constexpr int SPV = (ENC == MK_ENC_ASCII) ? 1 : 2;  // seeds (= units) per vector
+    uint32_t code[U * SPV];
+    uint32_t pass = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (ENC == MK_ENC_ASCII) {
+            code[u] = mk_pack_ascii_perm(v[u].x, v[u].y, v[u].z, v[u].w);
+            pass |= filter_probe<FMODE>(filt, code[u], lb) << u;
+        } else {
+            code[2 * u] = mk_pack_bam_perm(v[u].x, v[u].y);
+            code[2 * u + 1] = mk_pack_bam_perm(v[u].z, v[u].w);
+            pass |= filter_probe<FMODE>(filt, code[2 * u], lb) << (2 * u);
+            pass |= filter_probe<FMODE>(filt, code[2 * u + 1], lb) << (2 * u + 1);
+        }
+    }
+    if (__any_sync(0xFFFFFFFFu, pass != 0)) {
+#pragma unroll
+        for (int k = 0; k < U * SPV; ++k)
+            queue_push<ENC>(P, wq, lane, (pass >> k) & 1u, (v0 + (k / SPV) * 32) * SPV + (k % SPV), code[k]);
+    }
+}
+
+template <int U>
+__device__ __forceinline__ void load_rows(const uint4* __restrict__ p, uint64_t pol, uint4 (&v)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = ld_stream(p + u * 32, pol);
+}
+
+template <int ENC, int FMODE, int U>
+__global__ void __launch_bounds__(kScanThreads, 1) mk_scan_d16(const __grid_constant__ ScanParams P) {
+    extern __shared__ __align__(16) uint32_t s_filter[];
+    __shared__ uint2 s_queue[kScanWarps][kQueueCap];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lb = P.filter_log2_bits;
+    const uint64_t pol = make_evict_first_policy();
+    const uint32_t nwarps = gridDim.x * kScanWarps;
+    const uint32_t full_tiles = P.n_vec / (U * 32);
+    WarpQueue wq{s_queue[threadIdx.x >> 5], 0};
+    uint32_t t = blockIdx.x * kScanWarps + (threadIdx.x >> 5);
+    const uint32_t warp0 = t;
+    const size_t stride = (size_t)nwarps * (U * 32);
+    const uint4* p = P.text + (size_t)t * (U * 32) + lane;
+
+    uint4 a[U], b[U];
+    if (t < full_tiles) load_rows<U>(p, pol, a);  // in flight while the filter is staged
+    stage_filter<FMODE>(P, s_filter);
+    const uint32_t* __restrict__ filt = (FMODE == kFilterSmem) ? s_filter : P.filter;
+
+    while (t < full_tiles) {
+        uint32_t tn = t + nwarps;
+        if (tn < full_tiles) load_rows<U>(p + stride, pol, b);
+        process_tile<ENC, FMODE, U>(P, filt, lb, a, t * (U * 32) + lane, wq, lane);
+        t = tn;
+        p += stride;
+        if (t >= full_tiles) break;
+        tn = t + nwarps;
+        if (tn < full_tiles) load_rows<U>(p + stride, pol, a);
+        process_tile<ENC, FMODE, U>(P, filt, lb, b, t * (U * 32) + lane, wq, lane);
+        t = tn;
+        p += stride;
+    }
+    // ragged last tile
+    if (P.n_vec % (U * 32) != 0 && warp0 == full_tiles % nwarps) {
+        const uint32_t v0 = full_tiles * (U * 32) + lane;
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = (v0 + u * 32 < P.n_vec) ? ld_stream(P.text + v0 + u * 32, pol) : make_uint4(0, 0, 0, 0);
+        process_tile<ENC, FMODE, U>(P, filt, lb, a, v0, wq, lane);
+    }
+    queue_flush<ENC>(P, wq, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// D < 16: ordered unit codes; a seed at offset o of a unit is a funnel shift of (unit, next unit).
+// The next unit lives in the next lane (shuffle), in lane 0 of the next row, or in the first
+// vector of the next tile (one extra load by lane 0).
+// ---------------------------------------------------------------------------------------------
+template <int ENC, int D, int FMODE, int U>
+__global__ void __launch_bounds__(kScanThreads, 1) mk_scan_ord(const __grid_constant__ ScanParams P) {
+    extern __shared__ __align__(16) uint32_t s_filter[];
+    stage_filter<FMODE>(P, s_filter);
+    const uint32_t* __restrict__ filt = (FMODE == kFilterSmem) ? s_filter : P.filter;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lb = P.filter_log2_bits, q = P.q;
+    const uint64_t pol = make_evict_first_policy();
+    const uint64_t nwarps = (uint64_t)gridDim.x * kScanWarps;
+    const uint64_t n_vec = P.n_vec;
+    constexpr int SPV = (ENC == MK_ENC_ASCII) ? 1 : 2;  // units per vector
+
+    for (uint64_t tile = (uint64_t)blockIdx.x * kScanWarps + (threadIdx.x >> 5); tile * (U * 32) < n_vec; tile += nwarps) {
+        const uint64_t v0 = tile * (U * 32) + lane;
+        uint32_t c[(U + 1) * SPV];  // ordered unit codes of this lane's vectors, + the halo vector (valid in lane 0)
+#pragma unroll
+        for (int u = 0; u <= U; ++u) {
+            uint64_t idx = v0 + (uint64_t)u * 32;
+            bool want = (u < U || lane == 0) && idx < n_vec;
+            uint4 v = want ? ld_stream(P.text + idx, pol) : make_uint4(0, 0, 0, 0);
+            if (ENC == MK_ENC_ASCII) {
+                c[u] = mk_pack_ascii_ord(v.x, v.y, v.z, v.w);
+            } else {
+                c[2 * u] = mk_pack_bam_ord(v.x, v.y);
+                c[2 * u + 1] = mk_pack_bam_ord(v.z, v.w);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            // first unit code of the following vector
+            uint32_t from_next_lane = __shfl_down_sync(0xFFFFFFFFu, c[u * SPV], 1);
+            uint32_t from_next_row = __shfl_sync(0xFFFFFFFFu, c[(u + 1) * SPV], 0);
+            uint32_t succ_vec = (lane == 31) ? from_next_row : from_next_lane;
+#pragma unroll
+            for (int h = 0; h < SPV; ++h) {
+                uint32_t cur = c[u * SPV + h];
+                uint32_t nxt = (h + 1 < SPV) ? c[u * SPV + h + 1] : succ_vec;
+                uint64_t unit = (v0 + (uint64_t)u * 32) * SPV + h;
+                uint64_t base = unit * MK_UNIT_BASES;
+#pragma unroll 4
+                for (int o = 0; o < MK_UNIT_BASES; o += D) {
+                    uint32_t seed = mk_seed_ord(cur, nxt, o, q);
+                    if (filter_probe<FMODE>(filt, seed, lb) && base + o < P.n_units) verify_seed<ENC>(P, base + o, seed);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace mk

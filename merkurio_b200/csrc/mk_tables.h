@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 #include <stdexcept>
@@ -26,7 +27,7 @@ namespace mk {
 
 constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
 constexpr uint32_t kBucketSlots = 4;
-constexpr uint32_t kSmemFilterLog2Bits = 20;  // 128 KiB bitmap staged per CTA
+constexpr uint32_t kSmemFilterLog2Bits = MK_BLOOM_LOG2_WORDS + 5;  // 128 KiB filter staged per CTA
 constexpr uint32_t kMaxPatternId = (1u << 27) - 1;
 
 struct SeedSlot {
@@ -249,14 +250,25 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
         if (++lb > 28) throw std::runtime_error("seed table does not fit");
     }
 
-    // first-level filter
-    double nn = (double)t.n_seeds, m = std::ldexp(1.0, kSmemFilterLog2Bits);
-    double p1 = 1.0 - std::exp(-nn / m);
-    double p2 = std::pow(1.0 - std::exp(-2.0 * nn / m), 2.0);
-    if (std::min(p1, p2) <= 0.30) {
+    // first-level filter: blocked Bloom in shared memory while it stays selective
+    double nn = (double)t.n_seeds, lambda = nn / std::ldexp(1.0, MK_BLOOM_LOG2_WORDS);
+    double fp = 0.0, pmf = std::exp(-lambda);
+    for (int j = 0; j < 400; ++j) {  // Poisson(lambda) keys per word, 2 bits each
+        double set = 1.0 - std::pow(31.0 / 32.0, 2.0 * j);
+        fp += pmf * set * set;
+        pmf *= lambda / (j + 1);
+    }
+    // MK_FILTER_MODE=l2|smem overrides the choice (tests exercise both paths on small inputs)
+    const char* force = std::getenv("MK_FILTER_MODE");
+    bool want_smem = fp <= 0.30;
+    if (force && std::strcmp(force, "l2") == 0) want_smem = false;
+    if (force && std::strcmp(force, "smem") == 0) want_smem = true;
+    if (want_smem) {
         t.filter_in_smem = true;
         t.filter_log2_bits = kSmemFilterLog2Bits;
-        t.filter_hashes = (p2 < p1) ? 2 : 1;
+        t.filter_hashes = 2;
+        t.filter.assign((size_t)1 << MK_BLOOM_LOG2_WORDS, 0);
+        for (auto& kv : keys) t.filter[mk_bloom_word(kv.first)] |= mk_bloom_mask(kv.first);
     } else {
         // too many seeds for shared memory: L2-resident bitmap, ~32 bits per seed, one hash
         t.filter_in_smem = false;
@@ -264,13 +276,9 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
         uint32_t b = kSmemFilterLog2Bits + 1;
         while (b < 30 && std::ldexp(1.0, b) < nn * 32.0) ++b;
         t.filter_log2_bits = b;
-    }
-    t.filter.assign((size_t)1 << (t.filter_log2_bits - 5), 0);
-    for (auto& kv : keys) {
-        uint32_t h = mk_hash_f1(kv.first, t.filter_log2_bits);
-        t.filter[h >> 5] |= 1u << (h & 31);
-        if (t.filter_hashes == 2) {
-            h = mk_hash_f2(kv.first, t.filter_log2_bits);
+        t.filter.assign((size_t)1 << (t.filter_log2_bits - 5), 0);
+        for (auto& kv : keys) {
+            uint32_t h = mk_hash_f1(kv.first, t.filter_log2_bits);
             t.filter[h >> 5] |= 1u << (h & 31);
         }
     }

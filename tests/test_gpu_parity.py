@@ -221,15 +221,19 @@ def test_hit_overflow_rescan():
     assert r.n_rescans >= 1 and r.n_hits > 64
 
 
-def test_many_patterns_l2_filter():
-    # enough seeds to push the first-level filter out of shared memory
+def test_many_patterns_l2_filter(monkeypatch):
+    # the first-level filter left L2-resident (what a seed set too large for shared memory gets)
+    monkeypatch.setenv("MK_FILTER_MODE", "l2")
     rng = np.random.default_rng(29)
     genome = rand_seq(rng, 400000)
-    starts = rng.integers(0, len(genome) - 70, size=60000)
+    starts = rng.integers(0, len(genome) - 70, size=20000)
     pats = sorted({genome[s:s + int(k)] for s, k in zip(starts, rng.integers(21, 64, size=len(starts)))})
     with capi.Engine(pats, max_batch_bytes=len(genome) + 64, max_batch_records=4) as e:
         check_batch(pats, [genome[:150000], genome[150000:]], engine=e)
         assert e.info().filter_in_smem[0] == 0
+    for k in (8, 16, 31):
+        pats = sorted({rand_seq(rng, k) for _ in range(50)})
+        check_batch(pats, planted_records(rng, pats, 200, 0, 200, plant_p=0.5))
 
 
 def test_bam4_encoding():
