@@ -110,8 +110,9 @@ typedef struct {
     uint32_t n_patterns, min_len, max_len;
     uint32_t seed_q[2], seed_d[2];     /* per encoding (index = mk_encoding); 0 = tables not built yet */
     uint32_t n_seeds[2];               /* distinct seed codes */
-    uint32_t filter_log2_bits[2];      /* first-level bitmap size */
-    uint32_t filter_hashes[2];         /* 1 or 2 */
+    uint32_t filter_log2_bits[2];      /* first-level filter, L2-resident flavour: log2 of its bits (else 0) */
+    uint32_t filter_hashes[2];         /* bits tested per probe */
+    uint64_t filter_bytes[2];          /* size of the first-level filter */
     uint32_t filter_in_smem[2];        /* 1: bitmap staged in shared memory, 0: L2-resident */
     uint64_t table_bytes[2];           /* cuckoo seed table + postings + pattern bytes */
     uint32_t sm_count;

@@ -40,6 +40,7 @@ class MkEngineInfo(C.Structure):
     _fields_ = [("n_patterns", C.c_uint32), ("min_len", C.c_uint32), ("max_len", C.c_uint32),
                 ("seed_q", C.c_uint32 * 2), ("seed_d", C.c_uint32 * 2), ("n_seeds", C.c_uint32 * 2),
                 ("filter_log2_bits", C.c_uint32 * 2), ("filter_hashes", C.c_uint32 * 2),
+                ("filter_bytes", C.c_uint64 * 2),
                 ("filter_in_smem", C.c_uint32 * 2), ("table_bytes", C.c_uint64 * 2),
                 ("sm_count", C.c_uint32), ("reserved", C.c_uint32)]
 

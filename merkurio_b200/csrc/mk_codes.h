@@ -103,18 +103,27 @@ MK_HD uint32_t mk_seed_ord(uint32_t cur, uint32_t nxt, uint32_t o, uint32_t q) {
     return win >> (32u - 2u * q);
 }
 
-// First-level filter. Shared-memory flavour: a blocked Bloom filter of 2^15 32-bit words; a seed
-// selects one word with the top 15 bits of code * MK_BLOOM_MUL and two bit positions inside it from
-// bits 7..11 and 12..16 of the same product (one LDS per probe). Global flavour (seed sets too large
-// for shared memory): a plain bitmap of 2^log2_bits bits indexed by mk_hash_f1.
+// First-level filter. Shared-memory flavour: a blocked Bloom filter of `nblocks` 64-bit blocks (any
+// count; 16384 blocks = 128 KiB by default, more for large seed sets). A seed selects its block with
+// mulhi(code * MK_BLOOM_MUL, nblocks) and four bit positions from a second product: two in the low
+// word and two in the high word of the block — one LDS.64 per probe. Global flavour (seed sets too
+// large for shared memory): a plain bitmap of 2^log2_bits bits indexed by mk_hash_f1.
 #define MK_BLOOM_MUL 0x9E3779B1u
-#define MK_BLOOM_LOG2_WORDS 15
-MK_HD uint32_t mk_bloom_word(uint32_t code) { return (code * MK_BLOOM_MUL) >> (32 - MK_BLOOM_LOG2_WORDS); }
-MK_HD uint32_t mk_bloom_mask(uint32_t code) {
-    uint32_t h = code * MK_BLOOM_MUL;
-    return (1u << ((h >> 7) & 31)) | (1u << ((h >> 12) & 31));
+#define MK_BLOOM_MUL2 0x85EBCA77u
+#define MK_BLOOM_MIN_BLOCKS 16384u
+#define MK_BLOOM_MAX_BLOCKS 20480u   /* 160 KiB: beyond that the L1 left over cannot hold the loads in flight (measured) */
+MK_HD uint32_t mk_bloom_block(uint32_t code, uint32_t nblocks) {
+    return (uint32_t)(((uint64_t)(code * MK_BLOOM_MUL) * nblocks) >> 32);
+}
+// bit masks inside the low (x) and high (y) word of the block
+MK_HD void mk_bloom_masks(uint32_t code, uint32_t* lo, uint32_t* hi) {
+    uint32_t g = code * MK_BLOOM_MUL * MK_BLOOM_MUL2;
+    *lo = (1u << ((g >> 12) & 31)) | (1u << ((g >> 17) & 31));
+    *hi = (1u << ((g >> 22) & 31)) | (1u << (g >> 27));
 }
 MK_HD uint32_t mk_hash_f1(uint32_t code, uint32_t log2_bits) { return (code * 0x9E3779B1u) >> (32u - log2_bits); }
+// second-level filter (L2-resident bitmap probed by candidates only): bit index
+MK_HD uint32_t mk_hash_f2(uint32_t code, uint32_t log2_bits) { return ((code ^ (code >> 15)) * 0x85EBCA77u) >> (32u - log2_bits); }
 MK_HD uint32_t mk_mix32(uint32_t x) {
     x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
     return x;

@@ -72,12 +72,12 @@ struct PinBuf {
 struct DeviceTables {
     bool built = false;
     mk::Tables host;
-    DevBuf<uint32_t> filter, postings, pat_off;
+    DevBuf<uint32_t> filter, filter2, postings, pat_off;
     DevBuf<mk::SeedSlot> slots;
     DevBuf<uint8_t> pat_bytes;
     uint64_t bytes() const {
         return host.slots.size() * sizeof(mk::SeedSlot) + host.postings.size() * 4 + host.pat_bytes.size() +
-               host.pat_off.size() * 4 + host.filter.size() * 4;
+               host.pat_off.size() * 4 + host.filter.size() * 4 + host.filter2.size() * 4;
     }
 };
 
@@ -139,32 +139,60 @@ namespace {
 
 using ScanKernel = void (*)(const mk::ScanParams);
 
-// Launch shape of the stride-16 scan: U 16-byte vectors per lane and tile (two tiles in flight).
-// MK_TUNE_U overrides the default (used by scripts/tune_scan.py only).
-int scan_tune_u() {
-    int u = 2;
-    if (const char* s = std::getenv("MK_TUNE_U")) u = std::atoi(s);
-    return (u == 2 || u == 4 || u == 8) ? u : 2;
+// Launch shape of a scan kernel: threads per CTA (one CTA per SM) and 16-byte vectors per tile.
+struct ScanLaunch {
+    ScanKernel fn;
+    int threads;
+    int tile_vecs;
+};
+
+// Stride-16 scan: U vectors per lane and tile (two tiles in flight), T threads per CTA.
+// MK_TUNE_U / MK_TUNE_T override the defaults (used by scripts/tune_scan.py only).
+int tune_env(const char* name, int dflt) {
+    const char* s = std::getenv(name);
+    return s ? std::atoi(s) : dflt;
+}
+
+template <int ENC, int FMODE, int T>
+ScanKernel pick_d16_u(int u, bool v8) {
+    if (v8) {
+        switch (u) {
+            case 8: return mk::mk_scan_d16<ENC, FMODE, 8, T, true>;
+            case 4: return mk::mk_scan_d16<ENC, FMODE, 4, T, true>;
+            default: return mk::mk_scan_d16<ENC, FMODE, 2, T, true>;
+        }
+    }
+    switch (u) {
+        case 8: return mk::mk_scan_d16<ENC, FMODE, 8, T, false>;
+        case 4: return mk::mk_scan_d16<ENC, FMODE, 4, T, false>;
+        case 3: return mk::mk_scan_d16<ENC, FMODE, 3, T, false>;
+        default: return mk::mk_scan_d16<ENC, FMODE, 2, T, false>;
+    }
 }
 
 template <int ENC, int FMODE>
-ScanKernel pick_by_d(uint32_t d) {
+ScanLaunch pick_by_d(uint32_t d) {
+    if (d == 16) {
+        int u = tune_env("MK_TUNE_U", 4), t = tune_env("MK_TUNE_T", 896);
+        bool v8 = tune_env("MK_TUNE_V8", 0) != 0;
+        if (u != 2 && u != 3 && u != 4 && u != 8) u = 2;
+        if (v8 && u == 3) u = 4;
+        switch (t) {
+            case 512: return {pick_d16_u<ENC, FMODE, 512>(u, v8), 512, u * 32};
+            case 768: return {pick_d16_u<ENC, FMODE, 768>(u, v8), 768, u * 32};
+            case 896: return {pick_d16_u<ENC, FMODE, 896>(u, v8), 896, u * 32};
+            default: return {pick_d16_u<ENC, FMODE, 1024>(u, v8), 1024, u * 32};
+        }
+    }
     switch (d) {
-        case 16:
-            switch (scan_tune_u()) {
-                default: return mk::mk_scan_d16<ENC, FMODE, 2>;
-                case 8: return mk::mk_scan_d16<ENC, FMODE, 8>;
-                case 4: return mk::mk_scan_d16<ENC, FMODE, 4>;
-            }
-        case 8: return mk::mk_scan_ord<ENC, 8, FMODE, 4>;
-        case 4: return mk::mk_scan_ord<ENC, 4, FMODE, 4>;
-        case 2: return mk::mk_scan_ord<ENC, 2, FMODE, 2>;
-        default: return mk::mk_scan_ord<ENC, 1, FMODE, 2>;
+        case 8: return {mk::mk_scan_ord<ENC, 8, FMODE, 4>, mk::kScanThreads, 4 * 32};
+        case 4: return {mk::mk_scan_ord<ENC, 4, FMODE, 4>, mk::kScanThreads, 4 * 32};
+        case 2: return {mk::mk_scan_ord<ENC, 2, FMODE, 2>, mk::kScanThreads, 2 * 32};
+        default: return {mk::mk_scan_ord<ENC, 1, FMODE, 2>, mk::kScanThreads, 2 * 32};
     }
 }
-int tile_vectors(uint32_t d) { return (d == 16 ? scan_tune_u() : d >= 4 ? 4 : 2) * 32; }
 
-ScanKernel pick_kernel(int enc, uint32_t d, bool smemf) {
+ScanLaunch pick_kernel(int enc, uint32_t d, bool smemf) {
     if (enc == MK_ENC_ASCII)
         return smemf ? pick_by_d<MK_ENC_ASCII, mk::kFilterSmem>(d) : pick_by_d<MK_ENC_ASCII, mk::kFilterGlobal>(d);
     return smemf ? pick_by_d<MK_ENC_BAM4, mk::kFilterSmem>(d) : pick_by_d<MK_ENC_BAM4, mk::kFilterGlobal>(d);
@@ -202,13 +230,14 @@ int ensure_tables(mk_engine* e, int enc) {
         return fail(MK_ERR_INVALID, "table build failed: %s", ex.what());
     }
     CU(dt.filter.upload(dt.host.filter));
+    if (!dt.host.filter2.empty()) CU(dt.filter2.upload(dt.host.filter2));
     CU(dt.postings.upload(dt.host.postings));
     CU(dt.pat_off.upload(dt.host.pat_off));
     CU(dt.slots.upload(dt.host.slots));
     CU(dt.pat_bytes.upload(dt.host.pat_bytes));
-    ScanKernel k = pick_kernel(enc, dt.host.d, dt.host.filter_in_smem);
+    ScanLaunch k = pick_kernel(enc, dt.host.d, dt.host.filter_in_smem);
     if (dt.host.filter_in_smem)
-        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dt.host.filter.size() * 4)));
+        CU(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dt.host.filter.size() * 4)));
     dt.built = true;
     return MK_OK;
 }
@@ -230,6 +259,9 @@ int enqueue(mk_engine* e, Workspace& ws) {
     P.n_records = ws.n_records;
     P.filter = dt.filter.p;
     P.filter_log2_bits = t.filter_log2_bits;
+    P.filter_blocks = t.filter_blocks;
+    P.filter2 = t.filter2.empty() ? nullptr : dt.filter2.p;
+    P.filter2_log2_bits = t.filter2_log2_bits;
     P.slots = dt.slots.p;
     P.bucket_mask = t.bucket_mask;
     P.postings = dt.postings.p;
@@ -254,16 +286,19 @@ int enqueue(mk_engine* e, Workspace& ws) {
     if (ws.mode != MK_MODE_FLAG && key_bits > 64)
         return fail(MK_ERR_CAPACITY, "batch too large for the 64-bit hit sort key (%u bits)", key_bits);
 
+    if (t.d != 16 && ws.n_units >= (1ull << 32))
+        return fail(MK_ERR_CAPACITY, "batches of 2^32 bases or more need patterns of at least 31 bases; split the batch");
     CU(cudaMemsetAsync(ws.flags.p, 0, flag_words32 * 4, ws.stream));
     CU(cudaMemsetAsync(ws.counters.p, 0, 2 * sizeof(unsigned long long), ws.stream));
     CU(cudaEventRecord(ws.ev_begin, ws.stream));
     if (P.n_vec > 0 && ws.n_records > 0) {
-        ScanKernel k = pick_kernel(ws.enc, t.d, t.filter_in_smem);
-        uint64_t tiles = (P.n_vec + tile_vectors(t.d) - 1) / tile_vectors(t.d);
-        uint64_t want = (tiles + mk::kScanWarps - 1) / mk::kScanWarps;
+        ScanLaunch k = pick_kernel(ws.enc, t.d, t.filter_in_smem);
+        const uint64_t warps = k.threads / 32;
+        uint64_t tiles = ((uint64_t)P.n_vec + k.tile_vecs - 1) / k.tile_vecs;
+        uint64_t want = (tiles + warps - 1) / warps;
         int grid = (int)std::min<uint64_t>((uint64_t)e->sm_count, std::max<uint64_t>(want, 1));
         size_t smem = t.filter_in_smem ? t.filter.size() * 4 : 0;
-        k<<<grid, mk::kScanThreads, smem, ws.stream>>>(P);
+        k.fn<<<grid, k.threads, smem, ws.stream>>>(P);
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(ws.ev_scan, ws.stream));
@@ -455,7 +490,8 @@ int mk_engine_get_info(mk_engine* e, mk_engine_info* out) {
         out->seed_q[enc] = dt.host.q;
         out->seed_d[enc] = dt.host.d;
         out->n_seeds[enc] = dt.host.n_seeds;
-        out->filter_log2_bits[enc] = dt.host.filter_log2_bits;
+        out->filter_log2_bits[enc] = dt.host.filter_in_smem ? 0 : dt.host.filter_log2_bits;
+        out->filter_bytes[enc] = dt.host.filter.size() * 4;
         out->filter_hashes[enc] = dt.host.filter_hashes;
         out->filter_in_smem[enc] = dt.host.filter_in_smem ? 1 : 0;
         out->table_bytes[enc] = dt.bytes();

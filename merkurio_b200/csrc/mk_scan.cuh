@@ -35,7 +35,10 @@ struct ScanParams {
     const uint32_t* lens;           // optional record lengths
     // tables
     const uint32_t* filter;
-    uint32_t filter_log2_bits;
+    const uint32_t* filter2;        // optional second-level bitmap (nullptr: none)
+    uint32_t filter_log2_bits;      // global flavour
+    uint32_t filter_blocks;         // shared-memory flavour: 64-bit blocks
+    uint32_t filter2_log2_bits;
     uint32_t bucket_mask;
     const SeedSlot* slots;
     const uint32_t* postings;
@@ -57,7 +60,7 @@ constexpr int kScanThreads = 1024;
 constexpr int kScanWarps = kScanThreads / 32;
 
 // First-level filter flavours
-constexpr int kFilterSmem = 0;    // blocked Bloom in shared memory: 2 bits inside one 32-bit word
+constexpr int kFilterSmem = 0;    // blocked Bloom in shared memory: 4 bits inside one 64-bit block
 constexpr int kFilterGlobal = 1;  // plain 1-hash bitmap left in global memory (L2-resident)
 
 __device__ __forceinline__ uint64_t make_evict_first_policy() {
@@ -73,14 +76,23 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p, uint64_t pol) {
     return r;
 }
 
-// One probe of the first-level filter. kFilterSmem: `f` is the shared-memory copy.
+// 32-byte load (sm_100: ld.global.v8.b32), same cache behaviour without a policy operand
+__device__ __forceinline__ void ld_stream32(const uint4* p, uint4& lo, uint4& hi) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                 : "l"(p));
+}
+
+// One probe of the first-level filter. kFilterSmem: `f` is the shared-memory copy and `lb` the
+// number of 64-bit blocks; kFilterGlobal: `lb` is log2 of the bitmap size.
 template <int FMODE>
 __device__ __forceinline__ uint32_t filter_probe(const uint32_t* __restrict__ f, uint32_t code, uint32_t lb) {
     if (FMODE == kFilterSmem) {
         uint32_t h = code * MK_BLOOM_MUL;
-        uint32_t w = f[h >> (32 - (kSmemFilterLog2Bits - 5))];
+        uint2 w = reinterpret_cast<const uint2*>(f)[__umulhi(h, lb)];
+        uint32_t g = h * MK_BLOOM_MUL2;
         // shifts by a register use its low 5 bits (SHF.R.W), so the bit positions need no masking
-        return (w >> ((h >> 7) & 31)) & (w >> ((h >> 12) & 31)) & 1u;
+        return (w.x >> ((g >> 12) & 31)) & (w.x >> ((g >> 17) & 31)) & (w.y >> ((g >> 22) & 31)) & (w.y >> (g >> 27)) & 1u;
     } else {
         uint32_t h = mk_hash_f1(code, lb);
         return (__ldg(f + (h >> 5)) >> (h & 31)) & 1u;
@@ -110,6 +122,10 @@ __device__ __forceinline__ uint8_t text_symbol(const uint8_t* __restrict__ t, ui
 // Slow path: a seed at base position `pos` passed the first-level filter.
 template <int ENC>
 __device__ __noinline__ void verify_seed(const ScanParams& P, uint64_t pos, uint32_t code) {
+    if (P.filter2) {
+        uint32_t h = mk_hash_f2(code, P.filter2_log2_bits);
+        if (!((__ldg(P.filter2 + (h >> 5)) >> (h & 31)) & 1u)) return;
+    }
     // cuckoo lookup: two 32-byte buckets
     uint32_t first = kEmptySlot;
 #pragma unroll
@@ -173,7 +189,7 @@ __device__ __noinline__ void verify_seed(const ScanParams& P, uint64_t pos, uint
 template <int FMODE>
 __device__ __forceinline__ void stage_filter(const ScanParams& P, uint32_t* s_filter) {
     if (FMODE != kFilterSmem) return;
-    constexpr uint32_t n16 = 1u << (kSmemFilterLog2Bits - 7);  // uint4 count
+    const uint32_t n16 = P.filter_blocks / 2;  // uint4 count (the block count is even)
     const uint4* src = reinterpret_cast<const uint4*>(P.filter);
     uint4* dst = reinterpret_cast<uint4*>(s_filter);
     for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
@@ -196,30 +212,30 @@ __device__ __forceinline__ void stage_filter(const ScanParams& P, uint32_t* s_fi
 // this queue and verified 32 at a time, one candidate per lane, with all lookups in flight together.
 constexpr int kQueueCap = 64;
 struct WarpQueue {
-    uint2* slot;     // kQueueCap entries of {unit index, seed code}
+    uint2* slot;     // kQueueCap entries of {seed position / PM, seed code}; PM = 16 (stride-16 scan) or 1
     uint32_t count;  // warp-uniform
 };
 
-template <int ENC>
+template <int ENC, int PM>
 __device__ __forceinline__ void queue_drain32(const ScanParams& P, WarpQueue& wq, uint32_t lane) {
     wq.count -= 32;
     uint2 e = wq.slot[wq.count + lane];
     __syncwarp();
-    verify_seed<ENC>(P, (uint64_t)e.x * MK_UNIT_BASES, e.y);
+    verify_seed<ENC>(P, (uint64_t)e.x * PM, e.y);
     __syncwarp();
 }
-template <int ENC>
+template <int ENC, int PM>
 __device__ __forceinline__ void queue_flush(const ScanParams& P, WarpQueue& wq, uint32_t lane) {
     __syncwarp();
     if (lane < wq.count) {
         uint2 e = wq.slot[lane];
-        verify_seed<ENC>(P, (uint64_t)e.x * MK_UNIT_BASES, e.y);
+        verify_seed<ENC>(P, (uint64_t)e.x * PM, e.y);
     }
     wq.count = 0;
     __syncwarp();
 }
-// push the lanes whose `mine` is set; unit/code are per lane
-template <int ENC>
+// push the lanes whose `mine` is set; unit (= position / PM) and code are per lane
+template <int ENC, int PM>
 __device__ __forceinline__ void queue_push(const ScanParams& P, WarpQueue& wq, uint32_t lane, bool mine, uint32_t unit,
                                            uint32_t code) {
     uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
@@ -227,11 +243,13 @@ __device__ __forceinline__ void queue_push(const ScanParams& P, WarpQueue& wq, u
         if (mine) wq.slot[wq.count + __popc(m & ((1u << lane) - 1u))] = make_uint2(unit, code);
         wq.count += __popc(m);
         __syncwarp();
-        if (wq.count >= 32) queue_drain32<ENC>(P, wq, lane);
+        if (wq.count >= 32) queue_drain32<ENC, PM>(P, wq, lane);
     }
 }
 
-template <int ENC, int FMODE, int U>
+// v0 = index of the lane's first vector of the tile. V8: the lane owns pairs of adjacent vectors
+// (32-byte loads, rows of 64 vectors); else single vectors (rows of 32 vectors).
+template <int ENC, int FMODE, int U, bool V8>
 __device__ __forceinline__ void process_tile(const ScanParams& P, const uint32_t* __restrict__ filt, uint32_t lb,
                                              const uint4 (&v)[U], uint32_t v0, WarpQueue& wq, uint32_t lane) {
     constexpr int SPV = (ENC == MK_ENC_ASCII) ? 1 : 2;  // seeds (= units) per vector
@@ -252,57 +270,70 @@ __device__ __forceinline__ void process_tile(const ScanParams& P, const uint32_t
     if (__any_sync(0xFFFFFFFFu, pass != 0)) {
 #pragma unroll
         for (int k = 0; k < U * SPV; ++k)
-            queue_push<ENC>(P, wq, lane, (pass >> k) & 1u, (v0 + (k / SPV) * 32) * SPV + (k % SPV), code[k]);
+        {
+            const int u = k / SPV;
+            const uint32_t vec = V8 ? v0 + (u / 2) * 64 + (u % 2) : v0 + u * 32;
+            queue_push<ENC, MK_UNIT_BASES>(P, wq, lane, (pass >> k) & 1u, vec * SPV + (k % SPV), code[k]);
+        }
     }
 }
 
-template <int U>
+template <int U, bool V8>
 __device__ __forceinline__ void load_rows(const uint4* __restrict__ p, uint64_t pol, uint4 (&v)[U]) {
+    if (V8) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) v[u] = ld_stream(p + u * 32, pol);
+        for (int u = 0; u < U; u += 2) ld_stream32(p + (u / 2) * 64, v[u], v[u + 1]);
+    } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = ld_stream(p + u * 32, pol);
+    }
 }
 
-template <int ENC, int FMODE, int U>
-__global__ void __launch_bounds__(kScanThreads, 1) mk_scan_d16(const __grid_constant__ ScanParams P) {
+template <int ENC, int FMODE, int U, int T, bool V8>
+__global__ void __launch_bounds__(T, 1) mk_scan_d16(const __grid_constant__ ScanParams P) {
+    static_assert(!V8 || U % 2 == 0, "32-byte loads need an even number of vectors per lane");
+    constexpr int kScanWarps = T / 32;
     extern __shared__ __align__(16) uint32_t s_filter[];
     __shared__ uint2 s_queue[kScanWarps][kQueueCap];
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t lb = P.filter_log2_bits;
-    const uint64_t pol = make_evict_first_policy();
+    const uint32_t lane_vec = V8 ? lane * 2 : lane;
+    const uint32_t lb = (FMODE == kFilterSmem) ? P.filter_blocks : P.filter_log2_bits;
+    const uint64_t pol = V8 ? 0 : make_evict_first_policy();
     const uint32_t nwarps = gridDim.x * kScanWarps;
     const uint32_t full_tiles = P.n_vec / (U * 32);
     WarpQueue wq{s_queue[threadIdx.x >> 5], 0};
     uint32_t t = blockIdx.x * kScanWarps + (threadIdx.x >> 5);
     const uint32_t warp0 = t;
     const size_t stride = (size_t)nwarps * (U * 32);
-    const uint4* p = P.text + (size_t)t * (U * 32) + lane;
+    const uint4* p = P.text + (size_t)t * (U * 32) + lane_vec;
 
     uint4 a[U], b[U];
-    if (t < full_tiles) load_rows<U>(p, pol, a);  // in flight while the filter is staged
+    if (t < full_tiles) load_rows<U, V8>(p, pol, a);  // in flight while the filter is staged
     stage_filter<FMODE>(P, s_filter);
     const uint32_t* __restrict__ filt = (FMODE == kFilterSmem) ? s_filter : P.filter;
 
     while (t < full_tiles) {
         uint32_t tn = t + nwarps;
-        if (tn < full_tiles) load_rows<U>(p + stride, pol, b);
-        process_tile<ENC, FMODE, U>(P, filt, lb, a, t * (U * 32) + lane, wq, lane);
+        if (tn < full_tiles) load_rows<U, V8>(p + stride, pol, b);
+        process_tile<ENC, FMODE, U, V8>(P, filt, lb, a, t * (U * 32) + lane_vec, wq, lane);
         t = tn;
         p += stride;
         if (t >= full_tiles) break;
         tn = t + nwarps;
-        if (tn < full_tiles) load_rows<U>(p + stride, pol, a);
-        process_tile<ENC, FMODE, U>(P, filt, lb, b, t * (U * 32) + lane, wq, lane);
+        if (tn < full_tiles) load_rows<U, V8>(p + stride, pol, a);
+        process_tile<ENC, FMODE, U, V8>(P, filt, lb, b, t * (U * 32) + lane_vec, wq, lane);
         t = tn;
         p += stride;
     }
-    // ragged last tile
+    // ragged last tile (16-byte loads with bounds checks)
     if (P.n_vec % (U * 32) != 0 && warp0 == full_tiles % nwarps) {
+        const uint64_t pol16 = make_evict_first_policy();
         const uint32_t v0 = full_tiles * (U * 32) + lane;
 #pragma unroll
-        for (int u = 0; u < U; ++u) a[u] = (v0 + u * 32 < P.n_vec) ? ld_stream(P.text + v0 + u * 32, pol) : make_uint4(0, 0, 0, 0);
-        process_tile<ENC, FMODE, U>(P, filt, lb, a, v0, wq, lane);
+        for (int u = 0; u < U; ++u) a[u] = (v0 + u * 32 < P.n_vec) ? ld_stream(P.text + v0 + u * 32, pol16) : make_uint4(0, 0, 0, 0);
+        process_tile<ENC, FMODE, U, false>(P, filt, lb, a, v0, wq, lane);
     }
-    queue_flush<ENC>(P, wq, lane);
+    queue_flush<ENC, MK_UNIT_BASES>(P, wq, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -313,10 +344,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) mk_scan_d16(const __grid_cons
 template <int ENC, int D, int FMODE, int U>
 __global__ void __launch_bounds__(kScanThreads, 1) mk_scan_ord(const __grid_constant__ ScanParams P) {
     extern __shared__ __align__(16) uint32_t s_filter[];
+    __shared__ uint2 s_queue[kScanWarps][kQueueCap];
     stage_filter<FMODE>(P, s_filter);
     const uint32_t* __restrict__ filt = (FMODE == kFilterSmem) ? s_filter : P.filter;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t lb = P.filter_log2_bits, q = P.q;
+    WarpQueue wq{s_queue[threadIdx.x >> 5], 0};
+    const uint32_t lb = (FMODE == kFilterSmem) ? P.filter_blocks : P.filter_log2_bits, q = P.q;
     const uint64_t pol = make_evict_first_policy();
     const uint64_t nwarps = (uint64_t)gridDim.x * kScanWarps;
     const uint64_t n_vec = P.n_vec;
@@ -352,11 +385,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) mk_scan_ord(const __grid_cons
 #pragma unroll 4
                 for (int o = 0; o < MK_UNIT_BASES; o += D) {
                     uint32_t seed = mk_seed_ord(cur, nxt, o, q);
-                    if (filter_probe<FMODE>(filt, seed, lb) && base + o < P.n_units) verify_seed<ENC>(P, base + o, seed);
+                    bool pass = filter_probe<FMODE>(filt, seed, lb) && base + o < P.n_units;
+                    // positions fit 32 bits: the engine refuses batches of 2^32 bases or more on this path
+                    queue_push<ENC, 1>(P, wq, lane, pass, (uint32_t)(base + o), seed);
                 }
             }
         }
     }
+    queue_flush<ENC, 1>(P, wq, lane);
 }
 
 }  // namespace mk

@@ -27,7 +27,6 @@ namespace mk {
 
 constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
 constexpr uint32_t kBucketSlots = 4;
-constexpr uint32_t kSmemFilterLog2Bits = MK_BLOOM_LOG2_WORDS + 5;  // 128 KiB filter staged per CTA
 constexpr uint32_t kMaxPatternId = (1u << 27) - 1;
 
 struct SeedSlot {
@@ -45,8 +44,13 @@ struct Tables {
     uint32_t n_seeds = 0;
     // first-level filter
     uint32_t filter_log2_bits = 0, filter_hashes = 1;
+    uint32_t filter_blocks = 0;  // shared-memory flavour: number of 64-bit blocks
     bool filter_in_smem = true;
     std::vector<uint32_t> filter;
+    // second-level filter: L2-resident bitmap (~64 bits per seed) probed by the candidates the
+    // shared-memory filter lets through, before the cuckoo table is touched (empty: not used)
+    uint32_t filter2_log2_bits = 0;
+    std::vector<uint32_t> filter2;
     // cuckoo table
     uint32_t bucket_mask = 0;
     std::vector<SeedSlot> slots;  // (bucket_mask + 1) * kBucketSlots
@@ -243,37 +247,62 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
     if (t.postings.empty()) t.postings.push_back(make_posting(0, 0, true));  // keep device pointers non-null
     t.n_seeds = (uint32_t)keys.size();
 
-    // cuckoo table at <= 50 % load, grown until the insertion succeeds
+    // cuckoo table (4-slot buckets) at <= 80 % load, grown until the insertion succeeds
     uint32_t lb = 1;
-    while (((uint64_t)kBucketSlots << lb) < (uint64_t)keys.size() * 2) ++lb;
+    while (((uint64_t)kBucketSlots << lb) * 4 < (uint64_t)keys.size() * 5) ++lb;
     while (!cuckoo_build(keys, lb, &t.slots, &t.bucket_mask)) {
         if (++lb > 28) throw std::runtime_error("seed table does not fit");
     }
 
     // first-level filter: blocked Bloom in shared memory while it stays selective
-    double nn = (double)t.n_seeds, lambda = nn / std::ldexp(1.0, MK_BLOOM_LOG2_WORDS);
-    double fp = 0.0, pmf = std::exp(-lambda);
-    for (int j = 0; j < 400; ++j) {  // Poisson(lambda) keys per word, 2 bits each
-        double set = 1.0 - std::pow(31.0 / 32.0, 2.0 * j);
-        fp += pmf * set * set;
-        pmf *= lambda / (j + 1);
+    double nn = (double)t.n_seeds;
+    auto blocked_fp = [&](uint32_t nblocks) {
+        // Poisson(lambda) keys per block; each key sets 2 bits in each 32-bit half
+        double lambda = nn / nblocks, fp = 0.0, pmf = std::exp(-lambda);
+        for (int j = 0; j < 600; ++j) {
+            double set = 1.0 - std::pow(31.0 / 32.0, 2.0 * j);
+            fp += pmf * std::pow(set, 4.0);
+            pmf *= lambda / (j + 1);
+        }
+        return fp;
+    };
+    uint32_t nblocks = MK_BLOOM_MIN_BLOCKS;
+    if (blocked_fp(nblocks) > 0.002) nblocks = MK_BLOOM_MAX_BLOCKS;
+    if (const char* fb = std::getenv("MK_FILTER_BLOCKS")) {  // tuning override
+        uint32_t v = (uint32_t)std::atoi(fb) & ~1u;
+        if (v >= 1024 && v <= MK_BLOOM_MAX_BLOCKS) nblocks = v;
     }
+    double fp = blocked_fp(nblocks);
     // MK_FILTER_MODE=l2|smem overrides the choice (tests exercise both paths on small inputs)
     const char* force = std::getenv("MK_FILTER_MODE");
-    bool want_smem = fp <= 0.30;
+    bool want_smem = fp <= 0.25;
     if (force && std::strcmp(force, "l2") == 0) want_smem = false;
     if (force && std::strcmp(force, "smem") == 0) want_smem = true;
     if (want_smem) {
         t.filter_in_smem = true;
-        t.filter_log2_bits = kSmemFilterLog2Bits;
-        t.filter_hashes = 2;
-        t.filter.assign((size_t)1 << MK_BLOOM_LOG2_WORDS, 0);
-        for (auto& kv : keys) t.filter[mk_bloom_word(kv.first)] |= mk_bloom_mask(kv.first);
+        t.filter_blocks = nblocks;
+        t.filter_log2_bits = 0;
+        t.filter_hashes = 4;
+        t.filter.assign((size_t)nblocks * 2, 0);
+        for (auto& kv : keys) {
+            uint32_t blk = mk_bloom_block(kv.first, nblocks), lo, hi;
+            mk_bloom_masks(kv.first, &lo, &hi);
+            t.filter[2 * (size_t)blk] |= lo;
+            t.filter[2 * (size_t)blk + 1] |= hi;
+        }
+        uint32_t b2 = 16;
+        while (b2 < 30 && std::ldexp(1.0, b2) < nn * 64.0) ++b2;
+        t.filter2_log2_bits = b2;
+        t.filter2.assign((size_t)1 << (b2 - 5), 0);
+        for (auto& kv : keys) {
+            uint32_t h = mk_hash_f2(kv.first, b2);
+            t.filter2[h >> 5] |= 1u << (h & 31);
+        }
     } else {
         // too many seeds for shared memory: L2-resident bitmap, ~32 bits per seed, one hash
         t.filter_in_smem = false;
         t.filter_hashes = 1;
-        uint32_t b = kSmemFilterLog2Bits + 1;
+        uint32_t b = 21;
         while (b < 30 && std::ldexp(1.0, b) < nn * 32.0) ++b;
         t.filter_log2_bits = b;
         t.filter.assign((size_t)1 << (t.filter_log2_bits - 5), 0);

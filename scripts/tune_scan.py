@@ -15,13 +15,14 @@ from merkurio_b200.synth import Synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--reads", type=int, default=100_000_000)
 ap.add_argument("--queries", type=int, default=1000)
-ap.add_argument("--variants", default="4,1;2,1;8,1")
+ap.add_argument("--k", type=int, default=31)
+ap.add_argument("--variants", default="2,1024;4,768;2,768;4,512;8,512;2,512", help="U,T pairs")
 ap.add_argument("--env", default="", help="extra NAME=VALUE pairs, ';' separated, applied to every variant")
 ap.add_argument("--steps", type=int, default=8)
 args = ap.parse_args()
 
 n, L = args.reads, 150
-syn = Synth(0x5EED0002, n, L, 31, args.queries)
+syn = Synth(0x5EED0002, n, L, args.k, args.queries)
 pats = pt.parse_pattern_list(syn.query_list(), reverse_complement_=True)
 d_seq = torch.empty(n * L + 64, dtype=torch.uint8, device="cuda")
 d_off = torch.empty(n + 1, dtype=torch.int64, device="cuda")
@@ -33,8 +34,9 @@ for kv in filter(None, args.env.split(";")):
     os.environ[k] = v
 ref = None
 for var in args.variants.split(";"):
-    u, pf = var.split(",")
-    os.environ["MK_TUNE_U"], os.environ["MK_TUNE_PF"] = u, pf
+    u, pf, *rest = var.split(",")
+    os.environ["MK_TUNE_V8"] = rest[0] if rest else "0"
+    os.environ["MK_TUNE_U"], os.environ["MK_TUNE_T"] = u, pf
     with capi.Engine(pats, n_slots=0) as e:
         for _ in range(3):
             e.scan_device(d_seq.data_ptr(), d_off.data_ptr(), n, n * L)
@@ -44,4 +46,4 @@ for var in args.variants.split(";"):
         if ref is None:
             ref = cnt
         ms = np.median(ts) / 1e6
-        print(f"U={u} PF={pf}: scan {ms:.3f} ms (min {min(ts) / 1e6:.3f})  {n * L / ms / 1e6:.0f} GB/s  flagged={cnt} {'ok' if cnt == ref else 'MISMATCH'}", flush=True)
+        print(f"U={u} T={pf} V8={os.environ['MK_TUNE_V8']}: scan {ms:.3f} ms (min {min(ts) / 1e6:.3f})  {n * L / ms / 1e6:.0f} GB/s  flagged={cnt} {'ok' if cnt == ref else 'MISMATCH'}", flush=True)
