@@ -1,0 +1,323 @@
+// `extract`: same flags, outputs, logs and counters as the reference's extract_records
+// (src/cmd_extract.rs:143-717); the per-record matcher calls are replaced by batches on the GPU.
+#include <algorithm>
+#include <cstdio>
+#include <memory>
+
+#include "commands.h"
+#include "device.h"
+#include "helpers.h"
+#include "io.h"
+#include "logger.h"
+
+namespace mkh {
+
+namespace {
+
+struct OutFile {
+    FILE* f = nullptr;
+    bool owned = false;
+    std::string buf;
+    void open(const std::optional<std::string>& path, const char* what) {
+        if (!path) { f = stdout; return; }
+        f = std::fopen(path->c_str(), "wb");
+        if (!f) throw Error("No such file or directory (os error 2)").with_context(std::string(what) + rust_debug_string(*path));
+        owned = true;
+    }
+    void write(const FastxRecord& r) {
+        r.write(&buf);
+        if (buf.size() >= (1u << 20)) flush();
+    }
+    void flush() {
+        if (f && !buf.empty()) std::fwrite(buf.data(), 1, buf.size(), f);
+        buf.clear();
+        if (f) std::fflush(f);
+    }
+    ~OutFile() {
+        flush();
+        if (f && owned) std::fclose(f);
+    }
+};
+
+std::string join(const std::vector<std::string>& v, const char* sep) {
+    std::string s;
+    for (size_t i = 0; i < v.size(); ++i) { if (i) s += sep; s += v[i]; }
+    return s;
+}
+
+FastxRecord to_record(const RecMeta& m) {
+    FastxRecord r;
+    r.id = m.a; r.raw = m.b; r.qual = m.c; r.fastq = m.fastq; r.crlf = m.crlf;
+    return r;
+}
+
+}  // namespace
+
+void extract_records(CmdExtract args) {
+    check_log_flag_conflict(args.out_log, args.json_log, args.out_fastx, args.suppress_output);
+
+    std::vector<std::string> pattern_list;
+    try {
+        pattern_list = parse_pattern_list(args.kmer_file, args.kmer_seq, args.reverse_complement, args.canonical, args.lowercase, args.uppercase);
+    } catch (const Error& e) {
+        throw e.with_context("Problem parsing pattern list.");
+    }
+    // which algorithm the reference would run: decides report order, count semantics and the JSON string
+    args.aho_corasick = choose_aho_corasick(pattern_list, args.case_insensitive, args.q_size, args.aho_corasick);
+
+    std::unique_ptr<Sink> log_sink;
+    if (args.out_log) log_sink = Sink::open(*args.out_log, "Problem creating log file");
+
+    error_if_directory(args.in_fastx, "Record file path");
+    const std::string f1 = path_file_name(args.in_fastx);
+    std::string f2;
+    if (args.in_fastq_2) {
+        error_if_directory(*args.in_fastq_2, "Second read file path");
+        f2 = path_file_name(*args.in_fastq_2);
+    }
+    const bool paired = args.in_fastq_2.has_value();
+    const bool logging_active = log_sink || args.json_log;
+    BufferedLogger logger(std::move(log_sink), 8192);
+    std::unique_ptr<JsonLogger> jl;
+    if (args.json_log) jl.reset(new JsonLogger(Sink::open(*args.json_log, "Error creating JSON log file"), 8192));
+
+    if (logging_active) {
+        logger.write_header("#SeqKatcher extract log\n");
+        logger.write_header("#" + timestamp_now() + "\n");
+        logger.write_header(std::string("#Running ") + kProgram + " version " + kVersion + "\n");
+        logger.write_header("#Command line: " + join(args.argv, " ") + "\n");
+        logger.write_header("#Searching for " + std::to_string(pattern_list.size()) + " pattern" + (pattern_list.size() > 1 ? "s" : "") + " " +
+                            (args.invert_match ? "(inverted matching)" : "") + "\n");
+        logger.write_header("#\n#File\tRecord\tPattern\tPosition (zero-based)\n");
+        logger.flush();
+    }
+    if (!args.aho_corasick) validate_bndmq(pattern_list, args.q_size);
+
+    std::unique_ptr<FastxReader> reader, reader2;
+    try {
+        reader.reset(new FastxReader(args.in_fastx));
+    } catch (const Error& e) {
+        throw e.with_context("Invalid FASTQ/A input path or file: " + rust_debug_string(args.in_fastx));
+    }
+
+    uint64_t nb_records_tot = 0, nb_bases = 0, nb_records_extracted = 0;
+    uint64_t nb_hits_tot[2] = {0, 0}, nb_records_hit[2] = {0, 0};
+    std::vector<uint64_t> pattern_hit_counts(pattern_list.size(), 0);
+
+    OutFile writer, writer2;
+    if (!paired) {
+        std::optional<std::string> path;
+        if (args.out_fastx) path = path_with_extension(*args.out_fastx, identify_uncompressed_type(args.in_fastx));
+        writer.open(path, "Error writing to output file; no such directory: ");
+    } else {
+        try {
+            reader2.reset(new FastxReader(*args.in_fastq_2));
+        } catch (const Error& e) {
+            throw e.with_context("Invalid second FASTQ input path or file: Some(" + rust_debug_string(*args.in_fastq_2) + ")");
+        }
+        std::optional<std::string> p1, p2;
+        if (args.out_fastx) {
+            std::string base = path_with_extension(*args.out_fastx, identify_uncompressed_type(args.in_fastx));
+            p1 = add_suffix_to_file_prefix(base, "_1");
+            p2 = add_suffix_to_file_prefix(base, "_2");
+        }
+        writer.open(p1, "Error writing to paired-end file; no such directory: ");
+        writer2.open(p2, "Error writing second paired-end file; no such directory: ");
+    }
+
+    auto emit = [&](const std::string& fname, const RecMeta& m, const RecHit& h) {
+        logger.log_fields(fname, m.a, pattern_list[h.pattern], h.start);
+        if (jl) jl->log_fields(fname, m.a, pattern_list[h.pattern], h.start);
+    };
+    auto by_pattern_then_start = [](const RecHit& x, const RecHit& y) { return x.pattern != y.pattern ? x.pattern < y.pattern : x.start < y.start; };
+
+    // ---- per-record consumer (src/cmd_extract.rs:321-406) and per-pair consumer (:463-607) --------
+    RecMeta mate1;
+    bool mate1_found = false;
+    std::vector<RecHit> mate1_hits;
+
+    auto on_single = [&](RecMeta& m, bool found, std::vector<RecHit>& hits) {
+        bool found_occ = false;
+        if (logging_active) {
+            nb_records_tot += 1;
+            nb_bases += m.len;
+            if (args.aho_corasick) {
+                for (const RecHit& h : hits) {
+                    emit(f1, m, h);
+                    pattern_hit_counts[h.pattern] += 1;
+                    nb_hits_tot[0] += 1;
+                    found_occ = true;
+                }
+            } else {
+                std::stable_sort(hits.begin(), hits.end(), by_pattern_then_start);
+                for (size_t i = 0; i < hits.size(); ++i) {
+                    emit(f1, m, hits[i]);
+                    nb_hits_tot[0] += 1;
+                    if (i == 0 || hits[i - 1].pattern != hits[i].pattern) pattern_hit_counts[hits[i].pattern] += 1;
+                    found_occ = true;
+                }
+            }
+            if (found_occ) nb_records_hit[0] += 1;
+        } else {
+            found_occ = found;
+        }
+        if (found_occ != args.invert_match) {
+            nb_records_extracted += 1;
+            if (!args.suppress_output) writer.write(to_record(m));
+        }
+    };
+
+    auto on_paired = [&](RecMeta& m, bool found, std::vector<RecHit>& hits) {
+        if (m.file == 0) {
+            mate1 = std::move(m);
+            mate1_found = found;
+            mate1_hits = hits;
+            return;
+        }
+        RecMeta& m2 = m;
+        bool found_occ = false;
+        if (logging_active) {
+            nb_records_tot += 2;
+            nb_bases += mate1.len + m2.len;
+            if (args.aho_corasick) {
+                for (const RecHit& h : mate1_hits) { emit(f1, mate1, h); pattern_hit_counts[h.pattern] += 1; nb_hits_tot[0] += 1; }
+                for (const RecHit& h : hits) { emit(f2, m2, h); pattern_hit_counts[h.pattern] += 1; nb_hits_tot[1] += 1; }
+            } else {
+                // for each pattern: its positions in mate 1, then its positions in mate 2 (:543-585)
+                std::stable_sort(mate1_hits.begin(), mate1_hits.end(), by_pattern_then_start);
+                std::stable_sort(hits.begin(), hits.end(), by_pattern_then_start);
+                size_t i = 0, j = 0;
+                while (i < mate1_hits.size() || j < hits.size()) {
+                    uint32_t p = UINT32_MAX;
+                    if (i < mate1_hits.size()) p = mate1_hits[i].pattern;
+                    if (j < hits.size()) p = std::min(p, hits[j].pattern);
+                    bool any1 = false, any2 = false;
+                    for (; i < mate1_hits.size() && mate1_hits[i].pattern == p; ++i) { emit(f1, mate1, mate1_hits[i]); nb_hits_tot[0] += 1; any1 = true; }
+                    for (; j < hits.size() && hits[j].pattern == p; ++j) { emit(f2, m2, hits[j]); nb_hits_tot[1] += 1; any2 = true; }
+                    pattern_hit_counts[p] += (any1 ? 1 : 0) + (any2 ? 1 : 0);
+                }
+            }
+            if (!mate1_hits.empty()) nb_records_hit[0] += 1;
+            if (!hits.empty()) nb_records_hit[1] += 1;
+            found_occ = !mate1_hits.empty() || !hits.empty();
+        } else {
+            found_occ = mate1_found || found;
+        }
+        if (found_occ != args.invert_match) {
+            nb_records_extracted += 2;
+            if (!args.suppress_output) {
+                writer.write(to_record(mate1));
+                writer2.write(to_record(m2));
+            }
+        }
+    };
+
+    {
+        RecordCallback cb;
+        if (paired) cb = on_paired; else cb = on_single;
+        Scanner scanner(pattern_list, args.case_insensitive, MK_ENC_ASCII, logging_active ? MK_MODE_ALL_HITS : MK_MODE_FLAG, cb);
+        const bool keep_text = !args.suppress_output;
+        auto feed = [&](FastxRecord& rec, uint8_t file) {
+            RecMeta m;
+            m.a = std::move(rec.id);
+            if (keep_text) { m.b = std::move(rec.raw); m.c = std::move(rec.qual); }
+            m.file = file; m.fastq = rec.fastq; m.crlf = rec.crlf;
+            scanner.add_record(rec.seq.data(), rec.seq.size(), std::move(m));
+        };
+        FastxRecord r1, r2;
+        try {
+            if (!paired) {
+                for (;;) {
+                    bool more;
+                    try { more = reader->next(&r1); } catch (const Error& e) { throw e.with_context("Error during FASTQ/A record parsing."); }
+                    if (!more) break;
+                    feed(r1, 0);
+                }
+            } else {
+                for (;;) {
+                    bool more;
+                    try { more = reader->next(&r1); } catch (const Error& e) { throw e.with_context("Error during FASTQ record parsing of first file."); }
+                    if (!more) break;
+                    bool more2;
+                    try { more2 = reader2->next(&r2); } catch (const Error& e) {
+                        throw e.with_context("Error during FASTQ record parsing of second file. Do the two input files contain the same number of records?");
+                    }
+                    if (!more2) throw Error("Error during FASTQ record parsing of second file. Do the two input files contain the same number of records?");
+                    feed(r1, 0);
+                    feed(r2, 1);
+                }
+                if (reader2->next(&r2))
+                    throw Error("The two input files have a different number of records. Please provide valid paired-end read files.");
+            }
+        } catch (...) {
+            // the reference has already written everything up to the failing record
+            scanner.finish();
+            writer.flush(); writer2.flush(); logger.flush();
+            if (jl) jl->flush();
+            throw;
+        }
+        scanner.finish();
+    }
+    writer.flush();
+    writer2.flush();
+
+    size_t nb_patterns_found = 0;
+    for (uint64_t c : pattern_hit_counts) nb_patterns_found += c > 0;
+    if (logging_active) {
+        logger.flush();
+        char pct[64];
+        std::snprintf(pct, sizeof pct, "%.2f", (double)nb_patterns_found / (double)pattern_hit_counts.size() * 100.0);
+        logger.write_header("#\n#Number of patterns found: " + std::to_string(nb_patterns_found) + "/" + std::to_string(pattern_hit_counts.size()) + " (" + pct + " %)\n");
+        logger.write_header("#Pattern\tCount\n");
+        for (size_t i = 0; i < pattern_list.size(); ++i) logger.write_header("#" + pattern_list[i] + "\t" + std::to_string(pattern_hit_counts[i]) + "\n");
+        logger.write_header("#\n#Total number of records searched: " + std::to_string(nb_records_tot) + "\n");
+        logger.write_header("#Total number of characters searched: " + std::to_string(nb_bases) + "\n");
+        logger.write_header("#Total number of hits: " + std::to_string(nb_hits_tot[0] + nb_hits_tot[1]) + "\n");
+        logger.write_header("#Number of distinct records with a hit: " + std::to_string(nb_records_hit[0] + nb_records_hit[1]) + "\n");
+        if (paired) {
+            logger.write_header("#\n#Total number of hits in file 1: " + std::to_string(nb_hits_tot[0]) + "\n");
+            logger.write_header("#Total number of hits in file 2: " + std::to_string(nb_hits_tot[1]) + "\n");
+            logger.write_header("#Number of distinct records with a hit in file 1: " + std::to_string(nb_records_hit[0]) + "\n");
+            logger.write_header("#Number of distinct records with a hit in file 2: " + std::to_string(nb_records_hit[1]) + "\n");
+            logger.write_header("#Total number of extracted records: " + std::to_string(nb_records_extracted) + "\n");
+        }
+        logger.flush();
+    }
+    if (jl) {
+        Json input_files = Json::object();
+        input_files["kmer_file"] = args.kmer_file ? Json::string(*args.kmer_file) : Json::null();
+        input_files["record_file_1"] = Json::string(f1);
+        input_files["record_file_2"] = paired ? Json::string(f2) : Json::null();
+        Json counts = Json::object();
+        for (size_t i = 0; i < pattern_list.size(); ++i) counts[pattern_list[i]] = Json::integer((int64_t)pattern_hit_counts[i]);
+        Json cmdline = Json::array();
+        for (auto& a : args.argv) cmdline.a.push_back(Json::string(a));
+        Json meta = Json::object();
+        meta["program"] = Json::string(kProgram);
+        meta["version"] = Json::string(kVersion);
+        meta["timestamp"] = Json::string(timestamp_now());
+        meta["subcommand"] = Json::string("extract");
+        meta["command_line"] = cmdline;
+        meta["search_algorithm"] = Json::string(args.aho_corasick ? "Aho-Corasick" : "BNDMq");
+        meta["inverted_matching"] = Json::boolean(args.invert_match);
+        meta["case_insensitive"] = Json::boolean(args.case_insensitive);
+        meta["input_files"] = input_files;
+        Json summary = Json::object();
+        summary["number_of_patterns_searched"] = Json::integer((int64_t)pattern_list.size());
+        summary["number_of_patterns_found"] = Json::integer((int64_t)nb_patterns_found);
+        summary["number_of_records_searched"] = Json::integer((int64_t)nb_records_tot);
+        summary["number_of_characters_searched"] = Json::integer((int64_t)nb_bases);
+        summary["number_of_matches"] = Json::integer((int64_t)(nb_hits_tot[0] + nb_hits_tot[1]));
+        summary["number_of_distinct_records_with_a_hit"] = Json::integer((int64_t)(nb_records_hit[0] + nb_records_hit[1]));
+        Json pstats = Json::object();
+        pstats["searching_paired_end_reads"] = Json::boolean(paired);
+        pstats["number_of_hits_in_file_1"] = Json::integer((int64_t)nb_hits_tot[0]);
+        pstats["number_of_hits_in_file_2"] = paired ? Json::integer((int64_t)nb_hits_tot[1]) : Json::null();
+        pstats["number_of_distinct_records_with_a_hit_in_file_1"] = Json::integer((int64_t)nb_records_hit[0]);
+        pstats["number_of_distinct_records_with_a_hit_in_file_2"] = paired ? Json::integer((int64_t)nb_records_hit[1]) : Json::null();
+        pstats["number_of_extracted_records"] = Json::integer((int64_t)nb_records_extracted);
+        jl->finalize(meta, counts, summary, &pstats);
+    }
+}
+
+}  // namespace mkh

@@ -1,0 +1,180 @@
+#include "device.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+namespace mkh {
+
+static void check(int rc) {
+    if (rc != 0) throw Error(std::string("GPU matching engine: ") + mk_last_error());
+}
+
+static uint64_t env_u64(const char* name, uint64_t dflt) {
+    const char* s = std::getenv(name);
+    if (!s || !*s) return dflt;
+    return std::strtoull(s, nullptr, 10);
+}
+
+Scanner::Scanner(const std::vector<std::string>& patterns, bool case_insensitive, mk_encoding enc, mk_mode mode, RecordCallback cb)
+    : enc_(enc), mode_(mode), cb_(std::move(cb)) {
+    std::string blob;
+    std::vector<uint32_t> off{0};
+    for (auto& p : patterns) {
+        blob += p;
+        off.push_back((uint32_t)blob.size());
+        max_pattern_len_ = std::max<uint32_t>(max_pattern_len_, (uint32_t)p.size());
+    }
+    mk_patterns mp{reinterpret_cast<const uint8_t*>(blob.data()), off.data(), (uint32_t)patterns.size()};
+    // MERKURIO_GPUS: number of devices to spread batches over (default 1); MERKURIO_BATCH_MB: slot size
+    int n_gpus = (int)env_u64("MERKURIO_GPUS", 1);
+    max_bytes_ = env_u64("MERKURIO_BATCH_MB", 64) << 20;
+    if (uint64_t b = env_u64("MERKURIO_BATCH_BYTES", 0)) max_bytes_ = b;  // tests: tiny batches, many pieces
+    if (max_bytes_ < (uint64_t)4 * max_pattern_len_ + 16384) max_bytes_ = (uint64_t)4 * max_pattern_len_ + 16384;
+    max_records_ = (uint32_t)std::min<uint64_t>(max_bytes_ / 16 + 1, 1u << 26);
+    n_slots_ = (uint32_t)env_u64("MERKURIO_SLOTS", 3);
+    if (n_slots_ < 1) n_slots_ = 1;
+    for (int g = 0; g < std::max(n_gpus, 1); ++g) {
+        mk_config cfg{};
+        cfg.device = g;
+        cfg.case_insensitive = case_insensitive ? 1 : 0;
+        cfg.n_slots = n_slots_;
+        cfg.max_batch_records = max_records_;
+        cfg.max_batch_bytes = max_bytes_;
+        cfg.hit_capacity = 0;
+        mk_engine* e = nullptr;
+        check(mk_engine_create(&mp, &cfg, &e));
+        engines_.push_back(e);
+    }
+}
+
+Scanner::~Scanner() {
+    for (mk_engine* e : engines_) mk_engine_destroy(e);
+}
+
+void Scanner::open_batch() {
+    // batch i goes to engine i % G, slot (i / G) % S; at most G*S batches are in flight
+    const uint64_t G = engines_.size();
+    while (inflight_.size() >= G * n_slots_) consume_oldest();
+    open_.reset(new Batch);
+    open_->engine = (int)(batch_seq_ % G);
+    open_->slot = (uint32_t)((batch_seq_ / G) % n_slots_);
+    ++batch_seq_;
+    check(mk_slot_buffers(engines_[(size_t)open_->engine], open_->slot, &open_->seq, &open_->off, &open_->lens));
+}
+
+void Scanner::submit_open() {
+    if (!open_) return;
+    Batch& b = *open_;
+    if (b.n_records == 0) { --batch_seq_; open_.reset(); return; }
+    b.off[b.n_records] = b.n_units;
+    check(mk_scan_submit(engines_[(size_t)b.engine], b.slot, b.n_records, b.n_units, enc_ == MK_ENC_BAM4 ? 1 : 0, enc_, mode_));
+    inflight_.push_back(std::move(open_));
+}
+
+void Scanner::add_record(const char* seq, size_t len, RecMeta&& meta) {
+    meta.len = (uint32_t)len;
+    const uint64_t overlap = max_pattern_len_ ? max_pattern_len_ - 1 : 0;
+    uint64_t pos = 0;  // first base of the record not yet covered by a piece's own range
+    bool first = true;
+    for (;;) {
+        if (!open_) open_batch();
+        Batch* b = open_.get();
+        uint64_t lead = first ? 0 : std::min(overlap, pos);
+        uint64_t room = max_bytes_ - b->n_bytes;
+        // a piece carries its overlap plus new bases; close the batch if the rest of the record does not
+        // fit and there is not even room for a useful piece
+        if (b->n_records >= max_records_ || (b->n_records > 0 && room < std::min<uint64_t>(len - pos + lead, lead + 4096))) {
+            submit_open();
+            continue;
+        }
+        uint64_t take = std::min<uint64_t>(len - pos, room - lead);
+        Piece pc;
+        pc.first = first;
+        pc.base = pos - lead;
+        pc.own_from = (uint32_t)lead;
+        pc.last = (pos + take == len);
+        b->off[b->n_records] = b->n_units;
+        if (lead + take) std::memcpy(b->seq + b->n_bytes, seq + pos - lead, lead + take);
+        b->n_bytes += lead + take;
+        b->n_units += lead + take;
+        b->n_records++;
+        b->pieces.push_back(pc);
+        if (first) b->metas.push_back(std::move(meta));
+        pos += take;
+        first = false;
+        if (pc.last) break;
+        submit_open();
+    }
+}
+
+void Scanner::add_record_packed(const uint8_t* packed, uint32_t l_seq, RecMeta&& meta) {
+    meta.len = l_seq;
+    uint64_t nbytes = ((uint64_t)l_seq + 1) / 2;
+    if (nbytes > max_bytes_) throw Error("record with " + std::to_string(l_seq) + " bases exceeds the batch size (set MERKURIO_BATCH_MB)");
+    if (!open_) open_batch();
+    if (open_->n_records >= max_records_ || open_->n_bytes + nbytes > max_bytes_) {
+        submit_open();
+        open_batch();
+    }
+    Batch* b = open_.get();
+    b->off[b->n_records] = b->n_units;  // even: records are byte aligned
+    b->lens[b->n_records] = l_seq;
+    if (nbytes) std::memcpy(b->seq + b->n_bytes, packed, nbytes);
+    b->n_bytes += nbytes;
+    b->n_units += nbytes * 2;
+    b->n_records++;
+    b->pieces.push_back(Piece{true, true, 0, 0});
+    b->metas.push_back(std::move(meta));
+}
+
+void Scanner::deliver_piece(Batch& b, uint32_t r, bool flag, const mk_hit* hits, size_t n) {
+    const Piece& pc = b.pieces[r];
+    if (pc.first) {
+        cur_hits_.clear();
+        cur_found_ = false;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        const mk_hit& h = hits[i];
+        if (mode_ == MK_MODE_ALL_HITS) {
+            if (!pc.first && (uint64_t)h.start + h.len <= pc.own_from) continue;  // owned by the previous piece
+            cur_hits_.push_back(RecHit{pc.base + h.start, h.pattern, h.len});
+        } else {
+            cur_hits_.push_back(RecHit{0, h.pattern, h.len});
+        }
+    }
+    cur_found_ = cur_found_ || flag;
+}
+
+void Scanner::consume_oldest() {
+    std::unique_ptr<Batch> bp = std::move(inflight_.front());
+    inflight_.pop_front();
+    Batch& b = *bp;
+    mk_result res{};
+    check(mk_scan_wait(engines_[(size_t)b.engine], b.slot, &res));
+    size_t hi = 0, meta_i = 0;
+    for (uint32_t r = 0; r < b.n_records; ++r) {
+        size_t h0 = hi;
+        while (hi < res.n_hits && res.hits[hi].record == r) ++hi;
+        bool flag = (res.record_flags[r >> 6] >> (r & 63)) & 1;
+        const Piece& pc = b.pieces[r];
+        if (pc.first) cur_meta_ = std::move(b.metas[meta_i++]);
+        deliver_piece(b, r, flag, res.hits ? res.hits + h0 : nullptr, hi - h0);
+        if (pc.last) {
+            if (mode_ == MK_MODE_PATTERN_SET && cur_hits_.size() > 1) {  // pieces of one record may repeat a pattern
+                std::sort(cur_hits_.begin(), cur_hits_.end(), [](const RecHit& x, const RecHit& y) { return x.pattern < y.pattern; });
+                cur_hits_.erase(std::unique(cur_hits_.begin(), cur_hits_.end(),
+                                            [](const RecHit& x, const RecHit& y) { return x.pattern == y.pattern; }),
+                                cur_hits_.end());
+            }
+            cb_(cur_meta_, cur_found_, cur_hits_);
+        }
+    }
+}
+
+void Scanner::finish() {
+    submit_open();
+    while (!inflight_.empty()) consume_oldest();
+}
+
+}  // namespace mkh

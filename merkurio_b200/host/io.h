@@ -1,0 +1,82 @@
+// Input side: a buffered byte source over zlib (plain or gzip/BGZF transparently), the FASTA/FASTQ
+// record reader (the role needletail plays in src/cmd_extract.rs:281,321,412,463) and the SAM/BAM
+// record reader (the role of the `bam` crate in src/cmd_tag.rs:504-613).
+#pragma once
+#include <zlib.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "common.h"
+
+namespace mkh {
+
+class ByteSource {
+public:
+    explicit ByteSource(const std::string& path);
+    ~ByteSource();
+    ByteSource(const ByteSource&) = delete;
+    // Reads one line (without the '\n'; a trailing '\r' is kept). Returns false at end of input.
+    bool getline(std::string* line);
+    // Reads exactly n bytes; returns false on EOF before the first byte, throws on a short read.
+    bool read_exact(void* dst, size_t n);
+    int peek();  // next byte or -1
+private:
+    bool fill();
+    gzFile f_ = nullptr;
+    std::vector<char> buf_;
+    size_t pos_ = 0, end_ = 0;
+    bool eof_ = false;
+};
+
+// One FASTA/FASTQ record as needletail exposes it.
+struct FastxRecord {
+    std::string id;    // header line without '>' / '@' (and without the line break)
+    std::string seq;   // line breaks removed (record.seq())
+    std::string raw;   // FASTA: sequence lines as in the file, last line break dropped; FASTQ: == seq
+    std::string qual;  // FASTQ only
+    bool fastq = false;
+    bool crlf = false;
+    // record.write(writer, None): FASTA keeps its wrapping; FASTQ is four lines with a bare '+'
+    void write(std::string* out) const;
+};
+
+class FastxReader {
+public:
+    explicit FastxReader(const std::string& path);
+    bool next(FastxRecord* rec);  // throws Error on malformed input
+private:
+    ByteSource src_;
+    std::string pending_;  // a header line already consumed
+    bool have_pending_ = false, started_ = false, fastq_ = false;
+};
+
+// One alignment record. `packed` holds the sequence as BAM stores it (4 bits per base, first base in
+// the high nibble, "=ACMGRSVTWYHKDBN"); the device scans it directly.
+struct AlnRecord {
+    std::string name;
+    std::string sam_line;          // the record as a SAM text line (no line break)
+    std::vector<uint8_t> packed;   // (l_seq + 1) / 2 bytes
+    uint32_t l_seq = 0;
+};
+
+class AlnReader {
+public:
+    AlnReader(const std::string& path, bool is_bam);
+    const std::vector<std::string>& header_lines() const { return header_; }
+    bool next(AlnRecord* rec);
+private:
+    void read_bam_header();
+    bool next_sam(AlnRecord* rec);
+    bool next_bam(AlnRecord* rec);
+    ByteSource src_;
+    bool bam_;
+    std::vector<std::string> header_, refs_;
+    std::string pending_;
+    bool have_pending_ = false;
+};
+
+extern const char kNibbleChars[17];
+
+}  // namespace mkh

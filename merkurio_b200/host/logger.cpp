@@ -1,0 +1,124 @@
+#include "logger.h"
+
+#include "common.h"
+
+namespace mkh {
+
+std::string json_escape(const std::string& s) {
+    std::string o = "\"";
+    for (unsigned char c : s) {
+        switch (c) {
+            case '"': o += "\\\""; break;
+            case '\\': o += "\\\\"; break;
+            case '\n': o += "\\n"; break;
+            case '\r': o += "\\r"; break;
+            case '\t': o += "\\t"; break;
+            case '\b': o += "\\b"; break;
+            case '\f': o += "\\f"; break;
+            default:
+                if (c < 0x20) {
+                    char b[8];
+                    std::snprintf(b, sizeof b, "\\u%04x", c);
+                    o += b;
+                } else {
+                    o += (char)c;
+                }
+        }
+    }
+    return o + "\"";
+}
+
+std::string Json::pretty(int indent) const {
+    std::string pad(indent + 2, ' '), end(indent, ' ');
+    switch (kind) {
+        case Null: return "null";
+        case Bool: return b ? "true" : "false";
+        case Int: return std::to_string(i);
+        case Str: return json_escape(s);
+        case Arr: {
+            if (a.empty()) return "[]";
+            std::string r = "[\n";
+            for (size_t k = 0; k < a.size(); ++k) r += pad + a[k].pretty(indent + 2) + (k + 1 < a.size() ? ",\n" : "\n");
+            return r + end + "]";
+        }
+        case Obj: {
+            if (o.empty()) return "{}";
+            std::string r = "{\n";
+            size_t k = 0;
+            for (auto& kv : o) r += pad + json_escape(kv.first) + ": " + kv.second.pretty(indent + 2) + (++k < o.size() ? ",\n" : "\n");
+            return r + end + "}";
+        }
+    }
+    return "null";
+}
+
+std::unique_ptr<Sink> Sink::open(const std::string& path, const std::string& what) {
+    std::unique_ptr<Sink> s(new Sink);
+    if (path == "STDOUT") {
+        s->f_ = stdout;
+    } else {
+        s->f_ = std::fopen(path.c_str(), "wb");
+        if (!s->f_) throw Error(what + ": " + path);
+        s->owned_ = true;
+    }
+    return s;
+}
+Sink::~Sink() {
+    if (f_) std::fflush(f_);
+    if (f_ && owned_) std::fclose(f_);
+}
+
+void BufferedLogger::log_fields(const std::string& prefix, const std::string& record, const std::string& pattern, uint64_t index) {
+    buf_ += prefix; buf_ += '\t';
+    buf_ += record; buf_ += '\t';
+    buf_ += pattern; buf_ += '\t';
+    buf_ += std::to_string(index); buf_ += '\n';
+    if (buf_.size() >= cap_) flush();
+}
+void BufferedLogger::flush() {
+    if (sink_ && !buf_.empty()) sink_->write(buf_);
+    buf_.clear();
+}
+
+JsonLogger::JsonLogger(std::unique_ptr<Sink> sink, size_t buffer_size) : sink_(std::move(sink)), cap_(buffer_size) {
+    if (sink_) sink_->write("{\n  \"matching_records\": [\n");
+}
+void JsonLogger::log_fields(const std::string& file, const std::string& record, const std::string& pattern, uint64_t index) {
+    if (!first_) buf_ += ",\n";
+    first_ = false;
+    // keys in sorted order, 2-space pretty print, every line prefixed with 4 spaces
+    buf_ += "    {\n";
+    buf_ += "      \"file\": " + json_escape(file) + ",\n";
+    buf_ += "      \"pattern\": " + json_escape(pattern) + ",\n";
+    buf_ += "      \"position\": \"" + std::to_string(index) + "\",\n";
+    buf_ += "      \"record_id\": " + json_escape(record) + "\n";
+    buf_ += "    }\n";
+    if (buf_.size() >= cap_) flush();
+}
+void JsonLogger::flush() {
+    if (sink_ && !buf_.empty()) sink_->write(buf_);
+    buf_.clear();
+}
+void JsonLogger::write_indented_value(const Json& v, int indent) {
+    // continuation lines get `indent` extra spaces: the same as pretty-printing at that depth
+    buf_ += v.pretty(indent);
+    buf_ += '\n';
+}
+void JsonLogger::finalize(const Json& meta, const Json& counts, const Json& summary, const Json* paired) {
+    auto pop_nl = [&] { if (!buf_.empty() && buf_.back() == '\n') buf_.pop_back(); };
+    buf_ += "  ],\n  \"meta_information\": ";
+    write_indented_value(meta, 2); pop_nl();
+    if (paired) {
+        buf_ += ",\n  \"paired_end_reads_statistics\": ";
+        write_indented_value(*paired, 2); pop_nl();
+    }
+    buf_ += ",\n  \"pattern_hit_counts\": ";
+    write_indented_value(counts, 2); pop_nl();
+    buf_ += ",\n  \"summary_statistics\": ";
+    write_indented_value(summary, 2); pop_nl();
+    buf_ += "\n}\n";
+    flush();
+    if (sink_) sink_->flush();
+}
+
+}  // namespace mkh

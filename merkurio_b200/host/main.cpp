@@ -1,0 +1,319 @@
+// merkurio — command line with the reference's grammar (src/main.rs:14-54 and the clap structs in
+// src/cmd_extract.rs:33-141, src/cmd_tag.rs:29-150): the same subcommands, flags, value counts,
+// argument groups and exit codes (2 for usage errors, 1 for run-time errors, as clap / anyhow do).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "commands.h"
+#include "helpers.h"
+
+using namespace mkh;
+
+namespace {
+
+enum Kind { FLAG, VALUE, OPT_VALUE, MULTI };
+struct Opt {
+    char short_name;
+    const char* long_name;
+    Kind kind;
+    const char* value_name;
+    const char* help;
+};
+
+const Opt kExtract[] = {
+    {'i', "in-fastx", VALUE, "IN_FASTX", "Input path for (compressed) FASTQ/A file"},
+    {'2', "in-fastq-2", VALUE, "IN_FASTQ_2", "Input path for second FASTQ file (only for paired-end read processing)"},
+    {'s', "kmer-seq", MULTI, "KMER_SEQ", "Query sequences (accepts multiple sequences after the flag, separated by a space)"},
+    {'f', "kmer-file", VALUE, "KMER_FILE", "Input path for file containing list of k-mers, one per line"},
+    {'o', "out-fastx", VALUE, "OUT_FASTX", "Output file path for FASTQ/A file (extension derived from input file)"},
+    {'r', "reverse-complement", FLAG, nullptr, "Also search for reverse complements of k-mers"},
+    {'c', "canonical", FLAG, nullptr, "Search only for the canonical forms of k-mers"},
+    {'l', "out-log", OPT_VALUE, "OUT_LOG", "Print detailed match information to stdout, or to a file if a path is provided"},
+    {'j', "json-log", OPT_VALUE, "JSON_LOG", "Write JSON log to stdout, or to a file if a path is provided"},
+    {'S', "suppress-output", FLAG, nullptr, "Suppress output of found records"},
+    {'v', "invert-match", FLAG, nullptr, "Invert the sense of matching, to select non-matching records"},
+    {'I', "case-insensitive", FLAG, nullptr, "Use case-insensitive matching"},
+    {'L', "lowercase", FLAG, nullptr, "Convert all input sequences to lowercase"},
+    {'U', "uppercase", FLAG, nullptr, "Convert all input sequences to uppercase"},
+    {'q', "q-size", VALUE, "Q_SIZE", "Manually set size of q-grams (BNDMq report order and count semantics)"},
+    {'a', "aho-corasick", FLAG, nullptr, "Aho-Corasick report order and count semantics"},
+};
+const Opt kTag[] = {
+    {'i', "in-file", VALUE, "IN_FILE", "Input path for SAM/BAM file"},
+    {'o', "out-file", VALUE, "OUT_FILE", "Output path for SAM/BAM file with annotations"},
+    {'s', "kmer-seq", MULTI, "KMER_SEQ", "Query sequences (accepts multiple sequences after the flag, separated by a space)"},
+    {'f', "kmer-file", VALUE, "KMER_FILE", "Input path for file containing list of k-mers, one per line"},
+    {'r', "reverse-complement", FLAG, nullptr, "Also search for reverse complements of k-mers"},
+    {'c', "canonical", FLAG, nullptr, "Search only for the canonical forms of k-mers"},
+    {'t', "tag", VALUE, "TAG", "Tag to add to the SAM/BAM file with the presence of k-mers [default: km]"},
+    {'l', "out-log", OPT_VALUE, "OUT_LOG", "Print detailed match information to stdout, or to a file if a path is provided"},
+    {'j', "json-log", OPT_VALUE, "JSON_LOG", "Write JSON log to stdout, or to a file if a path is provided"},
+    {'p', "threads", VALUE, "THREADS", "Number of parallel threads to use for processing BAM files [default: 1]"},
+    {'S', "suppress-output", FLAG, nullptr, "Suppress output of found records"},
+    {'m', "filter-matching", FLAG, nullptr, "Filter records to keep only those with matching k-mers"},
+    {'v', "invert-match", FLAG, nullptr, "Invert the sense of matching"},
+    {'I', "case-insensitive", FLAG, nullptr, "Use case-insensitive matching"},
+    {'L', "lowercase", FLAG, nullptr, "Convert all input sequences to lowercase"},
+    {'U', "uppercase", FLAG, nullptr, "Convert all input sequences to uppercase"},
+    {'q', "q-size", VALUE, "Q_SIZE", "Manually set size of q-grams (BNDMq report order and count semantics)"},
+    {'a', "aho-corasick", FLAG, nullptr, "Aho-Corasick report order and count semantics"},
+};
+
+[[noreturn]] void usage_error(const std::string& msg, const char* sub) {
+    std::fprintf(stderr, "error: %s\n\nUsage: merkurio %s [OPTIONS]\n\nFor more information, try '--help'.\n", msg.c_str(), sub);
+    std::exit(2);
+}
+
+void print_help(const char* sub, const Opt* opts, size_t n) {
+    std::printf("Usage: merkurio %s [OPTIONS]\n\nOptions:\n", sub);
+    for (size_t i = 0; i < n; ++i) {
+        std::string left = std::string("  -") + opts[i].short_name + ", --" + opts[i].long_name;
+        if (opts[i].kind == VALUE) left += std::string(" <") + opts[i].value_name + ">";
+        if (opts[i].kind == OPT_VALUE) left += std::string(" [<") + opts[i].value_name + ">]";
+        if (opts[i].kind == MULTI) left += std::string(" <") + opts[i].value_name + ">...";
+        std::printf("%-40s %s\n", left.c_str(), opts[i].help);
+    }
+    std::printf("  -h, --help                               Print help\n");
+}
+
+std::string display(const Opt& o) {
+    std::string s = std::string("--") + o.long_name;
+    if (o.kind == VALUE) s += std::string(" <") + o.value_name + ">";
+    if (o.kind == OPT_VALUE) s += std::string(" [<") + o.value_name + ">]";
+    if (o.kind == MULTI) s += std::string(" <") + o.value_name + ">...";
+    return s;
+}
+
+struct Parsed {
+    std::map<std::string, std::vector<std::string>> values;  // long name -> values (flags: empty vector)
+    bool has(const char* k) const { return values.count(k) > 0; }
+    const std::string& one(const char* k) const { return values.at(k).front(); }
+};
+
+Parsed parse(int argc, char** argv, int first, const char* sub, const Opt* opts, size_t n) {
+    Parsed p;
+    auto find_long = [&](const std::string& name) -> const Opt* {
+        for (size_t i = 0; i < n; ++i) if (name == opts[i].long_name) return &opts[i];
+        return nullptr;
+    };
+    auto find_short = [&](char c) -> const Opt* {
+        if (std::strcmp(sub, "extract") == 0 && c == '1') c = 'i';  // short_alias = '1'
+        for (size_t i = 0; i < n; ++i) if (c == opts[i].short_name) return &opts[i];
+        return nullptr;
+    };
+    int i = first;
+    auto looks_like_flag = [](const char* s) { return s[0] == '-' && s[1] != '\0'; };
+    auto take = [&](const Opt& o, const std::string* attached) {
+        if (p.has(o.long_name) && o.kind != MULTI) usage_error("the argument '" + display(o) + "' cannot be used multiple times", sub);
+        std::vector<std::string>& v = p.values[o.long_name];
+        switch (o.kind) {
+            case FLAG:
+                if (attached) usage_error(std::string("unexpected value '") + *attached + "' for '--" + o.long_name + "' found; no more were expected", sub);
+                break;
+            case VALUE:
+                if (attached) v.push_back(*attached);
+                else if (i < argc && !(looks_like_flag(argv[i]) && !(argv[i][1] >= '0' && argv[i][1] <= '9'))) v.push_back(argv[i++]);
+                else usage_error("a value is required for '" + display(o) + "' but none was supplied", sub);
+                break;
+            case OPT_VALUE:
+                if (attached) v.push_back(*attached);
+                else if (i < argc && !looks_like_flag(argv[i])) v.push_back(argv[i++]);
+                else v.push_back("STDOUT");
+                break;
+            case MULTI:
+                if (attached) v.push_back(*attached);
+                while (i < argc && !looks_like_flag(argv[i])) v.push_back(argv[i++]);
+                if (v.empty()) usage_error("a value is required for '" + display(o) + "' but none was supplied", sub);
+                break;
+        }
+    };
+    while (i < argc) {
+        std::string tok = argv[i++];
+        if (tok == "-h" || tok == "--help") { print_help(sub, opts, n); std::exit(0); }
+        if (tok.rfind("--", 0) == 0) {
+            std::string name = tok.substr(2), val;
+            bool has_val = false;
+            size_t eq = name.find('=');
+            if (eq != std::string::npos) { val = name.substr(eq + 1); name = name.substr(0, eq); has_val = true; }
+            const Opt* o = find_long(name);
+            if (!o) usage_error("unexpected argument '--" + name + "' found", sub);
+            take(*o, has_val ? &val : nullptr);
+        } else if (tok.size() >= 2 && tok[0] == '-') {
+            for (size_t k = 1; k < tok.size(); ++k) {
+                const Opt* o = find_short(tok[k]);
+                if (!o) usage_error(std::string("unexpected argument '-") + tok[k] + "' found", sub);
+                if (o->kind != FLAG && k + 1 < tok.size()) {
+                    std::string rest = tok.substr(k + 1);
+                    if (!rest.empty() && rest[0] == '=') rest = rest.substr(1);
+                    take(*o, &rest);
+                    break;
+                }
+                take(*o, nullptr);
+            }
+        } else {
+            usage_error("unexpected argument '" + tok + "' found", sub);
+        }
+    }
+    return p;
+}
+
+void exclusive(const Parsed& p, const Opt* opts, size_t n, std::initializer_list<const char*> names, const char* sub) {
+    const Opt* seen = nullptr;
+    for (const char* nm : names) {
+        if (!p.has(nm)) continue;
+        const Opt* o = nullptr;
+        for (size_t i = 0; i < n; ++i) if (std::strcmp(opts[i].long_name, nm) == 0) o = &opts[i];
+        if (seen) usage_error("the argument '" + display(*seen) + "' cannot be used with '" + display(*o) + "'", sub);
+        seen = o;
+    }
+}
+
+size_t parse_usize(const std::string& s, const char* what, const char* sub) {
+    char* end = nullptr;
+    if (s.empty() || s[0] == '-') usage_error("invalid value '" + s + "' for '" + what + "': invalid digit found in string", sub);
+    unsigned long long v = std::strtoull(s.c_str(), &end, 10);
+    if (*end) usage_error("invalid value '" + s + "' for '" + what + "': invalid digit found in string", sub);
+    return (size_t)v;
+}
+
+std::optional<std::string> opt_str(const Parsed& p, const char* k) {
+    if (!p.has(k)) return std::nullopt;
+    return p.one(k);
+}
+
+int run(int argc, char** argv) {
+    const char* top_help =
+        "SeqKatcher has two subcommands, 'extract' and 'tag'. This build runs the matching on NVIDIA B200 GPUs.\n\n"
+        "Usage: merkurio <COMMAND>\n\nCommands:\n"
+        "  extract  Search for query sequences in FASTA/Q files and extract records containing the patterns\n"
+        "  tag      Tag records in a BAM/SAM file with the presence of query sequences\n"
+        "  help     Print this message\n\nOptions:\n  -h, --help     Print help\n  -V, --version  Print version\n";
+    if (argc < 2) { std::fputs(top_help, stderr); return 2; }
+    std::string cmd = argv[1];
+    if (cmd == "-h" || cmd == "--help" || cmd == "help") { std::fputs(top_help, stdout); return 0; }
+    if (cmd == "-V" || cmd == "--version") { std::printf("%s %s\n", kProgram, kVersion); return 0; }
+    std::vector<std::string> all(argv, argv + argc);
+    if (cmd == "extract") {
+        const size_t n = sizeof kExtract / sizeof kExtract[0];
+        if (argc == 2) { print_help("extract", kExtract, n); return 2; }
+        Parsed p = parse(argc, argv, 2, "extract", kExtract, n);
+        exclusive(p, kExtract, n, {"kmer-seq", "kmer-file"}, "extract");
+        exclusive(p, kExtract, n, {"q-size", "aho-corasick"}, "extract");
+        exclusive(p, kExtract, n, {"case-insensitive", "lowercase", "uppercase"}, "extract");
+        exclusive(p, kExtract, n, {"canonical", "reverse-complement"}, "extract");
+        exclusive(p, kExtract, n, {"suppress-output", "out-fastx"}, "extract");
+        std::string missing;
+        if (!p.has("in-fastx")) missing += "\n  --in-fastx <IN_FASTX>";
+        if (!p.has("kmer-seq") && !p.has("kmer-file")) missing += "\n  <--kmer-seq <KMER_SEQ>...|--kmer-file <KMER_FILE>>";
+        if (p.has("suppress-output") && !p.has("out-log") && !p.has("json-log")) missing += "\n  <--out-log [<OUT_LOG>]|--json-log [<JSON_LOG>]>";
+        if (!missing.empty()) usage_error("the following required arguments were not provided:" + missing, "extract");
+        CmdExtract a;
+        a.in_fastx = p.one("in-fastx");
+        a.in_fastq_2 = opt_str(p, "in-fastq-2");
+        if (p.has("kmer-seq")) a.kmer_seq = p.values.at("kmer-seq");
+        a.kmer_file = opt_str(p, "kmer-file");
+        a.out_fastx = opt_str(p, "out-fastx");
+        a.reverse_complement = p.has("reverse-complement");
+        a.canonical = p.has("canonical");
+        a.out_log = opt_str(p, "out-log");
+        a.json_log = opt_str(p, "json-log");
+        a.suppress_output = p.has("suppress-output");
+        a.invert_match = p.has("invert-match");
+        a.case_insensitive = p.has("case-insensitive");
+        a.lowercase = p.has("lowercase");
+        a.uppercase = p.has("uppercase");
+        if (p.has("q-size")) a.q_size = parse_usize(p.one("q-size"), "--q-size <Q_SIZE>", "extract");
+        a.aho_corasick = p.has("aho-corasick");
+        a.argv = all;
+        extract_records(std::move(a));
+        return 0;
+    }
+    if (cmd == "patterns") {
+        // diagnostic (not in the reference): print the query list after preprocessing and the algorithm
+        // the reference would choose — the host half of the hot path, testable without a GPU
+        const size_t n = sizeof kExtract / sizeof kExtract[0];
+        Parsed p = parse(argc, argv, 2, "patterns", kExtract, n);
+        exclusive(p, kExtract, n, {"kmer-seq", "kmer-file"}, "patterns");
+        exclusive(p, kExtract, n, {"canonical", "reverse-complement"}, "patterns");
+        exclusive(p, kExtract, n, {"case-insensitive", "lowercase", "uppercase"}, "patterns");
+        std::optional<std::vector<std::string>> seqs;
+        if (p.has("kmer-seq")) seqs = p.values.at("kmer-seq");
+        std::optional<size_t> q;
+        if (p.has("q-size")) q = parse_usize(p.one("q-size"), "--q-size <Q_SIZE>", "patterns");
+        std::vector<std::string> pats;
+        try {
+            pats = parse_pattern_list(opt_str(p, "kmer-file"), seqs, p.has("reverse-complement"), p.has("canonical"), p.has("lowercase"), p.has("uppercase"));
+        } catch (const Error& e) {
+            throw e.with_context("Problem parsing pattern list.");
+        }
+        bool ac = choose_aho_corasick(pats, p.has("case-insensitive"), q, p.has("aho-corasick"));
+        if (!ac) validate_bndmq(pats, q);
+        for (auto& s : pats) std::printf("%s\n", s.c_str());
+        std::printf("#search_algorithm\t%s\n", ac ? "Aho-Corasick" : "BNDMq");
+        return 0;
+    }
+    if (cmd == "tag") {
+        const size_t n = sizeof kTag / sizeof kTag[0];
+        if (argc == 2) { print_help("tag", kTag, n); return 2; }
+        Parsed p = parse(argc, argv, 2, "tag", kTag, n);
+        exclusive(p, kTag, n, {"kmer-seq", "kmer-file"}, "tag");
+        exclusive(p, kTag, n, {"filter-matching", "invert-match"}, "tag");
+        exclusive(p, kTag, n, {"q-size", "aho-corasick"}, "tag");
+        exclusive(p, kTag, n, {"case-insensitive", "lowercase", "uppercase"}, "tag");
+        exclusive(p, kTag, n, {"canonical", "reverse-complement"}, "tag");
+        exclusive(p, kTag, n, {"suppress-output", "out-file"}, "tag");
+        std::string missing;
+        if (!p.has("in-file")) missing += "\n  --in-file <IN_FILE>";
+        if (!p.has("kmer-seq") && !p.has("kmer-file")) missing += "\n  <--kmer-seq <KMER_SEQ>...|--kmer-file <KMER_FILE>>";
+        if (p.has("suppress-output") && !p.has("out-log") && !p.has("json-log")) missing += "\n  <--out-log [<OUT_LOG>]|--json-log [<JSON_LOG>]>";
+        if (!missing.empty()) usage_error("the following required arguments were not provided:" + missing, "tag");
+        CmdTag a;
+        a.in_file = p.one("in-file");
+        a.out_file = opt_str(p, "out-file");
+        if (p.has("kmer-seq")) a.kmer_seq = p.values.at("kmer-seq");
+        a.kmer_file = opt_str(p, "kmer-file");
+        a.reverse_complement = p.has("reverse-complement");
+        a.canonical = p.has("canonical");
+        if (p.has("tag")) a.tag = p.one("tag");
+        a.out_log = opt_str(p, "out-log");
+        a.json_log = opt_str(p, "json-log");
+        if (p.has("threads")) {
+            size_t t = parse_usize(p.one("threads"), "--threads <THREADS>", "tag");
+            if (t > 65535) usage_error("invalid value '" + p.one("threads") + "' for '--threads <THREADS>': number too large to fit in target type", "tag");
+            a.threads = (int)t;
+        }
+        a.suppress_output = p.has("suppress-output");
+        a.filter_matching = p.has("filter-matching");
+        a.invert_match = p.has("invert-match");
+        a.case_insensitive = p.has("case-insensitive");
+        a.lowercase = p.has("lowercase");
+        a.uppercase = p.has("uppercase");
+        if (p.has("q-size")) a.q_size = parse_usize(p.one("q-size"), "--q-size <Q_SIZE>", "tag");
+        a.aho_corasick = p.has("aho-corasick");
+        a.argv = all;
+        tag_records(std::move(a));
+        return 0;
+    }
+    std::fprintf(stderr, "error: unrecognized subcommand '%s'\n\nUsage: merkurio <COMMAND>\n\nFor more information, try '--help'.\n", cmd.c_str());
+    return 2;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    try {
+        return run(argc, argv);
+    } catch (const Error& e) {
+        std::fflush(stdout);
+        std::fputs(e.report().c_str(), stderr);
+        return 1;
+    } catch (const std::exception& e) {
+        std::fflush(stdout);
+        std::fprintf(stderr, "Error: %s\n", e.what());
+        return 1;
+    }
+}

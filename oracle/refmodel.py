@@ -822,7 +822,7 @@ def _bam_aux_to_sam(buf: bytes) -> List[bytes]:
             out.append(tag + b":i:" + str(struct.unpack_from(fmt, buf, i)[0]).encode()); i += sz
         elif typ == b"f":
             v = struct.unpack_from("<f", buf, i)[0]; i += 4
-            out.append(tag + b":f:" + repr(float(np.float32(v))).encode())
+            out.append(tag + b":f:" + str(np.float32(v)).encode())  # shortest float32 form (unpinned by the reference)
         elif typ in b"ZH":
             j = buf.index(b"\0", i)
             out.append(tag + b":" + typ + b":" + buf[i:j]); i = j + 1

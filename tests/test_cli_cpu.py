@@ -1,0 +1,159 @@
+"""CPU tests of the C++ host (merkurio_b200/host): query-list preprocessing, algorithm choice and
+flag rules against the oracle and the reference's own helper tests (src/helpers.rs:218-568,
+src/main.rs:60-293). Nothing here needs a GPU — these paths run before any engine is created."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+from oracle import refmodel as rm
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def exe():
+    from merkurio_b200.build import build_host
+    return str(build_host())
+
+
+def run(exe, *args):
+    return subprocess.run([exe, *map(str, args)], capture_output=True, text=True)
+
+
+def cli_patterns(exe, *args):
+    r = run(exe, "patterns", *args)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.split("\n")
+    pats = [ln for ln in lines if ln and not ln.startswith("#search_algorithm")]
+    algo = [ln.split("\t")[1] for ln in lines if ln.startswith("#search_algorithm")][0]
+    return pats, algo
+
+
+@pytest.mark.parametrize("flags,kw", [
+    ((), {}),
+    (("-r",), dict(reverse_complement_=True)),
+    (("-c",), dict(canonical_=True)),
+    (("-L",), dict(lowercase=True)),
+    (("-U", "-r"), dict(uppercase=True, reverse_complement_=True)),
+])
+@pytest.mark.parametrize("name", ["kmers.txt", "kmers.fasta", "kmers-duplicates.txt", "kmers-messy.txt", "kmers-many-40.txt", "kmers-aa.txt"])
+def test_pattern_list_matches_oracle(exe, ref_tree, name, flags, kw):
+    f = ref_tree / "tests" / "data" / name
+    want = rm.parse_pattern_list(f, None, kw.get("reverse_complement_", False), kw.get("canonical_", False),
+                                 kw.get("lowercase", False), kw.get("uppercase", False))
+    got, algo = cli_patterns(exe, "-f", f, *flags)
+    assert got == want
+    assert algo == ("Aho-Corasick" if rm.recommend_aho_corasick(want) else "BNDMq")
+
+
+def test_pattern_list_from_sequences(exe):
+    got, algo = cli_patterns(exe, "-s", "ACG", "-r")
+    assert got == ["ACG", "CGT"] and algo == "BNDMq"
+    got, _ = cli_patterns(exe, "-s", "ARYKMBVDHSWN*x", "acgtn", "-r")
+    assert got == rm.parse_pattern_list(None, ["ARYKMBVDHSWN*x", "acgtn"], True, False, False, False)
+    # palindromes collapse under -r (src/helpers.rs:124-126)
+    got, _ = cli_patterns(exe, "-s", "ACGT", "AATT", "-r")
+    assert got == ["AATT", "ACGT"]
+    # canonical keeps only one orientation
+    got, _ = cli_patterns(exe, "-s", "TTTT", "AAAA", "CCGG", "-c")
+    assert got == ["AAAA", "CCGG"]
+
+
+def test_algorithm_choice(exe):
+    # src/helpers.rs:203-211 and src/cmd_extract.rs:165-171
+    thirteen = [f"ACGT{'ACGT'[i % 4]}{'ACGT'[i // 4]}A" for i in range(13)]
+    assert cli_patterns(exe, "-s", *thirteen)[1] == "BNDMq"
+    assert cli_patterns(exe, "-s", *thirteen, "TTTTTTT")[1] == "Aho-Corasick"
+    assert cli_patterns(exe, "-s", "A" * 64)[1] == "BNDMq"
+    assert cli_patterns(exe, "-s", "A" * 65)[1] == "Aho-Corasick"
+    assert cli_patterns(exe, "-s", "ACGT", "-a")[1] == "Aho-Corasick"
+    assert cli_patterns(exe, "-s", "ACGT", "-I")[1] == "Aho-Corasick"
+    assert cli_patterns(exe, "-s", *thirteen, "TTTTTTT", "-q", "3")[1] == "BNDMq"
+
+
+def test_bndmq_errors_of_forced_q(exe):
+    r = run(exe, "patterns", "-s", "ACGT", "-q", "7")
+    assert r.returncode == 1 and "Invalid q-gram length: 7. Must be between 1 and pattern length." in r.stderr
+    r = run(exe, "patterns", "-s", "A" * 65, "-q", "4")
+    assert r.returncode == 1 and "is too large for this architecture when using BNDM (max 64)" in r.stderr
+    r = run(exe, "patterns", "-s", "ACGT", "-q", "0")
+    assert r.returncode == 1 and "Invalid q-gram length: 0" in r.stderr
+
+
+def test_pattern_file_errors(exe, ref_tree, tmp_path):
+    r = run(exe, "patterns", "-f", ref_tree / "tests" / "data" / "kmers-empty.txt")
+    assert r.returncode == 1 and "No k-mers found in the file." in r.stderr and "Problem parsing pattern list." in r.stderr
+    r = run(exe, "patterns", "-f", tmp_path / "missing.txt")
+    assert r.returncode == 1 and "File not found." in r.stderr
+    r = run(exe, "patterns", "-f", tmp_path)
+    assert r.returncode == 1 and "is a directory, not a file." in r.stderr
+    r = run(exe, "patterns", "-s", "")
+    assert r.returncode == 1 and "No k-mers found in file or provided sequence." in r.stderr
+
+
+def test_cfg1_literal_command_is_refused(exe, ref_tree):
+    # BASELINE config 1 as written: log and records both on stdout (src/helpers.rs:195-197)
+    em = ref_tree / "example-minimal"
+    r = run(exe, "extract", "-i", em / "sample.fasta", "-f", em / "kmers.txt", "-r", "-l")
+    assert r.returncode == 1
+    assert r.stderr.strip() == ("Error: Cannot write log to stdout when normal output is also stdout. "
+                                "Specify an output file with -o or suppress output with -S.")
+    assert r.stdout == ""
+
+
+def test_log_flag_conflicts(exe, ref_tree):
+    fa = ref_tree / "tests" / "fixtures" / "input" / "simple.fasta"
+    r = run(exe, "extract", "-i", fa, "-s", "ACG", "-l", "-j", "-o", "x")
+    assert r.returncode == 1 and "both to stdout" in r.stderr
+    r = run(exe, "extract", "-i", fa, "-s", "ACG", "-j")
+    assert r.returncode == 1 and "Cannot write log to stdout when normal output is also stdout" in r.stderr
+    sam = ref_tree / "tests" / "fixtures" / "input" / "simple.sam"
+    r = run(exe, "tag", "-i", sam, "-s", "CTC", "-l")
+    assert r.returncode == 1 and "Cannot write log to stdout" in r.stderr
+
+
+def test_clap_grammar(exe, ref_tree):
+    # src/main.rs:60-293: group exclusivity, -S rules, required arguments -> usage error, exit code 2
+    fa = ref_tree / "tests" / "fixtures" / "input" / "simple.fasta"
+    cases = [
+        ("extract", "-i", fa, "-s", "A", "-f", "k.txt"),
+        ("extract", "-i", fa, "-s", "A", "-r", "-c"),
+        ("extract", "-i", fa, "-s", "A", "-I", "-L"),
+        ("extract", "-i", fa, "-s", "A", "-L", "-U"),
+        ("extract", "-i", fa, "-s", "A", "-q", "2", "-a"),
+        ("extract", "-i", fa, "-s", "A", "-S"),                 # -S requires logging
+        ("extract", "-i", fa, "-s", "A", "-S", "-l", "-o", "x"),  # -S conflicts with -o
+        ("extract", "-i", fa),                                  # no k-mers
+        ("extract", "-s", "A"),                                 # no input
+        ("extract", "-i", fa, "-s", "A", "--bogus"),
+        ("tag", "-i", "x.sam", "-s", "A", "-m", "-v"),
+        ("tag", "-i", "x.sam", "-s", "A", "-p", "abc"),
+        ("frobnicate",),
+    ]
+    for c in cases:
+        r = run(exe, *c)
+        assert r.returncode == 2, (c, r.returncode, r.stderr)
+        assert r.stderr.startswith("error:"), c
+    assert run(exe).returncode == 2
+    assert run(exe, "--version").stdout.startswith("merkurio ")
+    assert run(exe, "extract", "--help").returncode == 0
+
+
+def test_tag_argument_checks(exe, ref_tree):
+    sam = ref_tree / "tests" / "fixtures" / "input" / "simple.sam"
+    r = run(exe, "tag", "-i", sam, "-s", "CTC", "-p", "0", "-o", "x.sam")
+    assert r.returncode == 1 and "Number of threads must be at least 1." in r.stderr
+    r = run(exe, "tag", "-i", sam, "-s", "CTC", "-t", "kmer", "-o", "x.sam")
+    assert r.returncode == 1 and "Tag must be exactly two characters long." in r.stderr
+    r = run(exe, "tag", "-i", ref_tree / "tests" / "data" / "sample.fasta", "-s", "CTC", "-o", "x.sam")
+    assert r.returncode == 1 and "Input file must be a BAM or SAM file." in r.stderr
+
+
+def test_no_cpu_fallback_in_the_cli(exe, ref_tree, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    fa = ref_tree / "tests" / "fixtures" / "input" / "simple.fasta"
+    r = run(exe, "extract", "-i", fa, "-s", "ACG", "-o", tmp_path / "o")
+    assert r.returncode == 1 and "no CPU path" in r.stderr

@@ -1,0 +1,288 @@
+"""GPU end-to-end tests of the C++ host binary (merkurio_b200/lib/merkurio): the reference's own
+end-to-end tests (src/cmd_extract.rs:885-1056, src/cmd_tag.rs:1009-1132) replayed through the CLI
+against the bundled goldens, plus randomised runs compared file-by-file with the oracle for the
+paths no reference fixture covers (Aho-Corasick mode, -I, -c, -v, gzip input, long records)."""
+import gzip
+import json
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import refmodel as rm
+from tests.golden_util import assert_json_equal, assert_log_equal, assert_sam_equal, json_layout
+
+ROOT = Path(__file__).resolve().parent.parent
+EXE = str(ROOT / "merkurio_b200" / "lib" / "merkurio")
+
+
+def run(*args, env=None, check=True):
+    e = dict(os.environ)
+    if env:
+        e.update(env)
+    r = subprocess.run([EXE, *map(str, args)], capture_output=True, env=e)
+    if check:
+        assert r.returncode == 0, r.stderr.decode()
+    return r
+
+
+# ------------------------------------------------------------------ reference fixtures: extract
+def test_extract_simple(ref_tree, tmp_path):
+    fx = ref_tree / "tests" / "fixtures"
+    run("extract", "-i", fx / "input" / "simple.fasta", "-r", "-s", "ACG", "-o", tmp_path / "out.fasta", "-l", tmp_path / "out.log", "-j", tmp_path / "out.json")
+    assert (tmp_path / "out.fasta").read_bytes() == (fx / "extract" / "simple.extracted.fasta").read_bytes()
+    assert_log_equal((tmp_path / "out.log").read_bytes(), (fx / "extract" / "simple.log").read_bytes())
+    assert_json_equal((tmp_path / "out.json").read_bytes(), (fx / "extract" / "simple.json").read_bytes())
+    assert json_layout((tmp_path / "out.json").read_bytes()) == json_layout((fx / "extract" / "simple.json").read_bytes())
+
+
+def test_extract_simple_inverted(ref_tree, tmp_path):
+    fx = ref_tree / "tests" / "fixtures"
+    run("extract", "-i", fx / "input" / "simple.fasta", "-r", "-s", "ACG", "-v", "-o", tmp_path / "out.fasta", "-l", tmp_path / "out.log", "-j", tmp_path / "out.json")
+    assert (tmp_path / "out.fasta").read_bytes() == (fx / "extract" / "simple-inv.extracted.fasta").read_bytes()
+    assert_log_equal((tmp_path / "out.log").read_bytes(), (fx / "extract" / "simple-inv.log").read_bytes())
+    assert_json_equal((tmp_path / "out.json").read_bytes(), (fx / "extract" / "simple-inv.json").read_bytes())
+
+
+def test_extract_fixed_width_aa(ref_tree, tmp_path):
+    fx = ref_tree / "tests" / "fixtures"
+    run("extract", "-i", fx / "input" / "fixed-width.faa", "-s", "DKAT", "-o", tmp_path / "out.faa", "-l", tmp_path / "out.log", "-j", tmp_path / "out.json")
+    assert (tmp_path / "out.faa").read_bytes() == (fx / "extract" / "fixed-width.extracted.faa").read_bytes()
+    assert_log_equal((tmp_path / "out.log").read_bytes(), (fx / "extract" / "fixed-width.log").read_bytes())
+    assert_json_equal((tmp_path / "out.json").read_bytes(), (fx / "extract" / "fixed-width.json").read_bytes())
+
+
+def test_extract_paired(ref_tree, tmp_path):
+    fx = ref_tree / "tests" / "fixtures"
+    run("extract", "-i", fx / "input" / "paired-1.fastq", "-2", fx / "input" / "paired-2.fastq", "-s", "CTT",
+        "-o", tmp_path / "paired.extracted.fastq", "-l", tmp_path / "out.log", "-j", tmp_path / "out.json")
+    assert (tmp_path / "paired_1.extracted.fastq").read_bytes() == (fx / "extract" / "paired_1.extracted.fastq").read_bytes()
+    assert (tmp_path / "paired_2.extracted.fastq").read_bytes() == (fx / "extract" / "paired_2.extracted.fastq").read_bytes()
+    assert_log_equal((tmp_path / "out.log").read_bytes(), (fx / "extract" / "paired.log").read_bytes())
+    assert_json_equal((tmp_path / "out.json").read_bytes(), (fx / "extract" / "paired.json").read_bytes())
+
+
+def test_extract_cfg1_example_minimal(ref_tree, tmp_path):
+    em = ref_tree / "example-minimal"
+    run("extract", "-i", em / "sample.fasta", "-f", em / "kmers.txt", "-r", "-o", tmp_path / "o", "-l", tmp_path / "o.log")
+    lines = (tmp_path / "o.log").read_text().split("\n")
+    hits = [ln for ln in lines if ln and not ln.startswith("#")]
+    assert len(hits) == 74 and "#AAC\t2" in lines and "#GTT\t2" in lines
+    assert "#Total number of characters searched: 1795" in lines
+    # and to stdout without logging (FLAG mode): both records
+    r = run("extract", "-i", em / "sample.fasta", "-f", em / "kmers.txt", "-r")
+    assert r.stdout == (tmp_path / "o.fasta").read_bytes()
+
+
+def test_extract_example_workflow(ref_tree, tmp_path):
+    ew = ref_tree / "example-workflow"
+    run("extract", "-i", ew / "data" / "mutant_R1.fastq", "-2", ew / "data" / "mutant_R2.fastq", "-f", ew / "data" / "significant_kmers.txt",
+        "-r", "-o", tmp_path / "mutant_extracted", "-l", tmp_path / "x.log", "-j", tmp_path / "x.json")
+    assert (tmp_path / "mutant_extracted_1.fastq").read_bytes() == (ew / "output" / "mutant_extracted_1.fastq").read_bytes()
+    assert (tmp_path / "mutant_extracted_2.fastq").read_bytes() == (ew / "output" / "mutant_extracted_2.fastq").read_bytes()
+    got = json.loads((tmp_path / "x.json").read_bytes())
+    want = json.loads((ew / "logs" / "mutant_extracted.stats.json").read_bytes())
+    for k in ("matching_records", "pattern_hit_counts", "summary_statistics", "paired_end_reads_statistics"):
+        assert got[k] == want[k], k
+    # the same extraction without logs (FLAG mode, early-exit semantics)
+    run("extract", "-i", ew / "data" / "mutant_R1.fastq", "-2", ew / "data" / "mutant_R2.fastq", "-f", ew / "data" / "significant_kmers.txt",
+        "-r", "-o", tmp_path / "nolog")
+    assert (tmp_path / "nolog_1.fastq").read_bytes() == (ew / "output" / "mutant_extracted_1.fastq").read_bytes()
+    assert (tmp_path / "nolog_2.fastq").read_bytes() == (ew / "output" / "mutant_extracted_2.fastq").read_bytes()
+
+
+# ------------------------------------------------------------------ reference fixtures: tag
+@pytest.mark.parametrize("inp,flags,stem,sam", [
+    ("simple.sam", ["-m"], "simple", "simple.extracted.sam"),
+    ("simple.sam", ["-v"], "simple-inv", "simple-inv.extracted.sam"),
+    ("simple.bam", [], "simple-bam", "simple.tagged.extracted.sam"),
+])
+def test_tag_fixtures(ref_tree, tmp_path, inp, flags, stem, sam):
+    fx = ref_tree / "tests" / "fixtures"
+    run("tag", "-i", fx / "input" / inp, "-o", tmp_path / "out.sam", "-s", "CTC", "-r", "-l", tmp_path / "out.log", "-j", tmp_path / "out.json", "-p", "2", *flags)
+    assert_sam_equal((tmp_path / "out.sam").read_bytes(), (fx / "tag" / sam).read_bytes())
+    assert_log_equal((tmp_path / "out.log").read_bytes(), (fx / "tag" / f"{stem}.log").read_bytes())
+    assert_json_equal((tmp_path / "out.json").read_bytes(), (fx / "tag" / f"{stem}.json").read_bytes())
+    assert json_layout((tmp_path / "out.json").read_bytes()) == json_layout((fx / "tag" / f"{stem}.json").read_bytes())
+
+
+def test_tag_aho_corasick_golden(ref_tree, tmp_path):
+    fx = ref_tree / "tests" / "fixtures"
+    run("tag", "-i", fx / "input" / "simple.bam", "-S", "-s", "CTC", "AC", "CT", "AA", "T", "A", "C", "G", "GA", "AG", "-r", "-j", tmp_path / "log.json")
+    got = json.loads((tmp_path / "log.json").read_bytes())
+    want = json.loads((fx / "extract" / "log.json").read_bytes())
+    assert got["matching_records"] == want["matching_records"] and len(got["matching_records"]) == 96
+    assert got["pattern_hit_counts"] == want["pattern_hit_counts"]
+    assert got["summary_statistics"] == want["summary_statistics"]
+    assert got["meta_information"]["search_algorithm"] == "Aho-Corasick"
+
+
+def test_tag_example_workflow(ref_tree, tmp_path):
+    ew = ref_tree / "example-workflow"
+    run("tag", "-i", ew / "output" / "mutant_extracted.sorted.sam", "-o", tmp_path / "t.sam", "-f", ew / "data" / "significant_kmers.txt", "-r")
+    assert_sam_equal((tmp_path / "t.sam").read_bytes(), (ew / "output" / "mutant_extracted.sorted.tagged.sam").read_bytes())
+
+
+# ------------------------------------------------------------------ randomised, against the oracle
+def _rand_reads(rng, n, lo, hi, pats, plant=0.3, alphabet=b"ACGT"):
+    al = np.frombuffer(alphabet, dtype=np.uint8)
+    out = []
+    for _ in range(n):
+        L = int(rng.integers(lo, hi + 1))
+        r = bytearray(rng.choice(al, size=L).tobytes())
+        if L and rng.random() < plant:
+            p = pats[int(rng.integers(len(pats)))]
+            if len(p) <= L:
+                s = int(rng.integers(0, L - len(p) + 1))
+                r[s:s + len(p)] = p
+        if L > 10 and rng.random() < 0.1:
+            s = int(rng.integers(0, L - 3))
+            r[s:s + 3] = b"NNN"
+        out.append(bytes(r))
+    return out
+
+
+def _write_fastq(path, reads, prefix):
+    with open(path, "wb") as f:
+        for i, r in enumerate(reads):
+            f.write(b"@%s%d some description\n%s\n+\n%s\n" % (prefix, i, r, b"I" * len(r)))
+
+
+def _write_fasta(path, reads, width=60):
+    with open(path, "wb") as f:
+        for i, r in enumerate(reads):
+            f.write(b">chr%d test\n" % i)
+            for s in range(0, len(r), width):
+                f.write(r[s:s + width] + b"\n")
+
+
+def _compare_with_oracle(tmp_path, cli_args, oracle_args, outputs, env=None):
+    """Run the CLI into tmp/cli and the oracle into tmp/ora; compare every output file."""
+    (tmp_path / "cli").mkdir()
+    (tmp_path / "ora").mkdir()
+    run(*[a.replace("@OUT@", str(tmp_path / "cli")) if isinstance(a, str) else a for a in cli_args], env=env)
+    oracle_args(tmp_path / "ora")
+    for name, kind in outputs:
+        a, b = (tmp_path / "cli" / name).read_bytes(), (tmp_path / "ora" / name).read_bytes()
+        if kind == "raw":
+            assert a == b, name
+        elif kind == "log":
+            assert_log_equal(a, b)
+        elif kind == "json":
+            assert_json_equal(a, b)
+            assert json_layout(a) == json_layout(b)
+        elif kind == "sam":
+            assert_sam_equal(a, b)
+
+
+@pytest.mark.parametrize("mode", ["ac", "bndmq", "insensitive", "canonical", "inverted"])
+def test_extract_random_single(tmp_path, mode):
+    rng = np.random.default_rng({"ac": 1, "bndmq": 2, "insensitive": 3, "canonical": 4, "inverted": 5}[mode])
+    n_pat = 6 if mode == "bndmq" else 30
+    pats = sorted({rng.choice(np.frombuffer(b"ACGT", np.uint8), size=int(rng.integers(12, 40))).tobytes() for _ in range(n_pat)})
+    reads = _rand_reads(rng, 3000, 0, 200, pats)
+    if mode == "insensitive":
+        reads = [r.lower() if i % 2 else r for i, r in enumerate(reads)]
+    fq = tmp_path / "reads.fastq"
+    _write_fastq(fq, reads, b"r")
+    kf = tmp_path / "k.txt"
+    kf.write_bytes(b"# queries\n" + b"\n".join(pats) + b"\n")
+    flags = {"ac": ["-r"], "bndmq": ["-r"], "insensitive": ["-I"], "canonical": ["-c"], "inverted": ["-r", "-v"]}[mode]
+    kw = dict(reverse_complement=mode in ("ac", "bndmq", "inverted"), case_insensitive=mode == "insensitive", canonical=mode == "canonical", invert_match=mode == "inverted")
+
+    def oracle(out):
+        rm.extract_records(rm.CmdExtract(in_fastx=str(fq), kmer_file=str(kf), out_fastx=str(out / "o"), out_log=str(out / "o.log"), json_log=str(out / "o.json"), **kw))
+
+    _compare_with_oracle(tmp_path, ["extract", "-i", fq, "-f", kf, *flags, "-o", "@OUT@/o", "-l", "@OUT@/o.log", "-j", "@OUT@/o.json"], oracle,
+                         [("o.fastq", "raw"), ("o.log", "log"), ("o.json", "json")], env={"MERKURIO_BATCH_BYTES": "100000", "MERKURIO_SLOTS": "2"})
+    # without logs: the same records
+    (tmp_path / "nolog").mkdir()
+    run("extract", "-i", fq, "-f", kf, *flags, "-o", tmp_path / "nolog" / "o")
+    assert (tmp_path / "nolog" / "o.fastq").read_bytes() == (tmp_path / "ora" / "o.fastq").read_bytes()
+
+
+@pytest.mark.parametrize("n_pat", [4, 40])
+def test_extract_random_paired_gz(tmp_path, n_pat):
+    rng = np.random.default_rng(n_pat)
+    pats = sorted({rng.choice(np.frombuffer(b"ACGT", np.uint8), size=31).tobytes() for _ in range(n_pat)})
+    r1 = _rand_reads(rng, 2500, 150, 150, pats, plant=0.05)
+    r2 = _rand_reads(rng, 2500, 150, 150, pats, plant=0.05)
+    _write_fastq(tmp_path / "a_1.fastq", r1, b"p")
+    _write_fastq(tmp_path / "a_2.fastq", r2, b"p")
+    for n in ("a_1.fastq", "a_2.fastq"):
+        (tmp_path / (n + ".gz")).write_bytes(gzip.compress((tmp_path / n).read_bytes()))
+    kf = tmp_path / "k.txt"
+    kf.write_bytes(b"\n".join(pats) + b"\n")
+
+    def oracle(out):
+        rm.extract_records(rm.CmdExtract(in_fastx=str(tmp_path / "a_1.fastq.gz"), in_fastq_2=str(tmp_path / "a_2.fastq.gz"), kmer_file=str(kf),
+                                         reverse_complement=True, out_fastx=str(out / "x"), out_log=str(out / "x.log"), json_log=str(out / "x.json")))
+
+    _compare_with_oracle(tmp_path, ["extract", "-i", tmp_path / "a_1.fastq.gz", "-2", tmp_path / "a_2.fastq.gz", "-f", kf, "-r", "-o", "@OUT@/x",
+                                    "-l", "@OUT@/x.log", "-j", "@OUT@/x.json"], oracle,
+                         [("x_1.fastq", "raw"), ("x_2.fastq", "raw"), ("x.log", "log"), ("x.json", "json")], env={"MERKURIO_BATCH_BYTES": "200000"})
+
+
+def test_extract_long_fasta_records_in_pieces(tmp_path):
+    # chromosomes much longer than a batch: cut into overlapping pieces, hits on every piece boundary
+    rng = np.random.default_rng(77)
+    pats = sorted({rng.choice(np.frombuffer(b"ACGT", np.uint8), size=int(k)).tobytes() for k in rng.integers(21, 64, size=40)} | {b"ACGTNACGTNACGTNACGTNACGT"})
+    chroms = []
+    for n in (300000, 5, 0, 123457):
+        c = bytearray(rng.choice(np.frombuffer(b"ACGTacgtN", np.uint8), size=n, p=[.22, .22, .22, .22, .02, .02, .02, .02, .04]).tobytes())
+        for s in range(100, max(n - 100, 0), 997):
+            p = pats[(s // 997) % len(pats)]
+            c[s:s + len(p)] = p
+        chroms.append(bytes(c))
+    fa = tmp_path / "g.fasta"
+    _write_fasta(fa, chroms)
+    kf = tmp_path / "k.txt"
+    kf.write_bytes(b"\n".join(pats) + b"\n")
+
+    def oracle(out):
+        rm.extract_records(rm.CmdExtract(in_fastx=str(fa), kmer_file=str(kf), suppress_output=True, json_log=str(out / "g.json"), out_log=str(out / "g.log")))
+
+    _compare_with_oracle(tmp_path, ["extract", "-i", fa, "-f", kf, "-S", "-j", "@OUT@/g.json", "-l", "@OUT@/g.log"], oracle,
+                         [("g.log", "log"), ("g.json", "json")], env={"MERKURIO_BATCH_BYTES": "20000", "MERKURIO_SLOTS": "2"})
+
+
+@pytest.mark.parametrize("flags,kw", [(["-m"], dict(filter_matching=True)), (["-v"], dict(invert_match=True)), ([], {})])
+def test_tag_random_sam(tmp_path, flags, kw):
+    rng = np.random.default_rng(len(flags) + 5)
+    pats = sorted({rng.choice(np.frombuffer(b"ACGT", np.uint8), size=31).tobytes() for _ in range(25)})
+    reads = _rand_reads(rng, 2000, 0, 151, pats, plant=0.2)
+    sam = tmp_path / "in.sam"
+    with open(sam, "wb") as f:
+        f.write(b"@HD\tVN:1.6\tSO:unsorted\n@SQ\tSN:1\tLN:100000\n")
+        for i, r in enumerate(reads):
+            seq = r if r else b"*"
+            extra = b"\tkm:Z:ZZZ,AAA" if i % 50 == 0 else b""
+            f.write(b"q%d\t0\t1\t%d\t60\t%dM\t*\t0\t0\t%s\t%s\tNM:i:0%s\n" % (i, i + 1, max(len(r), 1), seq, b"F" * len(r) if r else b"*", extra))
+    kf = tmp_path / "k.txt"
+    kf.write_bytes(b"\n".join(pats) + b"\n")
+
+    def oracle(out):
+        rm.tag_records(rm.CmdTag(in_file=str(sam), out_file=str(out / "t.sam"), kmer_file=str(kf), reverse_complement=True,
+                                 out_log=str(out / "t.log"), json_log=str(out / "t.json"), **kw))
+
+    _compare_with_oracle(tmp_path, ["tag", "-i", sam, "-o", "@OUT@/t.sam", "-f", kf, "-r", "-l", "@OUT@/t.log", "-j", "@OUT@/t.json", *flags], oracle,
+                         [("t.sam", "sam"), ("t.log", "log"), ("t.json", "json")], env={"MERKURIO_BATCH_BYTES": "50000"})
+    # without logs (PATTERN_SET mode): same SAM
+    (tmp_path / "nolog").mkdir()
+    run("tag", "-i", sam, "-o", tmp_path / "nolog" / "t.sam", "-f", kf, "-r", *flags)
+    assert_sam_equal((tmp_path / "nolog" / "t.sam").read_bytes(), (tmp_path / "ora" / "t.sam").read_bytes())
+
+
+def test_unequal_paired_files(ref_tree, tmp_path):
+    fx = ref_tree / "tests" / "fixtures" / "input"
+    one = (fx / "paired-1.fastq").read_bytes()
+    short = b"\n".join(one.split(b"\n")[:4]) + b"\n"
+    (tmp_path / "short.fastq").write_bytes(short)
+    r = run("extract", "-i", fx / "paired-1.fastq", "-2", tmp_path / "short.fastq", "-s", "CTT", "-o", tmp_path / "o", check=False)
+    assert r.returncode == 1 and b"Do the two input files contain the same number of records?" in r.stderr
+    r = run("extract", "-i", tmp_path / "short.fastq", "-2", fx / "paired-2.fastq", "-s", "CTT", "-o", tmp_path / "p", check=False)
+    assert r.returncode == 1 and b"The two input files have a different number of records." in r.stderr
