@@ -147,39 +147,24 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
-    import torch.distributed as dist
 
     from merkurio_b200 import capi
     from merkurio_b200 import patterns as pt
+    from merkurio_b200.shard import Dist, shard_range
     from merkurio_b200.synth import Synth
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the matching engine has no CPU path")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dctx = Dist("nccl", torch.device("cuda", local))  # barrier / max-over-ranks only: no data-path collective
+    rank, world = dctx.rank, dctx.world
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        dctx.barrier()
 
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    max_over_ranks, sum_over_ranks = dctx.max, dctx.sum
 
     n_reads, L = args.reads, args.read_len
     n_bytes = n_reads * L
@@ -191,7 +176,9 @@ def run_ours(args):
     d_off = torch.empty(n_reads + 1, dtype=torch.int64, device="cuda")
     d_q = torch.from_numpy(syn.queries).cuda()
     t0 = time.perf_counter()
-    syn.device_reads(d_q.data_ptr(), rank * n_reads, (rank + 1) * n_reads, d_seq.data_ptr(), d_off.data_ptr(), 0,
+    r_lo, r_hi = shard_range(n_reads * world, world, rank)  # this rank's records of the whole job
+    assert r_hi - r_lo == n_reads
+    syn.device_reads(d_q.data_ptr(), r_lo, r_hi, d_seq.data_ptr(), d_off.data_ptr(), 0,
                      torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     if rank == 0:
@@ -325,14 +312,13 @@ def run_ours(args):
                        "records_flagged": int(total_flagged)},
             "device_ms_per_step": dev_ms_max, "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "mk_scan_d16<ASCII>", "kernel_ms": scan_ms, "peak_source": peak_src,
+                         "traffic": None, "kernel": "mk_scan_d16<ASCII, smem filter, U=4, T=896>", "kernel_ms": scan_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes)},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+    dctx.close()
     return 0
 
 
