@@ -263,8 +263,8 @@ def run_ours(args):
         t1e = time.perf_counter()
         el = max_over_ranks(t1e - t0e)
         e2e = {"value": world * n_bytes * args.e2e_steps / el / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": int(n_bytes + n_batches * (batch_reads + 1) * 8),
-               "d2h_bytes_per_step": int(n_batches * ((batch_reads + 63) // 64 * 8 + 16)),
+               "h2d_bytes_per_step": int(world * (n_bytes + n_batches * (batch_reads + 1) * 8)),
+               "d2h_bytes_per_step": int(world * n_batches * ((batch_reads + 63) // 64 * 8 + 16)),
                "steps": args.e2e_steps, "ms_per_step": el / args.e2e_steps * 1e3,
                "records_per_s": world * n_reads * args.e2e_steps / el,
                "path": f"mk_scan_host/mk_scan_wait, {args.slots} slots, batches of {batch_reads} reads from pinned host memory"}
@@ -310,7 +310,7 @@ def run_ours(args):
                        "l2": "per-step input (15 GB) is far larger than the 126 MB L2; no flush needed",
                        "timing": "wall clock around K synchronous mk_scan_device calls between barriers; device_ms_per_step is the CUDA-event time on the engine's stream",
                        "records_flagged": int(total_flagged)},
-            "device_ms_per_step": dev_ms_max, "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps,
+            "device_ms_per_step": dev_ms_max, "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * world,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "mk_scan_d16<ASCII, smem filter, U=4, T=896>", "kernel_ms": scan_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes)},

@@ -119,13 +119,18 @@ __device__ __forceinline__ uint8_t text_symbol(const uint8_t* __restrict__ t, ui
     return (pos & 1) ? (b & 0xF) : (b >> 4);
 }
 
-// Slow path: a seed at base position `pos` passed the first-level filter.
+// Second-level filter, inlined at the drain sites: one L2 load and a handful of registers, so that
+// the out-of-line verify (whose call spills the prefetched tile registers) runs for real candidates
+// only.
+__device__ __forceinline__ bool second_level_pass(const ScanParams& P, uint32_t code) {
+    if (!P.filter2) return true;
+    uint32_t h = mk_hash_f2(code, P.filter2_log2_bits);
+    return (__ldg(P.filter2 + (h >> 5)) >> (h & 31)) & 1u;
+}
+
+// Slow path: a seed at base position `pos` passed both filters.
 template <int ENC>
 __device__ __noinline__ void verify_seed(const ScanParams& P, uint64_t pos, uint32_t code) {
-    if (P.filter2) {
-        uint32_t h = mk_hash_f2(code, P.filter2_log2_bits);
-        if (!((__ldg(P.filter2 + (h >> 5)) >> (h & 31)) & 1u)) return;
-    }
     // cuckoo lookup: two 32-byte buckets
     uint32_t first = kEmptySlot;
 #pragma unroll
@@ -221,7 +226,7 @@ __device__ __forceinline__ void queue_drain32(const ScanParams& P, WarpQueue& wq
     wq.count -= 32;
     uint2 e = wq.slot[wq.count + lane];
     __syncwarp();
-    verify_seed<ENC>(P, (uint64_t)e.x * PM, e.y);
+    if (second_level_pass(P, e.y)) verify_seed<ENC>(P, (uint64_t)e.x * PM, e.y);
     __syncwarp();
 }
 template <int ENC, int PM>
@@ -229,7 +234,7 @@ __device__ __forceinline__ void queue_flush(const ScanParams& P, WarpQueue& wq, 
     __syncwarp();
     if (lane < wq.count) {
         uint2 e = wq.slot[lane];
-        verify_seed<ENC>(P, (uint64_t)e.x * PM, e.y);
+        if (second_level_pass(P, e.y)) verify_seed<ENC>(P, (uint64_t)e.x * PM, e.y);
     }
     wq.count = 0;
     __syncwarp();

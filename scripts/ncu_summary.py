@@ -26,6 +26,9 @@ for i, h in enumerate(hdr):
     if "issue_stalled" in h and h.endswith("_per_issue_active.ratio") or (h.startswith("smsp__average_warp") and h.endswith(".ratio")):
         out.append(f"{h.replace('smsp__average_warps_issue_stalled_', '').replace('smsp__average_warp_latency_issue_stalled_', '')}: {data[0][i]}")
 text = "\n".join(out)
-print(text)
 if len(sys.argv) > 2:
     open(sys.argv[2], "w").write(text + "\n")
+try:
+    print(text)
+except BrokenPipeError:
+    pass
