@@ -204,11 +204,13 @@ def run_ours(args):
         time.sleep(0.3)
     barrier()
     t0 = time.perf_counter()
-    scan_ns, dev_ns = [], []
+    scan_ns, dev_ns, ver_ns, n_cand = [], [], [], 0
     for _ in range(args.steps):
         r = step()
         scan_ns.append(r.scan_ns)
         dev_ns.append(r.device_ns)
+        ver_ns.append(r.verify_ns)
+        n_cand = r.n_candidates
     barrier()
     t1 = time.perf_counter()
     clocks = sampler.stop(t0, t1) if rank == 0 else None
@@ -310,7 +312,8 @@ def run_ours(args):
                        "l2": "per-step input (15 GB) is far larger than the 126 MB L2; no flush needed",
                        "timing": "wall clock around K synchronous mk_scan_device calls between barriers; device_ms_per_step is the CUDA-event time on the engine's stream",
                        "records_flagged": int(total_flagged)},
-            "device_ms_per_step": dev_ms_max, "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * world,
+            "device_ms_per_step": dev_ms_max, "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps * world,
+            "kernels_per_step": {"mk_scan_d16": 1, "mk_verify_candidates": 1, "verify_ms": float(np.mean(ver_ns)) / 1e6, "candidates": int(n_cand)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "mk_scan_d16<ASCII, smem filter, U=4, T=896>", "kernel_ms": scan_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes)},

@@ -99,6 +99,8 @@ typedef struct {
     uint64_t bases_scanned;
     uint64_t device_ns;           /* CUDA-event time of the device work for this batch (kernels only) */
     uint64_t scan_ns;             /* CUDA-event time of the scan kernel alone */
+    uint64_t verify_ns;           /* CUDA-event time of the candidate verification kernel */
+    uint64_t n_candidates;        /* seeds that passed both filters and were verified */
     uint32_t n_rescans;           /* >0 if the hit list overflowed and the batch was scanned again */
     uint32_t reserved2;
     const uint64_t* d_record_flags; /* device copies of the above (valid like the host views) */

@@ -32,7 +32,8 @@ class MkConfig(C.Structure):
 class MkResult(C.Structure):
     _fields_ = [("record_flags", C.c_void_p), ("n_records", C.c_uint32), ("reserved", C.c_uint32),
                 ("hits", C.c_void_p), ("n_hits", C.c_uint64), ("bases_scanned", C.c_uint64),
-                ("device_ns", C.c_uint64), ("scan_ns", C.c_uint64), ("n_rescans", C.c_uint32),
+                ("device_ns", C.c_uint64), ("scan_ns", C.c_uint64), ("verify_ns", C.c_uint64),
+                ("n_candidates", C.c_uint64), ("n_rescans", C.c_uint32),
                 ("reserved2", C.c_uint32), ("d_record_flags", C.c_void_p), ("d_hits", C.c_void_p)]
 
 
@@ -104,6 +105,8 @@ class ScanResult:
         self.bases_scanned = int(r.bases_scanned)
         self.device_ns = int(r.device_ns)
         self.scan_ns = int(r.scan_ns)
+        self.verify_ns = int(r.verify_ns)
+        self.n_candidates = int(r.n_candidates)
         self.n_rescans = int(r.n_rescans)
         self.d_record_flags = r.d_record_flags
         self.d_hits = r.d_hits

@@ -66,8 +66,12 @@ MK_HD uint32_t mk_cls4_mid(uint32_t w) {
     uint32_t hi = (w | (w >> 1)) & 0x44444444u;   // bit2 = n2|n3
     return lo | hi;
 }
+// Stride-16 seed key of a BAM unit: BAM text and the nibble-encoded queries compare by plain equality
+// (no case folding: decoded BAM text is upper-case only and queries are upper-cased before encoding
+// under -I), so any hash of the 8 raw bytes is a valid key — two multiply-adds instead of a class
+// packing. Collisions only cost an extra exact verification.
 MK_HD uint32_t mk_pack_bam_perm(uint32_t w0, uint32_t w1) {
-    return (mk_cls4_mid(w0) << 1) | (mk_cls4_mid(w1) >> 1);
+    return w0 * 0x9E3779B1u + w1 * 0x85EBCA77u;
 }
 
 MK_HD uint32_t mk_bswap32(uint32_t w) {

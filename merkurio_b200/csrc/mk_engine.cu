@@ -84,12 +84,14 @@ struct DeviceTables {
 // Everything one in-flight batch needs on the device and for its results on the host.
 struct Workspace {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_scan = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_scan = nullptr, ev_verify = nullptr, ev_end = nullptr;
     DevBuf<uint32_t> flags;                  // bitmap, 2 words per 64 records
     DevBuf<mk::RawHit> raw_a, raw_b;
     DevBuf<mk_hit> out;
     DevBuf<uint32_t> heads, radix_table;
-    DevBuf<unsigned long long> counters;     // [0] hits appended, [1] distinct pairs
+    DevBuf<uint2> cand;                      // candidate list handed from the scan to the verify kernel
+    uint64_t cand_cap = 0;
+    DevBuf<unsigned long long> counters;     // [0] hits appended, [1] distinct pairs, [2] candidates
     PinBuf<unsigned long long> h_counters;
     PinBuf<uint64_t> h_flags;
     PinBuf<mk_hit> h_hits;
@@ -107,6 +109,7 @@ struct Workspace {
     ~Workspace() {
         if (ev_begin) cudaEventDestroy(ev_begin);
         if (ev_scan) cudaEventDestroy(ev_scan);
+        if (ev_verify) cudaEventDestroy(ev_verify);
         if (ev_end) cudaEventDestroy(ev_end);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -202,9 +205,10 @@ int init_workspace(Workspace& ws) {
     CU(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&ws.ev_begin));
     CU(cudaEventCreate(&ws.ev_scan));
+    CU(cudaEventCreate(&ws.ev_verify));
     CU(cudaEventCreate(&ws.ev_end));
-    CU(ws.counters.ensure(2));
-    CU(ws.h_counters.ensure(2));
+    CU(ws.counters.ensure(8));
+    CU(ws.h_counters.ensure(8));
     CU(ws.radix_table.ensure((size_t)256 * mk::kSortWarps));
     return MK_OK;
 }
@@ -270,6 +274,10 @@ int enqueue(mk_engine* e, Workspace& ws) {
     P.tie_rank = e->tie_rank.p;
     P.q = t.q;
     P.case_insensitive = e->ps.case_insensitive ? 1 : 0;
+    P.cand = ws.cand.p;
+    P.cand_capacity = ws.cand_cap;
+    P.cand_count = ws.counters.p + 2;
+    P.pos_mul = t.d == 16 ? MK_UNIT_BASES : 1;
     P.flags = ws.flags.p;
     P.hits = ws.raw_a.p;
     P.hit_capacity = ws.hit_cap;
@@ -289,7 +297,7 @@ int enqueue(mk_engine* e, Workspace& ws) {
     if (t.d != 16 && ws.n_units >= (1ull << 32))
         return fail(MK_ERR_CAPACITY, "batches of 2^32 bases or more need patterns of at least 31 bases; split the batch");
     CU(cudaMemsetAsync(ws.flags.p, 0, flag_words32 * 4, ws.stream));
-    CU(cudaMemsetAsync(ws.counters.p, 0, 2 * sizeof(unsigned long long), ws.stream));
+    CU(cudaMemsetAsync(ws.counters.p, 0, 8 * sizeof(unsigned long long), ws.stream));
     CU(cudaEventRecord(ws.ev_begin, ws.stream));
     if (P.n_vec > 0 && ws.n_records > 0) {
         ScanLaunch k = pick_kernel(ws.enc, t.d, t.filter_in_smem);
@@ -299,9 +307,14 @@ int enqueue(mk_engine* e, Workspace& ws) {
         int grid = (int)std::min<uint64_t>((uint64_t)e->sm_count, std::max<uint64_t>(want, 1));
         size_t smem = t.filter_in_smem ? t.filter.size() * 4 : 0;
         k.fn<<<grid, k.threads, smem, ws.stream>>>(P);
+        CU(cudaEventRecord(ws.ev_scan, ws.stream));
+        if (ws.enc == MK_ENC_ASCII) mk::mk_verify_candidates<MK_ENC_ASCII><<<e->sm_count * 8, 256, 0, ws.stream>>>(P);
+        else mk::mk_verify_candidates<MK_ENC_BAM4><<<e->sm_count * 8, 256, 0, ws.stream>>>(P);
         CU(cudaGetLastError());
+    } else {
+        CU(cudaEventRecord(ws.ev_scan, ws.stream));
     }
-    CU(cudaEventRecord(ws.ev_scan, ws.stream));
+    CU(cudaEventRecord(ws.ev_verify, ws.stream));
     if (ws.mode != MK_MODE_FLAG) {
         const unsigned long long* cnt = ws.counters.p;
         mk::RawHit *src = ws.raw_a.p, *dst = ws.raw_b.p;
@@ -323,7 +336,7 @@ int enqueue(mk_engine* e, Workspace& ws) {
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(ws.ev_end, ws.stream));
-    CU(cudaMemcpyAsync(ws.h_counters.p, ws.counters.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ws.stream));
+    CU(cudaMemcpyAsync(ws.h_counters.p, ws.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ws.stream));
     if (ws.fetch)
         CU(cudaMemcpyAsync(ws.h_flags.p, ws.flags.p, flag_words32 * 4, cudaMemcpyDeviceToHost, ws.stream));
     return MK_OK;
@@ -346,6 +359,14 @@ int begin_batch(mk_engine* e, Workspace& ws, const void* d_seq, const unsigned l
         rc = ensure_hit_capacity(ws, cap);
         if (rc) return rc;
     }
+    {   // candidate list: grown on demand like the hit list
+        uint64_t bytes = enc == MK_ENC_ASCII ? n_units : (n_units + 1) / 2;
+        uint64_t want = std::max<uint64_t>(1ull << 20, bytes / 1024);
+        if (ws.cand_cap < want) {
+            CU(ws.cand.ensure(want));
+            ws.cand_cap = want;
+        }
+    }
     rc = enqueue(e, ws);
     if (rc) return rc;
     ws.busy = true;
@@ -355,17 +376,29 @@ int begin_batch(mk_engine* e, Workspace& ws, const void* d_seq, const unsigned l
 int finish_batch(mk_engine* e, Workspace& ws, mk_result* out) {
     if (!ws.busy) return fail(MK_ERR_STATE, "no batch in flight");
     uint32_t rescans = 0;
-    float ms_total = 0.f, ms_scan = 0.f;
+    float ms_total = 0.f, ms_scan = 0.f, ms_verify = 0.f;
     for (;;) {
         CU(cudaStreamSynchronize(ws.stream));
-        float a = 0.f, b = 0.f;
+        float a = 0.f, b = 0.f, c = 0.f;
         CU(cudaEventElapsedTime(&a, ws.ev_begin, ws.ev_end));
         CU(cudaEventElapsedTime(&b, ws.ev_begin, ws.ev_scan));
-        ms_total += a; ms_scan += b;
-        if (ws.mode == MK_MODE_FLAG || ws.h_counters.p[0] <= ws.hit_cap) break;
-        // hit list overflowed: grow to the exact need and scan the batch again (never drop hits)
-        uint64_t need = ws.h_counters.p[0];
-        int rc = ensure_hit_capacity(ws, need + need / 8 + 1024);
+        CU(cudaEventElapsedTime(&c, ws.ev_scan, ws.ev_verify));
+        ms_total += a; ms_scan += b; ms_verify += c;
+        const bool cand_over = ws.h_counters.p[2] > ws.cand_cap;
+        const bool hits_over = ws.mode != MK_MODE_FLAG && ws.h_counters.p[0] > ws.hit_cap;
+        if (!cand_over && !hits_over) break;
+        // a list overflowed: grow it to the exact need and scan the batch again (never drop hits)
+        int rc = MK_OK;
+        if (cand_over) {
+            uint64_t need = ws.h_counters.p[2] + ws.h_counters.p[2] / 8 + 1024;
+            cudaError_t ce = ws.cand.ensure(need);
+            if (ce != cudaSuccess) rc = fail(MK_ERR_NOMEM, "cannot grow the candidate list to %llu entries: %s", (unsigned long long)need, cudaGetErrorString(ce));
+            else ws.cand_cap = need;
+        }
+        if (!rc && hits_over) {
+            uint64_t need = ws.h_counters.p[0];
+            rc = ensure_hit_capacity(ws, need + need / 8 + 1024);
+        }
         if (rc) { ws.busy = false; return rc; }
         ++rescans;
         rc = enqueue(e, ws);
@@ -389,8 +422,11 @@ int finish_batch(mk_engine* e, Workspace& ws, mk_result* out) {
         out->bases_scanned = ws.n_units;
         out->device_ns = (uint64_t)((double)ms_total * 1e6);
         out->scan_ns = (uint64_t)((double)ms_scan * 1e6);
+        out->verify_ns = (uint64_t)((double)ms_verify * 1e6);
+        out->n_candidates = ws.h_counters.p[2];
         out->n_rescans = rescans;
         out->reserved2 = 0;
+
         out->d_record_flags = reinterpret_cast<const uint64_t*>(ws.flags.p);
         out->d_hits = n_hits ? ws.out.p : nullptr;
     }

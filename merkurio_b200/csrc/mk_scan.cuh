@@ -47,6 +47,11 @@ struct ScanParams {
     const uint32_t* tie_rank;
     uint32_t q;
     int case_insensitive;
+    // candidates: seeds that passed both filters, handed from the scan to the verify kernel
+    uint2* cand;                    // {seed position / pos_mul, seed code}
+    unsigned long long cand_capacity;
+    unsigned long long* cand_count;
+    uint32_t pos_mul;               // 16 for the stride-16 scan, 1 otherwise
     // outputs
     uint32_t* flags;                // 1 bit / record
     RawHit* hits;
@@ -99,9 +104,27 @@ __device__ __forceinline__ uint32_t filter_probe(const uint32_t* __restrict__ f,
     }
 }
 
-// last record r with off[r] <= s  (records of length 0 are skipped by construction)
+// The record that contains unit position s: the last r with off[r] <= s (records of length 0 are
+// skipped by construction). Runs in one lane for one hit, so every dependent load costs a full L2 /
+// DRAM round trip: interpolate first (exact in one step for reads of uniform length), then bisect
+// what is left.
 __device__ __forceinline__ uint32_t find_record(const unsigned long long* __restrict__ off, uint32_t n, uint64_t s) {
-    uint32_t lo = 0, hi = n;
+    uint32_t lo = 0, hi = n;  // invariant: off[lo] <= s < off[hi]
+    unsigned long long olo = off[0], ohi = off[n];
+#ifndef MK_NO_INTERP
+    for (int it = 0; it < 4 && hi - lo > 1 && ohi > olo; ++it) {
+        double frac = (double)(s - olo) / (double)(ohi - olo);
+        uint32_t g = lo + (uint32_t)(frac * (double)(hi - lo));
+        if (g >= hi) g = hi - 1;
+        unsigned long long og = off[g], og1 = off[g + 1];
+        if (og <= s) {
+            if (s < og1) return g;
+            lo = g + 1; olo = og1;
+        } else {
+            hi = g; ohi = og;
+        }
+    }
+#endif
     while (hi - lo > 1) {
         uint32_t mid = lo + ((hi - lo) >> 1);
         if (off[mid] <= s) lo = mid; else hi = mid;
@@ -128,9 +151,10 @@ __device__ __forceinline__ bool second_level_pass(const ScanParams& P, uint32_t 
     return (__ldg(P.filter2 + (h >> 5)) >> (h & 31)) & 1u;
 }
 
-// Slow path: a seed at base position `pos` passed both filters.
+// A seed at base position `pos` passed both filters: look it up in the cuckoo table and compare the
+// patterns that own it byte by byte. Runs in the verify kernel, one candidate per thread.
 template <int ENC>
-__device__ __noinline__ void verify_seed(const ScanParams& P, uint64_t pos, uint32_t code) {
+__device__ __forceinline__ void verify_seed(const ScanParams& P, uint64_t pos, uint32_t code) {
     // cuckoo lookup: two 32-byte buckets
     uint32_t first = kEmptySlot;
 #pragma unroll
@@ -155,10 +179,25 @@ __device__ __noinline__ void verify_seed(const ScanParams& P, uint64_t pos, uint
             uint32_t L = __ldg(P.pat_off + pid + 1) - po;
             if (s + L <= P.n_units) {
                 const uint8_t* pat = P.pat_bytes + po;
+                // exact compare, eight symbols per round trip (the loads of a chunk are independent)
                 bool eq = true;
+#ifdef MK_NO_CHUNK
                 for (uint32_t k = 0; k < L; ++k) {
                     if (text_symbol<ENC>(text, s + k, P.case_insensitive) != __ldg(pat + k)) { eq = false; break; }
                 }
+#else
+                for (uint32_t k0 = 0; k0 < L && eq; k0 += 8) {
+                    uint8_t tx[8], px[8];
+#pragma unroll
+                    for (uint32_t i = 0; i < 8; ++i) {
+                        bool in = k0 + i < L;
+                        tx[i] = in ? text_symbol<ENC>(text, s + k0 + i, P.case_insensitive) : 0;
+                        px[i] = in ? __ldg(pat + k0 + i) : 0;
+                    }
+#pragma unroll
+                    for (uint32_t i = 0; i < 8; ++i) eq = eq && (tx[i] == px[i]);
+                }
+#endif
                 if (eq && s >= P.off[0]) {
                     uint32_t r = find_record(P.off, P.n_records, s);
                     uint64_t rend = P.lens ? P.off[r] + P.lens[r] : P.off[r + 1];
@@ -219,23 +258,38 @@ constexpr int kQueueCap = 64;
 struct WarpQueue {
     uint2* slot;     // kQueueCap entries of {seed position / PM, seed code}; PM = 16 (stride-16 scan) or 1
     uint32_t count;  // warp-uniform
+    uint32_t* cnt;   // shared-memory copy of `count`, the target of the lanes' slot-claiming atomics
 };
+
+// Lanes whose candidate also passes the second-level (L2-resident) filter append it to the global
+// candidate list: one warp-aggregated atomic per drain.
+__device__ __forceinline__ void emit_candidates(const ScanParams& P, bool mine, uint2 e, uint32_t lane) {
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
+    if (m == 0) return;
+    unsigned long long base = 0;
+    if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(P.cand_count, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, __ffs(m) - 1);
+    unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+    if (mine && slot < P.cand_capacity) P.cand[slot] = e;
+}
 
 template <int ENC, int PM>
 __device__ __forceinline__ void queue_drain32(const ScanParams& P, WarpQueue& wq, uint32_t lane) {
     wq.count -= 32;
     uint2 e = wq.slot[wq.count + lane];
     __syncwarp();
-    if (second_level_pass(P, e.y)) verify_seed<ENC>(P, (uint64_t)e.x * PM, e.y);
-    __syncwarp();
+    emit_candidates(P, second_level_pass(P, e.y), e, lane);
 }
 template <int ENC, int PM>
 __device__ __forceinline__ void queue_flush(const ScanParams& P, WarpQueue& wq, uint32_t lane) {
     __syncwarp();
+    uint2 e = make_uint2(0, 0);
+    bool mine = false;
     if (lane < wq.count) {
-        uint2 e = wq.slot[lane];
-        if (second_level_pass(P, e.y)) verify_seed<ENC>(P, (uint64_t)e.x * PM, e.y);
+        e = wq.slot[lane];
+        mine = second_level_pass(P, e.y);
     }
+    emit_candidates(P, mine, e, lane);
     wq.count = 0;
     __syncwarp();
 }
@@ -272,14 +326,37 @@ __device__ __forceinline__ void process_tile(const ScanParams& P, const uint32_t
             pass |= filter_probe<FMODE>(filt, code[2 * u + 1], lb) << (2 * u + 1);
         }
     }
-    if (__any_sync(0xFFFFFFFFu, pass != 0)) {
+    const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, __popc(pass));
+    if (total == 0) return;
+    if (wq.count + total <= kQueueCap) {
+        // common case: the few lanes that hold candidates claim their slots with one shared-memory
+        // atomic each; no per-seed warp votes
+        if (pass) {
+            uint32_t idx = atomicAdd(wq.cnt, __popc(pass));
 #pragma unroll
-        for (int k = 0; k < U * SPV; ++k)
-        {
+            for (int k = 0; k < U * SPV; ++k) {
+                const int u = k / SPV;
+                const uint32_t vec = V8 ? v0 + (u / 2) * 64 + (u % 2) : v0 + u * 32;
+                if ((pass >> k) & 1u) wq.slot[idx++] = make_uint2(vec * SPV + (k % SPV), code[k]);
+            }
+        }
+        __syncwarp();
+        wq.count += total;
+        if (wq.count >= 32) {
+            do queue_drain32<ENC, MK_UNIT_BASES>(P, wq, lane); while (wq.count >= 32);
+            if (lane == 0) *wq.cnt = wq.count;
+            __syncwarp();
+        }
+    } else {
+        // a burst of candidates that could overflow the queue: push seed by seed, draining on the way
+#pragma unroll
+        for (int k = 0; k < U * SPV; ++k) {
             const int u = k / SPV;
             const uint32_t vec = V8 ? v0 + (u / 2) * 64 + (u % 2) : v0 + u * 32;
             queue_push<ENC, MK_UNIT_BASES>(P, wq, lane, (pass >> k) & 1u, vec * SPV + (k % SPV), code[k]);
         }
+        if (lane == 0) *wq.cnt = wq.count;
+        __syncwarp();
     }
 }
 
@@ -300,13 +377,16 @@ __global__ void __launch_bounds__(T, 1) mk_scan_d16(const __grid_constant__ Scan
     constexpr int kScanWarps = T / 32;
     extern __shared__ __align__(16) uint32_t s_filter[];
     __shared__ uint2 s_queue[kScanWarps][kQueueCap];
+    __shared__ uint32_t s_qcount[kScanWarps];
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lane_vec = V8 ? lane * 2 : lane;
     const uint32_t lb = (FMODE == kFilterSmem) ? P.filter_blocks : P.filter_log2_bits;
     const uint64_t pol = V8 ? 0 : make_evict_first_policy();
     const uint32_t nwarps = gridDim.x * kScanWarps;
     const uint32_t full_tiles = P.n_vec / (U * 32);
-    WarpQueue wq{s_queue[threadIdx.x >> 5], 0};
+    WarpQueue wq{s_queue[threadIdx.x >> 5], 0, &s_qcount[threadIdx.x >> 5]};
+    if (lane == 0) *wq.cnt = 0;
+    __syncwarp();
     uint32_t t = blockIdx.x * kScanWarps + (threadIdx.x >> 5);
     const uint32_t warp0 = t;
     const size_t stride = (size_t)nwarps * (U * 32);
@@ -353,7 +433,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) mk_scan_ord(const __grid_cons
     stage_filter<FMODE>(P, s_filter);
     const uint32_t* __restrict__ filt = (FMODE == kFilterSmem) ? s_filter : P.filter;
     const uint32_t lane = threadIdx.x & 31;
-    WarpQueue wq{s_queue[threadIdx.x >> 5], 0};
+    WarpQueue wq{s_queue[threadIdx.x >> 5], 0, nullptr};
     const uint32_t lb = (FMODE == kFilterSmem) ? P.filter_blocks : P.filter_log2_bits, q = P.q;
     const uint64_t pol = make_evict_first_policy();
     const uint64_t nwarps = (uint64_t)gridDim.x * kScanWarps;
@@ -398,6 +478,21 @@ __global__ void __launch_bounds__(kScanThreads, 1) mk_scan_ord(const __grid_cons
         }
     }
     queue_flush<ENC, 1>(P, wq, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Verification of the candidate list: one candidate per thread, so the dependent lookups (cuckoo
+// bucket, postings, pattern bytes, record offsets) of thousands of candidates are in flight together
+// instead of stalling a streaming warp. The list length is read from device memory.
+// ---------------------------------------------------------------------------------------------
+template <int ENC>
+__global__ void __launch_bounds__(256) mk_verify_candidates(const __grid_constant__ ScanParams P) {
+    unsigned long long n = *P.cand_count;
+    if (n > P.cand_capacity) n = P.cand_capacity;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint2 e = P.cand[i];
+        verify_seed<ENC>(P, (uint64_t)e.x * P.pos_mul, e.y);
+    }
 }
 
 }  // namespace mk

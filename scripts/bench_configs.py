@@ -178,6 +178,11 @@ else:
     qs = off[chrom] + (rng.random(nq) * (lens[chrom] - ql)).astype(np.int64)
     idx = torch.from_numpy(qs).cuda()[:, None] + torch.arange(63, device="cuda")[None, :]
     qmat = d_seq[idx.clamp_(max=total - 1)].cpu().numpy()
+    # drop samples that fell inside an N run (more than 2 N); 1-2 N at a run edge stay: they occur verbatim
+    n_count = ((qmat == 78) & (np.arange(63)[None, :] < ql[:, None])).sum(axis=1)
+    keep = n_count <= 2
+    qmat, ql, chrom, qs = qmat[keep], ql[keep], chrom[keep], qs[keep]
+    nq = int(keep.sum())
     queries = [qmat[i, :ql[i]].tobytes() for i in range(nq)]
     # 1 % of the queries get one base replaced by N (these can only hit where the text has that N)
     for i in rng.choice(nq, size=nq // 100, replace=False):
