@@ -88,7 +88,7 @@ struct Workspace {
     DevBuf<uint32_t> flags;                  // bitmap, 2 words per 64 records
     DevBuf<mk::RawHit> raw_a, raw_b;
     DevBuf<mk_hit> out;
-    DevBuf<uint32_t> heads, radix_table;
+    DevBuf<uint32_t> heads, radix_table, radix_totals;  // heads: per-tile head counts of the pair de-duplication
     DevBuf<uint2> cand;                      // candidate list handed from the scan to the verify kernel
     uint64_t cand_cap = 0;
     DevBuf<unsigned long long> counters;     // [0] hits appended, [1] distinct pairs, [2] candidates
@@ -210,6 +210,7 @@ int init_workspace(Workspace& ws) {
     CU(ws.counters.ensure(8));
     CU(ws.h_counters.ensure(8));
     CU(ws.radix_table.ensure((size_t)256 * mk::kSortWarps));
+    CU(ws.radix_totals.ensure(256));
     return MK_OK;
 }
 
@@ -218,7 +219,7 @@ int ensure_hit_capacity(Workspace& ws, uint64_t cap) {
     CU(ws.raw_a.ensure(cap));
     CU(ws.raw_b.ensure(cap));
     CU(ws.out.ensure(cap));
-    CU(ws.heads.ensure(cap));
+    CU(ws.heads.ensure(cap / mk::kHeadTile + 2));
     ws.hit_cap = cap;
     return MK_OK;
 }
@@ -320,18 +321,18 @@ int enqueue(mk_engine* e, Workspace& ws) {
         mk::RawHit *src = ws.raw_a.p, *dst = ws.raw_b.p;
         for (uint32_t shift = 0; shift < key_bits; shift += 8) {
             mk::mk_radix_hist<<<mk::kSortBlocks, mk::kSortThreads, 0, ws.stream>>>(src, cnt, ws.hit_cap, shift, ws.radix_table.p);
-            mk::mk_radix_scan<<<1, 1024, 0, ws.stream>>>(cnt, ws.hit_cap, ws.radix_table.p);
+            mk::mk_radix_rowscan<<<256, 256, 0, ws.stream>>>(cnt, ws.hit_cap, ws.radix_table.p, ws.radix_totals.p);
             mk::mk_radix_scatter<<<mk::kSortBlocks, mk::kSortThreads, 0, ws.stream>>>(src, dst, cnt, ws.hit_cap, shift,
-                                                                                    ws.radix_table.p);
+                                                                                    ws.radix_table.p, ws.radix_totals.p);
             std::swap(src, dst);
         }
         if (ws.mode == MK_MODE_ALL_HITS) {
             mk::mk_finalize_hits<<<256, 256, 0, ws.stream>>>(src, ws.out.p, cnt, ws.hit_cap, ws.d_off, dt.pat_off.p,
                                                             P.len_bits + P.tie_bits);
         } else {
-            mk::mk_mark_heads<<<256, 256, 0, ws.stream>>>(src, cnt, ws.hit_cap, ws.heads.p);
-            mk::mk_scan_heads<<<1, 1024, 0, ws.stream>>>(cnt, ws.hit_cap, ws.heads.p, ws.counters.p + 1);
-            mk::mk_finalize_pairs<<<256, 256, 0, ws.stream>>>(src, ws.out.p, cnt, ws.hit_cap, ws.heads.p, dt.pat_off.p);
+            mk::mk_heads_count<<<e->sm_count * 4, 256, 0, ws.stream>>>(src, cnt, ws.hit_cap, ws.heads.p);
+            mk::mk_heads_scan<<<1, 1024, 0, ws.stream>>>(cnt, ws.hit_cap, ws.heads.p, ws.counters.p + 1);
+            mk::mk_finalize_pairs<<<e->sm_count * 4, 256, 0, ws.stream>>>(src, ws.out.p, cnt, ws.hit_cap, ws.heads.p, dt.pat_off.p);
         }
         CU(cudaGetLastError());
     }
