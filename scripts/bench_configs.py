@@ -139,7 +139,7 @@ if args.config in ("cfg3", "cfg4"):
         out.update(records=n, bases=n * L, patterns=len(pats), seeds=int(info.n_seeds[enc]), filter_bytes=int(info.filter_bytes[enc]),
                    scan_ms=scan_ms, device_ms=dev_ms, n_hits=int(full.n_hits), records_flagged=int(np.bitwise_count(full.flags).sum()),
                    oracle_checked_hits=checked, hits_reverified=ok, rescans=int(full.n_rescans),
-                   gbases_per_s=n * L / dev_ms / 1e6, scan_gbs=nbytes / scan_ms / 1e6, frac_of_peak=nbytes / scan_ms / 1e6 / PEAK)
+                   verify_ms=r.verify_ns / 1e6, candidates=r.n_candidates, gbases_per_s=n * L / dev_ms / 1e6, scan_gbs=nbytes / scan_ms / 1e6, frac_of_peak=nbytes / scan_ms / 1e6 / PEAK)
 else:
     # cfg5: 24 chromosomes, lengths proportional to hg38, total 3 Gbp; 2 % N runs; 30 % lower-case
     total = int(3_000_000_000 * args.scale)
@@ -228,7 +228,7 @@ else:
                    seed_d=int(info.seed_d[0]), seeds=int(info.n_seeds[0]), filter_in_smem=int(info.filter_in_smem[0]), filter_bytes=int(info.filter_bytes[0]),
                    table_bytes=int(info.table_bytes[0]), table_build_s=t_build, scan_ms=scan_ms, device_ms=dev_ms, n_hits=int(full.n_hits),
                    hits_reverified=ok, sampled_queries_missing=missing, oracle_slice_hits=checked, lower_case_frac=n_low / total, n_frac=n_N / total,
-                   gbases_per_s=total / dev_ms / 1e6, scan_gbs=total / scan_ms / 1e6, frac_of_peak=total / scan_ms / 1e6 / PEAK)
+                   verify_ms=r.verify_ns / 1e6, candidates=r.n_candidates, gbases_per_s=total / dev_ms / 1e6, scan_gbs=total / scan_ms / 1e6, frac_of_peak=total / scan_ms / 1e6 / PEAK)
 print(json.dumps(out))
 if args.out:
     Path(args.out).write_text(json.dumps(out, indent=1) + "\n")
