@@ -6,6 +6,7 @@
 #include <cstring>
 #include <memory>
 
+#include "bamwriter.h"
 #include "commands.h"
 #include "device.h"
 #include "helpers.h"
@@ -102,8 +103,14 @@ void tag_records(CmdTag args) {
 
     if (out_ext != "bam" && out_ext != "sam" && out_ext != "STDOUT")
         throw Error("Output file must be a BAM or SAM file.").with_context("Could not create writer.");
-    if (out_ext == "bam")
-        throw Error("BAM output is not implemented in this build; write SAM (-o <name>.sam).").with_context("Could not create writer.");
+    std::unique_ptr<BamWriter> bam_out;
+    if (out_ext == "bam") {
+        try {
+            bam_out.reset(new BamWriter(path_with_extension(*args.out_file, "bam"), header));
+        } catch (const Error& e) {
+            throw e.with_context("Could not create writer.");
+        }
+    }
     FILE* out = stdout;
     bool out_owned = false;
     if (out_ext == "sam") {
@@ -118,7 +125,7 @@ void tag_records(CmdTag args) {
         obuf.clear();
         std::fflush(out);
     };
-    for (auto& h : header) { obuf += h; obuf += '\n'; }
+    if (!bam_out) for (auto& h : header) { obuf += h; obuf += '\n'; }
 
     uint64_t nb_records_tot = 0, nb_bases = 0, nb_hits_tot = 0, nb_records_hit = 0;
     std::vector<uint64_t> pattern_hit_counts(pattern_list.size(), 0);
@@ -165,8 +172,12 @@ void tag_records(CmdTag args) {
         std::sort(kmers_found.begin(), kmers_found.end(), bytes_less);
         kmers_found.erase(std::unique(kmers_found.begin(), kmers_found.end()), kmers_found.end());
         if (!args.suppress_output) {
-            obuf += m.b; obuf += '\t'; obuf += args.tag; obuf += ":Z:"; obuf += join(kmers_found, ","); obuf += '\n';
-            if (obuf.size() >= (1u << 20)) flush_out();
+            if (bam_out) {
+                bam_out->write_sam_line(m.b + "\t" + args.tag + ":Z:" + join(kmers_found, ","));
+            } else {
+                obuf += m.b; obuf += '\t'; obuf += args.tag; obuf += ":Z:"; obuf += join(kmers_found, ","); obuf += '\n';
+                if (obuf.size() >= (1u << 20)) flush_out();
+            }
         }
     };
 
@@ -193,6 +204,7 @@ void tag_records(CmdTag args) {
     }
     flush_out();
     if (out_owned) std::fclose(out);
+    if (bam_out) bam_out->close();
 
     size_t nb_patterns_found = 0;
     for (uint64_t c : pattern_hit_counts) nb_patterns_found += c > 0;

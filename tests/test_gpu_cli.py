@@ -286,3 +286,57 @@ def test_unequal_paired_files(ref_tree, tmp_path):
     assert r.returncode == 1 and b"Do the two input files contain the same number of records?" in r.stderr
     r = run("extract", "-i", tmp_path / "short.fastq", "-2", fx / "paired-2.fastq", "-s", "CTT", "-o", tmp_path / "p", check=False)
     assert r.returncode == 1 and b"The two input files have a different number of records." in r.stderr
+
+
+# ------------------------------------------------------------------ BAM output (untested by the reference, src/cmd_tag.rs:1134)
+@pytest.mark.parametrize("inp", ["simple.sam", "simple.bam"])
+def test_tag_bam_output_round_trip(ref_tree, tmp_path, inp):
+    fx = ref_tree / "tests" / "fixtures" / "input"
+    run("tag", "-i", fx / inp, "-o", tmp_path / "out.bam", "-s", "CTC", "-r")
+    header, recs = rm.parse_bam((tmp_path / "out.bam").read_bytes())
+    res = rm.tag_records(rm.CmdTag(in_file=str(fx / inp), out_file=str(tmp_path / "ora.sam"), kmer_seq=["CTC"], reverse_complement=True))
+    want = [ln for ln in (tmp_path / "ora.sam").read_bytes().split(b"\n") if ln]
+    got = header + [r.line for r in recs]
+    assert [ln for ln in got if not ln.startswith(b"@PG")] == [ln for ln in want if not ln.startswith(b"@PG")]
+    assert any(ln.startswith(b"@PG\tID:merkurio") for ln in got)
+    # BGZF framing: gzip members with the BC extra field and the 28-byte EOF marker
+    raw = (tmp_path / "out.bam").read_bytes()
+    assert raw[:4] == b"\x1f\x8b\x08\x04" and raw[12:14] == b"BC" and raw.endswith(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+
+
+def test_tag_bam_output_random(tmp_path):
+    rng = np.random.default_rng(99)
+    pats = sorted({rng.choice(np.frombuffer(b"ACGT", np.uint8), size=25).tobytes() for _ in range(20)})
+    reads = _rand_reads(rng, 3000, 1, 151, pats, plant=0.3)
+    sam = tmp_path / "in.sam"
+    with open(sam, "wb") as f:
+        f.write(b"@HD\tVN:1.6\tSO:unsorted\n@SQ\tSN:chr1\tLN:1000000\n@SQ\tSN:chr2\tLN:5000\n")
+        for i, r in enumerate(reads):
+            f.write(b"q%d\t%d\tchr%d\t%d\t%d\t%dM\t%s\t%d\t%d\t%s\t%s\tNM:i:%d\tXS:A:+\tZZ:Z:hello world\tXB:B:s,-3,7,300\n" % (
+                i, 99 if i % 2 else 147, 1 + i % 2, 1 + (i * 37) % 4000, i % 61, len(r), b"=" if i % 3 else b"*", (i * 11) % 4000 if i % 3 else 0,
+                (i % 500) - 250, r, b"F" * len(r), (i * 7919) % 100000 - 300))
+    kf = tmp_path / "k.txt"
+    kf.write_bytes(b"\n".join(pats) + b"\n")
+    run("tag", "-i", sam, "-o", tmp_path / "o.bam", "-f", kf, "-r", "-m", env={"MERKURIO_BATCH_BYTES": "60000"})
+    rm.tag_records(rm.CmdTag(in_file=str(sam), out_file=str(tmp_path / "ora.sam"), kmer_file=str(kf), reverse_complement=True, filter_matching=True))
+    header, recs = rm.parse_bam((tmp_path / "o.bam").read_bytes())
+    want = [ln for ln in (tmp_path / "ora.sam").read_bytes().split(b"\n") if ln and not ln.startswith(b"@")]
+    assert [r.line for r in recs] == want
+    # and the BAM we wrote is a valid input of its own
+    run("tag", "-i", tmp_path / "o.bam", "-o", tmp_path / "again.sam", "-f", kf, "-r", "-t", "kk")
+    again = [ln for ln in (tmp_path / "again.sam").read_bytes().split(b"\n") if ln and not ln.startswith(b"@")]
+    assert len(again) == len(want) and all(a.startswith(w) for a, w in zip(again, want))
+
+
+def test_two_gpus_from_the_cli(ref_tree, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ew = ref_tree / "example-workflow"
+    run("extract", "-i", ew / "data" / "mutant_R1.fastq", "-2", ew / "data" / "mutant_R2.fastq", "-f", ew / "data" / "significant_kmers.txt",
+        "-r", "-o", tmp_path / "m", "-j", tmp_path / "m.json", env={"MERKURIO_GPUS": "2", "MERKURIO_BATCH_BYTES": "300000"})
+    assert (tmp_path / "m_1.fastq").read_bytes() == (ew / "output" / "mutant_extracted_1.fastq").read_bytes()
+    assert (tmp_path / "m_2.fastq").read_bytes() == (ew / "output" / "mutant_extracted_2.fastq").read_bytes()
+    got = json.loads((tmp_path / "m.json").read_bytes())
+    want = json.loads((ew / "logs" / "mutant_extracted.stats.json").read_bytes())
+    assert got["matching_records"] == want["matching_records"] and got["summary_statistics"] == want["summary_statistics"]
