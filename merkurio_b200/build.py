@@ -58,6 +58,8 @@ def build_cuda(force: bool = False, verbose: bool = False, ptxas_v: bool = False
         cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-I", ROOT / "include", "-o", out, CSRC / "mk_engine.cu"]
         if ptxas_v:
             cmd += ["-Xptxas", "-v"]
+        if os.environ.get("MK_TUNE_BUILD"):  # every launch shape scripts/tune_scan.py sweeps
+            cmd += ["-DMK_TUNE_BUILD"]
         _run(cmd, verbose)
     return out
 

@@ -106,6 +106,14 @@ MK_HD uint32_t mk_seed_ord(uint32_t cur, uint32_t nxt, uint32_t o, uint32_t q) {
 #endif
     return win >> (32u - 2u * q);
 }
+// The 16-base window itself (its top 2q bits are the q-base seed)
+MK_HD uint32_t mk_win_ord(uint32_t cur, uint32_t nxt, uint32_t o) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(nxt, cur, 2u * o);
+#else
+    return o ? ((cur << (2u * o)) | (nxt >> (32u - 2u * o))) : cur;
+#endif
+}
 
 // First-level filter. Shared-memory flavour: a blocked Bloom filter of `nblocks` 64-bit blocks (any
 // count; 16384 blocks = 128 KiB by default, more for large seed sets). A seed selects its block with
@@ -125,6 +133,22 @@ MK_HD void mk_bloom_masks(uint32_t code, uint32_t* lo, uint32_t* hi) {
     *lo = (1u << ((g >> 12) & 31)) | (1u << ((g >> 17) & 31));
     *hi = (1u << ((g >> 22) & 31)) | (1u << (g >> 27));
 }
+// same bit positions from an already mixed word g
+MK_HD void mk_bloom_masks_g(uint32_t g, uint32_t* lo, uint32_t* hi) {
+    *lo = (1u << ((g >> 12) & 31)) | (1u << ((g >> 17) & 31));
+    *hi = (1u << ((g >> 22) & 31)) | (1u << (g >> 27));
+}
+// Dual-key filter (L2-resident, stride < 16, large seed sets). Patterns long enough for a 16-base
+// seed at every one of their d offsets are indexed by that 16-base seed ("long" group); the others by
+// the q-base seed the shortest pattern allows ("short" group). Both keys of one text position select
+// the SAME 64-bit block (through the q-base prefix they share) and differ in their bit positions, so
+// one 8-byte L2 load answers both probes.
+#define MK_DUAL_MUL_LONG 0xCC9E2D51u
+MK_HD uint32_t mk_dual_block(uint32_t short_code, uint32_t nblocks) { return mk_bloom_block(short_code, nblocks); }
+MK_HD uint32_t mk_dual_g_short(uint32_t short_code) { return short_code * MK_BLOOM_MUL * MK_BLOOM_MUL2; }
+MK_HD uint32_t mk_dual_g_long(uint32_t code16) { return (code16 ^ (code16 >> 15)) * MK_DUAL_MUL_LONG; }
+// key of the cuckoo seed table: the group is folded into the hashed value
+MK_HD uint32_t mk_group_key(uint32_t code, uint32_t group) { return group ? (code ^ 0x3C6EF372u) : code; }
 MK_HD uint32_t mk_hash_f1(uint32_t code, uint32_t log2_bits) { return (code * 0x9E3779B1u) >> (32u - log2_bits); }
 // second-level filter (L2-resident bitmap probed by candidates only): bit index
 MK_HD uint32_t mk_hash_f2(uint32_t code, uint32_t log2_bits) { return ((code ^ (code >> 15)) * 0x85EBCA77u) >> (32u - log2_bits); }

@@ -156,6 +156,8 @@ int tune_env(const char* name, int dflt) {
     return s ? std::atoi(s) : dflt;
 }
 
+#ifdef MK_TUNE_BUILD
+// Every launch shape scripts/tune_scan.py sweeps (build with -DMK_TUNE_BUILD; ~100 extra kernels).
 template <int ENC, int FMODE, int T>
 ScanKernel pick_d16_u(int u, bool v8) {
     if (v8) {
@@ -172,10 +174,12 @@ ScanKernel pick_d16_u(int u, bool v8) {
         default: return mk::mk_scan_d16<ENC, FMODE, 2, T, false>;
     }
 }
+#endif
 
 template <int ENC, int FMODE>
 ScanLaunch pick_by_d(uint32_t d) {
     if (d == 16) {
+#ifdef MK_TUNE_BUILD
         int u = tune_env("MK_TUNE_U", 4), t = tune_env("MK_TUNE_T", 896);
         bool v8 = tune_env("MK_TUNE_V8", 0) != 0;
         if (u != 2 && u != 3 && u != 4 && u != 8) u = 2;
@@ -186,6 +190,10 @@ ScanLaunch pick_by_d(uint32_t d) {
             case 896: return {pick_d16_u<ENC, FMODE, 896>(u, v8), 896, u * 32};
             default: return {pick_d16_u<ENC, FMODE, 1024>(u, v8), 1024, u * 32};
         }
+#else
+        // measured best shape: 4 vectors per lane and tile, 896 threads, 16-byte loads
+        return {mk::mk_scan_d16<ENC, FMODE, 4, 896, false>, 896, 4 * 32};
+#endif
     }
     switch (d) {
         case 8: return {mk::mk_scan_ord<ENC, 8, FMODE, 4>, mk::kScanThreads, 4 * 32};
@@ -274,6 +282,8 @@ int enqueue(mk_engine* e, Workspace& ws) {
     P.pat_off = dt.pat_off.p;
     P.tie_rank = e->tie_rank.p;
     P.q = t.q;
+    P.short_shift = 32u - 2u * t.q;
+    P.has_long = t.q2 ? 1u : 0u;
     P.case_insensitive = e->ps.case_insensitive ? 1 : 0;
     P.cand = ws.cand.p;
     P.cand_capacity = ws.cand_cap;

@@ -46,6 +46,8 @@ struct ScanParams {
     const uint32_t* pat_off;
     const uint32_t* tie_rank;
     uint32_t q;
+    uint32_t short_shift;           // 32 - 2q: candidate code (16-base window) -> q-base seed code
+    uint32_t has_long;              // 1: patterns of the long group are keyed by the whole 16-base window
     int case_insensitive;
     // candidates: seeds that passed both filters, handed from the scan to the verify kernel
     uint2* cand;                    // {seed position / pos_mul, seed code}
@@ -66,7 +68,7 @@ constexpr int kScanWarps = kScanThreads / 32;
 
 // First-level filter flavours
 constexpr int kFilterSmem = 0;    // blocked Bloom in shared memory: 4 bits inside one 64-bit block
-constexpr int kFilterGlobal = 1;  // plain 1-hash bitmap left in global memory (L2-resident)
+constexpr int kFilterGlobal = 1;  // L2-resident: plain 1-hash bitmap (stride 16) or dual-key 64-bit blocks (stride < 16)
 
 __device__ __forceinline__ uint64_t make_evict_first_policy() {
     uint64_t pol;
@@ -102,6 +104,21 @@ __device__ __forceinline__ uint32_t filter_probe(const uint32_t* __restrict__ f,
         uint32_t h = mk_hash_f1(code, lb);
         return (__ldg(f + (h >> 5)) >> (h & 31)) & 1u;
     }
+}
+
+// Dual-key probe of the L2-resident blocked filter (stride < 16): `win` is the 16-base window at the
+// grid position; its q-base prefix selects the block, and the block is tested for the prefix (short
+// group, result bit 0) and, if a long group exists, for the whole window (bit 1). One 8-byte load.
+__device__ __forceinline__ uint32_t bloom_test(uint2 w, uint32_t g) {
+    return (w.x >> ((g >> 12) & 31)) & (w.x >> ((g >> 17) & 31)) & (w.y >> ((g >> 22) & 31)) & (w.y >> (g >> 27)) & 1u;
+}
+__device__ __forceinline__ uint32_t dual_probe(const uint32_t* __restrict__ f, uint32_t win, uint32_t short_shift,
+                                               uint32_t nblocks, uint32_t has_long) {
+    uint32_t sc = win >> short_shift;
+    uint2 w = __ldg(reinterpret_cast<const uint2*>(f) + mk_dual_block(sc, nblocks));
+    uint32_t pass = bloom_test(w, mk_dual_g_short(sc));           // bit 0: short key present
+    if (has_long) pass |= bloom_test(w, mk_dual_g_long(win)) << 1;  // bit 1: long key present
+    return pass;
 }
 
 // The record that contains unit position s: the last r with off[r] <= s (records of length 0 are
@@ -142,92 +159,166 @@ __device__ __forceinline__ uint8_t text_symbol(const uint8_t* __restrict__ t, ui
     return (pos & 1) ? (b & 0xF) : (b >> 4);
 }
 
+// Eight bytes from any byte address: two aligned 8-byte loads and a funnel shift. Reads up to 15 bytes
+// past p (the text and pattern buffers are padded for that).
+__device__ __forceinline__ uint64_t ld8_any(const uint8_t* p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(a & ~uintptr_t(7));
+    const uint32_t sh = (uint32_t)(a & 7u) * 8u;
+    unsigned long long lo = __ldg(q), hi = __ldg(q + 1);
+    return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+}
+// mk_fold on eight bytes at once: 'A'..'Z' -> 'a'..'z', every other byte (also >= 0x80) unchanged
+__device__ __forceinline__ uint64_t fold8(uint64_t c) {
+    const uint64_t t = c & 0x7F7F7F7F7F7F7F7Full;
+    const uint64_t ge_a = t + 0x3F3F3F3F3F3F3F3Full;  // bit 7 set iff t >= 'A'
+    const uint64_t gt_z = t + 0x2525252525252525ull;  // bit 7 set iff t >  'Z'
+    const uint64_t upper = ge_a & ~gt_z & ~c & 0x8080808080808080ull;
+    return c | (upper >> 2);
+}
+
 // Second-level filter, inlined at the drain sites: one L2 load and a handful of registers, so that
 // the out-of-line verify (whose call spills the prefetched tile registers) runs for real candidates
 // only.
 __device__ __forceinline__ bool second_level_pass(const ScanParams& P, uint32_t code) {
     if (!P.filter2) return true;
-    uint32_t h = mk_hash_f2(code, P.filter2_log2_bits);
+    uint32_t h = mk_hash_f2(code >> P.short_shift, P.filter2_log2_bits);
     return (__ldg(P.filter2 + (h >> 5)) >> (h & 31)) & 1u;
 }
 
-// A seed at base position `pos` passed both filters: look it up in the cuckoo table and compare the
-// patterns that own it byte by byte. Runs in the verify kernel, one candidate per thread.
-template <int ENC>
-__device__ __forceinline__ void verify_seed(const ScanParams& P, uint64_t pos, uint32_t code) {
-    // cuckoo lookup: two 32-byte buckets
-    uint32_t first = kEmptySlot;
+// Cuckoo lookup of (group, code): two 32-byte buckets. Returns the first posting or kEmptySlot.
+__device__ __forceinline__ uint32_t seed_lookup(const ScanParams& P, uint32_t code, uint32_t group) {
+    const uint32_t hk = mk_group_key(code, group);
 #pragma unroll
-    for (int h = 0; h < 2 && first == kEmptySlot; ++h) {
-        uint32_t b = h == 0 ? mk_hash_b1(code, P.bucket_mask) : mk_hash_b2(code, P.bucket_mask);
+    for (int h = 0; h < 2; ++h) {
+        uint32_t b = h == 0 ? mk_hash_b1(hk, P.bucket_mask) : mk_hash_b2(hk, P.bucket_mask);
         const uint4* bp = reinterpret_cast<const uint4*>(P.slots + (size_t)b * kBucketSlots);
         uint4 lo = __ldg(bp), hi = __ldg(bp + 1);
-        if (lo.x == code && lo.y != kEmptySlot) first = lo.y;
-        else if (lo.z == code && lo.w != kEmptySlot) first = lo.w;
-        else if (hi.x == code && hi.y != kEmptySlot) first = hi.y;
-        else if (hi.z == code && hi.w != kEmptySlot) first = hi.w;
+        if (lo.x == code && lo.y != kEmptySlot && (lo.y >> 31) == group) return lo.y & ~kGroupBit;
+        if (lo.z == code && lo.w != kEmptySlot && (lo.w >> 31) == group) return lo.w & ~kGroupBit;
+        if (hi.x == code && hi.y != kEmptySlot && (hi.y >> 31) == group) return hi.y & ~kGroupBit;
+        if (hi.z == code && hi.w != kEmptySlot && (hi.w >> 31) == group) return hi.w & ~kGroupBit;
     }
-    if (first == kEmptySlot) return;
+    return kEmptySlot;
+}
 
+// Hits found by one warp of the verify kernel are staged in shared memory and appended to the global
+// list 32 or more at a time with ONE atomicAdd (at BASELINE cfg5 a million hits would otherwise queue
+// up on the single list counter).
+constexpr int kHitStage = 64;
+struct HitSink {
+    RawHit* buf;    // kHitStage entries of the warp
+    uint32_t* cnt;  // hits staged (may exceed kHitStage: the excess went straight to the global list)
+};
+
+__device__ __forceinline__ void append_hit_global(const ScanParams& P, const RawHit& h) {
+    cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
+    unsigned long long base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(P.hit_count, (unsigned long long)g.size());
+    base = g.shfl(base, 0);
+    unsigned long long slot = base + g.thread_rank();
+    if (slot < P.hit_capacity) P.hits[slot] = h;
+}
+
+// Called by the whole warp: move the staged hits to the global list.
+__device__ __forceinline__ void sink_flush(const ScanParams& P, HitSink& sink, uint32_t lane) {
+    __syncwarp();
+    uint32_t n = *sink.cnt;
+    if (n > kHitStage) n = kHitStage;
+    if (n) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(P.hit_count, (unsigned long long)n);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        for (uint32_t k = lane; k < n; k += 32)
+            if (base + k < P.hit_capacity) P.hits[base + k] = sink.buf[k];
+    }
+    __syncwarp();
+    if (lane == 0) *sink.cnt = 0;
+    __syncwarp();
+}
+
+// One posting (pattern pid owns the seed at its offset j) of a seed key found at base position `pos`:
+// compare the pattern byte by byte. Runs in the verify kernel, one candidate per thread.
+template <int ENC>
+__device__ __forceinline__ void verify_one(const ScanParams& P, uint64_t pos, uint32_t pid, uint32_t j, HitSink& sink) {
+    if (pos < j) return;
     const uint8_t* text = reinterpret_cast<const uint8_t*>(P.text);
-    for (uint32_t i = first;; ++i) {
-        uint32_t e = __ldg(P.postings + i);
-        uint32_t pid = e >> 5, j = (e >> 1) & 15u;
-        if (pos >= j) {
-            uint64_t s = pos - j;
-            uint32_t po = __ldg(P.pat_off + pid);
-            uint32_t L = __ldg(P.pat_off + pid + 1) - po;
-            if (s + L <= P.n_units) {
-                const uint8_t* pat = P.pat_bytes + po;
-                // exact compare, eight symbols per round trip (the loads of a chunk are independent)
-                bool eq = true;
-#ifdef MK_NO_CHUNK
-                for (uint32_t k = 0; k < L; ++k) {
-                    if (text_symbol<ENC>(text, s + k, P.case_insensitive) != __ldg(pat + k)) { eq = false; break; }
-                }
-#else
-                for (uint32_t k0 = 0; k0 < L && eq; k0 += 8) {
-                    uint8_t tx[8], px[8];
-#pragma unroll
-                    for (uint32_t i = 0; i < 8; ++i) {
-                        bool in = k0 + i < L;
-                        tx[i] = in ? text_symbol<ENC>(text, s + k0 + i, P.case_insensitive) : 0;
-                        px[i] = in ? __ldg(pat + k0 + i) : 0;
-                    }
-#pragma unroll
-                    for (uint32_t i = 0; i < 8; ++i) eq = eq && (tx[i] == px[i]);
-                }
-#endif
-                if (eq && s >= P.off[0]) {
-                    uint32_t r = find_record(P.off, P.n_records, s);
-                    uint64_t rend = P.lens ? P.off[r] + P.lens[r] : P.off[r + 1];
-                    if (s + L <= rend) {
-                        atomicOr(P.flags + (r >> 5), 1u << (r & 31));
-                        if (P.mode != MK_MODE_FLAG) {
-                            // warp-aggregated append: one atomic per group of lanes that got here together
-                            cooperative_groups::coalesced_group g = cooperative_groups::coalesced_threads();
-                            unsigned long long base = 0;
-                            if (g.thread_rank() == 0) base = atomicAdd(P.hit_count, (unsigned long long)g.size());
-                            base = g.shfl(base, 0);
-                            unsigned long long slot = base + g.thread_rank();
-                            if (slot < P.hit_capacity) {
-                                RawHit hrec;
-                                if (P.mode == MK_MODE_ALL_HITS)
-                                    hrec.key = ((((unsigned long long)(s + L) << P.len_bits) | (P.max_len - L)) << P.tie_bits) |
-                                               __ldg(P.tie_rank + pid);
-                                else
-                                    hrec.key = ((unsigned long long)r << P.pat_bits) | pid;
-                                hrec.record = r;
-                                hrec.pattern = pid;
-                                P.hits[slot] = hrec;
-                            }
-                        }
-                    }
-                }
-            }
+    const uint64_t s = pos - j;
+    const uint32_t po = __ldg(P.pat_off + pid);
+    const uint32_t L = __ldg(P.pat_off + pid + 1) - po;
+    if (s + L > P.n_units) return;
+    const uint8_t* pat = P.pat_bytes + po;
+    bool eq = true;
+    if (ENC == MK_ENC_ASCII) {
+        // exact compare, eight bytes per step
+        for (uint32_t k0 = 0; k0 < L && eq; k0 += 8) {
+            uint64_t tx = ld8_any(text + s + k0), px = ld8_any(pat + k0);
+            if (P.case_insensitive) tx = fold8(tx);
+            uint64_t diff = tx ^ px;
+            if (L - k0 < 8) diff &= (1ull << (8 * (L - k0))) - 1ull;
+            eq = diff == 0;
         }
+    } else {
+        // nibble text against one-nibble-per-byte pattern codes, eight symbols per round trip
+        for (uint32_t k0 = 0; k0 < L && eq; k0 += 8) {
+            uint8_t tx[8], px[8];
+#pragma unroll
+            for (uint32_t i = 0; i < 8; ++i) {
+                bool in = k0 + i < L;
+                tx[i] = in ? text_symbol<ENC>(text, s + k0 + i, P.case_insensitive) : 0;
+                px[i] = in ? __ldg(pat + k0 + i) : 0;
+            }
+#pragma unroll
+            for (uint32_t i = 0; i < 8; ++i) eq = eq && (tx[i] == px[i]);
+        }
+    }
+    if (!eq || s < P.off[0]) return;
+    const uint32_t r = find_record(P.off, P.n_records, s);
+    const uint64_t rend = P.lens ? P.off[r] + P.lens[r] : P.off[r + 1];
+    if (s + L > rend) return;
+    // test before set: with few long records (chromosomes) every hit lands on the same word
+    const uint32_t bit = 1u << (r & 31);
+    if (!(__ldcg(P.flags + (r >> 5)) & bit)) atomicOr(P.flags + (r >> 5), bit);
+    if (P.mode == MK_MODE_FLAG) return;
+    RawHit hrec;
+    if (P.mode == MK_MODE_ALL_HITS)
+        hrec.key = ((((unsigned long long)(s + L) << P.len_bits) | (P.max_len - L)) << P.tie_bits) | __ldg(P.tie_rank + pid);
+    else
+        hrec.key = ((unsigned long long)r << P.pat_bits) | pid;
+    hrec.record = r;
+    hrec.pattern = pid;
+    const uint32_t k = atomicAdd(sink.cnt, 1u);
+    if (k < kHitStage) sink.buf[k] = hrec;
+    else append_hit_global(P, hrec);
+}
+
+// All postings of a key: `first` is what seed_lookup returned (group bit stripped).
+template <int ENC>
+__device__ __forceinline__ void verify_postings(const ScanParams& P, uint64_t pos, uint32_t first, HitSink& sink) {
+    if (first & kInlineBit) {
+        verify_one<ENC>(P, pos, (first & ~kInlineBit) >> 4, first & 15u, sink);
+        return;
+    }
+    for (uint32_t i = first;; ++i) {
+        const uint32_t e = __ldg(P.postings + i);
+        verify_one<ENC>(P, pos, e >> 5, (e >> 1) & 15u, sink);
         if (e & 1u) break;
     }
+}
+
+// A candidate: `code` is the seed code of the stride-16 scan, or the 16-base window of the other
+// scans (its q-base prefix is the short key, the whole window the long key).
+template <int ENC>
+__device__ __forceinline__ void verify_seed(const ScanParams& P, uint64_t pos, uint32_t code, HitSink& sink) {
+    bool long_only = false;
+    if (P.has_long) {  // bit 0 of the position is a flag of the scan (the stride is even)
+        long_only = pos & 1u;
+        pos &= ~1ull;
+    }
+    uint32_t f_long = P.has_long ? seed_lookup(P, code, 1u) : kEmptySlot;
+    uint32_t f_short = long_only ? kEmptySlot : seed_lookup(P, code >> P.short_shift, 0u);
+    if (f_long != kEmptySlot) verify_postings<ENC>(P, pos, f_long, sink);
+    if (f_short != kEmptySlot) verify_postings<ENC>(P, pos, f_short, sink);
 }
 
 template <int FMODE>
@@ -434,7 +525,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) mk_scan_ord(const __grid_cons
     const uint32_t* __restrict__ filt = (FMODE == kFilterSmem) ? s_filter : P.filter;
     const uint32_t lane = threadIdx.x & 31;
     WarpQueue wq{s_queue[threadIdx.x >> 5], 0, nullptr};
-    const uint32_t lb = (FMODE == kFilterSmem) ? P.filter_blocks : P.filter_log2_bits, q = P.q;
+    const uint32_t lb = P.filter_blocks, sshift = P.short_shift, has_long = P.has_long;
     const uint64_t pol = make_evict_first_policy();
     const uint64_t nwarps = (uint64_t)gridDim.x * kScanWarps;
     const uint64_t n_vec = P.n_vec;
@@ -469,10 +560,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) mk_scan_ord(const __grid_cons
                 uint64_t base = unit * MK_UNIT_BASES;
 #pragma unroll 4
                 for (int o = 0; o < MK_UNIT_BASES; o += D) {
-                    uint32_t seed = mk_seed_ord(cur, nxt, o, q);
-                    bool pass = filter_probe<FMODE>(filt, seed, lb) && base + o < P.n_units;
-                    // positions fit 32 bits: the engine refuses batches of 2^32 bases or more on this path
-                    queue_push<ENC, 1>(P, wq, lane, pass, (uint32_t)(base + o), seed);
+                    // the 16-base window at the grid position: its q-base prefix is the short key
+                    uint32_t win = mk_win_ord(cur, nxt, o);
+                    uint32_t hit = (FMODE == kFilterSmem) ? filter_probe<kFilterSmem>(filt, win >> sshift, lb)
+                                                          : dual_probe(filt, win, sshift, lb, has_long);
+                    bool pass = hit && base + o < P.n_units;
+                    // Positions fit 32 bits: the engine refuses batches of 2^32 bases or more on this path.
+                    // They are multiples of the stride (>= 2 whenever a long group exists), so bit 0 can say
+                    // "only the long key passed", which saves the verify kernel the short-key lookup.
+                    queue_push<ENC, 1>(P, wq, lane, pass, (uint32_t)(base + o) | ((FMODE != kFilterSmem && hit == 2u) ? 1u : 0u), win);
                 }
             }
         }
@@ -485,14 +581,29 @@ __global__ void __launch_bounds__(kScanThreads, 1) mk_scan_ord(const __grid_cons
 // bucket, postings, pattern bytes, record offsets) of thousands of candidates are in flight together
 // instead of stalling a streaming warp. The list length is read from device memory.
 // ---------------------------------------------------------------------------------------------
+constexpr int kVerifyThreads = 256;
 template <int ENC>
-__global__ void __launch_bounds__(256) mk_verify_candidates(const __grid_constant__ ScanParams P) {
+__global__ void __launch_bounds__(kVerifyThreads) mk_verify_candidates(const __grid_constant__ ScanParams P) {
+    __shared__ RawHit s_hits[kVerifyThreads / 32][kHitStage];
+    __shared__ uint32_t s_cnt[kVerifyThreads / 32];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    HitSink sink{s_hits[w], &s_cnt[w]};
+    if (lane == 0) s_cnt[w] = 0;
+    __syncwarp();
     unsigned long long n = *P.cand_count;
     if (n > P.cand_capacity) n = P.cand_capacity;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-        uint2 e = P.cand[i];
-        verify_seed<ENC>(P, (uint64_t)e.x * P.pos_mul, e.y);
+    const unsigned long long stride = (unsigned long long)gridDim.x * kVerifyThreads;
+    // warp-uniform loop: all lanes of a warp stay in it together so that the staged hits can be flushed
+    for (unsigned long long base = (unsigned long long)blockIdx.x * kVerifyThreads + w * 32; base < n; base += stride) {
+        unsigned long long i = base + lane;
+        if (i < n) {
+            uint2 e = P.cand[i];
+            verify_seed<ENC>(P, (uint64_t)e.x * P.pos_mul, e.y, sink);
+        }
+        __syncwarp();
+        if (*sink.cnt >= 32) sink_flush(P, sink, lane);
     }
+    sink_flush(P, sink, lane);
 }
 
 }  // namespace mk

@@ -27,12 +27,16 @@ namespace mk {
 
 constexpr uint32_t kEmptySlot = 0xFFFFFFFFu;
 constexpr uint32_t kBucketSlots = 4;
-constexpr uint32_t kMaxPatternId = (1u << 27) - 1;
+constexpr uint32_t kMaxPatternId = (1u << 25) - 2;
 
 struct SeedSlot {
     uint32_t code;
-    uint32_t first;  // index of the first posting, kEmptySlot if the slot is free
+    uint32_t first;  // bit 31: key group (1 = 16-base seed of the long group); bit 30: the key has a single
+                     // posting, stored right here as pattern_id << 4 | j (saves the verify kernel one
+                     // dependent load); else bits 0..29: index of the first posting. kEmptySlot: free slot
 };
+constexpr uint32_t kGroupBit = 0x80000000u;
+constexpr uint32_t kInlineBit = 0x40000000u;
 
 // posting = pattern_id << 5 | j << 1 | last_of_list
 inline uint32_t make_posting(uint32_t pid, uint32_t j, bool last) { return (pid << 5) | (j << 1) | (last ? 1u : 0u); }
@@ -40,7 +44,10 @@ inline uint32_t make_posting(uint32_t pid, uint32_t j, bool last) { return (pid 
 struct Tables {
     int enc = 0;
     uint32_t q = 0, d = 0;
+    uint32_t q2 = 0;       // 16 when patterns of >= long_min_len bases are indexed by 16-base seeds, else 0
+    uint32_t long_min_len = 0;
     bool perm = false;  // D == 16: permuted unit packing
+    bool filter_dual = false;  // L2-resident 64-bit blocked filter probed with both keys (stride < 16)
     uint32_t n_seeds = 0;
     // first-level filter
     uint32_t filter_log2_bits = 0, filter_hashes = 1;
@@ -165,17 +172,22 @@ inline uint32_t seed_code_perm(int enc, const uint8_t* sym) {
     return mk_pack_bam_perm(w[0], w[1]);
 }
 
-inline bool cuckoo_build(const std::vector<std::pair<uint32_t, uint32_t>>& keys /*code, first*/, uint32_t log2_buckets,
-                         std::vector<SeedSlot>* out, uint32_t* mask_out) {
+struct SeedKey {
+    uint32_t code, first, group;
+};
+
+inline bool cuckoo_build(const std::vector<SeedKey>& keys, uint32_t log2_buckets, std::vector<SeedSlot>* out,
+                         uint32_t* mask_out) {
     uint32_t nb = 1u << log2_buckets, mask = nb - 1;
     std::vector<SeedSlot> slots((size_t)nb * kBucketSlots, SeedSlot{0, kEmptySlot});
     std::mt19937 rng(0x5EEDu + log2_buckets);
-    for (auto kv : keys) {
-        SeedSlot cur{kv.first, kv.second};
+    for (const SeedKey& kv : keys) {
+        SeedSlot cur{kv.code, kv.first | (kv.group ? kGroupBit : 0u)};
         bool placed = false;
         uint32_t from = UINT32_MAX;
         for (int kick = 0; kick < 500 && !placed; ++kick) {
-            uint32_t cand[2] = {mk_hash_b1(cur.code, mask), mk_hash_b2(cur.code, mask)};
+            uint32_t hk = mk_group_key(cur.code, cur.first >> 31);
+            uint32_t cand[2] = {mk_hash_b1(hk, mask), mk_hash_b2(hk, mask)};
             for (int h = 0; h < 2 && !placed; ++h)
                 for (uint32_t s = 0; s < kBucketSlots && !placed; ++s) {
                     SeedSlot& sl = slots[(size_t)cand[h] * kBucketSlots + s];
@@ -192,6 +204,18 @@ inline bool cuckoo_build(const std::vector<std::pair<uint32_t, uint32_t>>& keys 
     *out = std::move(slots);
     *mask_out = mask;
     return true;
+}
+
+// Expected false-positive rate of one probe of a blocked Bloom filter with `nblocks` 64-bit blocks
+// holding nn keys: Poisson(lambda) keys per block, each key sets 2 bits in each 32-bit half.
+inline double blocked_fp(double nn, uint32_t nblocks) {
+    double lambda = nn / nblocks, fp = 0.0, pmf = std::exp(-lambda);
+    for (int j = 0; j < 600; ++j) {
+        double set = 1.0 - std::pow(31.0 / 32.0, 2.0 * j);
+        fp += pmf * std::pow(set, 4.0);
+        pmf *= lambda / (j + 1);
+    }
+    return fp;
 }
 
 inline Tables build_tables(const PatternSet& ps, int enc) {
@@ -216,32 +240,68 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
             }
         }
     }
+    t.pat_bytes.resize(ps.bytes.size() + 16, 0);  // the verify kernel compares with 8-byte loads at any offset
     choose_geometry(ps.min_len, &t.q, &t.d);
     t.perm = (t.d == 16);
 
-    // (code, pattern, j) triples
-    struct Trip { uint32_t code, pid, j; };
+    // (group, code, pattern, j) of every indexed seed, and the distinct keys with their first posting
+    struct Trip { uint32_t code, pid, j, grp; };
     std::vector<Trip> trips;
-    trips.reserve((size_t)n * t.d);
-    for (uint32_t p = 0; p < n; ++p) {
-        if (!t.pat_live[p]) continue;
-        const uint8_t* sym = t.pat_bytes.data() + t.pat_off[p];
-        for (uint32_t j = 0; j < t.d; ++j) {
-            uint32_t code = t.perm ? seed_code_perm(enc, sym + j) : seed_code_ord(enc, sym + j, t.q);
-            trips.push_back({code, p, j});
+    std::vector<SeedKey> keys;
+    auto index_seeds = [&](uint32_t long_min_len) {
+        trips.clear();
+        keys.clear();
+        trips.reserve((size_t)n * t.d);
+        for (uint32_t p = 0; p < n; ++p) {
+            if (!t.pat_live[p]) continue;
+            const uint8_t* sym = t.pat_bytes.data() + t.pat_off[p];
+            const bool lng = long_min_len && ps.len(p) >= long_min_len;
+            for (uint32_t j = 0; j < t.d; ++j) {
+                uint32_t code = t.perm ? seed_code_perm(enc, sym + j) : seed_code_ord(enc, sym + j, lng ? 16u : t.q);
+                trips.push_back({code, p, j, lng ? 1u : 0u});
+            }
         }
+        std::sort(trips.begin(), trips.end(), [](const Trip& a, const Trip& b) {
+            if (a.grp != b.grp) return a.grp < b.grp;
+            if (a.code != b.code) return a.code < b.code;
+            if (a.pid != b.pid) return a.pid < b.pid;
+            return a.j < b.j;
+        });
+        if (trips.size() >= (size_t)kInlineBit) throw std::runtime_error("too many seeds for the posting index");
+        auto same_key = [](const Trip& a, const Trip& b) { return a.grp == b.grp && a.code == b.code; };
+        for (size_t i = 0; i < trips.size(); ++i)
+            if (i == 0 || !same_key(trips[i - 1], trips[i])) {
+                const bool single = i + 1 == trips.size() || !same_key(trips[i], trips[i + 1]);
+                keys.push_back({trips[i].code, single ? (kInlineBit | (trips[i].pid << 4) | trips[i].j) : (uint32_t)i, trips[i].grp});
+            }
+    };
+    index_seeds(0);
+
+    // first-level filter flavour: blocked Bloom in shared memory while it stays selective
+    uint32_t nblocks = MK_BLOOM_MIN_BLOCKS;
+    if (blocked_fp((double)keys.size(), nblocks) > 0.002) nblocks = MK_BLOOM_MAX_BLOCKS;
+    if (const char* fb = std::getenv("MK_FILTER_BLOCKS")) {  // tuning override
+        uint32_t v = (uint32_t)std::atoi(fb) & ~1u;
+        if (v >= 1024 && v <= MK_BLOOM_MAX_BLOCKS) nblocks = v;
     }
-    std::sort(trips.begin(), trips.end(), [](const Trip& a, const Trip& b) {
-        if (a.code != b.code) return a.code < b.code;
-        if (a.pid != b.pid) return a.pid < b.pid;
-        return a.j < b.j;
-    });
-    std::vector<std::pair<uint32_t, uint32_t>> keys;
+    // MK_FILTER_MODE=l2|smem overrides the choice (tests exercise both paths on small inputs)
+    const char* force = std::getenv("MK_FILTER_MODE");
+    bool want_smem = blocked_fp((double)keys.size(), nblocks) <= 0.25;
+    if (force && std::strcmp(force, "l2") == 0) want_smem = false;
+    if (force && std::strcmp(force, "smem") == 0) want_smem = true;
+
+    // Seed sets too large for shared memory with a stride below 16: give every pattern that is long
+    // enough a 16-base seed (far fewer text positions carry one of those than one of the q-base seeds)
+    // (stride >= 2: the scan flags candidates in bit 0 of their position)
+    if (!want_smem && t.d < 16 && t.d >= 2 && t.q < 16 && ps.max_len >= t.d + 15 && !std::getenv("MK_NO_LONG_SEEDS")) {
+        t.q2 = 16;
+        t.long_min_len = t.d + 15;
+        index_seeds(t.long_min_len);
+    }
+
     t.postings.resize(trips.size());
     for (size_t i = 0; i < trips.size(); ++i) {
-        bool first = (i == 0) || trips[i - 1].code != trips[i].code;
-        bool last = (i + 1 == trips.size()) || trips[i + 1].code != trips[i].code;
-        if (first) keys.emplace_back(trips[i].code, (uint32_t)i);
+        bool last = (i + 1 == trips.size()) || trips[i + 1].grp != trips[i].grp || trips[i + 1].code != trips[i].code;
         t.postings[i] = make_posting(trips[i].pid, trips[i].j, last);
     }
     if (t.postings.empty()) t.postings.push_back(make_posting(0, 0, true));  // keep device pointers non-null
@@ -254,30 +314,7 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
         if (++lb > 28) throw std::runtime_error("seed table does not fit");
     }
 
-    // first-level filter: blocked Bloom in shared memory while it stays selective
-    double nn = (double)t.n_seeds;
-    auto blocked_fp = [&](uint32_t nblocks) {
-        // Poisson(lambda) keys per block; each key sets 2 bits in each 32-bit half
-        double lambda = nn / nblocks, fp = 0.0, pmf = std::exp(-lambda);
-        for (int j = 0; j < 600; ++j) {
-            double set = 1.0 - std::pow(31.0 / 32.0, 2.0 * j);
-            fp += pmf * std::pow(set, 4.0);
-            pmf *= lambda / (j + 1);
-        }
-        return fp;
-    };
-    uint32_t nblocks = MK_BLOOM_MIN_BLOCKS;
-    if (blocked_fp(nblocks) > 0.002) nblocks = MK_BLOOM_MAX_BLOCKS;
-    if (const char* fb = std::getenv("MK_FILTER_BLOCKS")) {  // tuning override
-        uint32_t v = (uint32_t)std::atoi(fb) & ~1u;
-        if (v >= 1024 && v <= MK_BLOOM_MAX_BLOCKS) nblocks = v;
-    }
-    double fp = blocked_fp(nblocks);
-    // MK_FILTER_MODE=l2|smem overrides the choice (tests exercise both paths on small inputs)
-    const char* force = std::getenv("MK_FILTER_MODE");
-    bool want_smem = fp <= 0.25;
-    if (force && std::strcmp(force, "l2") == 0) want_smem = false;
-    if (force && std::strcmp(force, "smem") == 0) want_smem = true;
+    const double nn = (double)t.n_seeds;
     if (want_smem) {
         t.filter_in_smem = true;
         t.filter_blocks = nblocks;
@@ -285,8 +322,8 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
         t.filter_hashes = 4;
         t.filter.assign((size_t)nblocks * 2, 0);
         for (auto& kv : keys) {
-            uint32_t blk = mk_bloom_block(kv.first, nblocks), lo, hi;
-            mk_bloom_masks(kv.first, &lo, &hi);
+            uint32_t blk = mk_bloom_block(kv.code, nblocks), lo, hi;
+            mk_bloom_masks(kv.code, &lo, &hi);
             t.filter[2 * (size_t)blk] |= lo;
             t.filter[2 * (size_t)blk + 1] |= hi;
         }
@@ -295,11 +332,29 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
         t.filter2_log2_bits = b2;
         t.filter2.assign((size_t)1 << (b2 - 5), 0);
         for (auto& kv : keys) {
-            uint32_t h = mk_hash_f2(kv.first, b2);
+            uint32_t h = mk_hash_f2(kv.code, b2);
             t.filter2[h >> 5] |= 1u << (h & 31);
         }
+    } else if (t.d < 16) {
+        // L2-resident blocked Bloom, ~32 bits per key, 4 bits per key inside one 64-bit block that the
+        // short and the long key of a text position share
+        t.filter_in_smem = false;
+        t.filter_dual = true;
+        t.filter_hashes = 4;
+        uint64_t nb = std::max<uint64_t>(1u << 15, (uint64_t)t.n_seeds / 2);
+        if (const char* bk = std::getenv("MK_DUAL_BITS_PER_KEY")) nb = std::max<uint64_t>(1u << 15, (uint64_t)t.n_seeds * (uint64_t)std::atoi(bk) / 64);
+        t.filter_blocks = (uint32_t)std::min<uint64_t>(nb, 1u << 27) & ~1u;
+        t.filter.assign((size_t)t.filter_blocks * 2, 0);
+        const uint32_t sshift = 32u - 2u * t.q;
+        for (auto& kv : keys) {
+            uint32_t short_code = kv.group ? (kv.code >> sshift) : kv.code;
+            uint32_t blk = mk_dual_block(short_code, t.filter_blocks), lo, hi;
+            mk_bloom_masks_g(kv.group ? mk_dual_g_long(kv.code) : mk_dual_g_short(short_code), &lo, &hi);
+            t.filter[2 * (size_t)blk] |= lo;
+            t.filter[2 * (size_t)blk + 1] |= hi;
+        }
     } else {
-        // too many seeds for shared memory: L2-resident bitmap, ~32 bits per seed, one hash
+        // stride 16, too many seeds for shared memory: L2-resident bitmap, ~32 bits per seed, one hash
         t.filter_in_smem = false;
         t.filter_hashes = 1;
         uint32_t b = 21;
@@ -307,7 +362,7 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
         t.filter_log2_bits = b;
         t.filter.assign((size_t)1 << (t.filter_log2_bits - 5), 0);
         for (auto& kv : keys) {
-            uint32_t h = mk_hash_f1(kv.first, t.filter_log2_bits);
+            uint32_t h = mk_hash_f1(kv.code, t.filter_log2_bits);
             t.filter[h >> 5] |= 1u << (h & 31);
         }
     }

@@ -1,5 +1,6 @@
 """Time scan-kernel launch shapes on a device-resident cfg2 data set (CUDA events inside the engine).
-    python scripts/tune_scan.py [--reads N] [--variants "U,PF;U,PF;..."]"""
+    MK_TUNE_BUILD=1 python -m merkurio_b200.build --force   # builds every launch shape
+    python scripts/tune_scan.py [--reads N] [--variants "U,T;U,T;..."]"""
 import argparse
 import os
 import sys

@@ -236,12 +236,8 @@ def test_many_patterns_l2_filter(monkeypatch):
         check_batch(pats, planted_records(rng, pats, 200, 0, 200, plant_p=0.5))
 
 
-def test_bam4_encoding():
-    rng = np.random.default_rng(31)
-    pats = sorted({rand_seq(rng, int(k)) for k in rng.integers(16, 50, size=40)} | {b"ACGTNNACGTACGTAAGGCTNAC", b"acgtacgtacgtacgtacgt"})
-    recs = planted_records(rng, [p for p in pats if p.isupper()], 300, 0, 180, alphabet=b"ACGTNRY", plant_p=0.6)
-    ac = rm.AhoCorasick(pats, False)
-    # pack as BAM: 2 bases / byte, records byte aligned, explicit lengths
+def pack_bam4(recs):
+    """BAM sequence layout: 2 bases / byte (first in the high nibble), records byte aligned, explicit lengths."""
     nib = np.full(256, 15, dtype=np.uint8)
     for i, c in enumerate(NIB):
         nib[c] = i
@@ -255,8 +251,12 @@ def test_bam4_encoding():
         pos += len(codes)
         off.append(pos)
     packed = np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
-    off = np.array(off, dtype=np.uint64)
-    lens = np.array(lens, dtype=np.uint32)
+    return packed, np.array(off, dtype=np.uint64), np.array(lens, dtype=np.uint32)
+
+
+def check_bam4(pats, recs):
+    ac = rm.AhoCorasick(pats, False)
+    packed, off, lens = pack_bam4(recs)
     seq, aoff = pack_records(recs)
     rec, st, pat = ac.batch_hits(seq, aoff)
     with capi.Engine(pats, max_batch_bytes=int(packed.size) + 64, max_batch_records=len(recs)) as e:
@@ -266,6 +266,54 @@ def test_bam4_encoding():
         np.testing.assert_array_equal(r.hits["pattern"], pat)
         p = e.scan(packed, off, capi.MK_MODE_PATTERN_SET, enc=capi.MK_ENC_BAM4, lens=lens, n_units=int(off[-1]))
         assert list(zip(p.hits["record"].tolist(), p.hits["pattern"].tolist())) == sorted(set(zip(rec.tolist(), pat.tolist())))
+        f = e.scan(packed, off, capi.MK_MODE_FLAG, enc=capi.MK_ENC_BAM4, lens=lens, n_units=int(off[-1]))
+        np.testing.assert_array_equal(f.flagged_records(), np.unique(rec))
+        return e.info()
+
+
+def test_bam4_encoding():
+    rng = np.random.default_rng(31)
+    pats = sorted({rand_seq(rng, int(k)) for k in rng.integers(16, 50, size=40)} | {b"ACGTNNACGTACGTAAGGCTNAC", b"acgtacgtacgtacgtacgt"})
+    recs = planted_records(rng, [p for p in pats if p.isupper()], 300, 0, 180, alphabet=b"ACGTNRY", plant_p=0.6)
+    check_bam4(pats, recs)
+
+
+@pytest.mark.parametrize("lo", [2, 5, 12, 17, 21, 25])
+@pytest.mark.parametrize("long_seeds", [True, False])
+def test_dual_key_filter_mixed_lengths(monkeypatch, lo, long_seeds):
+    """Large mixed-length query sets with a stride below 16 (BASELINE cfg5): patterns of >= d + 15 bases
+    are keyed by a 16-base seed, the others by the q-base seed; both are probed with one L2 load."""
+    monkeypatch.setenv("MK_FILTER_MODE", "l2")
+    if not long_seeds:
+        monkeypatch.setenv("MK_NO_LONG_SEEDS", "1")
+    rng = np.random.default_rng(100 + lo)
+    genome = rand_seq(rng, 120000)
+    starts = rng.integers(0, len(genome) - 70, size=3000)
+    pats = {genome[s:s + int(k)] for s, k in zip(starts, rng.integers(lo, lo + 44, size=len(starts)))}
+    # queries that straddle the group threshold by one base, queries with N, related prefixes / suffixes
+    some = sorted(pats)[:200]
+    pats |= {p[1:] for p in some if len(p) - 1 >= lo} | {p[:-1] for p in some if len(p) - 1 >= lo}
+    for p in some[:40]:
+        if len(p) >= 8:
+            b = bytearray(p)
+            b[len(b) // 2] = ord("N")
+            pats.add(bytes(b))
+    pats = sorted(pats)
+    text = bytearray(genome)
+    for i, p in enumerate(q for q in pats if b"N" in q):
+        text[1000 + 500 * i: 1000 + 500 * i + len(p)] = p
+    text[50000:50300] = bytes(text[50000:50300]).lower()
+    text = bytes(text)
+    recs = [text[:33333], text[33333:90001], text[90001:]]
+    with capi.Engine(pats, max_batch_bytes=len(text) + 64, max_batch_records=4) as e:
+        r = check_batch(pats, recs, engine=e)
+        info = e.info()
+        assert info.filter_in_smem[0] == 0 and r.n_hits >= len(starts)
+    with capi.Engine(pats, case_insensitive=True, max_batch_bytes=len(text) + 64, max_batch_records=4) as e:
+        check_batch(pats, recs, case_insensitive=True, engine=e)
+    if lo >= 12:
+        info = check_bam4(pats, [r.upper() for r in recs] + [b"", b"ACG"])
+        assert info.filter_in_smem[1] == 0
 
 
 def test_double_buffered_slots_match_single_batch():
