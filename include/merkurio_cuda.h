@@ -126,7 +126,7 @@ void mk_engine_destroy(mk_engine* e);
 int mk_engine_get_info(mk_engine* e, mk_engine_info* out);
 
 /* Slot staging (pinned host memory the caller fills in place). lens_pinned may be NULL if the
- * caller never passes explicit lengths. */
+ * caller never passes explicit lengths (that buffer is allocated by the first call that asks for it). */
 int mk_slot_buffers(mk_engine* e, uint32_t slot, uint8_t** seq_pinned, uint64_t** off_pinned,
                     uint32_t** lens_pinned);
 /* Asynchronous: H2D copy of the slot's buffers, scan, hit sort, D2H of the results.

@@ -151,10 +151,12 @@ struct ScanLaunch {
 
 // Stride-16 scan: U vectors per lane and tile (two tiles in flight), T threads per CTA.
 // MK_TUNE_U / MK_TUNE_T override the defaults (used by scripts/tune_scan.py only).
+#ifdef MK_TUNE_BUILD
 int tune_env(const char* name, int dflt) {
     const char* s = std::getenv(name);
     return s ? std::atoi(s) : dflt;
 }
+#endif
 
 #ifdef MK_TUNE_BUILD
 // Every launch shape scripts/tune_scan.py sweeps (build with -DMK_TUNE_BUILD; ~100 extra kernels).
@@ -509,8 +511,7 @@ int mk_engine_create(const mk_patterns* patterns, const mk_config* config, mk_en
         CU(sl->d_seq.ensure(seq_cap));
         CU(sl->h_off.ensure((size_t)config->max_batch_records + 1));
         CU(sl->d_off.ensure((size_t)config->max_batch_records + 1));
-        CU(sl->h_lens.ensure(std::max<size_t>(config->max_batch_records, 1)));
-        CU(sl->d_lens.ensure(std::max<size_t>(config->max_batch_records, 1)));
+        // the lens buffers are allocated on first use (only BAM batches carry explicit lengths)
         e->slots.push_back(std::move(sl));
     }
     *out = e.release();
@@ -552,7 +553,11 @@ int mk_slot_buffers(mk_engine* e, uint32_t slot, uint8_t** seq_pinned, uint64_t*
     if (rc) return rc;
     if (seq_pinned) *seq_pinned = s->h_seq.p;
     if (off_pinned) *off_pinned = s->h_off.p;
-    if (lens_pinned) *lens_pinned = s->h_lens.p;
+    if (lens_pinned) {
+        CU(cudaSetDevice(e->device));
+        CU(s->h_lens.ensure(std::max<size_t>(e->cfg.max_batch_records, 1)));
+        *lens_pinned = s->h_lens.p;
+    }
     return MK_OK;
 }
 
@@ -572,6 +577,7 @@ int mk_scan_host(mk_engine* e, uint32_t slot, const uint8_t* h_seq, const uint64
     // the last vector is read whole: clear its tail so that the scan input is deterministic
     if (bytes % 16) CU(cudaMemsetAsync(s->d_seq.p + bytes, 0, 16 - bytes % 16, st));
     CU(cudaMemcpyAsync(s->d_off.p, h_off, ((size_t)n_records + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (h_lens) CU(s->d_lens.ensure(std::max<size_t>(e->cfg.max_batch_records, 1)));
     if (h_lens && n_records) CU(cudaMemcpyAsync(s->d_lens.p, h_lens, (size_t)n_records * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     return begin_batch(e, s->ws, s->d_seq.p, s->d_off.p, h_lens ? s->d_lens.p : nullptr, n_records, n_units, enc, mode, true);
 }
@@ -581,6 +587,7 @@ int mk_scan_submit(mk_engine* e, uint32_t slot, uint32_t n_records, uint64_t n_u
     Slot* s = nullptr;
     int rc = get_slot(e, slot, &s);
     if (rc) return rc;
+    if (use_lens && !s->h_lens.p) return fail(MK_ERR_STATE, "use_lens without lens_pinned from mk_slot_buffers");
     return mk_scan_host(e, slot, s->h_seq.p, s->h_off.p, use_lens ? s->h_lens.p : nullptr, n_records, n_units, enc, mode);
 }
 

@@ -6,6 +6,7 @@
 
 #include "commands.h"
 #include "device.h"
+#include "fastq_stream.h"
 #include "helpers.h"
 #include "io.h"
 #include "logger.h"
@@ -26,6 +27,10 @@ struct OutFile {
     }
     void write(const FastxRecord& r) {
         r.write(&buf);
+        if (buf.size() >= (1u << 20)) flush();
+    }
+    void write_raw(const char* p, size_t n) {
+        buf.append(p, n);
         if (buf.size() >= (1u << 20)) flush();
     }
     void flush() {
@@ -49,6 +54,28 @@ FastxRecord to_record(const RecMeta& m) {
     FastxRecord r;
     r.id = m.a; r.raw = m.b; r.qual = m.c; r.fastq = m.fastq; r.crlf = m.crlf;
     return r;
+}
+
+// Records of the chunked FASTQ ingest carry a (chunk, span) reference instead of strings.
+std::string record_id(const RecMeta& m) {
+    if (!m.chunk) return m.a;
+    const Chunk* ch = static_cast<const Chunk*>(m.chunk);
+    const RecSpan& r = ch->recs[m.idx];
+    return std::string(ch->id(r), r.id_len);
+}
+
+void write_record(OutFile& w, const RecMeta& m) {
+    if (!m.chunk) { w.write(to_record(m)); return; }
+    const Chunk* ch = static_cast<const Chunk*>(m.chunk);
+    const RecSpan& r = ch->recs[m.idx];
+    if (r.plain) { w.write_raw(ch->data.data() + r.start, r.end - r.start); return; }
+    FastxRecord fr;
+    fr.id.assign(ch->id(r), r.id_len);
+    fr.raw.assign(ch->seq(r), r.seq_len);
+    fr.qual.assign(ch->qual(r), r.seq_len);
+    fr.fastq = true;
+    fr.crlf = r.crlf;
+    w.write(fr);
 }
 
 }  // namespace
@@ -126,8 +153,9 @@ void extract_records(CmdExtract args) {
     }
 
     auto emit = [&](const std::string& fname, const RecMeta& m, const RecHit& h) {
-        logger.log_fields(fname, m.a, pattern_list[h.pattern], h.start);
-        if (jl) jl->log_fields(fname, m.a, pattern_list[h.pattern], h.start);
+        const std::string id = record_id(m);
+        logger.log_fields(fname, id, pattern_list[h.pattern], h.start);
+        if (jl) jl->log_fields(fname, id, pattern_list[h.pattern], h.start);
     };
     auto by_pattern_then_start = [](const RecHit& x, const RecHit& y) { return x.pattern != y.pattern ? x.pattern < y.pattern : x.start < y.start; };
 
@@ -163,7 +191,7 @@ void extract_records(CmdExtract args) {
         }
         if (found_occ != args.invert_match) {
             nb_records_extracted += 1;
-            if (!args.suppress_output) writer.write(to_record(m));
+            if (!args.suppress_output) write_record(writer, m);
         }
     };
 
@@ -206,8 +234,8 @@ void extract_records(CmdExtract args) {
         if (found_occ != args.invert_match) {
             nb_records_extracted += 2;
             if (!args.suppress_output) {
-                writer.write(to_record(mate1));
-                writer2.write(to_record(m2));
+                write_record(writer, mate1);
+                write_record(writer2, m2);
             }
         }
     };
@@ -225,8 +253,60 @@ void extract_records(CmdExtract args) {
             scanner.add_record(rec.seq.data(), rec.seq.size(), std::move(m));
         };
         FastxRecord r1, r2;
+        // 4-line FASTQ (plain or gzip) goes through the chunked reader: one thread per file reads and
+        // indexes the records, this thread only copies sequence bytes into the pinned batches
+        const bool chunked = !std::getenv("MERKURIO_NO_CHUNKED_FASTQ") && looks_like_fastq(args.in_fastx) &&
+                             (!paired || looks_like_fastq(*args.in_fastq_2));
+        const size_t chunk_bytes = std::getenv("MERKURIO_CHUNK_BYTES") ? (size_t)std::strtoull(std::getenv("MERKURIO_CHUNK_BYTES"), nullptr, 10)
+                                                                       : (size_t)16 << 20;
+        auto feed_span = [&](const std::shared_ptr<Chunk>& ch, size_t i, uint8_t file) {
+            const RecSpan& r = ch->recs[i];
+            RecMeta m;
+            m.chunk = ch.get();
+            m.idx = (uint32_t)i;
+            m.file = file; m.fastq = true; m.crlf = r.crlf;
+            scanner.add_record(ch->seq(r), r.seq_len, std::move(m));
+        };
+        const Error parse_error("Error during FASTQ/A record parsing.");
         try {
-            if (!paired) {
+            if (chunked && !paired) {
+                reader.reset();
+                FastqChunkReader cr(args.in_fastx, chunk_bytes);
+                while (std::shared_ptr<Chunk> ch = cr.next()) {
+                    scanner.hold(0, ch);
+                    for (size_t i = 0; i < ch->recs.size(); ++i) feed_span(ch, i, 0);
+                    if (ch->failed) throw parse_error.with_context("Error during FASTQ/A record parsing.");
+                }
+            } else if (chunked) {
+                reader.reset();
+                reader2.reset();
+                FastqChunkReader cr1(args.in_fastx, chunk_bytes), cr2(*args.in_fastq_2, chunk_bytes);
+                const char* second_ctx = "Error during FASTQ record parsing of second file. Do the two input files contain the same number of records?";
+                std::shared_ptr<Chunk> c1 = cr1.next(), c2 = cr2.next();
+                size_t i1 = 0, i2 = 0;
+                scanner.hold(0, c1);
+                scanner.hold(1, c2);
+                // step to the next record of a file (c == nullptr at its end); a malformed record raises
+                // at the point where the reference would have tried to read it
+                auto advance = [&](FastqChunkReader& cr, std::shared_ptr<Chunk>& c, size_t& i, int file, const char* ctx) {
+                    while (c && i == c->recs.size()) {
+                        if (c->failed) throw ctx ? parse_error.with_context(ctx) : parse_error;
+                        c = cr.next();
+                        i = 0;
+                        scanner.hold(file, c);
+                    }
+                };
+                for (;;) {
+                    advance(cr1, c1, i1, 0, "Error during FASTQ record parsing of first file.");
+                    if (!c1) break;
+                    advance(cr2, c2, i2, 1, second_ctx);
+                    if (!c2) throw Error(second_ctx);
+                    feed_span(c1, i1++, 0);
+                    feed_span(c2, i2++, 1);
+                }
+                advance(cr2, c2, i2, 1, nullptr);
+                if (c2) throw Error("The two input files have a different number of records. Please provide valid paired-end read files.");
+            } else if (!paired) {
                 for (;;) {
                     bool more;
                     try { more = reader->next(&r1); } catch (const Error& e) { throw e.with_context("Error during FASTQ/A record parsing."); }

@@ -1,6 +1,8 @@
 #include "device.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -8,6 +10,10 @@ namespace mkh {
 
 static void check(int rc) {
     if (rc != 0) throw Error(std::string("GPU matching engine: ") + mk_last_error());
+}
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 static uint64_t env_u64(const char* name, uint64_t dflt) {
@@ -18,6 +24,7 @@ static uint64_t env_u64(const char* name, uint64_t dflt) {
 
 Scanner::Scanner(const std::vector<std::string>& patterns, bool case_insensitive, mk_encoding enc, mk_mode mode, RecordCallback cb)
     : enc_(enc), mode_(mode), cb_(std::move(cb)) {
+    t_start_ = now_s();
     std::string blob;
     std::vector<uint32_t> off{0};
     for (auto& p : patterns) {
@@ -31,7 +38,8 @@ Scanner::Scanner(const std::vector<std::string>& patterns, bool case_insensitive
     max_bytes_ = env_u64("MERKURIO_BATCH_MB", 64) << 20;
     if (uint64_t b = env_u64("MERKURIO_BATCH_BYTES", 0)) max_bytes_ = b;  // tests: tiny batches, many pieces
     if (max_bytes_ < (uint64_t)4 * max_pattern_len_ + 16384) max_bytes_ = (uint64_t)4 * max_pattern_len_ + 16384;
-    max_records_ = (uint32_t)std::min<uint64_t>(max_bytes_ / 16 + 1, 1u << 26);
+    // records per batch: sized for reads of >= 32 bases (shorter ones just close their batch early)
+    max_records_ = (uint32_t)std::min<uint64_t>(max_bytes_ / 32 + 1024, 1u << 26);
     n_slots_ = (uint32_t)env_u64("MERKURIO_SLOTS", 3);
     if (n_slots_ < 1) n_slots_ = 1;
     for (int g = 0; g < std::max(n_gpus, 1); ++g) {
@@ -46,21 +54,45 @@ Scanner::Scanner(const std::vector<std::string>& patterns, bool case_insensitive
         check(mk_engine_create(&mp, &cfg, &e));
         engines_.push_back(e);
     }
+    t_setup_ = now_s() - t_start_;
 }
 
 Scanner::~Scanner() {
     for (mk_engine* e : engines_) mk_engine_destroy(e);
+    if (std::getenv("MERKURIO_TIMING"))
+        std::fprintf(stderr, "[merkurio] engine setup %.3f s, %llu batches, %llu records, %.3f Gbases, waited %.3f s for the GPU, "
+                     "device time %.3f s, delivering results %.3f s, total %.3f s\n", t_setup_, (unsigned long long)batch_seq_, (unsigned long long)n_records_,
+                     (double)n_bases_ / 1e9, t_wait_, (double)device_ns_ / 1e9, t_consume_ - t_wait_, now_s() - t_start_);
 }
 
 void Scanner::open_batch() {
     // batch i goes to engine i % G, slot (i / G) % S; at most G*S batches are in flight
     const uint64_t G = engines_.size();
     while (inflight_.size() >= G * n_slots_) consume_oldest();
-    open_.reset(new Batch);
+    // batches are recycled so that their vectors keep their (already touched) storage
+    if (!spare_.empty()) {
+        open_ = std::move(spare_.back());
+        spare_.pop_back();
+        open_->n_records = 0;
+        open_->n_units = open_->n_bytes = 0;
+        open_->pieces.clear();
+        open_->metas.clear();
+        open_->owners.clear();
+    } else {
+        open_.reset(new Batch);
+    }
     open_->engine = (int)(batch_seq_ % G);
     open_->slot = (uint32_t)((batch_seq_ / G) % n_slots_);
     ++batch_seq_;
-    check(mk_slot_buffers(engines_[(size_t)open_->engine], open_->slot, &open_->seq, &open_->off, &open_->lens));
+    check(mk_slot_buffers(engines_[(size_t)open_->engine], open_->slot, &open_->seq, &open_->off,
+                          enc_ == MK_ENC_BAM4 ? &open_->lens : nullptr));
+    for (auto& h : held_)
+        if (h) open_->owners.push_back(h);
+}
+
+void Scanner::hold(int file, std::shared_ptr<const void> owner) {
+    held_[file & 1] = owner;
+    if (open_ && owner) open_->owners.push_back(std::move(owner));
 }
 
 void Scanner::submit_open() {
@@ -147,11 +179,17 @@ void Scanner::deliver_piece(Batch& b, uint32_t r, bool flag, const mk_hit* hits,
 }
 
 void Scanner::consume_oldest() {
+    const double t_in = now_s();
     std::unique_ptr<Batch> bp = std::move(inflight_.front());
     inflight_.pop_front();
     Batch& b = *bp;
     mk_result res{};
+    double t0 = now_s();
     check(mk_scan_wait(engines_[(size_t)b.engine], b.slot, &res));
+    t_wait_ += now_s() - t0;
+    device_ns_ += res.device_ns;
+    n_records_ += b.n_records;
+    n_bases_ += res.bases_scanned;
     size_t hi = 0, meta_i = 0;
     for (uint32_t r = 0; r < b.n_records; ++r) {
         size_t h0 = hi;
@@ -170,6 +208,11 @@ void Scanner::consume_oldest() {
             cb_(cur_meta_, cur_found_, cur_hits_);
         }
     }
+    grace_ = std::move(b.owners);
+    b.owners.clear();
+    b.metas.clear();
+    spare_.push_back(std::move(bp));
+    t_consume_ += now_s() - t_in;
 }
 
 void Scanner::finish() {

@@ -20,6 +20,10 @@ struct RecMeta {
     uint32_t len = 0;     // bases
     uint8_t file = 0;     // 0 / 1: mate
     bool fastq = false, crlf = false;
+    // chunked ingest (fastq_stream.h): the record is span `idx` of `chunk` and a, b, c stay empty; the
+    // chunk is kept alive through Scanner::hold until the record has been delivered
+    const void* chunk = nullptr;
+    uint32_t idx = 0;
 };
 
 struct RecHit {
@@ -41,6 +45,10 @@ public:
     void add_record(const char* seq, size_t len, RecMeta&& meta);
     // BAM 4-bit sequence of one record
     void add_record_packed(const uint8_t* packed, uint32_t l_seq, RecMeta&& meta);
+    // Keep `owner` (the buffer the next records' metadata points into) alive until every record added
+    // from now on has been delivered, plus one more batch (a pair's first mate may be delivered in the
+    // batch before its second mate). One owner per input file (`file` = 0 / 1); a new call replaces it.
+    void hold(int file, std::shared_ptr<const void> owner);
     void finish();  // flush the open batch and deliver every outstanding record
     int n_gpus() const { return (int)engines_.size(); }
 
@@ -60,6 +68,7 @@ private:
         uint64_t n_units = 0, n_bytes = 0;
         std::vector<Piece> pieces;
         std::vector<RecMeta> metas;  // one per piece with first == true
+        std::vector<std::shared_ptr<const void>> owners;
     };
     void open_batch();
     void submit_open();
@@ -74,10 +83,15 @@ private:
     uint64_t max_bytes_ = 0, batch_seq_ = 0;
     std::unique_ptr<Batch> open_;
     std::deque<std::unique_ptr<Batch>> inflight_;
+    std::vector<std::unique_ptr<Batch>> spare_;
     // record being assembled from its pieces
     RecMeta cur_meta_;
     bool cur_found_ = false;
     std::vector<RecHit> cur_hits_;
+    double t_start_ = 0, t_setup_ = 0, t_wait_ = 0, t_consume_ = 0;  // MERKURIO_TIMING=1 prints them
+    uint64_t device_ns_ = 0, n_records_ = 0, n_bases_ = 0;
+    std::shared_ptr<const void> held_[2];
+    std::vector<std::shared_ptr<const void>> grace_;  // owners of the batch consumed last
 };
 
 }  // namespace mkh

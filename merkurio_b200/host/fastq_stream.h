@@ -1,0 +1,69 @@
+// Chunked FASTQ ingest for the extract feeder: one thread per input file reads (or inflates) the
+// file into large buffers and indexes the 4-line records in place, so the thread that drives the GPU
+// only copies the sequence bytes into the pinned batch and keeps (chunk, record) references for the
+// writer — no per-record allocation. Replaces needletail's parse_fastx_file + per-record borrow in
+// src/cmd_extract.rs:281,321-327,412,463-475 for FASTQ input; FASTA and anything unusual stays on
+// FastxReader (io.h). Results are identical to FastxReader's by construction of the span rules
+// below (tests/test_gpu_cli.py compares both paths).
+#pragma once
+#include <condition_variable>
+#include <cstdint>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "common.h"
+
+namespace mkh {
+
+// One FASTQ record inside Chunk::data.
+struct RecSpan {
+    uint32_t start;    // the '@'
+    uint32_t id_len;   // header line without '@' and without its line break
+    uint32_t seq_off, seq_len;
+    uint32_t qual_off;  // qual_len == seq_len (checked)
+    uint32_t end;      // one past the record's last byte (its final '\n' if there is one)
+    uint8_t crlf;      // header line ended in "\r\n": the writer then ends every line with "\r\n"
+    uint8_t plain;     // bytes [start, end) are exactly "@id\nseq\n+\nqual\n": the writer copies them
+};
+
+struct Chunk {
+    std::vector<char> data;
+    size_t len = 0;
+    std::vector<RecSpan> recs;
+    bool failed = false;  // malformed input right after recs.back(): the consumer raises the parse error there
+    const char* id(const RecSpan& r) const { return data.data() + r.start + 1; }
+    const char* seq(const RecSpan& r) const { return data.data() + r.seq_off; }
+    const char* qual(const RecSpan& r) const { return data.data() + r.qual_off; }
+};
+
+// True if the file's first byte (after gzip decoding) is '@', i.e. needletail would parse it as FASTQ.
+bool looks_like_fastq(const std::string& path);
+
+class FastqChunkReader {
+public:
+    // chunk_bytes: size of the read buffers (a record larger than that grows its chunk)
+    explicit FastqChunkReader(const std::string& path, size_t chunk_bytes = 16u << 20, size_t depth = 4);
+    ~FastqChunkReader();
+    FastqChunkReader(const FastqChunkReader&) = delete;
+    // Next chunk in file order; nullptr after the last one. I/O errors are rethrown here.
+    std::shared_ptr<Chunk> next();
+
+private:
+    struct Shared;  // free list of chunk buffers; outlives the reader while chunks are still referenced
+    void run();
+    std::string path_;
+    size_t chunk_bytes_, depth_;
+    std::shared_ptr<Shared> pool_;
+    std::thread thread_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::shared_ptr<Chunk>> ready_;
+    bool done_ = false, stop_ = false;
+    std::string io_error_;
+};
+
+}  // namespace mkh

@@ -9,7 +9,9 @@
 #include <vector>
 
 #include "commands.h"
+#include "fastq_stream.h"
 #include "helpers.h"
+#include "io.h"
 
 using namespace mkh;
 
@@ -254,6 +256,65 @@ int run(int argc, char** argv) {
         if (!ac) validate_bndmq(pats, q);
         for (auto& s : pats) std::printf("%s\n", s.c_str());
         std::printf("#search_algorithm\t%s\n", ac ? "Aho-Corasick" : "BNDMq");
+        return 0;
+    }
+    if (cmd == "records") {
+        // diagnostic (not in the reference): merkurio records <file> <generic|chunked> [chunk_bytes]
+        // dumps what the record readers hand to the matcher and to the writer — the ingest half of the
+        // extract path, testable without a GPU. One block per record: id, sequence, then the bytes the
+        // FASTA/FASTQ writer would emit; a parse error ends the dump with "#error".
+        if (argc < 4) { std::fputs("usage: merkurio records <file> <generic|chunked> [chunk_bytes]\n", stderr); return 2; }
+        const std::string path = argv[2], how = argv[3];
+        std::string out;
+        auto dump = [&](const std::string& id, const std::string& seq, const FastxRecord& r) {
+            out += "#id\t" + id + "\n#seq\t" + seq + "\n";
+            r.write(&out);
+        };
+        if (how == "count" || how == "count-generic") {  // reader throughput: records and bases only
+            uint64_t n = 0, bases = 0;
+            if (how == "count") {
+                FastqChunkReader cr(path, argc > 4 ? (size_t)std::strtoull(argv[4], nullptr, 10) : (size_t)16 << 20);
+                while (std::shared_ptr<Chunk> ch = cr.next())
+                    for (const RecSpan& sp : ch->recs) { ++n; bases += sp.seq_len; }
+            } else {
+                FastxReader rd(path);
+                FastxRecord r;
+                while (rd.next(&r)) { ++n; bases += r.seq.size(); }
+            }
+            std::printf("%llu\t%llu\n", (unsigned long long)n, (unsigned long long)bases);
+            return 0;
+        }
+        if (how == "generic") {
+            FastxReader rd(path);
+            FastxRecord r;
+            try {
+                while (rd.next(&r)) dump(r.id, r.seq, r);
+            } catch (const Error& e) {
+                out += std::string("#error\t") + e.what() + "\n";
+            }
+        } else {
+            if (!looks_like_fastq(path)) { std::fputs("#not-fastq\n", stdout); return 0; }
+            FastqChunkReader cr(path, argc > 4 ? (size_t)std::strtoull(argv[4], nullptr, 10) : (size_t)16 << 20);
+            while (std::shared_ptr<Chunk> ch = cr.next()) {
+                for (const RecSpan& sp : ch->recs) {
+                    FastxRecord r;
+                    r.id.assign(ch->id(sp), sp.id_len);
+                    r.seq.assign(ch->seq(sp), sp.seq_len);
+                    r.raw = r.seq;
+                    r.qual.assign(ch->qual(sp), sp.seq_len);
+                    r.fastq = true;
+                    r.crlf = sp.crlf;
+                    if (sp.plain) {
+                        out += "#id\t" + r.id + "\n#seq\t" + r.seq + "\n";
+                        out.append(ch->data.data() + sp.start, sp.end - sp.start);
+                    } else {
+                        dump(r.id, r.seq, r);
+                    }
+                }
+                if (ch->failed) out += "#error\tError during FASTQ/A record parsing.\n";
+            }
+        }
+        std::fwrite(out.data(), 1, out.size(), stdout);
         return 0;
     }
     if (cmd == "tag") {

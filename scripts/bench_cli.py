@@ -1,0 +1,183 @@
+"""File-to-file throughput of the host binary (merkurio_b200/lib/merkurio) on synthetic files of the
+BASELINE shapes: wall-clock records/s of `merkurio extract` / `merkurio tag`, the numbers next to
+bench.py's device-timed and C-ABI end-to-end figures.
+
+    python scripts/bench_cli.py --config cfg2 --reads 4000000 [--gz] [--log]
+
+cfg2: single-end FASTQ, 1000 31-mers + reverse complements, `extract -f q.txt -r -o out.fastq`
+cfg3: paired FASTQ, 10000 canonical 31-mers, `extract -2 ... -c -j log.json -o out.fastq`
+cfg4: SAM or BAM (--bam), 10000 31-mers, `tag -f q.txt -m -o out.sam|bam`
+The flag bitmap of the run is checked against the oracle on the first --check-reads reads (the set
+of extracted read names must equal the oracle's)."""
+import argparse
+import gzip
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from merkurio_b200.synth import Synth
+from oracle import refmodel as rm
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", choices=["cfg2", "cfg3", "cfg4"], default="cfg2")
+ap.add_argument("--reads", type=int, default=4_000_000)
+ap.add_argument("--gz", action="store_true", help="gzip the FASTQ input")
+ap.add_argument("--bam", action="store_true", help="cfg4: BAM input and output instead of SAM")
+ap.add_argument("--log", action="store_true", help="cfg2: also write the text log (-l)")
+ap.add_argument("--check-reads", type=int, default=200_000)
+ap.add_argument("--gpus", type=int, default=1)
+ap.add_argument("--dir", default=None)
+ap.add_argument("--out", default=None)
+args = ap.parse_args()
+EXE = ROOT / "merkurio_b200" / "lib" / "merkurio"
+L = 150
+
+
+def fastq_bytes(seq: np.ndarray, n: int, r0: int, mate: str = "") -> bytes:
+    """n reads of L bases -> FASTQ text, vectorised (names read<r>, constant quality)."""
+    names = np.char.add(np.char.add("@read", np.arange(r0, r0 + n).astype(str)), mate).astype("S")
+    w = names.dtype.itemsize
+    nm = np.frombuffer(names.tobytes(), dtype=np.uint8).reshape(n, w)
+    rec = np.empty((n, w + 1 + L + 3 + L + 1), dtype=np.uint8)
+    rec[:, :w] = nm
+    rec[:, w] = 10
+    rec[:, w + 1:w + 1 + L] = seq.reshape(n, L)
+    rec[:, w + 1 + L] = 10
+    rec[:, w + 2 + L] = ord("+")
+    rec[:, w + 3 + L] = 10
+    rec[:, w + 4 + L:w + 4 + 2 * L] = ord("I")
+    rec[:, -1] = 10
+    flat = rec.reshape(-1)
+    return flat[flat != 0].tobytes()  # names are NUL padded to a common width
+
+
+def revcomp_rows(a: np.ndarray) -> np.ndarray:
+    t = np.arange(256, dtype=np.uint8)
+    for x, y in zip(b"ACGTN", b"TGCAN"):
+        t[x] = y
+    return t[a[:, ::-1]]
+
+
+tmp = Path(args.dir or tempfile.mkdtemp(prefix="mk_cli_"))
+tmp.mkdir(parents=True, exist_ok=True)
+n = args.reads
+nq = 1000 if args.config == "cfg2" else 10000
+seed = {"cfg2": 0x5EED0002, "cfg3": 0x5EED0003, "cfg4": 0x5EED0004}[args.config]
+syn = Synth(seed, n, L, 31, nq)
+queries = syn.query_list()
+(tmp / "q.txt").write_bytes(b"\n".join(queries) + b"\n")
+t_gen = time.perf_counter()
+CH = 500_000
+inputs = []
+if args.config in ("cfg2", "cfg3"):
+    ext = ".fastq.gz" if args.gz else ".fastq"
+    opener = (lambda p: gzip.open(p, "wb", compresslevel=1)) if args.gz else (lambda p: open(p, "wb"))
+    p1 = tmp / ("reads_1" + ext)
+    files = [opener(p1)]
+    inputs = [p1]
+    if args.config == "cfg3":
+        p2 = tmp / ("reads_2" + ext)
+        files.append(opener(p2))
+        inputs.append(p2)
+    for r0 in range(0, n, CH):
+        r1 = min(n, r0 + CH)
+        seq, _ = syn.host_reads(r0, r1, 0)
+        files[0].write(fastq_bytes(seq, r1 - r0, r0, "/1" if args.config == "cfg3" else ""))
+        if args.config == "cfg3":
+            # mate 2: reverse complement of the read shifted by 37 bases inside a 2L window of the same data
+            m2 = revcomp_rows(np.roll(seq.reshape(r1 - r0, L), 37, axis=1))
+            files[1].write(fastq_bytes(m2.reshape(-1), r1 - r0, r0, "/2"))
+    for f in files:
+        f.close()
+else:
+    p1 = tmp / "reads.sam"
+    with open(p1, "wb") as f:
+        f.write(b"@HD\tVN:1.6\tSO:unsorted\n@SQ\tSN:chr1\tLN:248956422\n")
+        for r0 in range(0, n, CH):
+            r1 = min(n, r0 + CH)
+            seq, _ = syn.host_reads(r0, r1, 0)
+            rows = seq.reshape(r1 - r0, L)
+            out = bytearray()
+            for i in range(r1 - r0):
+                out += b"read%d\t0\tchr1\t%d\t60\t150M\t*\t0\t0\t" % (r0 + i, 1 + ((r0 + i) * 977) % 200_000_000)
+                out += rows[i].tobytes()
+                out += b"\t*\n"
+            f.write(out)
+    inputs = [p1]
+    if args.bam:
+        # SAM -> BAM with the host binary itself (a query that cannot occur, keep every record)
+        pb = tmp / "reads.bam"
+        subprocess.run([str(EXE), "tag", "-i", str(p1), "-s", "NNNNNNNNNNNNNNNNNNNNNNNNNNNNNNN", "-S", "-o", str(pb)], check=True,
+                       stdout=subprocess.DEVNULL)
+        inputs = [pb]
+t_gen = time.perf_counter() - t_gen
+in_bytes = sum(p.stat().st_size for p in inputs)
+
+env = dict(os.environ, MERKURIO_GPUS=str(args.gpus), MERKURIO_TIMING="1")
+if args.config == "cfg2":
+    out = tmp / "out.fastq"
+    cmd = [str(EXE), "extract", "-i", str(inputs[0]), "-f", str(tmp / "q.txt"), "-r", "-o", str(out)]
+    if args.log:
+        cmd += ["-l", str(tmp / "out.log")]
+elif args.config == "cfg3":
+    out = tmp / "out_1.fastq"
+    cmd = [str(EXE), "extract", "-i", str(inputs[0]), "-2", str(inputs[1]), "-f", str(tmp / "q.txt"), "-c", "-j", str(tmp / "log.json"),
+           "-o", str(tmp / "out.fastq")]
+else:
+    out = tmp / ("out.bam" if args.bam else "out.sam")
+    cmd = [str(EXE), "tag", "-i", str(inputs[0]), "-f", str(tmp / "q.txt"), "-m", "-o", str(out)]
+runs = []
+for _ in range(3):
+    t0 = time.perf_counter()
+    subprocess.run(cmd, check=True, env=env, stdout=subprocess.DEVNULL)
+    runs.append(time.perf_counter() - t0)
+    print(f"run {len(runs)}: {runs[-1]:.3f} s", file=sys.stderr, flush=True)
+wall = min(runs)
+
+# parity of the extracted set with the oracle on the first reads
+nc = min(args.check_reads, n)
+seq, off = syn.host_reads(0, nc, 0)
+from merkurio_b200 import patterns as pt
+if args.config == "cfg2":
+    pats = pt.parse_pattern_list(queries, reverse_complement_=True)
+elif args.config == "cfg3":
+    pats = pt.parse_pattern_list(queries, canonical_=True)
+else:
+    pats = pt.parse_pattern_list(queries)
+ac = rm.AhoCorasick(pats)
+rec, _, _ = ac.batch_hits(seq, off)
+want = set(np.unique(rec).tolist())
+if args.config == "cfg3":
+    m2 = revcomp_rows(np.roll(seq.reshape(nc, L), 37, axis=1)).reshape(-1).copy()
+    rec2, _, _ = ac.batch_hits(m2, off)
+    want |= set(np.unique(rec2).tolist())
+got = set()
+with open(out, "rb") as f:
+    for line in f:
+        if args.config == "cfg4":
+            if line.startswith(b"read"):
+                r = int(line[4:line.index(b"\t")])
+                if r < nc:
+                    got.add(r)
+        elif line.startswith(b"@read"):
+            r = int(line[5:].split(b"/")[0])
+            if r < nc:
+                got.add(r)
+assert got == want, (len(got), len(want), sorted(got ^ want)[:10])
+
+mult = 2 if args.config == "cfg3" else 1
+res = {"config": args.config, "reads": n * mult, "input_bytes": in_bytes, "gz": args.gz, "gpus": args.gpus, "log": args.log,
+       "wall_s": wall, "runs_s": runs, "records_per_s": n * mult / wall, "gbases_per_s": n * mult * L / wall / 1e9,
+       "input_gb_per_s": in_bytes / wall / 1e9, "extracted_checked": len(want), "host_cores": os.cpu_count(),
+       "generate_s": t_gen, "cmd": " ".join(cmd[1:])}
+print(json.dumps(res))
+if args.out:
+    Path(args.out).write_text(json.dumps(res, indent=1) + "\n")

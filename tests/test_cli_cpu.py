@@ -157,3 +157,64 @@ def test_no_cpu_fallback_in_the_cli(exe, ref_tree, tmp_path):
     fa = ref_tree / "tests" / "fixtures" / "input" / "simple.fasta"
     r = run(exe, "extract", "-i", fa, "-s", "ACG", "-o", tmp_path / "o")
     assert r.returncode == 1 and "no CPU path" in r.stderr
+
+
+# ------------------------------------------------------------------------------------------------
+# FASTQ ingest: the chunked reader (one thread per file, records indexed in place) must hand the
+# matcher and the writer exactly what the line-by-line reader does, whatever the chunk size.
+FASTQ_CASES = {
+    "plain": b"@r1 desc\nACGT\n+\nIIII\n@r2\nGG\n+\nII\n",
+    "no_final_newline": b"@r1\nACGT\n+\nIIII\n@r2\nGGA\n+\nIII",
+    "plus_repeats_id": b"@r1\nACGT\n+r1\nIIII\n@r2\nGG\n+\nII\n",
+    "crlf": b"@r1\r\nACGT\r\n+\r\nIIII\r\n@r2\r\nGG\r\n+\r\nII\r\n",
+    "mixed_crlf": b"@r1\nACGT\r\n+\nIIII\n@r2\r\nGG\n+\nII\n",
+    "blank_lines_between": b"@r1\nACGT\n+\nIIII\n\n\r\n@r2\nGG\n+\nII\n\n\n",
+    "empty_sequence": b"@r1\n\n+\n\n@r2\nGG\n+\nII\n",
+    "quality_starts_with_at": b"@r1\nACGT\n+\n@III\n@r2\nGG\n+\n@@\n",
+    "truncated": b"@r1\nACGT\n+\nIIII\n@r2\nGG\n+\n",
+    "length_mismatch": b"@r1\nACGT\n+\nIIII\n@r2\nGGA\n+\nII\n@r3\nA\n+\nI\n",
+    "bad_header": b"@r1\nACGT\n+\nIIII\nr2\nGG\n+\nII\n",
+    "missing_plus": b"@r1\nACGT\n-\nIIII\n",
+    "only_header": b"@r1\n",
+    "long_record": b"@long\n" + b"ACGTTGCA" * 5000 + b"\n+\n" + b"I" * 40000 + b"\n@r2\nGG\n+\nII\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(FASTQ_CASES))
+@pytest.mark.parametrize("gz", [False, True])
+def test_chunked_fastq_reader_equals_line_reader(exe, tmp_path, name, gz):
+    import gzip
+    data = FASTQ_CASES[name]
+    p = tmp_path / ("x.fastq.gz" if gz else "x.fastq")
+    p.write_bytes(gzip.compress(data) if gz else data)
+    want = subprocess.run([exe, "records", str(p), "generic"], capture_output=True)
+    assert want.returncode == 0, want.stderr
+    assert want.stdout.startswith(b"#id\t") or name in ("only_header", "missing_plus")
+    for chunk in (4096, 5000, 1 << 20):
+        got = subprocess.run([exe, "records", str(p), "chunked", str(chunk)], capture_output=True)
+        assert got.returncode == 0, got.stderr
+        assert got.stdout == want.stdout, (name, chunk)
+
+
+def test_chunked_fastq_reader_many_records(exe, tmp_path):
+    import numpy as np
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(20000):
+        n = int(rng.integers(0, 300))
+        s = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=n).tobytes())
+        recs.append(b"@read%d some text\n%s\n+\n%s\n" % (i, s, b"F" * n))
+    p = tmp_path / "many.fastq"
+    p.write_bytes(b"".join(recs))
+    want = subprocess.run([exe, "records", str(p), "generic"], capture_output=True).stdout
+    assert want.count(b"#id\t") == 20000
+    for chunk in (4096, 70001, 1 << 22):
+        got = subprocess.run([exe, "records", str(p), "chunked", str(chunk)], capture_output=True).stdout
+        assert got == want
+
+
+def test_fasta_is_left_to_the_line_reader(exe, tmp_path):
+    p = tmp_path / "x.fasta"
+    p.write_bytes(b">s1\nACGT\nAC\n>s2\nGG\n")
+    got = subprocess.run([exe, "records", str(p), "chunked"], capture_output=True)
+    assert got.stdout == b"#not-fastq\n"
