@@ -6,6 +6,7 @@
 
 #include "commands.h"
 #include "device.h"
+#include "fastq_pipeline.h"
 #include "fastq_stream.h"
 #include "helpers.h"
 #include "io.h"
@@ -160,6 +161,9 @@ void extract_records(CmdExtract args) {
     auto by_pattern_then_start = [](const RecHit& x, const RecHit& y) { return x.pattern != y.pattern ? x.pattern < y.pattern : x.start < y.start; };
 
     // ---- per-record consumer (src/cmd_extract.rs:321-406) and per-pair consumer (:463-607) --------
+    // the FASTQ pipeline adds the totals of a whole batch at once and calls the consumers below only
+    // for the records that can produce output
+    bool bulk_totals = false;
     RecMeta mate1;
     bool mate1_found = false;
     std::vector<RecHit> mate1_hits;
@@ -167,8 +171,10 @@ void extract_records(CmdExtract args) {
     auto on_single = [&](RecMeta& m, bool found, std::vector<RecHit>& hits) {
         bool found_occ = false;
         if (logging_active) {
-            nb_records_tot += 1;
-            nb_bases += m.len;
+            if (!bulk_totals) {
+                nb_records_tot += 1;
+                nb_bases += m.len;
+            }
             if (args.aho_corasick) {
                 for (const RecHit& h : hits) {
                     emit(f1, m, h);
@@ -205,8 +211,10 @@ void extract_records(CmdExtract args) {
         RecMeta& m2 = m;
         bool found_occ = false;
         if (logging_active) {
-            nb_records_tot += 2;
-            nb_bases += mate1.len + m2.len;
+            if (!bulk_totals) {
+                nb_records_tot += 2;
+                nb_bases += mate1.len + m2.len;
+            }
             if (args.aho_corasick) {
                 for (const RecHit& h : mate1_hits) { emit(f1, mate1, h); pattern_hit_counts[h.pattern] += 1; nb_hits_tot[0] += 1; }
                 for (const RecHit& h : hits) { emit(f2, m2, h); pattern_hit_counts[h.pattern] += 1; nb_hits_tot[1] += 1; }
@@ -243,7 +251,19 @@ void extract_records(CmdExtract args) {
     {
         RecordCallback cb;
         if (paired) cb = on_paired; else cb = on_single;
-        Scanner scanner(pattern_list, args.case_insensitive, MK_ENC_ASCII, logging_active ? MK_MODE_ALL_HITS : MK_MODE_FLAG, cb);
+        const mk_mode mode = logging_active ? MK_MODE_ALL_HITS : MK_MODE_FLAG;
+        // 4-line FASTQ (plain or gzip) goes through the reader -> packer -> GPU pipeline (fastq_pipeline.h);
+        // this thread then only looks at the records the device flagged. The readers start first: the
+        // input is read and indexed while CUDA starts up.
+        const bool pipelined = !std::getenv("MERKURIO_NO_FASTQ_PIPELINE") && looks_like_fastq(args.in_fastx) &&
+                               (!paired || looks_like_fastq(*args.in_fastq_2));
+        std::unique_ptr<FastqChunkReader> chunks1, chunks2;
+        if (pipelined) {
+            chunks1 = FastqPipeline::open_reader(args.in_fastx);
+            if (paired) chunks2 = FastqPipeline::open_reader(*args.in_fastq_2);
+        }
+        EngineSet engines(pattern_list, args.case_insensitive, pipelined ? 16 : 64);
+        Scanner scanner(engines, MK_ENC_ASCII, mode, cb);
         const bool keep_text = !args.suppress_output;
         auto feed = [&](FastxRecord& rec, uint8_t file) {
             RecMeta m;
@@ -252,60 +272,55 @@ void extract_records(CmdExtract args) {
             m.file = file; m.fastq = rec.fastq; m.crlf = rec.crlf;
             scanner.add_record(rec.seq.data(), rec.seq.size(), std::move(m));
         };
-        FastxRecord r1, r2;
-        // 4-line FASTQ (plain or gzip) goes through the chunked reader: one thread per file reads and
-        // indexes the records, this thread only copies sequence bytes into the pinned batches
-        const bool chunked = !std::getenv("MERKURIO_NO_CHUNKED_FASTQ") && looks_like_fastq(args.in_fastx) &&
-                             (!paired || looks_like_fastq(*args.in_fastq_2));
-        const size_t chunk_bytes = std::getenv("MERKURIO_CHUNK_BYTES") ? (size_t)std::strtoull(std::getenv("MERKURIO_CHUNK_BYTES"), nullptr, 10)
-                                                                       : (size_t)16 << 20;
-        auto feed_span = [&](const std::shared_ptr<Chunk>& ch, size_t i, uint8_t file) {
-            const RecSpan& r = ch->recs[i];
-            RecMeta m;
-            m.chunk = ch.get();
-            m.idx = (uint32_t)i;
-            m.file = file; m.fastq = true; m.crlf = r.crlf;
-            scanner.add_record(ch->seq(r), r.seq_len, std::move(m));
-        };
-        const Error parse_error("Error during FASTQ/A record parsing.");
-        try {
-            if (chunked && !paired) {
-                reader.reset();
-                FastqChunkReader cr(args.in_fastx, chunk_bytes);
-                while (std::shared_ptr<Chunk> ch = cr.next()) {
-                    scanner.hold(0, ch);
-                    for (size_t i = 0; i < ch->recs.size(); ++i) feed_span(ch, i, 0);
-                    if (ch->failed) throw parse_error.with_context("Error during FASTQ/A record parsing.");
+        auto consume_batch = [&](const PackedBatch& b, const mk_result& res) {
+            const uint32_t F = paired ? 2 : 1;
+            const uint32_t n_units = b.n_records / F;  // records, or pairs
+            if (logging_active) {
+                nb_records_tot += b.n_records;
+                nb_bases += b.n_units;
+            }
+            size_t cursor[2] = {0, 0}, hi = 0;
+            std::vector<RecHit> hits;
+            auto deliver = [&](uint32_t u) {
+                for (uint32_t f = 0; f < F; ++f) {
+                    const uint32_t r = u * F + f;
+                    const BatchSeg& sg = b.locate((int)f, u, &cursor[f]);
+                    RecMeta m;
+                    m.chunk = sg.chunk.get();
+                    m.idx = sg.first + (u - sg.rec0);
+                    const RecSpan& sp = sg.chunk->recs[m.idx];
+                    m.file = (uint8_t)f; m.fastq = true; m.crlf = sp.crlf; m.len = sp.seq_len;
+                    hits.clear();
+                    while (hi < res.n_hits && res.hits[hi].record < r) ++hi;
+                    for (; hi < res.n_hits && res.hits[hi].record == r; ++hi)
+                        hits.push_back(RecHit{res.hits[hi].start, res.hits[hi].pattern, res.hits[hi].len});
+                    const bool found = (res.record_flags[r >> 6] >> (r & 63)) & 1;
+                    cb(m, found, hits);
                 }
-            } else if (chunked) {
+            };
+            if (args.invert_match) {
+                for (uint32_t u = 0; u < n_units; ++u) deliver(u);
+                return;
+            }
+            const size_t words = ((size_t)b.n_records + 63) / 64;
+            for (size_t w = 0; w < words; ++w) {
+                uint64_t x = res.record_flags[w];
+                if (paired) x = (x | (x >> 1)) & 0x5555555555555555ull;  // a pair is flagged through either mate
+                while (x) {
+                    const uint32_t r = (uint32_t)(w * 64 + (size_t)__builtin_ctzll(x));
+                    x &= x - 1;
+                    if (r < b.n_records) deliver(r / F);
+                }
+            }
+        };
+        FastxRecord r1, r2;
+        try {
+            if (pipelined) {
                 reader.reset();
                 reader2.reset();
-                FastqChunkReader cr1(args.in_fastx, chunk_bytes), cr2(*args.in_fastq_2, chunk_bytes);
-                const char* second_ctx = "Error during FASTQ record parsing of second file. Do the two input files contain the same number of records?";
-                std::shared_ptr<Chunk> c1 = cr1.next(), c2 = cr2.next();
-                size_t i1 = 0, i2 = 0;
-                scanner.hold(0, c1);
-                scanner.hold(1, c2);
-                // step to the next record of a file (c == nullptr at its end); a malformed record raises
-                // at the point where the reference would have tried to read it
-                auto advance = [&](FastqChunkReader& cr, std::shared_ptr<Chunk>& c, size_t& i, int file, const char* ctx) {
-                    while (c && i == c->recs.size()) {
-                        if (c->failed) throw ctx ? parse_error.with_context(ctx) : parse_error;
-                        c = cr.next();
-                        i = 0;
-                        scanner.hold(file, c);
-                    }
-                };
-                for (;;) {
-                    advance(cr1, c1, i1, 0, "Error during FASTQ record parsing of first file.");
-                    if (!c1) break;
-                    advance(cr2, c2, i2, 1, second_ctx);
-                    if (!c2) throw Error(second_ctx);
-                    feed_span(c1, i1++, 0);
-                    feed_span(c2, i2++, 1);
-                }
-                advance(cr2, c2, i2, 1, nullptr);
-                if (c2) throw Error("The two input files have a different number of records. Please provide valid paired-end read files.");
+                bulk_totals = true;
+                FastqPipeline pipe(engines, std::move(chunks1), std::move(chunks2), mode, consume_batch);
+                pipe.run();
             } else if (!paired) {
                 for (;;) {
                     bool more;

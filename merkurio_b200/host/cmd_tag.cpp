@@ -182,7 +182,8 @@ void tag_records(CmdTag args) {
     };
 
     try {
-        Scanner scanner(pattern_list, args.case_insensitive, MK_ENC_BAM4, logging_active ? MK_MODE_ALL_HITS : MK_MODE_PATTERN_SET, on_record);
+        EngineSet engines(pattern_list, args.case_insensitive);
+        Scanner scanner(engines, MK_ENC_BAM4, logging_active ? MK_MODE_ALL_HITS : MK_MODE_PATTERN_SET, on_record);
         AlnRecord rec;
         for (;;) {
             bool more;

@@ -22,48 +22,66 @@ static uint64_t env_u64(const char* name, uint64_t dflt) {
     return std::strtoull(s, nullptr, 10);
 }
 
-Scanner::Scanner(const std::vector<std::string>& patterns, bool case_insensitive, mk_encoding enc, mk_mode mode, RecordCallback cb)
-    : enc_(enc), mode_(mode), cb_(std::move(cb)) {
-    t_start_ = now_s();
+EngineSet::EngineSet(const std::vector<std::string>& patterns, bool case_insensitive, uint32_t default_batch_mb) {
+    t_start = now_s();
     std::string blob;
     std::vector<uint32_t> off{0};
     for (auto& p : patterns) {
         blob += p;
         off.push_back((uint32_t)blob.size());
-        max_pattern_len_ = std::max<uint32_t>(max_pattern_len_, (uint32_t)p.size());
+        max_pattern_len = std::max<uint32_t>(max_pattern_len, (uint32_t)p.size());
     }
     mk_patterns mp{reinterpret_cast<const uint8_t*>(blob.data()), off.data(), (uint32_t)patterns.size()};
-    // MERKURIO_GPUS: number of devices to spread batches over (default 1); MERKURIO_BATCH_MB: slot size
     int n_gpus = (int)env_u64("MERKURIO_GPUS", 1);
-    max_bytes_ = env_u64("MERKURIO_BATCH_MB", 64) << 20;
-    if (uint64_t b = env_u64("MERKURIO_BATCH_BYTES", 0)) max_bytes_ = b;  // tests: tiny batches, many pieces
-    if (max_bytes_ < (uint64_t)4 * max_pattern_len_ + 16384) max_bytes_ = (uint64_t)4 * max_pattern_len_ + 16384;
+    max_bytes = env_u64("MERKURIO_BATCH_MB", default_batch_mb) << 20;
+    if (uint64_t b = env_u64("MERKURIO_BATCH_BYTES", 0)) max_bytes = b;  // tests: tiny batches, many pieces
+    if (max_bytes < (uint64_t)4 * max_pattern_len + 16384) max_bytes = (uint64_t)4 * max_pattern_len + 16384;
     // records per batch: sized for reads of >= 32 bases (shorter ones just close their batch early)
-    max_records_ = (uint32_t)std::min<uint64_t>(max_bytes_ / 32 + 1024, 1u << 26);
-    n_slots_ = (uint32_t)env_u64("MERKURIO_SLOTS", 3);
-    if (n_slots_ < 1) n_slots_ = 1;
+    max_records = (uint32_t)std::min<uint64_t>(max_bytes / 32 + 1024, 1u << 26);
+    n_slots = (uint32_t)env_u64("MERKURIO_SLOTS", 3);
+    if (n_slots < 1) n_slots = 1;
     for (int g = 0; g < std::max(n_gpus, 1); ++g) {
         mk_config cfg{};
         cfg.device = g;
         cfg.case_insensitive = case_insensitive ? 1 : 0;
-        cfg.n_slots = n_slots_;
-        cfg.max_batch_records = max_records_;
-        cfg.max_batch_bytes = max_bytes_;
+        cfg.n_slots = n_slots;
+        cfg.max_batch_records = max_records;
+        cfg.max_batch_bytes = max_bytes;
         cfg.hit_capacity = 0;
         mk_engine* e = nullptr;
         check(mk_engine_create(&mp, &cfg, &e));
-        engines_.push_back(e);
+        engines.push_back(e);
     }
-    t_setup_ = now_s() - t_start_;
+    t_setup = now_s() - t_start;
 }
 
-Scanner::~Scanner() {
-    for (mk_engine* e : engines_) mk_engine_destroy(e);
+EngineSet::~EngineSet() {
+    for (mk_engine* e : engines) mk_engine_destroy(e);
     if (std::getenv("MERKURIO_TIMING"))
         std::fprintf(stderr, "[merkurio] engine setup %.3f s, %llu batches, %llu records, %.3f Gbases, waited %.3f s for the GPU, "
-                     "device time %.3f s, delivering results %.3f s, total %.3f s\n", t_setup_, (unsigned long long)batch_seq_, (unsigned long long)n_records_,
-                     (double)n_bases_ / 1e9, t_wait_, (double)device_ns_ / 1e9, t_consume_ - t_wait_, now_s() - t_start_);
+                     "device time %.3f s, delivering results %.3f s, total %.3f s\n", t_setup, (unsigned long long)n_batches,
+                     (unsigned long long)n_records, (double)n_bases / 1e9, t_wait, (double)device_ns / 1e9, t_deliver, now_s() - t_start);
 }
+
+void EngineSet::wait(int engine, uint32_t slot, mk_result* out) {
+    double t0 = now_s();
+    check(mk_scan_wait(engines[(size_t)engine], slot, out));
+    t_wait += now_s() - t0;
+    device_ns += out->device_ns;
+    n_records += out->n_records;
+    n_bases += out->bases_scanned;
+    n_batches += 1;
+}
+
+Scanner::Scanner(EngineSet& engines, mk_encoding enc, mk_mode mode, RecordCallback cb)
+    : es_(engines), engines_(engines.engines), enc_(enc), mode_(mode), cb_(std::move(cb)) {
+    n_slots_ = es_.n_slots;
+    max_records_ = es_.max_records;
+    max_pattern_len_ = es_.max_pattern_len;
+    max_bytes_ = es_.max_bytes;
+}
+
+Scanner::~Scanner() {}
 
 void Scanner::open_batch() {
     // batch i goes to engine i % G, slot (i / G) % S; at most G*S batches are in flight
@@ -77,7 +95,6 @@ void Scanner::open_batch() {
         open_->n_units = open_->n_bytes = 0;
         open_->pieces.clear();
         open_->metas.clear();
-        open_->owners.clear();
     } else {
         open_.reset(new Batch);
     }
@@ -86,13 +103,6 @@ void Scanner::open_batch() {
     ++batch_seq_;
     check(mk_slot_buffers(engines_[(size_t)open_->engine], open_->slot, &open_->seq, &open_->off,
                           enc_ == MK_ENC_BAM4 ? &open_->lens : nullptr));
-    for (auto& h : held_)
-        if (h) open_->owners.push_back(h);
-}
-
-void Scanner::hold(int file, std::shared_ptr<const void> owner) {
-    held_[file & 1] = owner;
-    if (open_ && owner) open_->owners.push_back(std::move(owner));
 }
 
 void Scanner::submit_open() {
@@ -179,17 +189,12 @@ void Scanner::deliver_piece(Batch& b, uint32_t r, bool flag, const mk_hit* hits,
 }
 
 void Scanner::consume_oldest() {
-    const double t_in = now_s();
     std::unique_ptr<Batch> bp = std::move(inflight_.front());
     inflight_.pop_front();
     Batch& b = *bp;
     mk_result res{};
-    double t0 = now_s();
-    check(mk_scan_wait(engines_[(size_t)b.engine], b.slot, &res));
-    t_wait_ += now_s() - t0;
-    device_ns_ += res.device_ns;
-    n_records_ += b.n_records;
-    n_bases_ += res.bases_scanned;
+    es_.wait(b.engine, b.slot, &res);
+    const double t_in = now_s();
     size_t hi = 0, meta_i = 0;
     for (uint32_t r = 0; r < b.n_records; ++r) {
         size_t h0 = hi;
@@ -208,11 +213,9 @@ void Scanner::consume_oldest() {
             cb_(cur_meta_, cur_found_, cur_hits_);
         }
     }
-    grace_ = std::move(b.owners);
-    b.owners.clear();
     b.metas.clear();
     spare_.push_back(std::move(bp));
-    t_consume_ += now_s() - t_in;
+    es_.t_deliver += now_s() - t_in;
 }
 
 void Scanner::finish() {

@@ -20,8 +20,8 @@ struct RecMeta {
     uint32_t len = 0;     // bases
     uint8_t file = 0;     // 0 / 1: mate
     bool fastq = false, crlf = false;
-    // chunked ingest (fastq_stream.h): the record is span `idx` of `chunk` and a, b, c stay empty; the
-    // chunk is kept alive through Scanner::hold until the record has been delivered
+    // FASTQ pipeline (fastq_pipeline.h): the record is span `idx` of `chunk` and a, b, c stay empty; the
+    // batch being delivered keeps the chunk alive
     const void* chunk = nullptr;
     uint32_t idx = 0;
 };
@@ -37,20 +37,31 @@ struct RecHit {
 // (start = 0); in MK_MODE_FLAG it is empty and only `found` is meaningful.
 using RecordCallback = std::function<void(RecMeta& meta, bool found, std::vector<RecHit>& hits)>;
 
+// One engine per GPU (MERKURIO_GPUS, default 1), each with MERKURIO_SLOTS (default 3) pinned slots of
+// MERKURIO_BATCH_MB (default 64) MiB. Batch i of a run goes to engine i % G, slot (i / G) % S.
+// MERKURIO_TIMING=1 prints where the time went when the set is destroyed.
+struct EngineSet {
+    EngineSet(const std::vector<std::string>& patterns, bool case_insensitive, uint32_t default_batch_mb = 64);
+    ~EngineSet();
+    EngineSet(const EngineSet&) = delete;
+    void wait(int engine, uint32_t slot, mk_result* out);  // mk_scan_wait + accounting
+    std::vector<mk_engine*> engines;
+    uint32_t n_slots = 3, max_records = 0, max_pattern_len = 0;
+    uint64_t max_bytes = 0;
+    double t_start = 0, t_setup = 0, t_wait = 0, t_deliver = 0;
+    uint64_t device_ns = 0, n_records = 0, n_bases = 0, n_batches = 0;
+};
+
 class Scanner {
 public:
-    Scanner(const std::vector<std::string>& patterns, bool case_insensitive, mk_encoding enc, mk_mode mode, RecordCallback cb);
+    Scanner(EngineSet& engines, mk_encoding enc, mk_mode mode, RecordCallback cb);
     ~Scanner();
     // ASCII sequence of one record (any length: long records are cut into overlapping pieces)
     void add_record(const char* seq, size_t len, RecMeta&& meta);
     // BAM 4-bit sequence of one record
     void add_record_packed(const uint8_t* packed, uint32_t l_seq, RecMeta&& meta);
-    // Keep `owner` (the buffer the next records' metadata points into) alive until every record added
-    // from now on has been delivered, plus one more batch (a pair's first mate may be delivered in the
-    // batch before its second mate). One owner per input file (`file` = 0 / 1); a new call replaces it.
-    void hold(int file, std::shared_ptr<const void> owner);
     void finish();  // flush the open batch and deliver every outstanding record
-    int n_gpus() const { return (int)engines_.size(); }
+    int n_gpus() const { return (int)es_.engines.size(); }
 
 private:
     struct Piece {
@@ -68,14 +79,14 @@ private:
         uint64_t n_units = 0, n_bytes = 0;
         std::vector<Piece> pieces;
         std::vector<RecMeta> metas;  // one per piece with first == true
-        std::vector<std::shared_ptr<const void>> owners;
     };
     void open_batch();
     void submit_open();
     void consume_oldest();
     void deliver_piece(Batch& b, uint32_t r, bool flag, const mk_hit* hits, size_t n);
 
-    std::vector<mk_engine*> engines_;
+    EngineSet& es_;
+    std::vector<mk_engine*>& engines_;
     mk_encoding enc_;
     mk_mode mode_;
     RecordCallback cb_;
@@ -88,10 +99,6 @@ private:
     RecMeta cur_meta_;
     bool cur_found_ = false;
     std::vector<RecHit> cur_hits_;
-    double t_start_ = 0, t_setup_ = 0, t_wait_ = 0, t_consume_ = 0;  // MERKURIO_TIMING=1 prints them
-    uint64_t device_ns_ = 0, n_records_ = 0, n_bases_ = 0;
-    std::shared_ptr<const void> held_[2];
-    std::vector<std::shared_ptr<const void>> grace_;  // owners of the batch consumed last
 };
 
 }  // namespace mkh
