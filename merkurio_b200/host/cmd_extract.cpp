@@ -288,7 +288,7 @@ void extract_records(CmdExtract args) {
                     RecMeta m;
                     m.chunk = sg.chunk.get();
                     m.idx = sg.first + (u - sg.rec0);
-                    const RecSpan& sp = sg.chunk->recs[m.idx];
+                    const RecSpan& sp = static_cast<const Chunk*>(sg.chunk.get())->recs[m.idx];
                     m.file = (uint8_t)f; m.fastq = true; m.crlf = sp.crlf; m.len = sp.seq_len;
                     hits.clear();
                     while (hi < res.n_hits && res.hits[hi].record < r) ++hi;

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <memory>
 
+#include "aln_pipeline.h"
 #include "bamwriter.h"
 #include "commands.h"
 #include "device.h"
@@ -131,6 +132,8 @@ void tag_records(CmdTag args) {
     std::vector<uint64_t> pattern_hit_counts(pattern_list.size(), 0);
     auto by_pattern_then_start = [](const RecHit& x, const RecHit& y) { return x.pattern != y.pattern ? x.pattern < y.pattern : x.start < y.start; };
 
+    // the SAM/BAM pipeline adds the totals of a whole batch at once
+    bool bulk_totals = false;
     // process_record, src/cmd_tag.rs:367-500
     auto on_record = [&](RecMeta& m, bool /*found*/, std::vector<RecHit>& hits) {
         std::vector<std::string> kmers_found;
@@ -149,8 +152,10 @@ void tag_records(CmdTag args) {
                     pattern_hit_counts[h.pattern] += 1;
                 }
             }
-            nb_records_tot += 1;
-            nb_bases += m.len;
+            if (!bulk_totals) {
+                nb_records_tot += 1;
+                nb_bases += m.len;
+            }
             if (!kmers_found.empty()) nb_records_hit += 1;
         } else {
             for (const RecHit& h : hits) kmers_found.push_back(pattern_list[h.pattern]);
@@ -182,14 +187,77 @@ void tag_records(CmdTag args) {
     };
 
     try {
+        const mk_mode mode = logging_active ? MK_MODE_ALL_HITS : MK_MODE_PATTERN_SET;
+        const char* kind_name = in_ext == "bam" ? "BAM" : "SAM";
+        if (!std::getenv("MERKURIO_NO_ALN_PIPELINE")) {
+            // reader -> packer -> GPU pipeline (aln_pipeline.h); the reader starts before the engines so that
+            // reading and indexing the input overlaps CUDA start-up
+            const size_t chunk_bytes = std::getenv("MERKURIO_CHUNK_BYTES") ? (size_t)std::strtoull(std::getenv("MERKURIO_CHUNK_BYTES"), nullptr, 10)
+                                                                           : (size_t)8 << 20;
+            std::unique_ptr<AlnChunkReader> chunks(new AlnChunkReader(std::move(reader), chunk_bytes));
+            const std::vector<std::string> refs = chunks->refs();
+            EngineSet engines(pattern_list, args.case_insensitive, 16);
+            bulk_totals = true;
+            auto consume_batch = [&](const PackedBatch& b, const mk_result& res) {
+                if (logging_active) {
+                    nb_records_tot += b.n_records;
+                    nb_bases += b.total_bases;
+                }
+                size_t cursor = 0, hi = 0;
+                std::vector<RecHit> hits;
+                RecMeta m;
+                auto deliver = [&](uint32_t r) {
+                    const BatchSeg& sg = b.locate(0, r, &cursor);
+                    const AlnChunk* ch = static_cast<const AlnChunk*>(sg.chunk.get());
+                    const AlnSpan& sp = ch->recs[sg.first + (r - sg.rec0)];
+                    hits.clear();
+                    while (hi < res.n_hits && res.hits[hi].record < r) ++hi;
+                    for (; hi < res.n_hits && res.hits[hi].record == r; ++hi)
+                        hits.push_back(RecHit{res.hits[hi].start, res.hits[hi].pattern, res.hits[hi].len});
+                    m.len = sp.l_seq;
+                    m.a.assign(ch->data.data() + sp.name_off, sp.name_len);
+                    const bool keep = args.filter_matching ? !hits.empty() : (args.invert_match ? hits.empty() : true);
+                    m.b.clear();
+                    if (keep) {  // the record's SAM text is only needed if it is written
+                        if (!ch->bam) {
+                            m.b.assign(ch->data.data() + sp.off, sp.len);
+                        } else {
+                            try {
+                                std::string name;
+                                bam_body_to_sam(ch->data.data() + sp.off, sp.len, refs, &name, &m.b, nullptr, nullptr);
+                            } catch (const Error& e) {
+                                throw Error(std::string("Error during BAM record parsing: ") + e.what());
+                            }
+                        }
+                    }
+                    on_record(m, !hits.empty(), hits);
+                };
+                if (!args.filter_matching) {
+                    for (uint32_t r = 0; r < b.n_records; ++r) deliver(r);
+                    return;
+                }
+                // keep-only-matching: only the records the device flagged produce output or log lines
+                const size_t words = ((size_t)b.n_records + 63) / 64;
+                for (size_t w = 0; w < words; ++w) {
+                    uint64_t x = res.record_flags[w];
+                    while (x) {
+                        const uint32_t r = (uint32_t)(w * 64 + (size_t)__builtin_ctzll(x));
+                        x &= x - 1;
+                        if (r < b.n_records) deliver(r);
+                    }
+                }
+            };
+            AlnPipeline pipe(engines, std::move(chunks), mode, consume_batch);
+            pipe.run();
+        } else {
         EngineSet engines(pattern_list, args.case_insensitive);
-        Scanner scanner(engines, MK_ENC_BAM4, logging_active ? MK_MODE_ALL_HITS : MK_MODE_PATTERN_SET, on_record);
+        Scanner scanner(engines, MK_ENC_BAM4, mode, on_record);
         AlnRecord rec;
         for (;;) {
             bool more;
             try { more = reader->next(&rec); } catch (const Error& e) {
                 scanner.finish();
-                throw Error(std::string("Error during ") + (in_ext == "bam" ? "BAM" : "SAM") + " record parsing: " + e.what());
+                throw Error(std::string("Error during ") + kind_name + " record parsing: " + e.what());
             }
             if (!more) break;
             RecMeta m;
@@ -198,6 +266,7 @@ void tag_records(CmdTag args) {
             scanner.add_record_packed(rec.packed.data(), rec.l_seq, std::move(m));
         }
         scanner.finish();
+        }
     } catch (...) {
         flush_out();
         if (out_owned) std::fclose(out);

@@ -49,6 +49,21 @@ bool ByteSource::getline(std::string* line) {
     }
 }
 
+size_t ByteSource::read_some(void* dst, size_t n) {
+    if (pos_ == end_) {
+        if (eof_) return 0;
+        // nothing buffered: read straight into the caller's memory
+        int got = gzread(f_, dst, (unsigned)std::min<size_t>(n, 1u << 30));
+        if (got < 0) throw Error("Error while decompressing the input");
+        if (got == 0) eof_ = true;
+        return (size_t)got;
+    }
+    size_t take = std::min(n, end_ - pos_);
+    std::memcpy(dst, buf_.data() + pos_, take);
+    pos_ += take;
+    return take;
+}
+
 bool ByteSource::read_exact(void* dst, size_t n) {
     char* d = (char*)dst;
     size_t got = 0;
@@ -147,7 +162,7 @@ bool FastxReader::next(FastxRecord* rec) {
 }
 
 // ---------------------------------------------------------------------------------------------
-static uint8_t nibble_of_sam_char(char c) {
+uint8_t nibble_of_sam_char(char c) {
     if (c >= 'a' && c <= 'z') c = (char)(c - 0x20);
     const char* p = (const char*)std::memchr(kNibbleChars, c, 16);
     return p ? (uint8_t)(p - kNibbleChars) : 15;  // unknown characters are stored as N
@@ -221,9 +236,9 @@ bool AlnReader::next_sam(AlnRecord* rec) {
 }
 
 template <typename T>
-static T rd(const std::vector<char>& b, size_t off) {
+static T rd(const char* b, size_t off) {
     T v;
-    std::memcpy(&v, b.data() + off, sizeof(T));
+    std::memcpy(&v, b + off, sizeof(T));
     return v;
 }
 
@@ -234,17 +249,17 @@ static void append_float(std::string* s, float v) {
     s->append(buf, r.ptr);
 }
 
-bool AlnReader::next_bam(AlnRecord* rec) {
-    int32_t block_size = 0;
-    if (!src_.read_exact(&block_size, 4)) return false;
-    std::vector<char> b((size_t)block_size);
-    src_.read_exact(b.data(), b.size());
+void bam_body_to_sam(const char* b, size_t len, const std::vector<std::string>& refs, std::string* name, std::string* line,
+                     const uint8_t** packed_out, uint32_t* l_seq_out) {
+    if (len < 32) throw Error("truncated record");
     int32_t ref_id = rd<int32_t>(b, 0), pos = rd<int32_t>(b, 4);
     uint8_t l_read_name = rd<uint8_t>(b, 8), mapq = rd<uint8_t>(b, 9);
     uint16_t n_cigar = rd<uint16_t>(b, 12), flag = rd<uint16_t>(b, 14);
     int32_t l_seq = rd<int32_t>(b, 16), next_ref = rd<int32_t>(b, 20), next_pos = rd<int32_t>(b, 24), tlen = rd<int32_t>(b, 28);
+    if (l_seq < 0 || 32 + (size_t)l_read_name + 4 * (size_t)n_cigar + ((size_t)l_seq + 1) / 2 + (size_t)l_seq > len) throw Error("truncated record");
+    if ((ref_id >= 0 && (size_t)ref_id >= refs.size()) || (next_ref >= 0 && (size_t)next_ref >= refs.size())) throw Error("reference id out of range");
     size_t q = 32;
-    rec->name.assign(b.data() + q, l_read_name ? l_read_name - 1 : 0);
+    name->assign(b + q, l_read_name ? l_read_name - 1 : 0);
     q += l_read_name;
     std::string cigar;
     for (uint16_t i = 0; i < n_cigar; ++i) {
@@ -255,49 +270,52 @@ bool AlnReader::next_bam(AlnRecord* rec) {
     if (cigar.empty()) cigar = "*";
     q += 4 * (size_t)n_cigar;
     size_t nbytes = ((size_t)l_seq + 1) / 2;
-    rec->l_seq = (uint32_t)l_seq;
-    rec->packed.assign((const uint8_t*)b.data() + q, (const uint8_t*)b.data() + q + nbytes);
+    const uint8_t* packed = reinterpret_cast<const uint8_t*>(b) + q;
+    if (packed_out) *packed_out = packed;
+    if (l_seq_out) *l_seq_out = (uint32_t)l_seq;
     q += nbytes;
     std::string seq((size_t)l_seq, '\0'), qual((size_t)l_seq, '\0');
-    for (int32_t i = 0; i < l_seq; ++i) seq[(size_t)i] = kNibbleChars[(rec->packed[(size_t)i >> 1] >> ((i & 1) ? 0 : 4)) & 0xF];
+    for (int32_t i = 0; i < l_seq; ++i) seq[(size_t)i] = kNibbleChars[(packed[(size_t)i >> 1] >> ((i & 1) ? 0 : 4)) & 0xF];
     bool no_qual = l_seq == 0 || (uint8_t)b[q] == 0xFF;
     for (int32_t i = 0; i < l_seq; ++i) qual[(size_t)i] = (char)((uint8_t)b[q + (size_t)i] + 33);
     q += (size_t)l_seq;
-    std::string& s = rec->sam_line;
-    s = rec->name; s += '\t';
+    std::string& s = *line;
+    s = *name; s += '\t';
     append_num(&s, flag); s += '\t';
-    s += ref_id >= 0 ? refs_[(size_t)ref_id] : "*"; s += '\t';
+    s += ref_id >= 0 ? refs[(size_t)ref_id] : "*"; s += '\t';
     append_num(&s, (long long)pos + 1); s += '\t';
     append_num(&s, mapq); s += '\t';
     s += cigar; s += '\t';
-    s += next_ref < 0 ? "*" : (next_ref == ref_id ? "=" : refs_[(size_t)next_ref]); s += '\t';
+    s += next_ref < 0 ? "*" : (next_ref == ref_id ? "=" : refs[(size_t)next_ref]); s += '\t';
     append_num(&s, (long long)next_pos + 1); s += '\t';
     append_num(&s, tlen); s += '\t';
     s += l_seq ? seq : "*"; s += '\t';
     s += no_qual ? "*" : qual;
-    while (q + 3 <= b.size()) {  // optional fields
+    auto need = [&](size_t n) { if (q + n > len) throw Error("truncated record"); };
+    while (q + 3 <= len) {  // optional fields
         s += '\t';
-        s.append(b.data() + q, 2);
+        s.append(b + q, 2);
         char typ = b[q + 2];
         q += 3;
         switch (typ) {
-            case 'A': s += ":A:"; s += b[q]; q += 1; break;
-            case 'c': s += ":i:"; append_num(&s, rd<int8_t>(b, q)); q += 1; break;
-            case 'C': s += ":i:"; append_num(&s, rd<uint8_t>(b, q)); q += 1; break;
-            case 's': s += ":i:"; append_num(&s, rd<int16_t>(b, q)); q += 2; break;
-            case 'S': s += ":i:"; append_num(&s, rd<uint16_t>(b, q)); q += 2; break;
-            case 'i': s += ":i:"; append_num(&s, rd<int32_t>(b, q)); q += 4; break;
-            case 'I': s += ":i:"; append_num(&s, rd<uint32_t>(b, q)); q += 4; break;
-            case 'f': s += ":f:"; append_float(&s, rd<float>(b, q)); q += 4; break;
+            case 'A': need(1); s += ":A:"; s += b[q]; q += 1; break;
+            case 'c': need(1); s += ":i:"; append_num(&s, rd<int8_t>(b, q)); q += 1; break;
+            case 'C': need(1); s += ":i:"; append_num(&s, rd<uint8_t>(b, q)); q += 1; break;
+            case 's': need(2); s += ":i:"; append_num(&s, rd<int16_t>(b, q)); q += 2; break;
+            case 'S': need(2); s += ":i:"; append_num(&s, rd<uint16_t>(b, q)); q += 2; break;
+            case 'i': need(4); s += ":i:"; append_num(&s, rd<int32_t>(b, q)); q += 4; break;
+            case 'I': need(4); s += ":i:"; append_num(&s, rd<uint32_t>(b, q)); q += 4; break;
+            case 'f': need(4); s += ":f:"; append_float(&s, rd<float>(b, q)); q += 4; break;
             case 'Z': case 'H': {
                 s += ':'; s += typ; s += ':';
                 size_t e = q;
-                while (e < b.size() && b[e]) ++e;
-                s.append(b.data() + q, e - q);
+                while (e < len && b[e]) ++e;
+                s.append(b + q, e - q);
                 q = e + 1;
                 break;
             }
             case 'B': {
+                need(5);
                 char sub = b[q];
                 uint32_t n = rd<uint32_t>(b, q + 1);
                 q += 5;
@@ -305,13 +323,13 @@ bool AlnReader::next_bam(AlnRecord* rec) {
                 for (uint32_t i = 0; i < n; ++i) {
                     s += ',';
                     switch (sub) {
-                        case 'c': append_num(&s, rd<int8_t>(b, q)); q += 1; break;
-                        case 'C': append_num(&s, rd<uint8_t>(b, q)); q += 1; break;
-                        case 's': append_num(&s, rd<int16_t>(b, q)); q += 2; break;
-                        case 'S': append_num(&s, rd<uint16_t>(b, q)); q += 2; break;
-                        case 'i': append_num(&s, rd<int32_t>(b, q)); q += 4; break;
-                        case 'I': append_num(&s, rd<uint32_t>(b, q)); q += 4; break;
-                        case 'f': append_float(&s, rd<float>(b, q)); q += 4; break;
+                        case 'c': need(1); append_num(&s, rd<int8_t>(b, q)); q += 1; break;
+                        case 'C': need(1); append_num(&s, rd<uint8_t>(b, q)); q += 1; break;
+                        case 's': need(2); append_num(&s, rd<int16_t>(b, q)); q += 2; break;
+                        case 'S': need(2); append_num(&s, rd<uint16_t>(b, q)); q += 2; break;
+                        case 'i': need(4); append_num(&s, rd<int32_t>(b, q)); q += 4; break;
+                        case 'I': need(4); append_num(&s, rd<uint32_t>(b, q)); q += 4; break;
+                        case 'f': need(4); append_float(&s, rd<float>(b, q)); q += 4; break;
                         default: throw Error("bad B-array subtype");
                     }
                 }
@@ -320,6 +338,17 @@ bool AlnReader::next_bam(AlnRecord* rec) {
             default: throw Error("bad tag type");
         }
     }
+}
+
+bool AlnReader::next_bam(AlnRecord* rec) {
+    int32_t block_size = 0;
+    if (!src_.read_exact(&block_size, 4)) return false;
+    if (block_size < 0) throw Error("truncated record");
+    std::vector<char> b((size_t)block_size);
+    if (block_size && !src_.read_exact(b.data(), b.size())) throw Error("unexpected end of file");
+    const uint8_t* packed = nullptr;
+    bam_body_to_sam(b.data(), b.size(), refs_, &rec->name, &rec->sam_line, &packed, &rec->l_seq);
+    rec->packed.assign(packed, packed + (rec->l_seq + 1) / 2);
     return true;
 }
 

@@ -21,6 +21,8 @@ public:
     bool getline(std::string* line);
     // Reads exactly n bytes; returns false on EOF before the first byte, throws on a short read.
     bool read_exact(void* dst, size_t n);
+    // Reads up to n bytes (what is buffered first); 0 at end of input.
+    size_t read_some(void* dst, size_t n);
     int peek();  // next byte or -1
 private:
     bool fill();
@@ -65,6 +67,9 @@ class AlnReader {
 public:
     AlnReader(const std::string& path, bool is_bam);
     const std::vector<std::string>& header_lines() const { return header_; }
+    const std::vector<std::string>& refs() const { return refs_; }
+    bool is_bam() const { return bam_; }
+    ByteSource& source() { return src_; }  // positioned after the header: the chunked reader continues from here
     bool next(AlnRecord* rec);
 private:
     void read_bam_header();
@@ -78,5 +83,13 @@ private:
 };
 
 extern const char kNibbleChars[17];
+
+// BAM code of a SAM sequence character: case-insensitive, anything outside "=ACMGRSVTWYHKDBN" is N.
+uint8_t nibble_of_sam_char(char c);
+
+// One BAM alignment (the `block_size` bytes after the length field) as a SAM text line without line
+// break. Throws Error on a malformed record. name: the read name; packed / l_seq: the 4-bit sequence.
+void bam_body_to_sam(const char* body, size_t len, const std::vector<std::string>& refs, std::string* name, std::string* line,
+                     const uint8_t** packed, uint32_t* l_seq);
 
 }  // namespace mkh

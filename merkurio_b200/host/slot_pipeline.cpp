@@ -1,0 +1,123 @@
+#include "slot_pipeline.h"
+
+#include <chrono>
+
+namespace mkh {
+
+namespace {
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+
+SlotPipeline::SlotPipeline(EngineSet& engines, mk_encoding enc, mk_mode mode, BatchConsumer consumer)
+    : es_(engines), enc_(enc), mode_(mode), consumer_(std::move(consumer)) {
+    // every slot of every engine, in the order the batches will use them
+    const size_t G = es_.engines.size();
+    for (uint32_t s = 0; s < es_.n_slots; ++s)
+        for (size_t g = 0; g < G; ++g) {
+            std::unique_ptr<PackedBatch> b(new PackedBatch);
+            b->engine = (int)g;
+            b->slot = s;
+            if (mk_slot_buffers(es_.engines[g], s, &b->seq, &b->off, enc_ == MK_ENC_BAM4 ? &b->lens : nullptr) != 0)
+                throw Error(std::string("GPU matching engine: ") + mk_last_error());
+            free_.push_back(std::move(b));
+        }
+}
+
+void SlotPipeline::stop_packer() {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    if (packer_.joinable()) packer_.join();
+}
+
+SlotPipeline::~SlotPipeline() { stop_packer(); }
+
+void SlotPipeline::pack() {
+    try {
+        begin();
+        for (;;) {
+            std::unique_ptr<PackedBatch> b;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return !free_.empty() || stop_; });
+                if (stop_) return;
+                b = std::move(free_.front());
+                free_.pop_front();
+            }
+            bool any = fill(*b);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (any) packed_.push_back(std::move(b));
+            else free_.push_front(std::move(b));
+            if (!any || input_done_) { packer_done_ = true; cv_.notify_all(); return; }
+            cv_.notify_all();
+        }
+    } catch (const std::exception& e) {
+        std::lock_guard<std::mutex> lk(mu_);
+        packer_error_ = e.what();
+        packer_done_ = true;
+        cv_.notify_all();
+    }
+}
+
+void SlotPipeline::run() {
+    packer_ = std::thread([this] { pack(); });
+    std::deque<std::unique_ptr<PackedBatch>> inflight;
+    std::vector<std::string> error_chain;
+    auto consume_oldest = [&] {
+        std::unique_ptr<PackedBatch> b = std::move(inflight.front());
+        inflight.pop_front();
+        mk_result res{};
+        es_.wait(b->engine, b->slot, &res);
+        const double t0 = now_s();
+        consumer_(*b, res);
+        if (!b->error_chain.empty()) error_chain = b->error_chain;
+        b->seg[0].clear();  // drop the chunk references before the slot goes back
+        b->seg[1].clear();
+        es_.t_deliver += now_s() - t0;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            free_.push_back(std::move(b));
+        }
+        cv_.notify_all();
+    };
+    for (;;) {
+        std::unique_ptr<PackedBatch> b;
+        bool done = false;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            // with batches in flight do not block on the packer: consuming them is what frees its slots
+            if (inflight.empty()) cv_.wait(lk, [this] { return !packed_.empty() || packer_done_; });
+            if (!packed_.empty()) {
+                b = std::move(packed_.front());
+                packed_.pop_front();
+            } else if (packer_done_) {
+                done = true;
+            }
+        }
+        if (b) {
+            if (b->n_records > 0) {
+                if (mk_scan_submit(es_.engines[(size_t)b->engine], b->slot, b->n_records, b->n_units, enc_ == MK_ENC_BAM4 ? 1 : 0, enc_, mode_) != 0)
+                    throw Error(std::string("GPU matching engine: ") + mk_last_error());
+                inflight.push_back(std::move(b));
+            } else {
+                // nothing but the input's error
+                while (!inflight.empty()) consume_oldest();
+                error_chain = b->error_chain;
+            }
+            continue;
+        }
+        if (!inflight.empty()) { consume_oldest(); continue; }
+        if (done) break;
+    }
+    if (packer_.joinable()) packer_.join();
+    if (!packer_error_.empty()) throw Error(packer_error_);
+    if (!error_chain.empty()) {
+        Error e(error_chain.back());
+        for (size_t i = error_chain.size() - 1; i-- > 0;) e = e.with_context(error_chain[i]);
+        throw e;
+    }
+}
+
+}  // namespace mkh
