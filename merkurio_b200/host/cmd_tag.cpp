@@ -92,6 +92,8 @@ void tag_records(CmdTag args) {
     }
 
     if (in_ext != "bam" && in_ext != "sam") throw Error("Input file must be a BAM or SAM file.");
+    // -p: additional (de)compression threads in the reference (src/cmd_tag.rs:504-507); here a lower bound
+    set_decompression_threads(std::max(decompression_threads(), args.threads));
     std::unique_ptr<AlnReader> reader;
     try {
         reader.reset(new AlnReader(args.in_file, in_ext == "bam"));

@@ -6,6 +6,8 @@
 
 #include <cstring>
 
+#include "io.h"
+
 namespace mkh {
 
 namespace {
@@ -18,7 +20,10 @@ public:
         if (fd_ < 0) throw Error("No such file or directory (os error 2)");
         unsigned char magic[2] = {0, 0};
         ssize_t n = ::pread(fd_, magic, 2, 0);
-        if (n == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+        if (n == 2 && magic[0] == 0x1f && magic[1] == 0x8b && decompression_threads() > 1 && is_bgzf(fd_)) {
+            bgzf_.reset(new BgzfReader(fd_, decompression_threads()));  // bgzip'ed FASTQ: block-parallel
+            fd_ = -1;
+        } else if (n == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
             gz_ = gzdopen(fd_, "rb");
             if (!gz_) { ::close(fd_); throw Error("cannot open the gzip stream"); }
             gzbuffer(gz_, 1 << 20);
@@ -30,6 +35,7 @@ public:
     }
     // Reads up to n bytes; 0 at end of input.
     size_t read(char* dst, size_t n) {
+        if (bgzf_) return bgzf_->read(dst, n);
         if (gz_) {
             int got = gzread(gz_, dst, (unsigned)std::min<size_t>(n, 1u << 30));
             if (got < 0) throw Error("Error while decompressing the input");
@@ -48,6 +54,7 @@ public:
 private:
     int fd_ = -1;
     gzFile gz_ = nullptr;
+    std::unique_ptr<BgzfReader> bgzf_;
 };
 
 struct Line {

@@ -5,12 +5,19 @@
 #include <zlib.h>
 
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
+#include "bgzf.h"
 #include "common.h"
 
 namespace mkh {
+
+// Threads used to inflate BGZF input (BAM, bgzip'ed text). Default: half the cores, at most 8; `tag -p N`
+// raises it to at least N. 1 = plain zlib stream.
+void set_decompression_threads(int n);
+int decompression_threads();
 
 class ByteSource {
 public:
@@ -26,7 +33,9 @@ public:
     int peek();  // next byte or -1
 private:
     bool fill();
+    size_t raw_read(void* dst, size_t n);  // plain, gzip or (block-parallel) BGZF
     gzFile f_ = nullptr;
+    std::unique_ptr<BgzfReader> bgzf_;
     std::vector<char> buf_;
     size_t pos_ = 0, end_ = 0;
     bool eof_ = false;

@@ -218,3 +218,53 @@ def test_fasta_is_left_to_the_line_reader(exe, tmp_path):
     p.write_bytes(b">s1\nACGT\nAC\n>s2\nGG\n")
     got = subprocess.run([exe, "records", str(p), "chunked"], capture_output=True)
     assert got.stdout == b"#not-fastq\n"
+
+
+def bgzf_compress(data: bytes, rng, eof_marker=True) -> bytes:
+    """BGZF as bgzip / BAM writers produce it: gzip members of <= 64 KiB with a 'BC' extra field."""
+    import struct
+    import zlib
+    out = bytearray()
+    pos = 0
+    chunks = []
+    while pos < len(data):
+        n = int(rng.integers(1, 65000))
+        chunks.append(data[pos:pos + n])
+        pos += n
+    if eof_marker:
+        chunks.append(b"")
+    for ch in chunks:
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = co.compress(ch) + co.flush()
+        bsize = 12 + 6 + len(body) + 8
+        out += b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+        out += body + struct.pack("<II", zlib.crc32(ch), len(ch))
+    return bytes(out)
+
+
+def test_bgzf_input_is_inflated_block_parallel(exe, tmp_path):
+    import numpy as np
+    rng = np.random.default_rng(11)
+    recs = []
+    for i in range(30000):
+        n = int(rng.integers(1, 400))
+        s = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n).tobytes())
+        recs.append(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * n))
+    data = b"".join(recs)
+    plain = tmp_path / "p.fastq"
+    plain.write_bytes(data)
+    bg = tmp_path / "b.fastq.gz"
+    bg.write_bytes(bgzf_compress(data, rng))
+    want = subprocess.run([exe, "records", str(plain), "generic"], capture_output=True).stdout
+    assert want.count(b"#id\t") == 30000
+    for how in ("generic", "chunked"):
+        got = subprocess.run([exe, "records", str(bg), how], capture_output=True)
+        assert got.returncode == 0, got.stderr
+        assert got.stdout == want, how
+    # a flipped byte inside a block is caught by its CRC (or by inflate)
+    bad = bytearray(bg.read_bytes())
+    bad[len(bad) // 2] ^= 0x55
+    (tmp_path / "bad.fastq.gz").write_bytes(bytes(bad))
+    r = subprocess.run([exe, "records", str(tmp_path / "bad.fastq.gz"), "generic"], capture_output=True)
+    assert r.returncode != 0 or b"#error" in r.stdout
+    assert r.stdout != want
