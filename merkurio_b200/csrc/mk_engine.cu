@@ -205,7 +205,12 @@ ScanLaunch pick_by_d(uint32_t d) {
     }
 }
 
-ScanLaunch pick_kernel(int enc, uint32_t d, bool smemf) {
+ScanLaunch pick_kernel(int enc, uint32_t d, bool smemf, bool win = false) {
+    if (win) {  // stride 8 / 4, shared-memory filter, window seeds in the permuted packing
+        if (enc == MK_ENC_ASCII && d == 8) return {mk::mk_scan_win<MK_ENC_ASCII, 8, 4, 896>, 896, 4 * 32};
+        if (enc == MK_ENC_ASCII) return {mk::mk_scan_win<MK_ENC_ASCII, 4, 4, 768>, 768, 4 * 32};
+        return {mk::mk_scan_win<MK_ENC_BAM4, 8, 4, 768>, 768, 4 * 32};
+    }
     if (enc == MK_ENC_ASCII)
         return smemf ? pick_by_d<MK_ENC_ASCII, mk::kFilterSmem>(d) : pick_by_d<MK_ENC_ASCII, mk::kFilterGlobal>(d);
     return smemf ? pick_by_d<MK_ENC_BAM4, mk::kFilterSmem>(d) : pick_by_d<MK_ENC_BAM4, mk::kFilterGlobal>(d);
@@ -250,7 +255,7 @@ int ensure_tables(mk_engine* e, int enc) {
     CU(dt.pat_off.upload(dt.host.pat_off));
     CU(dt.slots.upload(dt.host.slots));
     CU(dt.pat_bytes.upload(dt.host.pat_bytes));
-    ScanLaunch k = pick_kernel(enc, dt.host.d, dt.host.filter_in_smem);
+    ScanLaunch k = pick_kernel(enc, dt.host.d, dt.host.filter_in_smem, dt.host.win);
     if (dt.host.filter_in_smem)
         CU(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dt.host.filter.size() * 4)));
     dt.built = true;
@@ -284,13 +289,15 @@ int enqueue(mk_engine* e, Workspace& ws) {
     P.pat_off = dt.pat_off.p;
     P.tie_rank = e->tie_rank.p;
     P.q = t.q;
-    P.short_shift = 32u - 2u * t.q;
+    P.short_shift = (t.perm || t.win) ? 0u : 32u - 2u * t.q;
+    P.win_mask0 = t.win_mask0;
+    P.win_mask1 = t.win_mask1;
     P.has_long = t.q2 ? 1u : 0u;
     P.case_insensitive = e->ps.case_insensitive ? 1 : 0;
     P.cand = ws.cand.p;
     P.cand_capacity = ws.cand_cap;
     P.cand_count = ws.counters.p + 2;
-    P.pos_mul = t.d == 16 ? MK_UNIT_BASES : 1;
+    P.pos_mul = t.d == 16 ? MK_UNIT_BASES : (t.win ? t.d : 1);
     P.flags = ws.flags.p;
     P.hits = ws.raw_a.p;
     P.hit_capacity = ws.hit_cap;
@@ -307,13 +314,13 @@ int enqueue(mk_engine* e, Workspace& ws) {
     if (ws.mode != MK_MODE_FLAG && key_bits > 64)
         return fail(MK_ERR_CAPACITY, "batch too large for the 64-bit hit sort key (%u bits)", key_bits);
 
-    if (t.d != 16 && ws.n_units >= (1ull << 32))
+    if (t.d != 16 && !t.win && ws.n_units >= (1ull << 32))
         return fail(MK_ERR_CAPACITY, "batches of 2^32 bases or more need patterns of at least 31 bases; split the batch");
     CU(cudaMemsetAsync(ws.flags.p, 0, flag_words32 * 4, ws.stream));
     CU(cudaMemsetAsync(ws.counters.p, 0, 8 * sizeof(unsigned long long), ws.stream));
     CU(cudaEventRecord(ws.ev_begin, ws.stream));
     if (P.n_vec > 0 && ws.n_records > 0) {
-        ScanLaunch k = pick_kernel(ws.enc, t.d, t.filter_in_smem);
+        ScanLaunch k = pick_kernel(ws.enc, t.d, t.filter_in_smem, t.win);
         const uint64_t warps = k.threads / 32;
         uint64_t tiles = ((uint64_t)P.n_vec + k.tile_vecs - 1) / k.tile_vecs;
         uint64_t want = (tiles + warps - 1) / warps;

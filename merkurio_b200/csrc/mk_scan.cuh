@@ -46,7 +46,8 @@ struct ScanParams {
     const uint32_t* pat_off;
     const uint32_t* tie_rank;
     uint32_t q;
-    uint32_t short_shift;           // 32 - 2q: candidate code (16-base window) -> q-base seed code
+    uint32_t short_shift;           // 32 - 2q: candidate code (16-base window) -> q-base seed code (0: the code is the seed code)
+    uint32_t win_mask0, win_mask1;  // mk_scan_win: the q bases of a window that form the seed (ASCII: code bits; BAM4: the two words)
     uint32_t has_long;              // 1: patterns of the long group are keyed by the whole 16-base window
     int case_insensitive;
     // candidates: seeds that passed both filters, handed from the scan to the verify kernel
@@ -510,6 +511,143 @@ __global__ void __launch_bounds__(T, 1) mk_scan_d16(const __grid_constant__ Scan
         process_tile<ENC, FMODE, U, false>(P, filt, lb, a, v0, wq, lane);
     }
     queue_flush<ENC, MK_UNIT_BASES>(P, wq, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// D == 8 or 4 with the shared-memory filter: same tile loop as the stride-16 scan. A seed is the
+// 16-base window that starts D, 2D, ... bases into a unit; in the permuted packing (base i of a unit
+// in field i / 4 of byte lane i % 4) that window is two shifts and a select of (unit code, next unit
+// code) — no ordered packing, no funnel shifts — and for BAM4 it is a pair of adjacent words. Seeds
+// shorter than 16 bases (k < D + 15) mask the window's tail. The unit after a lane's vector comes
+// from the next lane, from lane 0 of the next row, or (last row, lane 31) from one extra 16-byte
+// load of the first vector of the following tile.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void push_tile_candidates(const ScanParams& P, WarpQueue& wq, uint32_t lane, uint32_t pass,
+                                                     const uint32_t (&code)[K], uint32_t unit0, uint32_t unit_row_stride, int per_row) {
+    const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, __popc(pass));
+    if (total == 0) return;
+    if (wq.count + total <= kQueueCap) {
+        if (pass) {
+            uint32_t idx = atomicAdd(wq.cnt, __popc(pass));
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if ((pass >> k) & 1u) wq.slot[idx++] = make_uint2(unit0 + (k / per_row) * unit_row_stride + (k % per_row), code[k]);
+        }
+        __syncwarp();
+        wq.count += total;
+        if (wq.count >= 32) {
+            do queue_drain32<0, 0>(P, wq, lane); while (wq.count >= 32);
+            if (lane == 0) *wq.cnt = wq.count;
+            __syncwarp();
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            queue_push<0, 0>(P, wq, lane, (pass >> k) & 1u, unit0 + (k / per_row) * unit_row_stride + (k % per_row), code[k]);
+        if (lane == 0) *wq.cnt = wq.count;
+        __syncwarp();
+    }
+}
+
+template <int ENC, int D, int U>
+__device__ __forceinline__ void process_tile_win(const ScanParams& P, const uint32_t* __restrict__ filt, uint32_t lb, const uint4 (&v)[U],
+                                                 const uint4& halo, uint32_t v0, WarpQueue& wq, uint32_t lane) {
+    constexpr int PPV = (ENC == MK_ENC_ASCII ? 16 : 32) / D;  // probes per vector
+    constexpr int K = U * PPV;
+    static_assert(K <= 32, "the pass mask of a tile is one 32-bit word");
+    uint32_t win[K];
+    uint32_t pass = 0;
+    if (ENC == MK_ENC_ASCII) {
+        const uint32_t mask = P.win_mask0;
+        uint32_t c[U + 1];
+#pragma unroll
+        for (int u = 0; u < U; ++u) c[u] = mk_pack_ascii_perm(v[u].x, v[u].y, v[u].z, v[u].w);
+        c[U] = mk_pack_ascii_perm(halo.x, halo.y, halo.z, halo.w);  // meaningful in lane 31 only
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t from_next_lane = __shfl_down_sync(0xFFFFFFFFu, c[u], 1);
+            const uint32_t from_next_row = (u + 1 < U) ? __shfl_sync(0xFFFFFFFFu, c[u + 1], 0) : c[U];
+            const uint32_t succ = (lane == 31) ? from_next_row : from_next_lane;
+#pragma unroll
+            for (int m = 0; m < PPV; ++m) {
+                const int sh = 2 * (m * D / 4);  // the window starts m * D bases into the unit
+                const uint32_t low = 0x01010101u * (0xFFu >> sh);
+                const uint32_t w = (sh == 0) ? c[u] : (((c[u] >> sh) & low) | ((succ << (8 - sh)) & ~low));
+                win[u * PPV + m] = w & mask;
+            }
+        }
+    } else {
+        const uint32_t m0 = P.win_mask0, m1 = P.win_mask1;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t from_next_lane = __shfl_down_sync(0xFFFFFFFFu, v[u].x, 1);
+            const uint32_t from_next_row = (u + 1 < U) ? __shfl_sync(0xFFFFFFFFu, v[u + 1].x, 0) : halo.x;
+            const uint32_t nx = (lane == 31) ? from_next_row : from_next_lane;
+            static_assert(ENC == MK_ENC_ASCII || D == 8, "BAM4 windows are word aligned for a stride of 8 only");
+            win[u * PPV + 0] = mk_pack_bam_perm(v[u].x & m0, v[u].y & m1);
+            win[u * PPV + 1] = mk_pack_bam_perm(v[u].y & m0, v[u].z & m1);
+            win[u * PPV + 2] = mk_pack_bam_perm(v[u].z & m0, v[u].w & m1);
+            win[u * PPV + 3] = mk_pack_bam_perm(v[u].w & m0, nx & m1);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) pass |= filter_probe<kFilterSmem>(filt, win[k], lb) << k;
+    // candidate position / D: vector index * PPV + window index
+    push_tile_candidates<K>(P, wq, lane, pass, win, v0 * PPV, 32 * PPV, PPV);
+}
+
+template <int ENC, int D, int U, int T>
+__global__ void __launch_bounds__(T, 1) mk_scan_win(const __grid_constant__ ScanParams P) {
+    constexpr int kWarps = T / 32;
+    extern __shared__ __align__(16) uint32_t s_filter[];
+    __shared__ uint2 s_queue[kWarps][kQueueCap];
+    __shared__ uint32_t s_qcount[kWarps];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lb = P.filter_blocks;
+    const uint64_t pol = make_evict_first_policy();
+    const uint32_t nwarps = gridDim.x * kWarps;
+    const uint32_t full_tiles = P.n_vec / (U * 32);
+    WarpQueue wq{s_queue[threadIdx.x >> 5], 0, &s_qcount[threadIdx.x >> 5]};
+    if (lane == 0) *wq.cnt = 0;
+    __syncwarp();
+    uint32_t t = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const uint32_t warp0 = t;
+    const size_t stride = (size_t)nwarps * (U * 32);
+    const uint4* p = P.text + (size_t)t * (U * 32) + lane;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    // first vector of the tile after tile `tt` (lane 31 only; zero past the end of the text)
+    auto load_halo = [&](uint32_t tt) {
+        const uint64_t hv = ((uint64_t)tt + 1) * (U * 32);
+        return (lane == 31 && hv < P.n_vec) ? ld_stream(P.text + hv, pol) : zero;
+    };
+
+    uint4 a[U], b[U], ha = zero, hb = zero;
+    if (t < full_tiles) { load_rows<U, false>(p, pol, a); ha = load_halo(t); }
+    stage_filter<kFilterSmem>(P, s_filter);
+    const uint32_t* __restrict__ filt = s_filter;
+
+    while (t < full_tiles) {
+        uint32_t tn = t + nwarps;
+        if (tn < full_tiles) { load_rows<U, false>(p + stride, pol, b); hb = load_halo(tn); }
+        process_tile_win<ENC, D, U>(P, filt, lb, a, ha, t * (U * 32) + lane, wq, lane);
+        t = tn;
+        p += stride;
+        if (t >= full_tiles) break;
+        tn = t + nwarps;
+        if (tn < full_tiles) { load_rows<U, false>(p + stride, pol, a); ha = load_halo(tn); }
+        process_tile_win<ENC, D, U>(P, filt, lb, b, hb, t * (U * 32) + lane, wq, lane);
+        t = tn;
+        p += stride;
+    }
+    // ragged last tile (bounds-checked loads; nothing follows it)
+    if (P.n_vec % (U * 32) != 0 && warp0 == full_tiles % nwarps) {
+        const uint32_t v0 = full_tiles * (U * 32) + lane;
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = (v0 + u * 32 < P.n_vec) ? ld_stream(P.text + v0 + u * 32, pol) : zero;
+        process_tile_win<ENC, D, U>(P, filt, lb, a, zero, v0, wq, lane);
+    }
+    queue_flush<0, 0>(P, wq, lane);
 }
 
 // ---------------------------------------------------------------------------------------------

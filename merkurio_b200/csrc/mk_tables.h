@@ -47,6 +47,8 @@ struct Tables {
     uint32_t q2 = 0;       // 16 when patterns of >= long_min_len bases are indexed by 16-base seeds, else 0
     uint32_t long_min_len = 0;
     bool perm = false;  // D == 16: permuted unit packing
+    bool win = false;   // D == 8 / 4 with the shared-memory filter: seeds are masked 16-base windows in the permuted packing
+    uint32_t win_mask0 = 0xFFFFFFFFu, win_mask1 = 0xFFFFFFFFu;
     bool filter_dual = false;  // L2-resident 64-bit blocked filter probed with both keys (stride < 16)
     uint32_t n_seeds = 0;
     // first-level filter
@@ -176,6 +178,37 @@ struct SeedKey {
     uint32_t code, first, group;
 };
 
+// Window layout of mk_scan_win: the q bases of a 16-base window that form the seed, as a mask of the
+// permuted ASCII code (base t: byte lane t % 4, 2-bit field t / 4) or of the two BAM4 words (base t:
+// byte t / 2 of the 8-byte window, high nibble first).
+inline void window_masks(int enc, uint32_t q, uint32_t* m0, uint32_t* m1) {
+    *m0 = *m1 = 0;
+    for (uint32_t t = 0; t < q && t < 16; ++t) {
+        if (enc == 0) {
+            *m0 |= 3u << (8 * (t % 4) + 2 * (t / 4));
+        } else {
+            uint32_t byte = t / 2, bits = 0xFu << (8 * (byte % 4) + (t % 2 == 0 ? 4 : 0));
+            if (byte < 4) *m0 |= bits; else *m1 |= bits;
+        }
+    }
+    if (enc == 0) *m1 = 0;
+}
+// seed code of the first q (<= 16) symbols at sym in the window layout
+inline uint32_t seed_code_win(int enc, const uint8_t* sym, uint32_t q, uint32_t m0, uint32_t m1) {
+    uint8_t s16[16] = {0};
+    for (uint32_t t = 0; t < q && t < 16; ++t) s16[t] = sym[t];
+    if (enc == 0) {
+        uint32_t w[4];
+        std::memcpy(w, s16, 16);
+        return mk_pack_ascii_perm(w[0], w[1], w[2], w[3]) & m0;
+    }
+    uint8_t b[8];
+    for (int i = 0; i < 8; ++i) b[i] = (uint8_t)((s16[2 * i] << 4) | (s16[2 * i + 1] & 0xF));
+    uint32_t w[2];
+    std::memcpy(w, b, 8);
+    return mk_pack_bam_perm(w[0] & m0, w[1] & m1);
+}
+
 inline bool cuckoo_build(const std::vector<SeedKey>& keys, uint32_t log2_buckets, std::vector<SeedSlot>* out,
                          uint32_t* mask_out) {
     uint32_t nb = 1u << log2_buckets, mask = nb - 1;
@@ -248,6 +281,9 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
     struct Trip { uint32_t code, pid, j, grp; };
     std::vector<Trip> trips;
     std::vector<SeedKey> keys;
+    // stride 8 / 4 (BAM4: 8 only) can use the window layout of mk_scan_win if the filter fits shared memory
+    bool win_layout = (enc == 0 ? (t.d == 8 || t.d == 4) : t.d == 8) && !std::getenv("MK_NO_WIN_SCAN");
+    if (win_layout) window_masks(enc, t.q, &t.win_mask0, &t.win_mask1);
     auto index_seeds = [&](uint32_t long_min_len) {
         trips.clear();
         keys.clear();
@@ -257,7 +293,9 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
             const uint8_t* sym = t.pat_bytes.data() + t.pat_off[p];
             const bool lng = long_min_len && ps.len(p) >= long_min_len;
             for (uint32_t j = 0; j < t.d; ++j) {
-                uint32_t code = t.perm ? seed_code_perm(enc, sym + j) : seed_code_ord(enc, sym + j, lng ? 16u : t.q);
+                uint32_t code = t.perm ? seed_code_perm(enc, sym + j)
+                              : win_layout ? seed_code_win(enc, sym + j, t.q, t.win_mask0, t.win_mask1)
+                                           : seed_code_ord(enc, sym + j, lng ? 16u : t.q);
                 trips.push_back({code, p, j, lng ? 1u : 0u});
             }
         }
@@ -289,6 +327,11 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
     bool want_smem = blocked_fp((double)keys.size(), nblocks) <= 0.25;
     if (force && std::strcmp(force, "l2") == 0) want_smem = false;
     if (force && std::strcmp(force, "smem") == 0) want_smem = true;
+    if (win_layout && !want_smem) {  // the L2-resident flavours use the ordered packing
+        win_layout = false;
+        index_seeds(0);
+    }
+    t.win = win_layout;
 
     // Seed sets too large for shared memory with a stride below 16: give every pattern that is long
     // enough a 16-base seed (far fewer text positions carry one of those than one of the q-base seeds)

@@ -130,7 +130,7 @@ def test_example_workflow_reads(ref_tree):
     assert a.n_hits + b.n_hits == 36 and len(a.flagged_records()) == 9 and len(b.flagged_records()) == 15
 
 
-@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 11, 12, 13, 14, 15, 16, 17, 18, 19, 21, 22, 23, 27, 30, 31, 32, 33, 47, 63, 64, 65, 100])
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 27, 30, 31, 32, 33, 47, 63, 64, 65, 100])
 def test_random_single_length(k):
     rng = np.random.default_rng(1000 + k)
     n_pat = 3 if k < 4 else 40
@@ -214,6 +214,24 @@ def test_long_record_every_alignment():
     check_batch(pats, [bytes(big[:300000]), bytes(big[300000:])])
 
 
+@pytest.mark.parametrize("k", [15, 18, 19, 22, 23, 30])
+def test_window_scan_equals_ordered_scan(monkeypatch, k):
+    """Strides 8 and 4 have two kernels (window seeds in the permuted packing / ordered packing): both
+    must report the oracle's hits, also for long records that cross every tile boundary."""
+    rng = np.random.default_rng(500 + k)
+    pats = sorted({rand_seq(rng, int(x)) for x in rng.integers(k, k + 20, size=30)})
+    big = bytearray(rand_seq(rng, 300000))
+    pos = 100
+    for i in range(400):
+        p = pats[i % len(pats)]
+        big[pos:pos + len(p)] = p
+        pos += 700 + (i % 53)
+    recs = [bytes(big[:100001]), bytes(big[100001:])] + planted_records(rng, pats, 200, 0, 200, plant_p=0.5)
+    check_batch(pats, recs)
+    monkeypatch.setenv("MK_NO_WIN_SCAN", "1")
+    check_batch(pats, recs)
+
+
 def test_hit_overflow_rescan():
     rng = np.random.default_rng(23)
     recs = [rand_seq(rng, 150) for _ in range(200)]
@@ -271,9 +289,11 @@ def check_bam4(pats, recs):
         return e.info()
 
 
-def test_bam4_encoding():
-    rng = np.random.default_rng(31)
-    pats = sorted({rand_seq(rng, int(k)) for k in rng.integers(16, 50, size=40)} | {b"ACGTNNACGTACGTAAGGCTNAC", b"acgtacgtacgtacgtacgt"})
+@pytest.mark.parametrize("kmin", [16, 19, 21, 22, 23, 27, 31])
+def test_bam4_encoding(kmin):
+    # kmin 16: stride 4 (ordered packing); 19..30: stride 8 (word-aligned windows, masked below 23); 31: stride 16
+    rng = np.random.default_rng(31 + kmin)
+    pats = sorted({rand_seq(rng, int(k)) for k in rng.integers(kmin, kmin + 34, size=40)} | {b"ACGTNNACGTACGTAAGGCTNACACGTTGCAAT", b"acgtacgtacgtacgtacgtacgtacgtacgtac"})
     recs = planted_records(rng, [p for p in pats if p.isupper()], 300, 0, 180, alphabet=b"ACGTNRY", plant_p=0.6)
     check_bam4(pats, recs)
 
