@@ -208,6 +208,17 @@ ScanLaunch pick_by_d(uint32_t d) {
 ScanLaunch pick_kernel(int enc, uint32_t d, bool smemf, bool win = false) {
     if (win) {  // stride 8 / 4, shared-memory filter, window seeds in the permuted packing
         if (enc == MK_ENC_ASCII && d == 8) return {mk::mk_scan_win<MK_ENC_ASCII, 8, 4, 896>, 896, 4 * 32};
+#ifdef MK_TUNE_BUILD
+        if (enc == MK_ENC_ASCII) {
+            switch (tune_env("MK_WIN_VARIANT", 0)) {
+                case 1: return {mk::mk_scan_win<MK_ENC_ASCII, 4, 2, 1024>, 1024, 2 * 32};
+                case 2: return {mk::mk_scan_win<MK_ENC_ASCII, 4, 4, 640>, 640, 4 * 32};
+                case 3: return {mk::mk_scan_win<MK_ENC_ASCII, 4, 2, 896>, 896, 2 * 32};
+                case 4: return {mk::mk_scan_win<MK_ENC_ASCII, 4, 4, 896>, 896, 4 * 32};
+                default: break;
+            }
+        }
+#endif
         if (enc == MK_ENC_ASCII) return {mk::mk_scan_win<MK_ENC_ASCII, 4, 4, 768>, 768, 4 * 32};
         return {mk::mk_scan_win<MK_ENC_BAM4, 8, 4, 768>, 768, 4 * 32};
     }
