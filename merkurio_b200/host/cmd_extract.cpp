@@ -314,6 +314,8 @@ void extract_records(CmdExtract args) {
             }
         };
         FastxRecord r1, r2;
+        if (reader) reader->set_keep_raw(keep_text);
+        if (reader2) reader2->set_keep_raw(keep_text);
         try {
             if (pipelined) {
                 reader.reset();

@@ -74,6 +74,22 @@ bool ByteSource::getline(std::string* line) {
     }
 }
 
+bool ByteSource::getline_view(const char** p, size_t* n, std::string* spill) {
+    if (pos_ == end_ && !fill()) return false;
+    const char* b = buf_.data() + pos_;
+    const char* nl = (const char*)std::memchr(b, '\n', end_ - pos_);
+    if (nl) {
+        *p = b;
+        *n = (size_t)(nl - b);
+        pos_ += *n + 1;
+        return true;
+    }
+    bool got = getline(spill);  // the line straddles the buffer end (or is the unterminated last one)
+    *p = spill->data();
+    *n = spill->size();
+    return got;
+}
+
 size_t ByteSource::read_some(void* dst, size_t n) {
     if (pos_ == end_) {
         if (eof_) return 0;
@@ -172,13 +188,16 @@ bool FastxReader::next(FastxRecord* rec) {
     for (;;) {
         int c = src_.peek();
         if (c < 0 || c == '>') break;
-        src_.getline(&line);
-        if (!first) rec->raw += '\n';
+        const char* lp = nullptr;
+        size_t ln = 0;
+        src_.getline_view(&lp, &ln, &line);
+        if (keep_raw_) {
+            if (!first) rec->raw += '\n';
+            rec->raw.append(lp, ln);  // keeps a '\r' of CRLF files inside the wrapped text, like the file
+        }
         first = false;
-        rec->raw += line;  // keeps a '\r' of CRLF files inside the wrapped text, like the file
-        std::string t = line;
-        strip_cr(&t, nullptr);
-        rec->seq += t;
+        if (ln && lp[ln - 1] == '\r') --ln;
+        rec->seq.append(lp, ln);
     }
     // the final line break of the record is not part of raw_seq
     if (!rec->raw.empty() && rec->raw.back() == '\r') rec->raw.pop_back();

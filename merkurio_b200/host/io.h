@@ -26,6 +26,9 @@ public:
     ByteSource(const ByteSource&) = delete;
     // Reads one line (without the '\n'; a trailing '\r' is kept). Returns false at end of input.
     bool getline(std::string* line);
+    // Same, without a copy when the whole line is already buffered: *p / *n then point into the buffer
+    // (valid until the next call); otherwise into *spill.
+    bool getline_view(const char** p, size_t* n, std::string* spill);
     // Reads exactly n bytes; returns false on EOF before the first byte, throws on a short read.
     bool read_exact(void* dst, size_t n);
     // Reads up to n bytes (what is buffered first); 0 at end of input.
@@ -57,10 +60,12 @@ class FastxReader {
 public:
     explicit FastxReader(const std::string& path);
     bool next(FastxRecord* rec);  // throws Error on malformed input
+    // FASTA: do not keep the wrapped text of the records (FastxRecord::raw stays empty) when nothing will be written
+    void set_keep_raw(bool keep) { keep_raw_ = keep; }
 private:
     ByteSource src_;
     std::string pending_;  // a header line already consumed
-    bool have_pending_ = false, started_ = false, fastq_ = false;
+    bool have_pending_ = false, started_ = false, fastq_ = false, keep_raw_ = true;
 };
 
 // One alignment record. `packed` holds the sequence as BAM stores it (4 bits per base, first base in

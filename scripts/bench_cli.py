@@ -7,6 +7,8 @@ bench.py's device-timed and C-ABI end-to-end figures.
 cfg2: single-end FASTQ, 1000 31-mers + reverse complements, `extract -f q.txt -r -o out.fastq`
 cfg3: paired FASTQ, 10000 canonical 31-mers, `extract -2 ... -c -j log.json -o out.fastq`
 cfg4: SAM or BAM (--bam) input, 10000 31-mers, `tag -f q.txt -m -o out.sam`
+cfg5: multi-record FASTA (60 columns, N runs, soft-masked spans), mixed-length queries (21-63, 1 % with N),
+      `extract -f q.txt -S -j log.json`; every unaltered query must be logged at the place it was sampled
 The flag bitmap of the run is checked against the oracle on the first --check-reads reads (the set
 of extracted read names must equal the oracle's)."""
 import argparse
@@ -27,7 +29,8 @@ from merkurio_b200.synth import Synth
 from oracle import refmodel as rm
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--config", choices=["cfg2", "cfg3", "cfg4"], default="cfg2")
+ap.add_argument("--config", choices=["cfg2", "cfg3", "cfg4", "cfg5"], default="cfg2")
+ap.add_argument("--scale", type=float, default=0.1, help="cfg5: fraction of 3 Gbp / 1 M queries")
 ap.add_argument("--reads", type=int, default=4_000_000)
 ap.add_argument("--gz", action="store_true", help="gzip the FASTQ input")
 ap.add_argument("--bam", action="store_true", help="cfg4: BAM input and output instead of SAM")
@@ -68,6 +71,76 @@ def revcomp_rows(a: np.ndarray) -> np.ndarray:
 
 tmp = Path(args.dir or tempfile.mkdtemp(prefix="mk_cli_"))
 tmp.mkdir(parents=True, exist_ok=True)
+if args.config == "cfg5":
+    rng = np.random.default_rng(5)
+    total = int(3_000_000_000 * args.scale)
+    n_chr = 24
+    w = rng.random(n_chr) + 0.3
+    lens = (w / w.sum() * total).astype(np.int64) // 60 * 60
+    nq = int(1_000_000 * args.scale)
+    t_gen = time.perf_counter()
+    fa = tmp / "genome.fa"
+    queries, where = [], []
+    with open(fa, "wb") as f:
+        for c in range(n_chr):
+            L_c = int(lens[c])
+            a = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=L_c, dtype=np.uint8)]
+            pos = 0
+            while pos < L_c:  # 30 % soft-masked, 2 % N
+                span = int(rng.integers(2000, 200000))
+                kind = rng.random()
+                e = min(L_c, pos + span)
+                if kind < 0.30:
+                    a[pos:e] |= 0x20
+                elif kind < 0.32:
+                    a[pos:e] = 78
+                pos = e
+            k_c = nq * L_c // int(lens.sum())
+            ql = rng.integers(21, 64, size=k_c)
+            qs = (rng.random(k_c) * (L_c - 64)).astype(np.int64)
+            for s_, l_ in zip(qs.tolist(), ql.tolist()):
+                q = a[s_:s_ + l_].tobytes()
+                if q.count(b"N") > 2:
+                    continue
+                if rng.random() < 0.01:
+                    b_ = bytearray(q)
+                    b_[int(rng.integers(len(b_)))] = 78
+                    queries.append(bytes(b_))
+                    where.append(None)
+                else:
+                    queries.append(q)
+                    where.append((c, s_))
+            rows = np.empty((L_c // 60, 61), dtype=np.uint8)
+            rows[:, :60] = a.reshape(-1, 60)
+            rows[:, 60] = 10
+            f.write(b">chr%d synthetic\n" % c)
+            f.write(rows.tobytes())
+    (tmp / "q.txt").write_bytes(b"\n".join(queries) + b"\n")
+    t_gen = time.perf_counter() - t_gen
+    in_bytes = fa.stat().st_size
+    env = dict(os.environ, MERKURIO_GPUS=str(args.gpus), MERKURIO_TIMING="1")
+    cmd = [str(EXE), "extract", "-i", str(fa), "-f", str(tmp / "q.txt"), "-S", "-j", str(tmp / "log.json")]
+    runs, setups = [], []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        pr = subprocess.run(cmd, check=True, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+        runs.append(time.perf_counter() - t0)
+        m = [ln for ln in pr.stderr.splitlines() if ln.startswith("[merkurio] engine setup")]
+        setups.append(float(m[-1].split()[3]) if m else 0.0)
+        print(f"run {len(runs)}: {runs[-1]:.3f} s  {m[-1] if m else ''}", file=sys.stderr, flush=True)
+    log = json.loads((tmp / "log.json").read_bytes())
+    got = {(h["record_id"], int(h["position"]), h["pattern"]) for h in log["matching_records"]}
+    missing = sum(1 for q, wh in zip(queries, where) if wh is not None and ("chr%d synthetic" % wh[0], wh[1], q.decode()) not in got)
+    assert missing == 0, missing
+    wall = min(runs)
+    steady = min(r - s_ for r, s_ in zip(runs, setups))
+    res = {"config": "cfg5", "scale": args.scale, "bases": int(lens.sum()), "queries": len(queries), "input_bytes": in_bytes, "hits_logged": len(got),
+           "sampled_queries_missing": missing, "wall_s": wall, "runs_s": runs, "engine_setup_s": setups, "gbases_per_s": int(lens.sum()) / wall / 1e9,
+           "gbases_per_s_after_setup": int(lens.sum()) / steady / 1e9, "host_cores": os.cpu_count(), "generate_s": t_gen, "cmd": " ".join(cmd[1:])}
+    print(json.dumps(res))
+    if args.out:
+        Path(args.out).write_text(json.dumps(res, indent=1) + "\n")
+    sys.exit(0)
 n = args.reads
 nq = 1000 if args.config == "cfg2" else 10000
 seed = {"cfg2": 0x5EED0002, "cfg3": 0x5EED0003, "cfg4": 0x5EED0004}[args.config]

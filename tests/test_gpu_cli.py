@@ -340,3 +340,122 @@ def test_two_gpus_from_the_cli(ref_tree, tmp_path):
     got = json.loads((tmp_path / "m.json").read_bytes())
     want = json.loads((ew / "logs" / "mutant_extracted.stats.json").read_bytes())
     assert got["matching_records"] == want["matching_records"] and got["summary_statistics"] == want["summary_statistics"]
+
+
+# ------------------------------------------------------------------ ingest pipelines vs the line-by-line readers
+def _outputs(tmp_path, tag, args, env):
+    d = tmp_path / tag
+    d.mkdir()
+    r = run(*[a.replace("@OUT@", str(d)) if isinstance(a, str) else a for a in args], env=env, check=False)
+    files = {p.name: p.read_bytes() for p in sorted(d.iterdir())}
+    return r.returncode, r.stderr, files
+
+
+def _strip_volatile(name, data):
+    if name.endswith(".log"):
+        return b"\n".join(data.split(b"\n")[4:])
+    if name.endswith(".json"):
+        try:
+            d = json.loads(data)
+        except json.JSONDecodeError:
+            return data  # a run that ended with an error leaves the hit objects without the closing sections
+        d["meta_information"] = {k: v for k, v in d["meta_information"].items() if k not in ("timestamp", "command_line")}
+        return json.dumps(d, sort_keys=True).encode()
+    if name.endswith(".sam"):
+        return b"\n".join(ln for ln in data.split(b"\n") if not ln.startswith(b"@PG"))
+    return data
+
+
+def _same_both_ways(tmp_path, args, off_switch, env=None):
+    """The reader -> packer -> GPU pipeline and the record-by-record path must agree on every output
+    file, the exit status and the error text — also when the input breaks off half way."""
+    e = dict(env or {})
+    a = _outputs(tmp_path, "pipe", args, e)
+    b = _outputs(tmp_path, "plain", args, dict(e, **{off_switch: "1"}))
+    assert a[0] == b[0], (a[1], b[1])
+    assert a[1].replace(b"[merkurio]", b"") == b[1].replace(b"[merkurio]", b"")
+    assert a[2].keys() == b[2].keys()
+    for name in a[2]:
+        assert _strip_volatile(name, a[2][name]) == _strip_volatile(name, b[2][name]), name
+    return a
+
+
+@pytest.mark.parametrize("flavour", ["plain", "crlf", "odd", "gz", "truncated", "bad_second_file"])
+@pytest.mark.parametrize("logs", [False, True])
+def test_fastq_pipeline_equals_record_path(tmp_path, flavour, logs):
+    rng = np.random.default_rng(77)
+    pats = sorted({rng.choice(np.frombuffer(b"ACGT", np.uint8), size=int(k)).tobytes() for k in rng.integers(18, 40, size=30)})
+    r1 = _rand_reads(rng, 3000, 0, 160, pats, plant=0.3)
+    r2 = _rand_reads(rng, 3000, 0, 160, pats, plant=0.3)
+
+    def fastq(reads, prefix):
+        out = bytearray()
+        for i, r in enumerate(reads):
+            le = b"\r\n" if flavour == "crlf" else b"\n"
+            plus = b"+" + (b"%s%d" % (prefix, i) if flavour == "odd" and i % 3 == 0 else b"")
+            out += b"@%s%d d=%d" % (prefix, i, i) + le + r + le + plus + le + b"F" * len(r) + le
+            if flavour == "odd" and i % 7 == 0:
+                out += b"\n"
+        if flavour == "odd":
+            out = out.rstrip(b"\n")  # no final newline
+        return bytes(out)
+
+    d1, d2 = fastq(r1, b"a"), fastq(r2, b"b")
+    if flavour == "truncated":
+        d1 = d1[: len(d1) // 2]
+    if flavour == "bad_second_file":
+        d2 = d2[: len(d2) // 3] + b"garbage\n" + d2[len(d2) // 3:]
+    ext = ".fastq.gz" if flavour == "gz" else ".fastq"
+    p1, p2 = tmp_path / ("r1" + ext), tmp_path / ("r2" + ext)
+    p1.write_bytes(gzip.compress(d1) if flavour == "gz" else d1)
+    p2.write_bytes(gzip.compress(d2) if flavour == "gz" else d2)
+    kf = tmp_path / "k.txt"
+    kf.write_bytes(b"\n".join(pats) + b"\n")
+    log_args = ["-l", "@OUT@/x.log", "-j", "@OUT@/x.json"] if logs else []
+    env = {"MERKURIO_BATCH_BYTES": "70000", "MERKURIO_CHUNK_BYTES": "50000"}
+    # single end
+    (tmp_path / "se").mkdir()
+    rc, err, files = _same_both_ways(tmp_path / "se", ["extract", "-i", p1, "-f", kf, "-r", "-o", "@OUT@/x.fastq", *log_args],
+                                     "MERKURIO_NO_FASTQ_PIPELINE", env)
+    assert (rc != 0) == (flavour == "truncated")
+    assert files["x.fastq"].count(b"\n@a") > 50
+    # paired, also inverted
+    for extra, tag in (([], "pe"), (["-v"], "pev")):
+        (tmp_path / tag).mkdir()
+        rc, err, files = _same_both_ways(tmp_path / tag, ["extract", "-i", p1, "-2", p2, "-f", kf, "-r", "-o", "@OUT@/x.fastq", *extra, *log_args],
+                                         "MERKURIO_NO_FASTQ_PIPELINE", env)
+        assert (rc != 0) == (flavour in ("truncated", "bad_second_file"))
+        assert set(files) >= {"x_1.fastq", "x_2.fastq"}
+
+
+@pytest.mark.parametrize("kind", ["sam", "bam", "sam_truncated"])
+@pytest.mark.parametrize("flags", [["-m"], ["-v"], [], ["-m", "-l", "@OUT@/t.log", "-j", "@OUT@/t.json"]])
+def test_aln_pipeline_equals_record_path(tmp_path, kind, flags):
+    rng = np.random.default_rng(91)
+    pats = sorted({rng.choice(np.frombuffer(b"ACGT", np.uint8), size=31).tobytes() for _ in range(25)})
+    reads = _rand_reads(rng, 3000, 0, 151, pats, plant=0.2, alphabet=b"ACGTNacgtRY")
+    sam = tmp_path / "in.sam"
+    with open(sam, "wb") as f:
+        f.write(b"@HD\tVN:1.6\tSO:unsorted\n@SQ\tSN:1\tLN:100000\n@SQ\tSN:2\tLN:5000\n")
+        for i, r in enumerate(reads):
+            extra = b"\tkm:Z:ZZZ,AAA" if i % 50 == 0 else b""
+            f.write(b"q%d\t%d\t%d\t%d\t%d\t%s\t%s\t%d\t0\t%s\t%s\tNM:i:%d\tXA:Z:x,y;%s\n" % (
+                i, 99 if i % 2 else 147, 1 + i % 2, 1 + (i * 37) % 4000, i % 61, b"%dM" % len(r) if r else b"*",
+                b"=" if i % 3 else b"*", (i * 11) % 4000 if i % 3 else 0, r.upper() if r else b"*", b"F" * len(r) if r else b"*", i % 5, extra))
+            if i % 400 == 0:
+                f.write(b"\n")
+    kf = tmp_path / "k.txt"
+    kf.write_bytes(b"\n".join(pats) + b"\n")
+    src = sam
+    if kind == "bam":
+        src = tmp_path / "in.bam"
+        run("tag", "-i", sam, "-o", src, "-s", "NNNNNNNNNNNNNNNNNNNNNNNNNNNNNNN", env={"MERKURIO_BATCH_BYTES": "60000"})
+    if kind == "sam_truncated":
+        src = tmp_path / "cut.sam"
+        data = sam.read_bytes()
+        src.write_bytes(data[: len(data) // 2].rsplit(b"\t", 4)[0] + b"\n" + data[len(data) // 2:])
+    env = {"MERKURIO_BATCH_BYTES": "50000", "MERKURIO_CHUNK_BYTES": "40000"}
+    rc, err, files = _same_both_ways(tmp_path, ["tag", "-i", src, "-o", "@OUT@/t.sam", "-f", kf, "-r", *flags], "MERKURIO_NO_ALN_PIPELINE", env)
+    assert (rc != 0) == (kind == "sam_truncated")
+    if rc == 0:
+        assert files["t.sam"].count(b"\tkm:Z:") > 100
