@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <future>
 #include <memory>
 #include <new>
 #include <string>
@@ -72,6 +73,7 @@ struct PinBuf {
 struct DeviceTables {
     bool built = false;
     mk::Tables host;
+    std::future<mk::Tables> pending;  // large pattern sets: built on a host thread while CUDA starts up
     DevBuf<uint32_t> filter, filter2, postings, pat_off;
     DevBuf<mk::SeedSlot> slots;
     DevBuf<uint8_t> pat_bytes;
@@ -254,7 +256,11 @@ int ensure_tables(mk_engine* e, int enc) {
     DeviceTables& dt = e->tables[enc];
     if (dt.built) return MK_OK;
     try {
-        dt.host = mk::build_tables(e->ps, enc);
+        if (dt.pending.valid()) dt.host = dt.pending.get();
+        else dt.host = mk::build_tables(e->ps, enc);
+        // the tables of the other encoding are only needed if that encoding shows up: drop a pending build
+        DeviceTables& other = e->tables[1 - enc];
+        if (other.pending.valid()) { other.pending.wait(); other.pending = std::future<mk::Tables>(); }
     } catch (const std::bad_alloc&) {
         return fail(MK_ERR_NOMEM, "out of host memory while building the seed tables");
     } catch (const std::exception& ex) {
@@ -498,6 +504,21 @@ int mk_engine_create(const mk_patterns* patterns, const mk_config* config, mk_en
         if (patterns->off[p + 1] < patterns->off[p]) return fail(MK_ERR_INVALID, "pattern offsets must be non-decreasing");
         if (patterns->off[p + 1] == patterns->off[p]) return fail(MK_ERR_EMPTY_PATTERN, "Pattern is empty.");
     }
+    std::unique_ptr<mk_engine> e(new (std::nothrow) mk_engine);
+    if (!e) return fail(MK_ERR_NOMEM, "out of memory");
+    try {
+        e->ps = mk::make_pattern_set(patterns->bytes, patterns->off, patterns->n, config->case_insensitive != 0);
+    } catch (const std::bad_alloc&) {
+        return fail(MK_ERR_NOMEM, "out of host memory");
+    }
+    // Large query sets take seconds to index (sort + cuckoo insertion): do it on host threads now, while
+    // the CUDA context is created below (also seconds on a multi-GPU box). Which encoding the caller
+    // will scan is not known yet, so both are prepared; the unused one is dropped at the first scan.
+    if (patterns->n >= 50000 && !std::getenv("MK_NO_ASYNC_TABLES")) {
+        const mk::PatternSet* ps = &e->ps;
+        for (int enc = 0; enc < 2; ++enc)
+            e->tables[enc].pending = std::async(std::launch::async, [ps, enc] { return mk::build_tables(*ps, enc); });
+    }
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0)
@@ -505,17 +526,9 @@ int mk_engine_create(const mk_patterns* patterns, const mk_config* config, mk_en
                     ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
     if (config->device < 0 || config->device >= ndev) return fail(MK_ERR_INVALID, "device %d out of range", config->device);
     CU(cudaSetDevice(config->device));
-
-    std::unique_ptr<mk_engine> e(new (std::nothrow) mk_engine);
-    if (!e) return fail(MK_ERR_NOMEM, "out of memory");
     e->device = config->device;
     e->cfg = *config;
     CU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device));
-    try {
-        e->ps = mk::make_pattern_set(patterns->bytes, patterns->off, patterns->n, config->case_insensitive != 0);
-    } catch (const std::bad_alloc&) {
-        return fail(MK_ERR_NOMEM, "out of host memory");
-    }
     CU(e->tie_rank.upload(e->ps.tie_rank));
     int rc = init_workspace(e->direct);
     if (rc) return rc;

@@ -289,6 +289,20 @@ def check_bam4(pats, recs):
         return e.info()
 
 
+def test_large_pattern_set_tables_built_in_the_background():
+    # >= 50 000 patterns: the seed tables of both encodings are built on host threads while CUDA starts up
+    rng = np.random.default_rng(61)
+    genome = rand_seq(rng, 300000)
+    starts = rng.integers(0, len(genome) - 70, size=70000)
+    pats = sorted({genome[s:s + int(k)] for s, k in zip(starts, rng.integers(24, 60, size=len(starts)))})
+    assert len(pats) >= 50000
+    recs = [genome[:100000], genome[100000:200001], genome[200001:]]
+    with capi.Engine(pats, max_batch_bytes=len(genome) + 64, max_batch_records=4) as e:
+        r = check_batch(pats, recs, engine=e)
+        assert r.n_hits >= len(pats) - 100
+    check_bam4(pats[:60000], recs)
+
+
 @pytest.mark.parametrize("kmin", [16, 19, 21, 22, 23, 27, 31])
 def test_bam4_encoding(kmin):
     # kmin 16: stride 4 (ordered packing); 19..30: stride 8 (word-aligned windows, masked below 23); 31: stride 16
