@@ -140,7 +140,7 @@ def run_reference(args):
         "e2e": {"value": gb, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "records_hit_in_sample": int(nrec),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -322,13 +322,27 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": int(algo_bytes)},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     dctx.close()
     return 0
 
 
+_real_stdout = None
+
+
+def emit(line: dict):
+    """The one JSON line, on the process's real stdout (see main)."""
+    os.write(_real_stdout if _real_stdout is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    # Libraries chat on stdout (NCCL prints its version there when NCCL_DEBUG is set): route file
+    # descriptor 1 to stderr for the whole run and keep the original for the JSON line alone.
+    global _real_stdout
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
