@@ -11,7 +11,8 @@
  *   mk_scan_submit /   <- the per-record search calls: BNDMq::find_iter / find_match
  *   mk_scan_wait /        (src/pattern_matching.rs:128-140,165-209) and
  *   mk_scan_device /      AhoCorasick::find_overlapping_iter, as used by the extract loops
- *   mk_scan_host          (src/cmd_extract.rs:321-406 single, :463-607 paired) and by
+ *   mk_scan_device_submit (src/cmd_extract.rs:321-406 single, :463-607 paired) and by
+ *   mk_scan_host          process_record (src/cmd_tag.rs:387-443) -- see the next entry
  *                         process_record (src/cmd_tag.rs:387-443)
  *   mk_result          <- what those loops consume: found_occ (cmd_extract.rs:323,400),
  *                         kmers_found (cmd_tag.rs:387,398,429,439) and the (pattern, start) stream
@@ -148,6 +149,13 @@ int mk_scan_host(mk_engine* e, uint32_t slot, const uint8_t* h_seq, const uint64
 int mk_scan_device(mk_engine* e, const void* d_seq, const uint64_t* d_off, const uint32_t* d_lens,
                    uint32_t n_records, uint64_t n_units, mk_encoding enc, mk_mode mode, int fetch,
                    mk_result* out);
+
+/* Asynchronous flavour of mk_scan_device: enqueue the batch on `slot`'s stream and return; mk_scan_wait
+ * on the same slot delivers the result. Lets a caller whose data already sits in device memory keep
+ * several batches in flight (the device-timed benchmark; a decoder that produces batches on the GPU). */
+int mk_scan_device_submit(mk_engine* e, uint32_t slot, const void* d_seq, const uint64_t* d_off,
+                          const uint32_t* d_lens, uint32_t n_records, uint64_t n_units,
+                          mk_encoding enc, mk_mode mode, int fetch);
 
 const char* mk_last_error(void);
 const char* mk_version(void);

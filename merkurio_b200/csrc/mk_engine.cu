@@ -138,6 +138,7 @@ struct mk_engine {
     DevBuf<uint32_t> tie_rank;
     std::vector<std::unique_ptr<Slot>> slots;
     Workspace direct;  // mk_scan_device
+    cudaEvent_t last_device_submit = nullptr;  // end of the latest mk_scan_device_submit batch (its slot's ev_end)
 };
 
 namespace {
@@ -628,6 +629,24 @@ int mk_scan_wait(mk_engine* e, uint32_t slot, mk_result* out) {
     if (rc) return rc;
     CU(cudaSetDevice(e->device));
     return finish_batch(e, s->ws, out);
+}
+
+int mk_scan_device_submit(mk_engine* e, uint32_t slot, const void* d_seq, const uint64_t* d_off, const uint32_t* d_lens,
+                          uint32_t n_records, uint64_t n_units, mk_encoding enc, mk_mode mode, int fetch) {
+    Slot* s = nullptr;
+    int rc = get_slot(e, slot, &s);
+    if (rc) return rc;
+    if (s->ws.busy) return fail(MK_ERR_STATE, "slot %u still has a batch in flight", slot);
+    if ((!d_seq && n_units) || !d_off) return fail(MK_ERR_INVALID, "null device buffers");
+    if (reinterpret_cast<uintptr_t>(d_seq) % 16) return fail(MK_ERR_INVALID, "d_seq must be 16-byte aligned");
+    CU(cudaSetDevice(e->device));
+    // device-resident batches run in submission order: they would only compete for the same SMs, and the
+    // per-batch CUDA-event times stay those of the batch alone
+    if (e->last_device_submit && e->last_device_submit != s->ws.ev_end) CU(cudaStreamWaitEvent(s->ws.stream, e->last_device_submit, 0));
+    rc = begin_batch(e, s->ws, d_seq, reinterpret_cast<const unsigned long long*>(d_off), d_lens, n_records, n_units, enc, mode,
+                     fetch != 0);
+    if (rc == MK_OK) e->last_device_submit = s->ws.ev_end;
+    return rc;
 }
 
 int mk_scan_device(mk_engine* e, const void* d_seq, const uint64_t* d_off, const uint32_t* d_lens, uint32_t n_records,

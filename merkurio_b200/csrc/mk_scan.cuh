@@ -365,14 +365,12 @@ __device__ __forceinline__ void emit_candidates(const ScanParams& P, bool mine, 
     if (mine && slot < P.cand_capacity) P.cand[slot] = e;
 }
 
-template <int ENC, int PM>
 __device__ __forceinline__ void queue_drain32(const ScanParams& P, WarpQueue& wq, uint32_t lane) {
     wq.count -= 32;
     uint2 e = wq.slot[wq.count + lane];
     __syncwarp();
     emit_candidates(P, second_level_pass(P, e.y), e, lane);
 }
-template <int ENC, int PM>
 __device__ __forceinline__ void queue_flush(const ScanParams& P, WarpQueue& wq, uint32_t lane) {
     __syncwarp();
     uint2 e = make_uint2(0, 0);
@@ -386,7 +384,6 @@ __device__ __forceinline__ void queue_flush(const ScanParams& P, WarpQueue& wq, 
     __syncwarp();
 }
 // push the lanes whose `mine` is set; unit (= position / PM) and code are per lane
-template <int ENC, int PM>
 __device__ __forceinline__ void queue_push(const ScanParams& P, WarpQueue& wq, uint32_t lane, bool mine, uint32_t unit,
                                            uint32_t code) {
     uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
@@ -394,7 +391,7 @@ __device__ __forceinline__ void queue_push(const ScanParams& P, WarpQueue& wq, u
         if (mine) wq.slot[wq.count + __popc(m & ((1u << lane) - 1u))] = make_uint2(unit, code);
         wq.count += __popc(m);
         __syncwarp();
-        if (wq.count >= 32) queue_drain32<ENC, PM>(P, wq, lane);
+        if (wq.count >= 32) queue_drain32(P, wq, lane);
     }
 }
 
@@ -435,7 +432,7 @@ __device__ __forceinline__ void process_tile(const ScanParams& P, const uint32_t
         __syncwarp();
         wq.count += total;
         if (wq.count >= 32) {
-            do queue_drain32<ENC, MK_UNIT_BASES>(P, wq, lane); while (wq.count >= 32);
+            do queue_drain32(P, wq, lane); while (wq.count >= 32);
             if (lane == 0) *wq.cnt = wq.count;
             __syncwarp();
         }
@@ -445,7 +442,7 @@ __device__ __forceinline__ void process_tile(const ScanParams& P, const uint32_t
         for (int k = 0; k < U * SPV; ++k) {
             const int u = k / SPV;
             const uint32_t vec = V8 ? v0 + (u / 2) * 64 + (u % 2) : v0 + u * 32;
-            queue_push<ENC, MK_UNIT_BASES>(P, wq, lane, (pass >> k) & 1u, vec * SPV + (k % SPV), code[k]);
+            queue_push(P, wq, lane, (pass >> k) & 1u, vec * SPV + (k % SPV), code[k]);
         }
         if (lane == 0) *wq.cnt = wq.count;
         __syncwarp();
@@ -510,7 +507,7 @@ __global__ void __launch_bounds__(T, 1) mk_scan_d16(const __grid_constant__ Scan
         for (int u = 0; u < U; ++u) a[u] = (v0 + u * 32 < P.n_vec) ? ld_stream(P.text + v0 + u * 32, pol16) : make_uint4(0, 0, 0, 0);
         process_tile<ENC, FMODE, U, false>(P, filt, lb, a, v0, wq, lane);
     }
-    queue_flush<ENC, MK_UNIT_BASES>(P, wq, lane);
+    queue_flush(P, wq, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -537,14 +534,14 @@ __device__ __forceinline__ void push_tile_candidates(const ScanParams& P, WarpQu
         __syncwarp();
         wq.count += total;
         if (wq.count >= 32) {
-            do queue_drain32<0, 0>(P, wq, lane); while (wq.count >= 32);
+            do queue_drain32(P, wq, lane); while (wq.count >= 32);
             if (lane == 0) *wq.cnt = wq.count;
             __syncwarp();
         }
     } else {
 #pragma unroll
         for (int k = 0; k < K; ++k)
-            queue_push<0, 0>(P, wq, lane, (pass >> k) & 1u, unit0 + (k / per_row) * unit_row_stride + (k % per_row), code[k]);
+            queue_push(P, wq, lane, (pass >> k) & 1u, unit0 + (k / per_row) * unit_row_stride + (k % per_row), code[k]);
         if (lane == 0) *wq.cnt = wq.count;
         __syncwarp();
     }
@@ -647,7 +644,7 @@ __global__ void __launch_bounds__(T, 1) mk_scan_win(const __grid_constant__ Scan
         for (int u = 0; u < U; ++u) a[u] = (v0 + u * 32 < P.n_vec) ? ld_stream(P.text + v0 + u * 32, pol) : zero;
         process_tile_win<ENC, D, U>(P, filt, lb, a, zero, v0, wq, lane);
     }
-    queue_flush<0, 0>(P, wq, lane);
+    queue_flush(P, wq, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -706,12 +703,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) mk_scan_ord(const __grid_cons
                     // Positions fit 32 bits: the engine refuses batches of 2^32 bases or more on this path.
                     // They are multiples of the stride (>= 2 whenever a long group exists), so bit 0 can say
                     // "only the long key passed", which saves the verify kernel the short-key lookup.
-                    queue_push<ENC, 1>(P, wq, lane, pass, (uint32_t)(base + o) | ((FMODE != kFilterSmem && hit == 2u) ? 1u : 0u), win);
+                    queue_push(P, wq, lane, pass, (uint32_t)(base + o) | ((FMODE != kFilterSmem && hit == 2u) ? 1u : 0u), win);
                 }
             }
         }
     }
-    queue_flush<ENC, 1>(P, wq, lane);
+    queue_flush(P, wq, lane);
 }
 
 // ---------------------------------------------------------------------------------------------

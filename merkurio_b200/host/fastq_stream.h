@@ -1,10 +1,10 @@
 // Chunked FASTQ ingest for the extract feeder: one thread per input file reads (or inflates) the
-// file into large buffers and indexes the 4-line records in place, so the thread that drives the GPU
-// only copies the sequence bytes into the pinned batch and keeps (chunk, record) references for the
-// writer — no per-record allocation. Replaces needletail's parse_fastx_file + per-record borrow in
-// src/cmd_extract.rs:281,321-327,412,463-475 for FASTQ input; FASTA and anything unusual stays on
-// FastxReader (io.h). Results are identical to FastxReader's by construction of the span rules
-// below (tests/test_gpu_cli.py compares both paths).
+// file into large buffers and indexes the 4-line records in place; the packer thread of the pipeline
+// (fastq_pipeline.h) copies the sequence bytes into the pinned batch and the batch keeps (chunk,
+// record) references for the writer — no per-record allocation. Replaces needletail's
+// parse_fastx_file + per-record borrow in src/cmd_extract.rs:281,321-327,412,463-475 for FASTQ input;
+// FASTA and anything unusual stays on FastxReader (io.h). Results are identical to FastxReader's by
+// construction of the span rules below (tests/test_cli_cpu.py and tests/test_gpu_cli.py compare both).
 #pragma once
 #include <condition_variable>
 #include <cstdint>

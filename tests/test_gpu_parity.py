@@ -395,3 +395,33 @@ def test_errors_across_the_boundary():
         with pytest.raises(capi.MkError) as ei:
             e.wait(0)
         assert ei.value.code == -7
+
+
+def test_device_resident_batches_in_flight():
+    """mk_scan_device_submit: two batches that already sit in device memory, in flight on two slots."""
+    import torch
+    rng = np.random.default_rng(71)
+    pats = sorted({rand_seq(rng, 31) for _ in range(60)})
+    parts = [planted_records(rng, pats, 1500, 100, 160, plant_p=0.2) for _ in range(3)]
+    with capi.Engine(pats, n_slots=2, max_batch_bytes=64, max_batch_records=4) as e:
+        dev = []
+        for recs in parts:
+            seq, off = pack_records(recs)
+            d_seq = torch.from_numpy(np.concatenate([seq, np.zeros(64, np.uint8)])).cuda()
+            d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+            dev.append((d_seq, d_off, len(recs), int(seq.size)))
+        got = []
+        for i, (d_seq, d_off, n, nb) in enumerate(dev):
+            if i >= 2:
+                got.append(e.wait(i % 2))
+            e.scan_device_submit(i % 2, d_seq.data_ptr(), d_off.data_ptr(), n, nb, capi.MK_MODE_ALL_HITS, fetch=True)
+        got.append(e.wait(1))
+        got.append(e.wait(0))
+        with pytest.raises(capi.MkError):
+            e.wait(0)  # nothing in flight any more
+        for recs, r in zip(parts, got):
+            rec, st, pat = oracle_hits(pats, recs)
+            np.testing.assert_array_equal(r.hits["record"], rec)
+            np.testing.assert_array_equal(r.hits["start"], st)
+            np.testing.assert_array_equal(r.hits["pattern"], pat)
+            np.testing.assert_array_equal(r.flagged_records(), np.unique(rec))
