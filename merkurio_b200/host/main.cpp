@@ -5,10 +5,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "commands.h"
+#include "aln_stream.h"
 #include "fastq_stream.h"
 #include "helpers.h"
 #include "io.h"
@@ -312,6 +314,52 @@ int run(int argc, char** argv) {
                     }
                 }
                 if (ch->failed) out += "#error\tError during FASTQ/A record parsing.\n";
+            }
+        }
+        std::fwrite(out.data(), 1, out.size(), stdout);
+        return 0;
+    }
+    if (cmd == "alnrecords") {
+        // diagnostic (not in the reference): merkurio alnrecords <file.sam|file.bam> <generic|chunked> [chunk_bytes]
+        // dumps what the alignment readers hand to the matcher (name, length, 4-bit sequence) and to the
+        // writer (the SAM text of the record) — the ingest half of the tag path, testable without a GPU.
+        if (argc < 4) { std::fputs("usage: merkurio alnrecords <file> <generic|chunked> [chunk_bytes]\n", stderr); return 2; }
+        const std::string path = argv[2], how = argv[3];
+        const bool bam = path.size() > 4 && path.compare(path.size() - 4, 4, ".bam") == 0;
+        std::string out;
+        auto dump = [&](const std::string& name, uint32_t l_seq, const uint8_t* packed, const std::string& line) {
+            out += "#name\t" + name + "\t" + std::to_string(l_seq) + "\t";
+            for (uint32_t i = 0; i < l_seq; ++i) out += kNibbleChars[(packed[i >> 1] >> ((i & 1) ? 0 : 4)) & 0xF];
+            out += "\n" + line + "\n";
+        };
+        std::unique_ptr<AlnReader> rd(new AlnReader(path, bam));
+        for (auto& h : rd->header_lines()) out += "#header\t" + h + "\n";
+        if (how == "generic") {
+            AlnRecord r;
+            try {
+                while (rd->next(&r)) dump(r.name, r.l_seq, r.packed.data(), r.sam_line);
+            } catch (const Error& e) {
+                out += std::string("#error\t") + e.what() + "\n";
+            }
+        } else {
+            const std::vector<std::string> refs = rd->refs();
+            AlnChunkReader cr(std::move(rd), argc > 4 ? (size_t)std::strtoull(argv[4], nullptr, 10) : (size_t)8 << 20);
+            while (std::shared_ptr<AlnChunk> ch = cr.next()) {
+                for (const AlnSpan& sp : ch->recs) {
+                    std::string name(ch->data.data() + sp.name_off, sp.name_len), line;
+                    std::vector<uint8_t> packed((sp.l_seq + 1) / 2, 0);
+                    if (ch->bam) {
+                        std::string nm;
+                        bam_body_to_sam(ch->data.data() + sp.off, sp.len, refs, &nm, &line, nullptr, nullptr);
+                        std::memcpy(packed.data(), ch->data.data() + sp.seq_off, packed.size());
+                    } else {
+                        line.assign(ch->data.data() + sp.off, sp.len);
+                        for (uint32_t i = 0; i < sp.l_seq; ++i)
+                            packed[i >> 1] |= (uint8_t)(nibble_of_sam_char(ch->data[sp.seq_off + i]) << ((i & 1) ? 0 : 4));
+                    }
+                    dump(name, sp.l_seq, packed.data(), line);
+                }
+                if (!ch->error.empty()) out += "#error\t" + ch->error + "\n";
             }
         }
         std::fwrite(out.data(), 1, out.size(), stdout);

@@ -268,3 +268,91 @@ def test_bgzf_input_is_inflated_block_parallel(exe, tmp_path):
     r = subprocess.run([exe, "records", str(tmp_path / "bad.fastq.gz"), "generic"], capture_output=True)
     assert r.returncode != 0 or b"#error" in r.stdout
     assert r.stdout != want
+
+
+# ------------------------------------------------------------------------------------------------
+# SAM / BAM ingest: the chunked record index must hand over what the record-by-record readers do.
+def _sam_text(n=3000, seed=3):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    out = [b"@HD\tVN:1.6\tSO:unsorted", b"@SQ\tSN:chr1\tLN:100000", b"@SQ\tSN:chr2\tLN:5000"]
+    for i in range(n):
+        L = int(rng.integers(0, 200))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTNacgtRYK", dtype=np.uint8), size=L).tobytes()) if L else b"*"
+        qual = b"F" * L if L else b"*"
+        tags = b"\tNM:i:%d\tXS:Z:a,b;c" % (i % 7) + (b"\tkm:Z:AAA,CCC" if i % 40 == 0 else b"")
+        out.append(b"r%d\t%d\t%s\t%d\t%d\t%s\t%s\t%d\t%d\t%s\t%s%s" % (
+            i, 99 if i % 2 else 147, b"chr1" if i % 3 else b"chr2", 1 + i * 13 % 4000, i % 61, b"%dM" % L if L else b"*",
+            b"=" if i % 4 else b"*", 1 + i * 7 % 4000 if i % 4 else 0, i % 300 - 150, seq, qual, tags))
+        if i % 500 == 0:
+            out.append(b"")  # blank lines are skipped
+    return b"\n".join(out) + b"\n"
+
+
+@pytest.mark.parametrize("variant", ["plain", "crlf", "no_final_newline", "truncated"])
+def test_chunked_sam_reader_equals_line_reader(exe, tmp_path, variant):
+    data = _sam_text()
+    if variant == "crlf":
+        data = data.replace(b"\n", b"\r\n")
+    if variant == "no_final_newline":
+        data = data.rstrip(b"\n")
+    if variant == "truncated":
+        cut = len(data) // 2
+        data = data[:cut].rsplit(b"\t", 3)[0] + b"\n" + data[cut:]
+    p = tmp_path / "x.sam"
+    p.write_bytes(data)
+    want = subprocess.run([exe, "alnrecords", str(p), "generic"], capture_output=True)
+    assert want.returncode == 0, want.stderr
+    assert (b"#error" in want.stdout) == (variant == "truncated")
+    assert want.stdout.count(b"#name\t") >= (1000 if variant == "truncated" else 3000)
+    for chunk in (4096, 30011, 1 << 22):
+        got = subprocess.run([exe, "alnrecords", str(p), "chunked", str(chunk)], capture_output=True)
+        assert got.returncode == 0, got.stderr
+        assert got.stdout == want.stdout, (variant, chunk)
+
+
+def _sam_to_bam(sam: bytes, rng) -> bytes:
+    """Minimal SAM -> BAM encoder for test inputs (BGZF blocks of random size: records cross them)."""
+    import struct
+    lines = [ln for ln in sam.replace(b"\r\n", b"\n").split(b"\n") if ln]
+    header = [ln for ln in lines if ln.startswith(b"@")]
+    refs = [(f[1][3:], int(f[2][3:])) for f in (ln.split(b"\t") for ln in header) if f[0] == b"@SQ"]
+    ref_id = {name: i for i, (name, _) in enumerate(refs)}
+    text = b"\n".join(header) + b"\n"
+    out = bytearray(b"BAM\x01" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs)))
+    for name, ln in refs:
+        out += struct.pack("<i", len(name) + 1) + name + b"\x00" + struct.pack("<i", ln)
+    nib = {c: i for i, c in enumerate(b"=ACMGRSVTWYHKDBN")}
+    for ln in lines[len(header):]:
+        f = ln.split(b"\t")
+        seq = b"" if f[9] == b"*" else f[9].upper()
+        cigar = b"" if f[5] == b"*" else struct.pack("<I", (int(f[5][:-1]) << 4) | 0)
+        rid = ref_id.get(f[2], -1)
+        nrid = rid if f[6] == b"=" else ref_id.get(f[6], -1)
+        codes = [nib.get(c, 15) for c in seq] + [0]
+        packed = bytes((codes[i] << 4) | codes[i + 1] for i in range(0, len(seq), 2))
+        qual = b"\xff" * len(seq) if f[10] == b"*" else bytes(c - 33 for c in f[10])
+        aux = bytearray()
+        for t in f[11:]:
+            tag, typ, val = t[:2], t[3:4], t[5:]
+            aux += tag + (b"C" + struct.pack("<B", int(val)) if typ == b"i" else b"Z" + val + b"\x00")
+        body = struct.pack("<iiBBHHHiiii", rid, int(f[3]) - 1, len(f[0]) + 1, int(f[4]), 4680, len(cigar) // 4, int(f[1]), len(seq), nrid,
+                           int(f[7]) - 1, int(f[8])) + f[0] + b"\x00" + cigar + packed + qual + bytes(aux)
+        out += struct.pack("<i", len(body)) + body
+    return bgzf_compress(bytes(out), rng)
+
+
+def test_chunked_bam_reader_equals_record_reader(exe, ref_tree, tmp_path):
+    import numpy as np
+    bam = tmp_path / "x.bam"
+    bam.write_bytes(_sam_to_bam(_sam_text(4000, seed=9), np.random.default_rng(4)))
+    for src in [ref_tree / "tests" / "fixtures" / "input" / "simple.bam", bam]:
+        want = subprocess.run([exe, "alnrecords", str(src), "generic"], capture_output=True)
+        assert want.returncode == 0 and want.stdout.count(b"#name\t") > 0, want.stderr
+        assert b"#error" not in want.stdout
+        if src == bam:
+            assert want.stdout.count(b"#name\t") == 4000 and b"\tkm:Z:AAA,CCC" in want.stdout
+        for chunk in (4096, 50021, 1 << 22):
+            got = subprocess.run([exe, "alnrecords", str(src), "chunked", str(chunk)], capture_output=True)
+            assert got.returncode == 0, got.stderr
+            assert got.stdout == want.stdout, (src.name, chunk)
