@@ -86,7 +86,7 @@ def build_host(force: bool = False, verbose: bool = False) -> Path:
     deps = srcs + sorted(HOST.glob("*.h")) + [ROOT / "include" / "merkurio_cuda.h", build_cuda(force, verbose)]
     if force or _stale(out, deps):
         _run(["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-I", ROOT / "include", "-o", out, *srcs,
-              "-L", LIBDIR, "-lmerkurio_cuda", "-Wl,-rpath,$ORIGIN", "-lz"], verbose)
+              "-L", LIBDIR, "-lmerkurio_cuda", "-Wl,-rpath,$ORIGIN", "-lz", "-ldl"], verbose)
     return out
 
 

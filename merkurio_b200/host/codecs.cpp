@@ -1,0 +1,209 @@
+#include "codecs.h"
+
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <cerrno>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "bgzf.h"
+#include "common.h"
+#include "io.h"
+
+namespace mkh {
+
+namespace {
+
+size_t read_fd(int fd, void* dst, size_t n) {
+    for (;;) {
+        ssize_t got = ::read(fd, dst, n);
+        if (got < 0) {
+            if (errno == EINTR) continue;
+            throw Error(std::string("read failed: ") + std::strerror(errno));
+        }
+        return (size_t)got;
+    }
+}
+
+class PlainStream : public InputStream {
+public:
+    explicit PlainStream(int fd) : fd_(fd) {}
+    ~PlainStream() override { ::close(fd_); }
+    size_t read(char* dst, size_t n) override { return read_fd(fd_, dst, n); }
+private:
+    int fd_;
+};
+
+class GzipStream : public InputStream {
+public:
+    explicit GzipStream(int fd) {
+        gz_ = gzdopen(fd, "rb");
+        if (!gz_) { ::close(fd); throw Error("cannot open the gzip stream"); }
+        gzbuffer(gz_, 1 << 20);
+    }
+    ~GzipStream() override { gzclose(gz_); }
+    size_t read(char* dst, size_t n) override {
+        int got = gzread(gz_, dst, (unsigned)std::min<size_t>(n, 1u << 30));
+        if (got < 0) throw Error("Error while decompressing the input");
+        return (size_t)got;
+    }
+private:
+    gzFile gz_;
+};
+
+class BgzfStream : public InputStream {
+public:
+    BgzfStream(int fd, int threads) : rd_(fd, threads) {}
+    size_t read(char* dst, size_t n) override { return rd_.read(dst, n); }
+private:
+    BgzfReader rd_;
+};
+
+void* load_symbol(void* lib, const char* name, const char* libname) {
+    void* p = dlsym(lib, name);
+    if (!p) throw Error(std::string(libname) + " lacks " + name);
+    return p;
+}
+
+// ---- bzip2 (libbz2.so.1.0) ---------------------------------------------------------------------
+struct bz_stream {
+    char* next_in; unsigned avail_in; unsigned total_in_lo32, total_in_hi32;
+    char* next_out; unsigned avail_out; unsigned total_out_lo32, total_out_hi32;
+    void* state; void* (*bzalloc)(void*, int, int); void (*bzfree)(void*, void*); void* opaque;
+};
+
+class Bzip2Stream : public InputStream {
+public:
+    explicit Bzip2Stream(int fd) : fd_(fd), in_(1 << 20) {
+        lib_ = dlopen("libbz2.so.1.0", RTLD_NOW);
+        if (!lib_) lib_ = dlopen("libbz2.so.1", RTLD_NOW);
+        if (!lib_) { ::close(fd_); throw Error("bzip2 input needs libbz2.so.1.0, which is not installed"); }
+        init_ = (int (*)(bz_stream*, int, int))load_symbol(lib_, "BZ2_bzDecompressInit", "libbz2");
+        run_ = (int (*)(bz_stream*))load_symbol(lib_, "BZ2_bzDecompress", "libbz2");
+        end_ = (int (*)(bz_stream*))load_symbol(lib_, "BZ2_bzDecompressEnd", "libbz2");
+        std::memset(&s_, 0, sizeof s_);
+        if (init_(&s_, 0, 0) != 0) throw Error("BZ2_bzDecompressInit failed");
+        open_ = true;
+    }
+    ~Bzip2Stream() override {
+        if (open_) end_(&s_);
+        ::close(fd_);
+    }
+    size_t read(char* dst, size_t n) override {
+        if (done_) return 0;
+        s_.next_out = dst;
+        s_.avail_out = (unsigned)std::min<size_t>(n, 1u << 30);
+        const unsigned want = s_.avail_out;
+        while (s_.avail_out == want) {
+            if (s_.avail_in == 0 && !eof_) {
+                size_t got = read_fd(fd_, in_.data(), in_.size());
+                if (got == 0) eof_ = true;
+                s_.next_in = in_.data();
+                s_.avail_in = (unsigned)got;
+            }
+            if (!open_) {  // a further stream of a multi-stream file, or trailing nothing
+                if (s_.avail_in == 0) { done_ = true; break; }
+                char* ni = s_.next_in; unsigned ai = s_.avail_in;
+                std::memset(&s_, 0, sizeof s_);
+                if (init_(&s_, 0, 0) != 0) throw Error("BZ2_bzDecompressInit failed");
+                open_ = true;
+                s_.next_in = ni; s_.avail_in = ai;
+                s_.next_out = dst + (want - want); s_.avail_out = want;
+            }
+            if (s_.avail_in == 0 && eof_) throw Error("Error while decompressing the input (truncated bzip2 stream)");
+            int rc = run_(&s_);
+            if (rc == 4) {  // BZ_STREAM_END
+                end_(&s_);
+                open_ = false;
+                if (s_.avail_out != want) break;
+            } else if (rc != 0) {
+                throw Error("Error while decompressing the input (bzip2)");
+            }
+        }
+        return want - s_.avail_out;
+    }
+private:
+    int fd_;
+    void* lib_ = nullptr;
+    int (*init_)(bz_stream*, int, int) = nullptr;
+    int (*run_)(bz_stream*) = nullptr;
+    int (*end_)(bz_stream*) = nullptr;
+    bz_stream s_;
+    std::vector<char> in_;
+    bool open_ = false, eof_ = false, done_ = false;
+};
+
+// ---- xz (liblzma.so.5) -------------------------------------------------------------------------
+struct lzma_stream {
+    const uint8_t* next_in; size_t avail_in; uint64_t total_in;
+    uint8_t* next_out; size_t avail_out; uint64_t total_out;
+    const void* allocator; void* internal;
+    void *reserved_ptr1, *reserved_ptr2, *reserved_ptr3, *reserved_ptr4;
+    uint64_t reserved_int1, reserved_int2; size_t reserved_int3, reserved_int4;
+    int reserved_enum1, reserved_enum2;
+};
+
+class XzStream : public InputStream {
+public:
+    explicit XzStream(int fd) : fd_(fd), in_(1 << 20) {
+        lib_ = dlopen("liblzma.so.5", RTLD_NOW);
+        if (!lib_) { ::close(fd_); throw Error("xz input needs liblzma.so.5, which is not installed"); }
+        auto decoder = (int (*)(lzma_stream*, uint64_t, uint32_t))load_symbol(lib_, "lzma_stream_decoder", "liblzma");
+        code_ = (int (*)(lzma_stream*, int))load_symbol(lib_, "lzma_code", "liblzma");
+        end_ = (void (*)(lzma_stream*))load_symbol(lib_, "lzma_end", "liblzma");
+        std::memset(&s_, 0, sizeof s_);
+        if (decoder(&s_, UINT64_MAX, 0x08 /* LZMA_CONCATENATED */) != 0) throw Error("lzma_stream_decoder failed");
+    }
+    ~XzStream() override {
+        end_(&s_);
+        ::close(fd_);
+    }
+    size_t read(char* dst, size_t n) override {
+        if (done_) return 0;
+        s_.next_out = reinterpret_cast<uint8_t*>(dst);
+        s_.avail_out = n;
+        while (s_.avail_out == n) {
+            if (s_.avail_in == 0 && !eof_) {
+                size_t got = read_fd(fd_, in_.data(), in_.size());
+                if (got == 0) eof_ = true;
+                s_.next_in = reinterpret_cast<const uint8_t*>(in_.data());
+                s_.avail_in = got;
+            }
+            int rc = code_(&s_, eof_ ? 3 /* LZMA_FINISH */ : 0 /* LZMA_RUN */);
+            if (rc == 1) { done_ = true; break; }  // LZMA_STREAM_END
+            if (rc != 0) throw Error("Error while decompressing the input (xz)");
+        }
+        return n - s_.avail_out;
+    }
+private:
+    int fd_;
+    void* lib_ = nullptr;
+    int (*code_)(lzma_stream*, int) = nullptr;
+    void (*end_)(lzma_stream*) = nullptr;
+    lzma_stream s_;
+    std::vector<char> in_;
+    bool eof_ = false, done_ = false;
+};
+
+}  // namespace
+
+std::unique_ptr<InputStream> InputStream::open(const std::string& path) {
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw Error("No such file or directory (os error 2)");
+    unsigned char m[6] = {0, 0, 0, 0, 0, 0};
+    ssize_t n = ::pread(fd, m, sizeof m, 0);
+    if (n >= 2 && m[0] == 0x1f && m[1] == 0x8b) {
+        if (decompression_threads() > 1 && is_bgzf(fd)) return std::unique_ptr<InputStream>(new BgzfStream(fd, decompression_threads()));
+        return std::unique_ptr<InputStream>(new GzipStream(fd));
+    }
+    if (n >= 3 && m[0] == 'B' && m[1] == 'Z' && m[2] == 'h') return std::unique_ptr<InputStream>(new Bzip2Stream(fd));
+    if (n >= 6 && m[0] == 0xFD && m[1] == '7' && m[2] == 'z' && m[3] == 'X' && m[4] == 'Z' && m[5] == 0x00)
+        return std::unique_ptr<InputStream>(new XzStream(fd));
+    return std::unique_ptr<InputStream>(new PlainStream(fd));
+}
+
+}  // namespace mkh

@@ -1,60 +1,21 @@
 #include "fastq_stream.h"
 
-#include <fcntl.h>
-#include <unistd.h>
-#include <zlib.h>
-
 #include <cstring>
 
-#include "io.h"
+#include "codecs.h"
 
 namespace mkh {
 
 namespace {
 
-// Plain files are read with read(2); gzip (also multi-member / BGZF) through zlib.
+// The input's bytes, whatever its compression (codecs.h).
 class RawSource {
 public:
-    explicit RawSource(const std::string& path) {
-        fd_ = ::open(path.c_str(), O_RDONLY);
-        if (fd_ < 0) throw Error("No such file or directory (os error 2)");
-        unsigned char magic[2] = {0, 0};
-        ssize_t n = ::pread(fd_, magic, 2, 0);
-        if (n == 2 && magic[0] == 0x1f && magic[1] == 0x8b && decompression_threads() > 1 && is_bgzf(fd_)) {
-            bgzf_.reset(new BgzfReader(fd_, decompression_threads()));  // bgzip'ed FASTQ: block-parallel
-            fd_ = -1;
-        } else if (n == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
-            gz_ = gzdopen(fd_, "rb");
-            if (!gz_) { ::close(fd_); throw Error("cannot open the gzip stream"); }
-            gzbuffer(gz_, 1 << 20);
-        }
-    }
-    ~RawSource() {
-        if (gz_) gzclose(gz_);
-        else if (fd_ >= 0) ::close(fd_);
-    }
-    // Reads up to n bytes; 0 at end of input.
-    size_t read(char* dst, size_t n) {
-        if (bgzf_) return bgzf_->read(dst, n);
-        if (gz_) {
-            int got = gzread(gz_, dst, (unsigned)std::min<size_t>(n, 1u << 30));
-            if (got < 0) throw Error("Error while decompressing the input");
-            return (size_t)got;
-        }
-        for (;;) {
-            ssize_t got = ::read(fd_, dst, n);
-            if (got < 0) {
-                if (errno == EINTR) continue;
-                throw Error(std::string("read failed: ") + std::strerror(errno));
-            }
-            return (size_t)got;
-        }
-    }
+    explicit RawSource(const std::string& path) : in_(InputStream::open(path)) {}
+    size_t read(char* dst, size_t n) { return in_->read(dst, n); }
 
 private:
-    int fd_ = -1;
-    gzFile gz_ = nullptr;
-    std::unique_ptr<BgzfReader> bgzf_;
+    std::unique_ptr<InputStream> in_;
 };
 
 struct Line {

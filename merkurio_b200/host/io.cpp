@@ -21,32 +21,15 @@ int decompression_threads() {
     return (int)std::min(8u, std::max(1u, hw / 2));
 }
 
-ByteSource::ByteSource(const std::string& path) : buf_(1 << 22) {
-    int fd = ::open(path.c_str(), O_RDONLY);
-    if (fd < 0) throw Error("No such file or directory (os error 2)");
-    if (decompression_threads() > 1 && is_bgzf(fd)) {
-        bgzf_.reset(new BgzfReader(fd, decompression_threads()));
-        return;
-    }
-    f_ = gzdopen(fd, "rb");
-    if (!f_) { ::close(fd); throw Error("No such file or directory (os error 2)"); }
-    gzbuffer(f_, 1 << 20);
-}
-ByteSource::~ByteSource() { if (f_) gzclose(f_); }
-
-size_t ByteSource::raw_read(void* dst, size_t n) {
-    if (bgzf_) return bgzf_->read(static_cast<char*>(dst), n);
-    int got = gzread(f_, dst, (unsigned)std::min<size_t>(n, 1u << 30));
-    if (got < 0) throw Error("Error while decompressing the input");
-    return (size_t)got;
-}
+ByteSource::ByteSource(const std::string& path) : in_(InputStream::open(path)), buf_(1 << 22) {}
+ByteSource::~ByteSource() {}
 
 bool ByteSource::fill() {
     if (eof_) return false;
     if (pos_ < end_) std::memmove(buf_.data(), buf_.data() + pos_, end_ - pos_);
     end_ -= pos_;
     pos_ = 0;
-    size_t n = raw_read(buf_.data() + end_, buf_.size() - end_);
+    size_t n = in_->read(buf_.data() + end_, buf_.size() - end_);
     if (n == 0) { eof_ = true; return false; }
     end_ += n;
     return true;
@@ -94,7 +77,7 @@ size_t ByteSource::read_some(void* dst, size_t n) {
     if (pos_ == end_) {
         if (eof_) return 0;
         // nothing buffered: read straight into the caller's memory
-        size_t got = raw_read(dst, n);
+        size_t got = in_->read(static_cast<char*>(dst), n);
         if (got == 0) eof_ = true;
         return got;
     }

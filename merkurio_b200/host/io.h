@@ -1,4 +1,4 @@
-// Input side: a buffered byte source over zlib (plain or gzip/BGZF transparently), the FASTA/FASTQ
+// Input side: a buffered byte source over any supported compression (codecs.h), the FASTA/FASTQ
 // record reader (the role needletail plays in src/cmd_extract.rs:281,321,412,463) and the SAM/BAM
 // record reader (the role of the `bam` crate in src/cmd_tag.rs:504-613).
 #pragma once
@@ -9,7 +9,7 @@
 #include <string>
 #include <vector>
 
-#include "bgzf.h"
+#include "codecs.h"
 #include "common.h"
 
 namespace mkh {
@@ -36,9 +36,7 @@ public:
     int peek();  // next byte or -1
 private:
     bool fill();
-    size_t raw_read(void* dst, size_t n);  // plain, gzip or (block-parallel) BGZF
-    gzFile f_ = nullptr;
-    std::unique_ptr<BgzfReader> bgzf_;
+    std::unique_ptr<InputStream> in_;  // plain, gzip, BGZF (block-parallel), bzip2 or xz
     std::vector<char> buf_;
     size_t pos_ = 0, end_ = 0;
     bool eof_ = false;

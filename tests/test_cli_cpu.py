@@ -356,3 +356,43 @@ def test_chunked_bam_reader_equals_record_reader(exe, ref_tree, tmp_path):
             got = subprocess.run([exe, "alnrecords", str(src), "chunked", str(chunk)], capture_output=True)
             assert got.returncode == 0, got.stderr
             assert got.stdout == want.stdout, (src.name, chunk)
+
+
+@pytest.mark.parametrize("codec", ["gz", "bz2", "bz2_multi", "xz", "xz_multi"])
+def test_compressed_inputs_are_recognised_by_their_magic_bytes(exe, tmp_path, codec):
+    """needletail opens .gz / .bz2 / .xz by content, not by name (README.md:39): same records as the plain file."""
+    import bz2
+    import gzip
+    import lzma
+    import numpy as np
+    rng = np.random.default_rng(13)
+    recs = []
+    for i in range(6000):
+        n = int(rng.integers(1, 300))
+        s = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=n).tobytes())
+        recs.append(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * n))
+    data = b"".join(recs)
+    half = data.index(b"\n@r3000\n") + 1
+    packed = {"gz": gzip.compress(data), "bz2": bz2.compress(data), "bz2_multi": bz2.compress(data[:half]) + bz2.compress(data[half:]),
+              "xz": lzma.compress(data), "xz_multi": lzma.compress(data[:half]) + lzma.compress(data[half:])}[codec]
+    plain = tmp_path / "p.fastq"
+    plain.write_bytes(data)
+    comp = tmp_path / "reads.fastq.dat"  # the name says nothing
+    comp.write_bytes(packed)
+    want = subprocess.run([exe, "records", str(plain), "generic"], capture_output=True).stdout
+    assert want.count(b"#id\t") == 6000
+    for how in ("generic", "chunked"):
+        got = subprocess.run([exe, "records", str(comp), how, "100000"], capture_output=True)
+        assert got.returncode == 0, got.stderr
+        assert got.stdout == want, (codec, how)
+    # a truncated stream is an error, not a silently shorter input
+    (tmp_path / "cut.dat").write_bytes(packed[: len(packed) // 2])
+    r = subprocess.run([exe, "records", str(tmp_path / "cut.dat"), "generic"], capture_output=True)
+    assert r.returncode != 0 or b"#error" in r.stdout
+    # FASTA through the same streams
+    fa = b"".join(b">s%d\n%s\n" % (i, b"ACGTTGCA" * 20) for i in range(500))
+    (tmp_path / "g.fa").write_bytes(fa)
+    (tmp_path / "g.fa.z").write_bytes({"gz": gzip.compress, "bz2": bz2.compress, "bz2_multi": bz2.compress, "xz": lzma.compress, "xz_multi": lzma.compress}[codec](fa))
+    a = subprocess.run([exe, "records", str(tmp_path / "g.fa"), "generic"], capture_output=True).stdout
+    b = subprocess.run([exe, "records", str(tmp_path / "g.fa.z"), "generic"], capture_output=True).stdout
+    assert a == b and a.count(b"#id\t") == 500
