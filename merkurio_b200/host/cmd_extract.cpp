@@ -262,9 +262,20 @@ void extract_records(CmdExtract args) {
             chunks1 = FastqPipeline::open_reader(args.in_fastx);
             if (paired) chunks2 = FastqPipeline::open_reader(*args.in_fastq_2);
         }
+        // the record-by-record path (FASTA, and whatever the FASTQ pipeline does not take) reads ahead on its own
+        // threads, also started before the engines
+        const bool keep_text = !args.suppress_output;
+        std::unique_ptr<PrefetchingFastxReader> ahead1, ahead2;
+        if (!pipelined) {
+            reader->set_keep_raw(keep_text);
+            ahead1.reset(new PrefetchingFastxReader(reader.get()));
+            if (paired) {
+                reader2->set_keep_raw(keep_text);
+                ahead2.reset(new PrefetchingFastxReader(reader2.get()));
+            }
+        }
         EngineSet engines(pattern_list, args.case_insensitive, pipelined ? 16 : 64);
         Scanner scanner(engines, MK_ENC_ASCII, mode, cb);
-        const bool keep_text = !args.suppress_output;
         auto feed = [&](FastxRecord& rec, uint8_t file) {
             RecMeta m;
             m.a = std::move(rec.id);
@@ -314,8 +325,7 @@ void extract_records(CmdExtract args) {
             }
         };
         FastxRecord r1, r2;
-        if (reader) reader->set_keep_raw(keep_text);
-        if (reader2) reader2->set_keep_raw(keep_text);
+
         try {
             if (pipelined) {
                 reader.reset();
@@ -326,24 +336,24 @@ void extract_records(CmdExtract args) {
             } else if (!paired) {
                 for (;;) {
                     bool more;
-                    try { more = reader->next(&r1); } catch (const Error& e) { throw e.with_context("Error during FASTQ/A record parsing."); }
+                    try { more = ahead1->next(&r1); } catch (const Error& e) { throw e.with_context("Error during FASTQ/A record parsing."); }
                     if (!more) break;
                     feed(r1, 0);
                 }
             } else {
                 for (;;) {
                     bool more;
-                    try { more = reader->next(&r1); } catch (const Error& e) { throw e.with_context("Error during FASTQ record parsing of first file."); }
+                    try { more = ahead1->next(&r1); } catch (const Error& e) { throw e.with_context("Error during FASTQ record parsing of first file."); }
                     if (!more) break;
                     bool more2;
-                    try { more2 = reader2->next(&r2); } catch (const Error& e) {
+                    try { more2 = ahead2->next(&r2); } catch (const Error& e) {
                         throw e.with_context("Error during FASTQ record parsing of second file. Do the two input files contain the same number of records?");
                     }
                     if (!more2) throw Error("Error during FASTQ record parsing of second file. Do the two input files contain the same number of records?");
                     feed(r1, 0);
                     feed(r2, 1);
                 }
-                if (reader2->next(&r2))
+                if (ahead2->next(&r2))
                     throw Error("The two input files have a different number of records. Please provide valid paired-end read files.");
             }
         } catch (...) {

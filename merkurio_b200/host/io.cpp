@@ -5,7 +5,10 @@
 
 #include <algorithm>
 #include <charconv>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <thread>
 
 namespace mkh {
@@ -185,6 +188,75 @@ bool FastxReader::next(FastxRecord* rec) {
     // the final line break of the record is not part of raw_seq
     if (!rec->raw.empty() && rec->raw.back() == '\r') rec->raw.pop_back();
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct PrefetchingFastxReader::State {
+    FastxReader* rd;
+    size_t depth;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::unique_ptr<FastxRecord>> ready;
+    std::unique_ptr<Error> error;  // raised after the records before it have been handed out
+    bool done = false, stop = false;
+};
+
+PrefetchingFastxReader::PrefetchingFastxReader(FastxReader* reader, size_t depth) : st_(new State) {
+    st_->rd = reader;
+    st_->depth = std::max<size_t>(depth, 1);
+    State* s = st_.get();
+    s->th = std::thread([s] {
+        try {
+            for (;;) {
+                std::unique_ptr<FastxRecord> r(new FastxRecord);
+                if (!s->rd->next(r.get())) break;
+                std::unique_lock<std::mutex> lk(s->mu);
+                s->cv.wait(lk, [s] { return s->ready.size() < s->depth || s->stop; });
+                if (s->stop) return;
+                s->ready.push_back(std::move(r));
+                lk.unlock();
+                s->cv.notify_all();
+            }
+        } catch (const Error& e) {
+            std::lock_guard<std::mutex> lk(s->mu);
+            s->error.reset(new Error(e));
+        } catch (const std::exception& e) {
+            std::lock_guard<std::mutex> lk(s->mu);
+            s->error.reset(new Error(e.what()));
+        }
+        std::lock_guard<std::mutex> lk(s->mu);
+        s->done = true;
+        s->cv.notify_all();
+    });
+}
+
+PrefetchingFastxReader::~PrefetchingFastxReader() {
+    {
+        std::lock_guard<std::mutex> lk(st_->mu);
+        st_->stop = true;
+    }
+    st_->cv.notify_all();
+    if (st_->th.joinable()) st_->th.join();
+}
+
+bool PrefetchingFastxReader::next(FastxRecord* rec) {
+    std::unique_lock<std::mutex> lk(st_->mu);
+    st_->cv.wait(lk, [this] { return !st_->ready.empty() || st_->done; });
+    if (!st_->ready.empty()) {
+        std::unique_ptr<FastxRecord> r = std::move(st_->ready.front());
+        st_->ready.pop_front();
+        lk.unlock();
+        st_->cv.notify_all();
+        std::swap(*rec, *r);
+        return true;
+    }
+    if (st_->error) {
+        Error e = *st_->error;
+        st_->error.reset();
+        throw e;
+    }
+    return false;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -66,6 +66,20 @@ private:
     bool have_pending_ = false, started_ = false, fastq_ = false, keep_raw_ = true;
 };
 
+// Runs a FastxReader on its own thread, a few records ahead of the consumer (FASTA input: the next
+// chromosome is read and unwrapped while the current one is being scanned). Same results and errors,
+// raised at the same record, as calling FastxReader::next directly.
+class PrefetchingFastxReader {
+public:
+    explicit PrefetchingFastxReader(FastxReader* reader, size_t depth = 2);
+    ~PrefetchingFastxReader();
+    bool next(FastxRecord* rec);
+
+private:
+    struct State;
+    std::unique_ptr<State> st_;
+};
+
 // One alignment record. `packed` holds the sequence as BAM stores it (4 bits per base, first base in
 // the high nibble, "=ACMGRSVTWYHKDBN"); the device scans it directly.
 struct AlnRecord {

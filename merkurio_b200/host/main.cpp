@@ -413,16 +413,72 @@ int run(int argc, char** argv) {
 
 }  // namespace
 
-int main(int argc, char** argv) {
+static int guarded_run(int argc, char** argv, FILE* err) {
     try {
         return run(argc, argv);
     } catch (const Error& e) {
         std::fflush(stdout);
-        std::fputs(e.report().c_str(), stderr);
+        std::fputs(e.report().c_str(), err);
         return 1;
     } catch (const std::exception& e) {
         std::fflush(stdout);
-        std::fprintf(stderr, "Error: %s\n", e.what());
+        std::fprintf(err, "Error: %s\n", e.what());
         return 1;
     }
+}
+
+// merkurio batch <file>: run several command lines in ONE process (diagnostic, not in the reference).
+// Creating a CUDA context costs seconds on a multi-GPU box; the test-suite pays it once per group of
+// runs this way. One command per line, fields separated by tabs; leading NAME=VALUE fields are
+// environment settings for that command only. The exit status of command i goes to <file>.<i>.rc, what
+// it would have printed to stderr to <file>.<i>.err.
+static int run_batch(const char* argv0, const std::string& path) {
+    std::FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) { std::fprintf(stderr, "Error: cannot open %s\n", path.c_str()); return 1; }
+    std::string all;
+    char buf[65536];
+    size_t n;
+    while ((n = std::fread(buf, 1, sizeof buf, f)) > 0) all.append(buf, n);
+    std::fclose(f);
+    int index = 0;
+    size_t pos = 0;
+    while (pos < all.size()) {
+        size_t nl = all.find('\n', pos);
+        std::string line = all.substr(pos, nl == std::string::npos ? std::string::npos : nl - pos);
+        pos = nl == std::string::npos ? all.size() : nl + 1;
+        if (line.empty()) continue;
+        std::vector<std::string> fields;
+        for (size_t q = 0;;) {
+            size_t tab = line.find('\t', q);
+            fields.push_back(line.substr(q, tab == std::string::npos ? std::string::npos : tab - q));
+            if (tab == std::string::npos) break;
+            q = tab + 1;
+        }
+        std::vector<std::string> env_names;
+        size_t first = 0;
+        for (; first < fields.size(); ++first) {
+            const std::string& t = fields[first];
+            size_t eq = t.find('=');
+            bool is_env = eq != std::string::npos && eq > 0;
+            for (size_t i = 0; is_env && i < eq; ++i) is_env = (t[i] >= 'A' && t[i] <= 'Z') || (t[i] >= '0' && t[i] <= '9') || t[i] == '_';
+            if (!is_env) break;
+            setenv(t.substr(0, eq).c_str(), t.substr(eq + 1).c_str(), 1);
+            env_names.push_back(t.substr(0, eq));
+        }
+        std::vector<char*> av;
+        av.push_back(const_cast<char*>(argv0));
+        for (size_t i = first; i < fields.size(); ++i) av.push_back(const_cast<char*>(fields[i].c_str()));
+        const std::string stem = path + "." + std::to_string(index++);
+        std::FILE* err = std::fopen((stem + ".err").c_str(), "wb");
+        int rc = guarded_run((int)av.size(), av.data(), err ? err : stderr);
+        if (err) std::fclose(err);
+        if (std::FILE* r = std::fopen((stem + ".rc").c_str(), "wb")) { std::fprintf(r, "%d\n", rc); std::fclose(r); }
+        for (auto& name : env_names) unsetenv(name.c_str());
+    }
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc == 3 && std::strcmp(argv[1], "batch") == 0) return run_batch(argv[0], argv[2]);
+    return guarded_run(argc, argv, stderr);
 }

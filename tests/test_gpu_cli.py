@@ -366,12 +366,32 @@ def _strip_volatile(name, data):
     return data
 
 
+def _outputs_batched(tmp_path, runs):
+    """Several (tag, args, env) runs in ONE process (`merkurio batch`): one CUDA start-up for all of them."""
+    lines = []
+    for tag, args, env in runs:
+        d = tmp_path / tag
+        d.mkdir()
+        fields = ["%s=%s" % kv for kv in env.items()] + [str(a).replace("@OUT@", str(d)) for a in args]
+        assert not any("\t" in x or "\n" in x for x in fields)
+        lines.append("\t".join(fields))
+    script = tmp_path / "batch.txt"
+    script.write_text("\n".join(lines) + "\n")
+    r = subprocess.run([EXE, "batch", str(script)], capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    out = []
+    for i, (tag, _, _) in enumerate(runs):
+        rc = int((tmp_path / ("batch.txt.%d.rc" % i)).read_text())
+        err = (tmp_path / ("batch.txt.%d.err" % i)).read_bytes()
+        out.append((rc, err, {p.name: p.read_bytes() for p in sorted((tmp_path / tag).iterdir())}))
+    return out
+
+
 def _same_both_ways(tmp_path, args, off_switch, env=None):
     """The reader -> packer -> GPU pipeline and the record-by-record path must agree on every output
     file, the exit status and the error text — also when the input breaks off half way."""
     e = dict(env or {})
-    a = _outputs(tmp_path, "pipe", args, e)
-    b = _outputs(tmp_path, "plain", args, dict(e, **{off_switch: "1"}))
+    a, b = _outputs_batched(tmp_path, [("pipe", args, e), ("plain", args, dict(e, **{off_switch: "1"}))])
     assert a[0] == b[0], (a[1], b[1])
     assert a[1].replace(b"[merkurio]", b"") == b[1].replace(b"[merkurio]", b"")
     assert a[2].keys() == b[2].keys()
