@@ -91,6 +91,7 @@ struct Workspace {
     DevBuf<mk::RawHit> raw_a, raw_b;
     DevBuf<mk_hit> out;
     DevBuf<uint32_t> heads, radix_table, radix_totals;  // heads: per-tile head counts of the pair de-duplication
+    DevBuf<uint32_t> buckets;                // bucket sort: counts [kBuckets], starts [kBuckets + 1], cursors [kBuckets]
     DevBuf<uint2> cand;                      // candidate list handed from the scan to the verify kernel
     uint64_t cand_cap = 0;
     DevBuf<unsigned long long> counters;     // [0] hits appended, [1] distinct pairs, [2] candidates
@@ -100,6 +101,9 @@ struct Workspace {
     uint64_t hit_cap = 0;
     // description of the batch in flight
     bool busy = false;
+    bool prefer_radix = false;  // a bucket of the bucket sort overflowed once: this workspace sorts with the radix passes
+    bool used_buckets = false;  // the batch in flight was sorted with the bucket sort
+    uint32_t key_bits = 0;
     const void* d_seq = nullptr;
     const unsigned long long* d_off = nullptr;
     const uint32_t* d_lens = nullptr;
@@ -240,6 +244,9 @@ int init_workspace(Workspace& ws) {
     CU(ws.h_counters.ensure(8));
     CU(ws.radix_table.ensure((size_t)256 * mk::kSortWarps));
     CU(ws.radix_totals.ensure(256));
+    CU(ws.buckets.ensure(3 * mk::kBuckets + 16));
+    CU(cudaMemset(ws.buckets.p, 0, (3 * mk::kBuckets + 16) * sizeof(uint32_t)));
+    if (std::getenv("MK_NO_BUCKET_SORT")) ws.prefer_radix = true;
     return MK_OK;
 }
 
@@ -247,6 +254,7 @@ int ensure_hit_capacity(Workspace& ws, uint64_t cap) {
     if (cap <= ws.hit_cap) return MK_OK;
     CU(ws.raw_a.ensure(cap));
     CU(ws.raw_b.ensure(cap));
+    CU(cudaMemset(ws.raw_b.p, 0, cap * sizeof(mk::RawHit)));  // never holds anything but valid pattern ids (see enqueue_sort)
     CU(ws.out.ensure(cap));
     CU(ws.heads.ensure(cap / mk::kHeadTile + 2));
     ws.hit_cap = cap;
@@ -277,6 +285,60 @@ int ensure_tables(mk_engine* e, int enc) {
     if (dt.host.filter_in_smem)
         CU(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dt.host.filter.size() * 4)));
     dt.built = true;
+    return MK_OK;
+}
+
+// Sort the raw hit list of ws (raw_a) into the report order and convert it (ws.out). buckets: the bucket
+// sort (4 launches; raises counters[3] if a bucket overflows, see finish_batch), else the radix passes.
+int enqueue_sort(mk_engine* e, Workspace& ws, bool buckets) {
+    DeviceTables& dt = e->tables[ws.enc];
+    const uint32_t key_bits = ws.key_bits;
+    const uint32_t len_tie_bits = e->ps.len_bits + e->ps.tie_bits;
+    const unsigned long long* cnt = ws.counters.p;
+    ws.used_buckets = buckets;
+    if (buckets) {
+        // the largest key of the batch: ALL_HITS (end <= n_units | len field | tie), PATTERN_SET (record | pattern)
+        const unsigned long long max_key = ws.mode == MK_MODE_ALL_HITS
+                                               ? ((((unsigned long long)ws.n_units + 1) << len_tie_bits) - 1)
+                                               : ((((unsigned long long)ws.n_records) << mk::bits_for(e->ps.n ? e->ps.n - 1 : 0)) - 1);
+        const mk::BucketMap shift = mk::make_bucket_map(max_key);
+        (void)key_bits;
+        uint32_t* bcount = ws.buckets.p;
+        uint32_t* bstart = ws.buckets.p + mk::kBuckets;
+        uint32_t* bcursor = ws.buckets.p + 2 * mk::kBuckets + 8;
+        unsigned long long* overflow = ws.counters.p + 3;
+        mk::mk_bucket_count<<<e->sm_count * 2, 256, 0, ws.stream>>>(ws.raw_a.p, cnt, ws.hit_cap, shift, bcount);
+        mk::mk_bucket_scan<<<1, 1024, 0, ws.stream>>>(bcount, bstart, bcursor, overflow);
+        mk::mk_bucket_scatter<<<e->sm_count * 2, 256, 0, ws.stream>>>(ws.raw_a.p, ws.raw_b.p, cnt, ws.hit_cap, shift, bcursor, overflow);
+        if (ws.mode == MK_MODE_ALL_HITS) {
+            mk::mk_bucket_sort<<<e->sm_count * 4, 256, 0, ws.stream>>>(ws.raw_b.p, bstart, overflow, ws.out.p, ws.d_off, dt.pat_off.p, len_tie_bits);
+        } else {
+            mk::mk_bucket_sort<<<e->sm_count * 4, 256, 0, ws.stream>>>(ws.raw_b.p, bstart, overflow, nullptr, nullptr, nullptr, 0);
+            mk::mk_heads_count<<<e->sm_count * 4, 256, 0, ws.stream>>>(ws.raw_b.p, cnt, ws.hit_cap, ws.heads.p);
+            mk::mk_heads_scan<<<1, 1024, 0, ws.stream>>>(cnt, ws.hit_cap, ws.heads.p, ws.counters.p + 1);
+            mk::mk_finalize_pairs<<<e->sm_count * 4, 256, 0, ws.stream>>>(ws.raw_b.p, ws.out.p, cnt, ws.hit_cap, ws.heads.p, dt.pat_off.p);
+        }
+        CU(cudaGetLastError());
+        return MK_OK;
+    }
+    {
+        mk::RawHit *src = ws.raw_a.p, *dst = ws.raw_b.p;
+        for (uint32_t shift = 0; shift < key_bits; shift += 8) {
+            mk::mk_radix_hist<<<mk::kSortBlocks, mk::kSortThreads, 0, ws.stream>>>(src, cnt, ws.hit_cap, shift, ws.radix_table.p);
+            mk::mk_radix_rowscan<<<256, 256, 0, ws.stream>>>(cnt, ws.hit_cap, ws.radix_table.p, ws.radix_totals.p);
+            mk::mk_radix_scatter<<<mk::kSortBlocks, mk::kSortThreads, 0, ws.stream>>>(src, dst, cnt, ws.hit_cap, shift,
+                                                                                    ws.radix_table.p, ws.radix_totals.p);
+            std::swap(src, dst);
+        }
+        if (ws.mode == MK_MODE_ALL_HITS) {
+            mk::mk_finalize_hits<<<256, 256, 0, ws.stream>>>(src, ws.out.p, cnt, ws.hit_cap, ws.d_off, dt.pat_off.p, len_tie_bits);
+        } else {
+            mk::mk_heads_count<<<e->sm_count * 4, 256, 0, ws.stream>>>(src, cnt, ws.hit_cap, ws.heads.p);
+            mk::mk_heads_scan<<<1, 1024, 0, ws.stream>>>(cnt, ws.hit_cap, ws.heads.p, ws.counters.p + 1);
+            mk::mk_finalize_pairs<<<e->sm_count * 4, 256, 0, ws.stream>>>(src, ws.out.p, cnt, ws.hit_cap, ws.heads.p, dt.pat_off.p);
+        }
+        CU(cudaGetLastError());
+    }
     return MK_OK;
 }
 
@@ -353,25 +415,11 @@ int enqueue(mk_engine* e, Workspace& ws) {
         CU(cudaEventRecord(ws.ev_scan, ws.stream));
     }
     CU(cudaEventRecord(ws.ev_verify, ws.stream));
+    ws.key_bits = key_bits;
+    ws.used_buckets = false;
     if (ws.mode != MK_MODE_FLAG) {
-        const unsigned long long* cnt = ws.counters.p;
-        mk::RawHit *src = ws.raw_a.p, *dst = ws.raw_b.p;
-        for (uint32_t shift = 0; shift < key_bits; shift += 8) {
-            mk::mk_radix_hist<<<mk::kSortBlocks, mk::kSortThreads, 0, ws.stream>>>(src, cnt, ws.hit_cap, shift, ws.radix_table.p);
-            mk::mk_radix_rowscan<<<256, 256, 0, ws.stream>>>(cnt, ws.hit_cap, ws.radix_table.p, ws.radix_totals.p);
-            mk::mk_radix_scatter<<<mk::kSortBlocks, mk::kSortThreads, 0, ws.stream>>>(src, dst, cnt, ws.hit_cap, shift,
-                                                                                    ws.radix_table.p, ws.radix_totals.p);
-            std::swap(src, dst);
-        }
-        if (ws.mode == MK_MODE_ALL_HITS) {
-            mk::mk_finalize_hits<<<256, 256, 0, ws.stream>>>(src, ws.out.p, cnt, ws.hit_cap, ws.d_off, dt.pat_off.p,
-                                                            P.len_bits + P.tie_bits);
-        } else {
-            mk::mk_heads_count<<<e->sm_count * 4, 256, 0, ws.stream>>>(src, cnt, ws.hit_cap, ws.heads.p);
-            mk::mk_heads_scan<<<1, 1024, 0, ws.stream>>>(cnt, ws.hit_cap, ws.heads.p, ws.counters.p + 1);
-            mk::mk_finalize_pairs<<<e->sm_count * 4, 256, 0, ws.stream>>>(src, ws.out.p, cnt, ws.hit_cap, ws.heads.p, dt.pat_off.p);
-        }
-        CU(cudaGetLastError());
+        int rc = enqueue_sort(e, ws, !ws.prefer_radix);
+        if (rc) return rc;
     }
     CU(cudaEventRecord(ws.ev_end, ws.stream));
     CU(cudaMemcpyAsync(ws.h_counters.p, ws.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ws.stream));
@@ -424,6 +472,19 @@ int finish_batch(mk_engine* e, Workspace& ws, mk_result* out) {
         ms_total += a; ms_scan += b; ms_verify += c;
         const bool cand_over = ws.h_counters.p[2] > ws.cand_cap;
         const bool hits_over = ws.mode != MK_MODE_FLAG && ws.h_counters.p[0] > ws.hit_cap;
+        if (!cand_over && !hits_over && ws.used_buckets && ws.h_counters.p[3]) {
+            // a bucket of the bucket sort overflowed (hits piled up in one key range): the raw list is untouched,
+            // sort it with the radix passes, and keep to them on this workspace
+            ws.prefer_radix = true;
+            int rc = enqueue_sort(e, ws, false);
+            if (rc) { ws.busy = false; return rc; }
+            CU(cudaEventRecord(ws.ev_end, ws.stream));
+            CU(cudaMemcpyAsync(ws.h_counters.p, ws.counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ws.stream));
+            CU(cudaStreamSynchronize(ws.stream));
+            float extra = 0.f;
+            CU(cudaEventElapsedTime(&extra, ws.ev_verify, ws.ev_end));
+            ms_total += extra;
+        }
         if (!cand_over && !hits_over) break;
         // a list overflowed: grow it to the exact need and scan the batch again (never drop hits)
         int rc = MK_OK;

@@ -134,6 +134,178 @@ __global__ void __launch_bounds__(kSortThreads) mk_radix_scatter(const RawHit* _
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Bucket sort: the usual hit list is a few hundred thousand entries whose keys are spread evenly
+// (hits are scattered over the batch), so one MSD split into kBuckets ranges followed by a sort of
+// each range in shared memory replaces five radix passes (15 launches) by 4 launches. A range with
+// more than kBucketMax entries (hits piled up in one region) raises a flag; the host then runs the
+// radix sort on the untouched input instead, and keeps doing so for that workspace.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kBucketBits = 13;
+constexpr uint32_t kBuckets = 1u << kBucketBits;
+constexpr uint32_t kBucketMax = 2048;
+
+// Bucket of a key: monotonic in the key and spread over the keys that can actually occur (the largest
+// key is rarely close to a power of two): the top 32 bits of the key range, scaled by `mult` / 2^32.
+struct BucketMap {
+    uint32_t shift;  // key >> shift fits 32 bits
+    uint32_t mult;   // bucket = ((key >> shift) * mult) >> 32
+};
+__host__ __device__ __forceinline__ uint32_t bucket_of(unsigned long long key, BucketMap bm) {
+    uint32_t b = (uint32_t)((((unsigned long long)(uint32_t)(key >> bm.shift)) * bm.mult) >> 32);
+    return b < kBuckets ? b : kBuckets - 1;
+}
+inline BucketMap make_bucket_map(unsigned long long max_key) {
+    BucketMap bm;
+    bm.shift = 0;
+    while ((max_key >> bm.shift) >> 32) ++bm.shift;
+    const unsigned long long top = (max_key >> bm.shift) + 1;  // number of distinct key tops, <= 2^32
+    unsigned long long mult = (((unsigned long long)kBuckets) << 32) / top;
+    if (mult > 0xFFFFFFFFull) mult = 0xFFFFFFFFull;  // tiny key ranges: at most one bucket per key top (mult saturates)
+    bm.mult = (uint32_t)mult;
+    return bm;
+}
+
+__global__ void __launch_bounds__(256) mk_bucket_count(const RawHit* __restrict__ in, const unsigned long long* count,
+                                                      unsigned long long cap, BucketMap bm, uint32_t* __restrict__ bucket_count) {
+    unsigned long long n = *count;
+    if (n > cap) n = cap;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&bucket_count[bucket_of(in[i].key, bm)], 1u);
+}
+
+// one block: bucket_start = exclusive scan of bucket_count (kBuckets + 1 entries), cursor = copy of it,
+// bucket_count zeroed for the next batch, *overflow = 1 if a bucket exceeds kBucketMax
+__global__ void __launch_bounds__(1024) mk_bucket_scan(uint32_t* __restrict__ bucket_count, uint32_t* __restrict__ bucket_start,
+                                                      uint32_t* __restrict__ cursor, unsigned long long* overflow) {
+    __shared__ uint32_t warp_sum[32];
+    constexpr int PER = kBuckets / 1024;
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t v[PER], s = 0, big = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        v[k] = bucket_count[threadIdx.x * PER + k];
+        bucket_count[threadIdx.x * PER + k] = 0;
+        s += v[k];
+        big |= v[k] > kBucketMax;
+    }
+    uint32_t x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_sum[w] = x;
+    const int any_big = __syncthreads_or((int)big);
+    uint32_t pre = 0;
+    for (uint32_t k = 0; k < w; ++k) pre += warp_sum[k];
+    uint32_t run = pre + x - s;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        bucket_start[threadIdx.x * PER + k] = run;
+        cursor[threadIdx.x * PER + k] = run;
+        run += v[k];
+    }
+    if (threadIdx.x == 1023) bucket_start[kBuckets] = run;
+    if (threadIdx.x == 0) *overflow = any_big ? 1ull : 0ull;
+}
+
+__global__ void __launch_bounds__(256) mk_bucket_scatter(const RawHit* __restrict__ in, RawHit* __restrict__ out,
+                                                        const unsigned long long* count, unsigned long long cap, BucketMap bm,
+                                                        uint32_t* __restrict__ cursor, const unsigned long long* overflow) {
+    if (*overflow) return;
+    unsigned long long n = *count;
+    if (n > cap) n = cap;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        RawHit h = in[i];
+        out[atomicAdd(&cursor[bucket_of(h.key, bm)], 1u)] = h;
+    }
+}
+
+// Bitonic sort of the bucket by key in shared memory, then either the conversion to mk_hit (ALL_HITS:
+// hits != nullptr) or the sorted raw hits written back in place (PATTERN_SET, de-duplicated afterwards by
+// mk_heads_* / mk_finalize_pairs). Buckets of up to kWarpBucket entries — nearly all — are sorted by one
+// warp each (8 at a time per block, only __syncwarp between the stages); the few larger ones by whole blocks.
+constexpr uint32_t kWarpBucket = 256;
+static_assert(kBucketMax == 8 * kWarpBucket, "the block path reuses the eight warp regions as one");
+
+template <bool WARP>
+__device__ __forceinline__ void bucket_sort_one(RawHit* __restrict__ data, uint32_t lo, uint32_t m, unsigned long long* s_key, uint2* s_pay,
+                                                mk_hit* __restrict__ hits, const unsigned long long* __restrict__ off,
+                                                const uint32_t* __restrict__ pat_off, uint32_t key_shift) {
+    const uint32_t tid = WARP ? (threadIdx.x & 31) : threadIdx.x, nt = WARP ? 32 : blockDim.x;
+    auto sync = [] { if (WARP) __syncwarp(); else __syncthreads(); };
+    uint32_t p2 = 1;
+    while (p2 < m) p2 <<= 1;
+    for (uint32_t i = tid; i < p2; i += nt) {
+        if (i < m) {
+            RawHit h = data[lo + i];
+            s_key[i] = h.key;
+            s_pay[i] = make_uint2(h.record, h.pattern);
+        } else {
+            s_key[i] = ~0ull;
+        }
+    }
+    sync();
+    for (uint32_t k = 2; k <= p2; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            // one compare-exchange per thread and step: pair t is (i, i | j) with bit j of i clear
+            for (uint32_t t = tid; t < (p2 >> 1); t += nt) {
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                const bool up = (i & k) == 0;
+                const unsigned long long a = s_key[i], c = s_key[l];
+                if ((a > c) == up) {
+                    s_key[i] = c; s_key[l] = a;
+                    const uint2 x = s_pay[i]; s_pay[i] = s_pay[l]; s_pay[l] = x;
+                }
+            }
+            sync();
+        }
+    }
+    for (uint32_t i = tid; i < m; i += nt) {
+        const uint2 pr = s_pay[i];
+        if (hits) {
+            const uint32_t L = pat_off[pr.y + 1] - pat_off[pr.y];
+            mk_hit o;
+            o.record = pr.x;
+            o.start = (uint32_t)((s_key[i] >> key_shift) - L - off[pr.x]);
+            o.pattern = pr.y;
+            o.len = L;
+            hits[lo + i] = o;
+        } else {
+            RawHit h;
+            h.key = s_key[i];
+            h.record = pr.x;
+            h.pattern = pr.y;
+            data[lo + i] = h;
+        }
+    }
+    sync();
+}
+
+__global__ void __launch_bounds__(256) mk_bucket_sort(RawHit* __restrict__ data, const uint32_t* __restrict__ bucket_start,
+                                                     const unsigned long long* overflow, mk_hit* __restrict__ hits,
+                                                     const unsigned long long* __restrict__ off, const uint32_t* __restrict__ pat_off,
+                                                     uint32_t key_shift) {
+    __shared__ unsigned long long s_key[kBucketMax];
+    __shared__ uint2 s_pay[kBucketMax];
+    if (*overflow) return;
+    const uint32_t w = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    // small buckets: one warp each
+    for (uint32_t b = blockIdx.x * warps + w; b < kBuckets; b += gridDim.x * warps) {
+        const uint32_t lo = bucket_start[b], m = bucket_start[b + 1] - lo;
+        if (m == 0 || m > kWarpBucket) continue;
+        bucket_sort_one<true>(data, lo, m, s_key + w * kWarpBucket, s_pay + w * kWarpBucket, hits, off, pat_off, key_shift);
+    }
+    __syncthreads();
+    // large buckets: one block each
+    for (uint32_t b = blockIdx.x; b < kBuckets; b += gridDim.x) {
+        const uint32_t lo = bucket_start[b], m = bucket_start[b + 1] - lo;
+        if (m <= kWarpBucket) continue;
+        bucket_sort_one<false>(data, lo, m, s_key, s_pay, hits, off, pat_off, key_shift);
+    }
+}
+
 // ALL_HITS: sorted raw hits -> mk_hit
 __global__ void mk_finalize_hits(const RawHit* __restrict__ in, mk_hit* __restrict__ out, const unsigned long long* count,
                                  unsigned long long cap, const unsigned long long* __restrict__ off,

@@ -232,6 +232,25 @@ def test_window_scan_equals_ordered_scan(monkeypatch, k):
     check_batch(pats, recs)
 
 
+def test_bucket_sort_and_its_radix_fallback(monkeypatch):
+    """The hit list is sorted by a bucket split + shared-memory sort; hits piled up in one region overflow
+    a bucket and the batch falls back to the radix passes. Both give the oracle's order."""
+    rng = np.random.default_rng(41)
+    # (a) evenly spread hits, many of them: bucket path
+    pats = sorted({rand_seq(rng, int(k)) for k in rng.integers(5, 9, size=40)})
+    recs = [rand_seq(rng, int(rng.integers(50, 400))) for _ in range(3000)]
+    check_batch(pats, recs)
+    # (b) a poly-A island in a long record, 24 nested patterns: > 2048 hits in one bucket
+    pile = [b"A" * k for k in range(1, 25)]
+    text = rand_seq(rng, 600000, b"CGT") + b"A" * 3000 + rand_seq(rng, 600000, b"CGT")
+    r = check_batch(pile, [text, rand_seq(rng, 5000, b"CGT")])
+    assert r.n_hits > 60000
+    # the same through the radix passes only
+    monkeypatch.setenv("MK_NO_BUCKET_SORT", "1")
+    check_batch(pats, recs)
+    check_batch(pile, [text])
+
+
 def test_hit_overflow_rescan():
     rng = np.random.default_rng(23)
     recs = [rand_seq(rng, 150) for _ in range(200)]
