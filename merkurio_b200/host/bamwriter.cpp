@@ -1,5 +1,9 @@
 #include "bamwriter.h"
 
+#include <atomic>
+#include <mutex>
+#include <thread>
+
 #include <zlib.h>
 
 #include <cstdlib>
@@ -57,7 +61,7 @@ void push_int_tag(std::vector<uint8_t>* v, long long x) {
 
 }  // namespace
 
-BamWriter::BamWriter(const std::string& path, const std::vector<std::string>& header_lines) {
+BamWriter::BamWriter(const std::string& path, const std::vector<std::string>& header_lines, int threads) : threads_(std::max(threads, 1)) {
     f_ = std::fopen(path.c_str(), "wb");
     if (!f_) throw Error("No such file or directory (os error 2)").with_context("Error writing BAM file: " + path);
     std::string text;
@@ -74,6 +78,7 @@ BamWriter::BamWriter(const std::string& path, const std::vector<std::string>& he
             }
             ref_ids_[name] = (int32_t)refs.size();
             refs.emplace_back(name, len);
+            ref_names_.push_back(name);
         }
     }
     std::vector<uint8_t> h;
@@ -106,35 +111,117 @@ void BamWriter::put(const void* p, size_t n) {
     }
 }
 
-void BamWriter::flush_block() {
-    if (!f_ || buf_.empty()) return;
-    uint8_t out[0x10000 + 64];
+// One BGZF block: header with the block size, raw deflate of `in`, CRC32 and input size.
+static void bgzf_compress_block(const std::vector<uint8_t>& in, std::vector<uint8_t>* out) {
+    out->resize(0x10000 + 64);
     z_stream zs{};
     if (deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw Error("deflateInit2 failed");
-    zs.next_in = buf_.data();
-    zs.avail_in = (uInt)buf_.size();
-    zs.next_out = out + 18;
-    zs.avail_out = sizeof out - 18 - 8;
+    zs.next_in = const_cast<uint8_t*>(in.data());
+    zs.avail_in = (uInt)in.size();
+    zs.next_out = out->data() + 18;
+    zs.avail_out = (uInt)(out->size() - 18 - 8);
     int rc = deflate(&zs, Z_FINISH);
     deflateEnd(&zs);
     if (rc != Z_STREAM_END) throw Error("deflate failed while writing BAM");
     size_t clen = zs.total_out, total = 18 + clen + 8;
     const uint8_t head[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 'B', 'C', 2, 0, (uint8_t)((total - 1) & 0xFF), (uint8_t)((total - 1) >> 8)};
-    std::memcpy(out, head, 18);
-    uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), buf_.data(), (uInt)buf_.size()), isize = (uint32_t)buf_.size();
-    std::memcpy(out + 18 + clen, &crc, 4);
-    std::memcpy(out + 18 + clen + 4, &isize, 4);
-    std::fwrite(out, 1, total, f_);
-    buf_.clear();
+    std::memcpy(out->data(), head, 18);
+    uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), in.data(), (uInt)in.size()), isize = (uint32_t)in.size();
+    std::memcpy(out->data() + 18 + clen, &crc, 4);
+    std::memcpy(out->data() + 18 + clen + 4, &isize, 4);
+    out->resize(total);
+}
+
+void BamWriter::flush_block() {
+    if (!f_ || buf_.empty()) return;
+    pending_.emplace_back();
+    pending_.back().swap(buf_);
+    buf_.reserve(kBlockData);
+    if (pending_.size() >= 64) compress_pending();
+}
+
+// Compress the waiting blocks on `threads_` threads and write them in order.
+void BamWriter::compress_pending() {
+    if (!f_ || pending_.empty()) return;
+    std::vector<std::vector<uint8_t>> out(pending_.size());
+    std::atomic<size_t> next{0};
+    std::string error;
+    std::mutex mu;
+    auto work = [&] {
+        try {
+            for (size_t i; (i = next.fetch_add(1)) < pending_.size();) bgzf_compress_block(pending_[i], &out[i]);
+        } catch (const std::exception& e) {
+            std::lock_guard<std::mutex> lk(mu);
+            error = e.what();
+        }
+    };
+    std::vector<std::thread> pool;
+    const size_t extra = std::min<size_t>(threads_ > 1 ? (size_t)threads_ - 1 : 0, pending_.size() > 1 ? pending_.size() - 1 : 0);
+    for (size_t t = 0; t < extra; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (!error.empty()) throw Error(error);
+    for (auto& o : out) std::fwrite(o.data(), 1, o.size(), f_);
+    pending_.clear();
 }
 
 void BamWriter::close() {
     if (!f_) return;
     flush_block();
+    compress_pending();
     static const uint8_t eof[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     std::fwrite(eof, 1, sizeof eof, f_);
     std::fclose(f_);
     f_ = nullptr;
+}
+
+void BamWriter::write_bam_record(const char* body, size_t len, const std::string& tag, const std::string& value) {
+    int32_t block_size = (int32_t)(len + 3 + value.size() + 1);
+    put(&block_size, 4);
+    put(body, len);
+    const char head[3] = {tag[0], tag[1], 'Z'};
+    put(head, 3);
+    put(value.c_str(), value.size() + 1);
+}
+
+int bam_find_tag(const char* b, size_t len, const std::string& tag, std::string* val) {
+    if (len < 32) return 0;
+    uint8_t l_read_name = (uint8_t)b[8];
+    uint16_t n_cigar;
+    int32_t l_seq;
+    std::memcpy(&n_cigar, b + 12, 2);
+    std::memcpy(&l_seq, b + 16, 4);
+    size_t q = 32 + (size_t)l_read_name + 4 * (size_t)n_cigar + ((size_t)l_seq + 1) / 2 + (size_t)l_seq;
+    auto elem = [](char t) -> size_t { return (t == 'c' || t == 'C' || t == 'A') ? 1 : (t == 's' || t == 'S') ? 2 : (t == 'i' || t == 'I' || t == 'f') ? 4 : 0; };
+    while (q + 3 <= len) {
+        const bool hit = b[q] == tag[0] && b[q + 1] == tag[1];
+        const char typ = b[q + 2];
+        q += 3;
+        if (typ == 'Z' || typ == 'H') {
+            size_t e = q;
+            while (e < len && b[e]) ++e;
+            if (hit) {
+                if (typ != 'Z') return 2;
+                val->assign(b + q, e - q);
+                return 1;
+            }
+            q = e + 1;
+        } else if (typ == 'B') {
+            if (hit) return 2;
+            if (q + 5 > len) return 0;
+            uint32_t n;
+            std::memcpy(&n, b + q + 1, 4);
+            size_t w = elem(b[q]);
+            if (!w) return 0;
+            q += 5 + (size_t)n * w;
+        } else {
+            if (hit) return 2;
+            size_t w = elem(typ);
+            if (!w) return 0;
+            q += w;
+        }
+    }
+    return 0;
 }
 
 void BamWriter::write_sam_line(const std::string& line) {

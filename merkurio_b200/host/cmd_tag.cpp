@@ -109,7 +109,7 @@ void tag_records(CmdTag args) {
     std::unique_ptr<BamWriter> bam_out;
     if (out_ext == "bam") {
         try {
-            bam_out.reset(new BamWriter(path_with_extension(*args.out_file, "bam"), header));
+            bam_out.reset(new BamWriter(path_with_extension(*args.out_file, "bam"), header, std::max(decompression_threads(), args.threads)));
         } catch (const Error& e) {
             throw e.with_context("Could not create writer.");
         }
@@ -165,7 +165,10 @@ void tag_records(CmdTag args) {
         bool keep = args.filter_matching ? !kmers_found.empty() : (args.invert_match ? kmers_found.empty() : true);
         if (!keep) return;
         std::string val;
-        int kind = existing_tag(m.b, args.tag, &val);
+        // BAM -> BAM: the record stays in its binary form (m.chunk / m.idx name it); else its SAM text is in m.b
+        const AlnChunk* raw_chunk = static_cast<const AlnChunk*>(m.chunk);
+        const AlnSpan* raw = raw_chunk ? &raw_chunk->recs[m.idx] : nullptr;
+        int kind = raw ? bam_find_tag(raw_chunk->data.data() + raw->off, raw->len, args.tag, &val) : existing_tag(m.b, args.tag, &val);
         if (kind == 2) throw Error("Invalid tag value format. Expected string value.");
         if (kind == 1 && !val.empty()) {
             size_t pos = 0;
@@ -179,7 +182,9 @@ void tag_records(CmdTag args) {
         std::sort(kmers_found.begin(), kmers_found.end(), bytes_less);
         kmers_found.erase(std::unique(kmers_found.begin(), kmers_found.end()), kmers_found.end());
         if (!args.suppress_output) {
-            if (bam_out) {
+            if (raw) {
+                bam_out->write_bam_record(raw_chunk->data.data() + raw->off, raw->len, args.tag, join(kmers_found, ","));
+            } else if (bam_out) {
                 bam_out->write_sam_line(m.b + "\t" + args.tag + ":Z:" + join(kmers_found, ","));
             } else {
                 obuf += m.b; obuf += '\t'; obuf += args.tag; obuf += ":Z:"; obuf += join(kmers_found, ","); obuf += '\n';
@@ -198,6 +203,9 @@ void tag_records(CmdTag args) {
                                                                            : (size_t)8 << 20;
             std::unique_ptr<AlnChunkReader> chunks(new AlnChunkReader(std::move(reader), chunk_bytes));
             const std::vector<std::string> refs = chunks->refs();
+            // BAM in, BAM out, same reference list: kept records are copied as they are, with the tag appended
+            const bool passthrough = chunks->is_bam() && bam_out && !args.suppress_output && refs == bam_out->ref_names() &&
+                                     !std::getenv("MERKURIO_NO_BAM_PASSTHROUGH");
             EngineSet engines(pattern_list, args.case_insensitive, 16);
             bulk_totals = true;
             auto consume_batch = [&](const PackedBatch& b, const mk_result& res) {
@@ -220,7 +228,11 @@ void tag_records(CmdTag args) {
                     m.a.assign(ch->data.data() + sp.name_off, sp.name_len);
                     const bool keep = args.filter_matching ? !hits.empty() : (args.invert_match ? hits.empty() : true);
                     m.b.clear();
-                    if (keep) {  // the record's SAM text is only needed if it is written
+                    m.chunk = nullptr;
+                    if (keep && passthrough) {
+                        m.chunk = ch;
+                        m.idx = sg.first + (r - sg.rec0);
+                    } else if (keep) {  // the record's SAM text is only needed if it is written
                         if (!ch->bam) {
                             m.b.assign(ch->data.data() + sp.off, sp.len);
                         } else {

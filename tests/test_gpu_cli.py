@@ -482,3 +482,38 @@ def test_aln_pipeline_equals_record_path(tmp_path, kind, flags):
     assert (rc != 0) == (kind == "sam_truncated")
     if rc == 0:
         assert files["t.sam"].count(b"\tkm:Z:") > 100
+
+
+@pytest.mark.parametrize("flags", [[], ["-m"]])
+def test_tag_bam_to_bam_passthrough(tmp_path, flags):
+    """BAM in, BAM out: kept records are copied in their binary form with the tag appended (no SAM text round
+    trip), blocks compressed on several threads. Must decode to the same records as the text round trip and
+    as the oracle's SAM output."""
+    rng = np.random.default_rng(97)
+    pats = sorted({rng.choice(np.frombuffer(b"ACGT", np.uint8), size=31).tobytes() for _ in range(25)})
+    reads = _rand_reads(rng, 4000, 0, 151, pats, plant=0.2)
+    sam = tmp_path / "in.sam"
+    with open(sam, "wb") as f:
+        f.write(b"@HD\tVN:1.6\tSO:unsorted\n@SQ\tSN:1\tLN:100000\n@SQ\tSN:2\tLN:5000\n")
+        for i, r in enumerate(reads):
+            extra = b"\tkm:Z:ZZZ,AAA" if i % 50 == 0 else b""
+            f.write(b"q%d\t%d\t%d\t%d\t%d\t%s\t%s\t%d\t0\t%s\t%s\tNM:i:%d\tXB:B:s,1,-2,300%s\n" % (
+                i, 99 if i % 2 else 147, 1 + i % 2, 1 + (i * 37) % 4000, i % 61, b"%dM" % len(r) if r else b"*",
+                b"=" if i % 3 else b"*", (i * 11) % 4000 if i % 3 else 0, r if r else b"*", b"F" * len(r) if r else b"*", i % 5, extra))
+    kf = tmp_path / "k.txt"
+    kf.write_bytes(b"\n".join(pats) + b"\n")
+    bam = tmp_path / "in.bam"
+    run("tag", "-i", sam, "-o", bam, "-s", "NNNNNNNNNNNNNNNNNNNNNNNNNNNNNNN")
+    # the input BAM itself carries an (empty) km tag from that run: existing tags are merged, the old field stays
+    runs = [("a", ["tag", "-i", bam, "-o", "@OUT@/o.bam", "-f", kf, "-r", "-p", "4", *flags], {"MERKURIO_BATCH_BYTES": "60000"}),
+            ("b", ["tag", "-i", bam, "-o", "@OUT@/o.bam", "-f", kf, "-r", *flags], {"MERKURIO_NO_BAM_PASSTHROUGH": "1"}),
+            ("c", ["tag", "-i", bam, "-o", "@OUT@/o.sam", "-f", kf, "-r", *flags], {})]
+    (a, b, c) = _outputs_batched(tmp_path, runs)
+    assert a[0] == b[0] == c[0] == 0, (a[1], b[1], c[1])
+    ha, ra = rm.parse_bam(a[2]["o.bam"])
+    hb, rb = rm.parse_bam(b[2]["o.bam"])
+    assert [x for x in ha if not x.startswith(b"@PG")] == [x for x in hb if not x.startswith(b"@PG")]
+    assert [r.line for r in ra] == [r.line for r in rb]
+    sam_lines = [ln for ln in c[2]["o.sam"].split(b"\n") if ln and not ln.startswith(b"@")]
+    assert [r.line for r in ra] == sam_lines
+    assert len(ra) == (4000 if not flags else sum(1 for ln in sam_lines)) and len(ra) > 300
