@@ -396,3 +396,63 @@ def test_compressed_inputs_are_recognised_by_their_magic_bytes(exe, tmp_path, co
     a = subprocess.run([exe, "records", str(tmp_path / "g.fa"), "generic"], capture_output=True).stdout
     b = subprocess.run([exe, "records", str(tmp_path / "g.fa.z"), "generic"], capture_output=True).stdout
     assert a == b and a.count(b"#id\t") == 500
+
+
+def test_chunked_fastq_reader_fuzz(exe, tmp_path):
+    """Random FASTQ with random damage (cut ranges, inserted bytes, CRLF islands, doubled newlines): the
+    chunked reader and the line reader must print the same records and stop with the same error at the
+    same record, whatever the chunk size."""
+    import numpy as np
+    rng = np.random.default_rng(2024)
+    for trial in range(120):
+        recs = []
+        for i in range(int(rng.integers(1, 400))):
+            n = int(rng.integers(0, 120))
+            s = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=n).tobytes())
+            le = b"\r\n" if rng.random() < 0.05 else b"\n"
+            plus = b"+" + (b"x%d" % i if rng.random() < 0.1 else b"")
+            q = bytes(rng.choice(np.frombuffer(b"@+IF#", dtype=np.uint8), size=n).tobytes())
+            recs.append(b"@q%d/%d" % (trial, i) + le + s + le + plus + le + q + le + (b"\n" if rng.random() < 0.05 else b""))
+        data = bytearray(b"".join(recs))
+        kind = trial % 4
+        if kind == 1 and len(data) > 10:  # cut a range
+            a = int(rng.integers(0, len(data) - 1))
+            del data[a:a + int(rng.integers(1, 60))]
+        elif kind == 2 and len(data) > 10:  # insert bytes
+            a = int(rng.integers(0, len(data)))
+            data[a:a] = bytes(rng.choice(np.frombuffer(b"@+\nACGT\r", dtype=np.uint8), size=int(rng.integers(1, 8))).tobytes())
+        elif kind == 3:  # no final newline
+            while data and data[-1] in b"\r\n":
+                data.pop()
+        if not data or data[0] != ord("@"):
+            continue  # the chunked reader only takes files that start like FASTQ
+        p = tmp_path / ("f%d.fastq" % trial)
+        p.write_bytes(bytes(data))
+        want = subprocess.run([exe, "records", str(p), "generic"], capture_output=True)
+        assert want.returncode == 0, want.stderr
+        for chunk in (4096, int(rng.integers(4097, 20000))):
+            got = subprocess.run([exe, "records", str(p), "chunked", str(chunk)], capture_output=True)
+            assert got.returncode == 0, got.stderr
+            assert got.stdout == want.stdout, (trial, kind, chunk)
+
+
+def test_chunked_sam_reader_fuzz(exe, tmp_path):
+    """Damaged SAM text: both alignment readers stop at the same record with the same message."""
+    import numpy as np
+    rng = np.random.default_rng(7)
+    base = _sam_text(300, seed=21)
+    for trial in range(60):
+        data = bytearray(base)
+        for _ in range(int(rng.integers(0, 3))):
+            a = int(rng.integers(60, len(data) - 1))  # past the header
+            if rng.random() < 0.5:
+                del data[a:a + int(rng.integers(1, 40))]
+            else:
+                data[a:a] = bytes(rng.choice(np.frombuffer(b"\t\n\rACGT*", dtype=np.uint8), size=int(rng.integers(1, 6))).tobytes())
+        p = tmp_path / ("s%d.sam" % trial)
+        p.write_bytes(bytes(data))
+        want = subprocess.run([exe, "alnrecords", str(p), "generic"], capture_output=True)
+        assert want.returncode == 0, want.stderr
+        got = subprocess.run([exe, "alnrecords", str(p), "chunked", str(int(rng.integers(4096, 9000)))], capture_output=True)
+        assert got.returncode == 0, got.stderr
+        assert got.stdout == want.stdout, trial
