@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <charconv>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -193,7 +194,7 @@ bool FastxReader::next(FastxRecord* rec) {
 // ---------------------------------------------------------------------------------------------
 struct PrefetchingFastxReader::State {
     FastxReader* rd;
-    size_t depth;
+    size_t budget, held = 0;  // bytes of record text the queue may hold / holds
     std::thread th;
     std::mutex mu;
     std::condition_variable cv;
@@ -202,18 +203,24 @@ struct PrefetchingFastxReader::State {
     bool done = false, stop = false;
 };
 
-PrefetchingFastxReader::PrefetchingFastxReader(FastxReader* reader, size_t depth) : st_(new State) {
+static size_t record_bytes(const FastxRecord& r) { return r.id.size() + r.seq.size() + r.raw.size() + r.qual.size() + 64; }
+
+PrefetchingFastxReader::PrefetchingFastxReader(FastxReader* reader, size_t budget_bytes) : st_(new State) {
     st_->rd = reader;
-    st_->depth = std::max<size_t>(depth, 1);
+    st_->budget = budget_bytes;
+    if (const char* mb = std::getenv("MERKURIO_PREFETCH_MB")) st_->budget = (size_t)std::strtoull(mb, nullptr, 10) << 20;
     State* s = st_.get();
     s->th = std::thread([s] {
         try {
             for (;;) {
                 std::unique_ptr<FastxRecord> r(new FastxRecord);
                 if (!s->rd->next(r.get())) break;
+                const size_t bytes = record_bytes(*r);
                 std::unique_lock<std::mutex> lk(s->mu);
-                s->cv.wait(lk, [s] { return s->ready.size() < s->depth || s->stop; });
+                // at least one record is always allowed in, however large
+                s->cv.wait(lk, [s, bytes] { return s->ready.empty() || s->held + bytes <= s->budget || s->stop; });
                 if (s->stop) return;
+                s->held += bytes;
                 s->ready.push_back(std::move(r));
                 lk.unlock();
                 s->cv.notify_all();
@@ -246,6 +253,7 @@ bool PrefetchingFastxReader::next(FastxRecord* rec) {
     if (!st_->ready.empty()) {
         std::unique_ptr<FastxRecord> r = std::move(st_->ready.front());
         st_->ready.pop_front();
+        st_->held -= std::min(st_->held, record_bytes(*r));
         lk.unlock();
         st_->cv.notify_all();
         std::swap(*rec, *r);

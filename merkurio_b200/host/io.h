@@ -66,12 +66,12 @@ private:
     bool have_pending_ = false, started_ = false, fastq_ = false, keep_raw_ = true;
 };
 
-// Runs a FastxReader on its own thread, a few records ahead of the consumer (FASTA input: the next
-// chromosome is read and unwrapped while the current one is being scanned). Same results and errors,
-// raised at the same record, as calling FastxReader::next directly.
+// Runs a FastxReader on its own thread, ahead of the consumer by up to `budget_bytes` of record text
+// (FASTA input: chromosomes are read and unwrapped while CUDA starts up and while earlier ones are
+// scanned). Same results and errors, raised at the same record, as calling FastxReader::next directly.
 class PrefetchingFastxReader {
 public:
-    explicit PrefetchingFastxReader(FastxReader* reader, size_t depth = 2);
+    explicit PrefetchingFastxReader(FastxReader* reader, size_t budget_bytes = (size_t)1 << 30);
     ~PrefetchingFastxReader();
     bool next(FastxRecord* rec);
 
