@@ -317,8 +317,8 @@ def run_ours(args):
         algo_bytes = n_bytes + (n_reads + 7) // 8  # sequence bytes + flag bitmap; offsets are only read for hits
         achieved = algo_bytes / (scan_ms / 1e3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of mk_scan_d16 from the ncu --set full capture of exactly this
-        # workload (profiles/r1_ncu_full_cfg2_100Mreads.txt); null for any other size
-        traffic = 15_000_647_000 + 9_536_256 if (n_reads, L, args.queries) == (100_000_000, 150, 1000) else None
+        # workload (profiles/r1_ncu_full_cfg2.txt: 15.001007 GB read + 14.089984 MB written); null for any other size
+        traffic = 15_001_007_000 + 14_089_984 if (n_reads, L, args.queries) == (100_000_000, 150, 1000) else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
