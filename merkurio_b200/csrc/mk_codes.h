@@ -149,6 +149,15 @@ MK_HD uint32_t mk_dual_g_short(uint32_t short_code) { return short_code * MK_BLO
 MK_HD uint32_t mk_dual_g_long(uint32_t code16) { return (code16 ^ (code16 >> 15)) * MK_DUAL_MUL_LONG; }
 // key of the cuckoo seed table: the group is folded into the hashed value
 MK_HD uint32_t mk_group_key(uint32_t code, uint32_t group) { return group ? (code ^ 0x3C6EF372u) : code; }
+// Shared-memory flavour with 32-bit blocks and 3 bits per key (small seed sets): one LDS.32 per probe.
+// `nblocks64` counts 64-bit units like the other flavour; the 32-bit block count is twice that.
+MK_HD uint32_t mk_bloom32_block(uint32_t code, uint32_t nblocks64) {
+    return (uint32_t)(((uint64_t)(code * MK_BLOOM_MUL) * (2u * nblocks64)) >> 32);
+}
+MK_HD uint32_t mk_bloom32_mask(uint32_t code) {
+    uint32_t g = code * MK_BLOOM_MUL * MK_BLOOM_MUL2;
+    return (1u << ((g >> 17) & 31)) | (1u << ((g >> 22) & 31)) | (1u << (g >> 27));
+}
 MK_HD uint32_t mk_hash_f1(uint32_t code, uint32_t log2_bits) { return (code * 0x9E3779B1u) >> (32u - log2_bits); }
 // second-level filter (L2-resident bitmap probed by candidates only): bit index
 MK_HD uint32_t mk_hash_f2(uint32_t code, uint32_t log2_bits) { return ((code ^ (code >> 15)) * 0x85EBCA77u) >> (32u - log2_bits); }

@@ -212,7 +212,16 @@ ScanLaunch pick_by_d(uint32_t d) {
     }
 }
 
-ScanLaunch pick_kernel(int enc, uint32_t d, bool smemf, bool win = false) {
+ScanLaunch pick_kernel(int enc, uint32_t d, bool smemf, bool win = false, bool f32 = false) {
+    if (f32) {  // shared-memory filter with 32-bit blocks (small seed sets)
+        if (win) {
+            if (enc == MK_ENC_ASCII && d == 8) return {mk::mk_scan_win<MK_ENC_ASCII, 8, 4, 896, true>, 896, 4 * 32};
+            if (enc == MK_ENC_ASCII) return {mk::mk_scan_win<MK_ENC_ASCII, 4, 4, 768, true>, 768, 4 * 32};
+            return {mk::mk_scan_win<MK_ENC_BAM4, 8, 4, 768, true>, 768, 4 * 32};
+        }
+        if (enc == MK_ENC_ASCII) return {mk::mk_scan_d16<MK_ENC_ASCII, mk::kFilterSmem, 4, 896, false, true>, 896, 4 * 32};
+        return {mk::mk_scan_d16<MK_ENC_BAM4, mk::kFilterSmem, 4, 896, false, true>, 896, 4 * 32};
+    }
     if (win) {  // stride 8 / 4, shared-memory filter, window seeds in the permuted packing
         if (enc == MK_ENC_ASCII && d == 8) return {mk::mk_scan_win<MK_ENC_ASCII, 8, 4, 896>, 896, 4 * 32};
 #ifdef MK_TUNE_BUILD
@@ -281,7 +290,7 @@ int ensure_tables(mk_engine* e, int enc) {
     CU(dt.pat_off.upload(dt.host.pat_off));
     CU(dt.slots.upload(dt.host.slots));
     CU(dt.pat_bytes.upload(dt.host.pat_bytes));
-    ScanLaunch k = pick_kernel(enc, dt.host.d, dt.host.filter_in_smem, dt.host.win);
+    ScanLaunch k = pick_kernel(enc, dt.host.d, dt.host.filter_in_smem, dt.host.win, dt.host.filter32);
     if (dt.host.filter_in_smem)
         CU(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dt.host.filter.size() * 4)));
     dt.built = true;
@@ -360,6 +369,7 @@ int enqueue(mk_engine* e, Workspace& ws) {
     P.filter = dt.filter.p;
     P.filter_log2_bits = t.filter_log2_bits;
     P.filter_blocks = t.filter_blocks;
+    P.filter32 = t.filter32 ? 1u : 0u;
     P.filter2 = t.filter2.empty() ? nullptr : dt.filter2.p;
     P.filter2_log2_bits = t.filter2_log2_bits;
     P.slots = dt.slots.p;
@@ -400,7 +410,7 @@ int enqueue(mk_engine* e, Workspace& ws) {
     CU(cudaMemsetAsync(ws.counters.p, 0, 8 * sizeof(unsigned long long), ws.stream));
     CU(cudaEventRecord(ws.ev_begin, ws.stream));
     if (P.n_vec > 0 && ws.n_records > 0) {
-        ScanLaunch k = pick_kernel(ws.enc, t.d, t.filter_in_smem, t.win);
+        ScanLaunch k = pick_kernel(ws.enc, t.d, t.filter_in_smem, t.win, t.filter32);
         const uint64_t warps = k.threads / 32;
         uint64_t tiles = ((uint64_t)P.n_vec + k.tile_vecs - 1) / k.tile_vecs;
         uint64_t want = (tiles + warps - 1) / warps;

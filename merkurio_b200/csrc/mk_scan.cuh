@@ -38,6 +38,7 @@ struct ScanParams {
     const uint32_t* filter2;        // optional second-level bitmap (nullptr: none)
     uint32_t filter_log2_bits;      // global flavour
     uint32_t filter_blocks;         // shared-memory flavour: 64-bit blocks
+    uint32_t filter32;              // shared-memory flavour: 1 = 32-bit blocks, 3 bits per key (filter_probe32)
     uint32_t filter2_log2_bits;
     uint32_t bucket_mask;
     const SeedSlot* slots;
@@ -105,6 +106,16 @@ __device__ __forceinline__ uint32_t filter_probe(const uint32_t* __restrict__ f,
         uint32_t h = mk_hash_f1(code, lb);
         return (__ldg(f + (h >> 5)) >> (h & 31)) & 1u;
     }
+}
+
+// Shared-memory filter with 32-bit blocks and 3 bits per key: one LDS.32 per probe, half the bank traffic of
+// the 64-bit flavour. Chosen by the table builder while it stays selective (small seed sets); `lb` counts
+// 64-bit units as for the other flavour.
+__device__ __forceinline__ uint32_t filter_probe32(const uint32_t* __restrict__ f, uint32_t code, uint32_t lb) {
+    uint32_t h = code * MK_BLOOM_MUL;
+    uint32_t w = f[__umulhi(h, 2u * lb)];
+    uint32_t g = h * MK_BLOOM_MUL2;
+    return (w >> ((g >> 17) & 31)) & (w >> ((g >> 22) & 31)) & (w >> (g >> 27)) & 1u;
 }
 
 // Dual-key probe of the L2-resident blocked filter (stride < 16): `win` is the 16-base window at the
@@ -397,7 +408,7 @@ __device__ __forceinline__ void queue_push(const ScanParams& P, WarpQueue& wq, u
 
 // v0 = index of the lane's first vector of the tile. V8: the lane owns pairs of adjacent vectors
 // (32-byte loads, rows of 64 vectors); else single vectors (rows of 32 vectors).
-template <int ENC, int FMODE, int U, bool V8>
+template <int ENC, int FMODE, int U, bool V8, bool B32>
 __device__ __forceinline__ void process_tile(const ScanParams& P, const uint32_t* __restrict__ filt, uint32_t lb,
                                              const uint4 (&v)[U], uint32_t v0, WarpQueue& wq, uint32_t lane) {
     constexpr int SPV = (ENC == MK_ENC_ASCII) ? 1 : 2;  // seeds (= units) per vector
@@ -407,14 +418,13 @@ __device__ __forceinline__ void process_tile(const ScanParams& P, const uint32_t
     for (int u = 0; u < U; ++u) {
         if (ENC == MK_ENC_ASCII) {
             code[u] = mk_pack_ascii_perm(v[u].x, v[u].y, v[u].z, v[u].w);
-            pass |= filter_probe<FMODE>(filt, code[u], lb) << u;
         } else {
             code[2 * u] = mk_pack_bam_perm(v[u].x, v[u].y);
             code[2 * u + 1] = mk_pack_bam_perm(v[u].z, v[u].w);
-            pass |= filter_probe<FMODE>(filt, code[2 * u], lb) << (2 * u);
-            pass |= filter_probe<FMODE>(filt, code[2 * u + 1], lb) << (2 * u + 1);
         }
     }
+#pragma unroll
+    for (int k = 0; k < U * SPV; ++k) pass |= (B32 ? filter_probe32(filt, code[k], lb) : filter_probe<FMODE>(filt, code[k], lb)) << k;
     const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, __popc(pass));
     if (total == 0) return;
     if (wq.count + total <= kQueueCap) {
@@ -460,7 +470,7 @@ __device__ __forceinline__ void load_rows(const uint4* __restrict__ p, uint64_t 
     }
 }
 
-template <int ENC, int FMODE, int U, int T, bool V8>
+template <int ENC, int FMODE, int U, int T, bool V8, bool B32 = false>
 __global__ void __launch_bounds__(T, 1) mk_scan_d16(const __grid_constant__ ScanParams P) {
     static_assert(!V8 || U % 2 == 0, "32-byte loads need an even number of vectors per lane");
     constexpr int kScanWarps = T / 32;
@@ -489,13 +499,13 @@ __global__ void __launch_bounds__(T, 1) mk_scan_d16(const __grid_constant__ Scan
     while (t < full_tiles) {
         uint32_t tn = t + nwarps;
         if (tn < full_tiles) load_rows<U, V8>(p + stride, pol, b);
-        process_tile<ENC, FMODE, U, V8>(P, filt, lb, a, t * (U * 32) + lane_vec, wq, lane);
+        process_tile<ENC, FMODE, U, V8, B32>(P, filt, lb, a, t * (U * 32) + lane_vec, wq, lane);
         t = tn;
         p += stride;
         if (t >= full_tiles) break;
         tn = t + nwarps;
         if (tn < full_tiles) load_rows<U, V8>(p + stride, pol, a);
-        process_tile<ENC, FMODE, U, V8>(P, filt, lb, b, t * (U * 32) + lane_vec, wq, lane);
+        process_tile<ENC, FMODE, U, V8, B32>(P, filt, lb, b, t * (U * 32) + lane_vec, wq, lane);
         t = tn;
         p += stride;
     }
@@ -505,7 +515,7 @@ __global__ void __launch_bounds__(T, 1) mk_scan_d16(const __grid_constant__ Scan
         const uint32_t v0 = full_tiles * (U * 32) + lane;
 #pragma unroll
         for (int u = 0; u < U; ++u) a[u] = (v0 + u * 32 < P.n_vec) ? ld_stream(P.text + v0 + u * 32, pol16) : make_uint4(0, 0, 0, 0);
-        process_tile<ENC, FMODE, U, false>(P, filt, lb, a, v0, wq, lane);
+        process_tile<ENC, FMODE, U, false, B32>(P, filt, lb, a, v0, wq, lane);
     }
     queue_flush(P, wq, lane);
 }
@@ -547,7 +557,7 @@ __device__ __forceinline__ void push_tile_candidates(const ScanParams& P, WarpQu
     }
 }
 
-template <int ENC, int D, int U>
+template <int ENC, int D, int U, bool B32>
 __device__ __forceinline__ void process_tile_win(const ScanParams& P, const uint32_t* __restrict__ filt, uint32_t lb, const uint4 (&v)[U],
                                                  const uint4& halo, uint32_t v0, WarpQueue& wq, uint32_t lane) {
     constexpr int PPV = (ENC == MK_ENC_ASCII ? 16 : 32) / D;  // probes per vector
@@ -589,12 +599,12 @@ __device__ __forceinline__ void process_tile_win(const ScanParams& P, const uint
         }
     }
 #pragma unroll
-    for (int k = 0; k < K; ++k) pass |= filter_probe<kFilterSmem>(filt, win[k], lb) << k;
+    for (int k = 0; k < K; ++k) pass |= (B32 ? filter_probe32(filt, win[k], lb) : filter_probe<kFilterSmem>(filt, win[k], lb)) << k;
     // candidate position / D: vector index * PPV + window index
     push_tile_candidates<K>(P, wq, lane, pass, win, v0 * PPV, 32 * PPV, PPV);
 }
 
-template <int ENC, int D, int U, int T>
+template <int ENC, int D, int U, int T, bool B32 = false>
 __global__ void __launch_bounds__(T, 1) mk_scan_win(const __grid_constant__ ScanParams P) {
     constexpr int kWarps = T / 32;
     extern __shared__ __align__(16) uint32_t s_filter[];
@@ -627,13 +637,13 @@ __global__ void __launch_bounds__(T, 1) mk_scan_win(const __grid_constant__ Scan
     while (t < full_tiles) {
         uint32_t tn = t + nwarps;
         if (tn < full_tiles) { load_rows<U, false>(p + stride, pol, b); hb = load_halo(tn); }
-        process_tile_win<ENC, D, U>(P, filt, lb, a, ha, t * (U * 32) + lane, wq, lane);
+        process_tile_win<ENC, D, U, B32>(P, filt, lb, a, ha, t * (U * 32) + lane, wq, lane);
         t = tn;
         p += stride;
         if (t >= full_tiles) break;
         tn = t + nwarps;
         if (tn < full_tiles) { load_rows<U, false>(p + stride, pol, a); ha = load_halo(tn); }
-        process_tile_win<ENC, D, U>(P, filt, lb, b, hb, t * (U * 32) + lane, wq, lane);
+        process_tile_win<ENC, D, U, B32>(P, filt, lb, b, hb, t * (U * 32) + lane, wq, lane);
         t = tn;
         p += stride;
     }
@@ -642,7 +652,7 @@ __global__ void __launch_bounds__(T, 1) mk_scan_win(const __grid_constant__ Scan
         const uint32_t v0 = full_tiles * (U * 32) + lane;
 #pragma unroll
         for (int u = 0; u < U; ++u) a[u] = (v0 + u * 32 < P.n_vec) ? ld_stream(P.text + v0 + u * 32, pol) : zero;
-        process_tile_win<ENC, D, U>(P, filt, lb, a, zero, v0, wq, lane);
+        process_tile_win<ENC, D, U, B32>(P, filt, lb, a, zero, v0, wq, lane);
     }
     queue_flush(P, wq, lane);
 }

@@ -214,6 +214,24 @@ def test_long_record_every_alignment():
     check_batch(pats, [bytes(big[:300000]), bytes(big[300000:])])
 
 
+def test_filter_flavours_of_the_shared_memory_filter(monkeypatch):
+    """Small seed sets use 32-bit filter blocks (one LDS.32 per probe), larger ones 64-bit blocks; both are
+    only filters: the hits are the oracle's either way, for unit seeds (k >= 31), window seeds and BAM4."""
+    rng = np.random.default_rng(88)
+    for k in (21, 27, 31, 40):
+        pats = sorted({rand_seq(rng, k) for _ in range(40)})
+        recs = planted_records(rng, pats, 400, 0, 300, plant_p=0.5)
+        with capi.Engine(pats, max_batch_bytes=200000, max_batch_records=1000) as e:
+            check_batch(pats, recs, engine=e)
+        check_bam4(pats, recs)
+    monkeypatch.setenv("MK_NO_FILTER32", "1")
+    for k in (21, 31):
+        pats = sorted({rand_seq(rng, k) for _ in range(40)})
+        recs = planted_records(rng, pats, 400, 0, 300, plant_p=0.5)
+        check_batch(pats, recs)
+        check_bam4(pats, recs)
+
+
 @pytest.mark.parametrize("k", [15, 18, 19, 22, 23, 30])
 def test_window_scan_equals_ordered_scan(monkeypatch, k):
     """Strides 8 and 4 have two kernels (window seeds in the permuted packing / ordered packing): both
