@@ -10,10 +10,9 @@
  *                         (src/cmd_extract.rs:259-277, src/cmd_tag.rs:234-252)
  *   mk_scan_submit /   <- the per-record search calls: BNDMq::find_iter / find_match
  *   mk_scan_wait /        (src/pattern_matching.rs:128-140,165-209) and
- *   mk_scan_device /      AhoCorasick::find_overlapping_iter, as used by the extract loops
- *   mk_scan_device_submit (src/cmd_extract.rs:321-406 single, :463-607 paired) and by
- *   mk_scan_host          process_record (src/cmd_tag.rs:387-443) -- see the next entry
- *                         process_record (src/cmd_tag.rs:387-443)
+ *   mk_scan_host /        AhoCorasick::find_overlapping_iter, as used by the extract loops
+ *   mk_scan_device /      (src/cmd_extract.rs:321-406 single, :463-607 paired) and by
+ *   mk_scan_device_submit process_record (src/cmd_tag.rs:387-443)
  *   mk_result          <- what those loops consume: found_occ (cmd_extract.rs:323,400),
  *                         kmers_found (cmd_tag.rs:387,398,429,439) and the (pattern, start) stream
  *                         handed to the loggers (src/logger.rs:41-60,108-133)
@@ -113,7 +112,7 @@ typedef struct {
     uint32_t n_patterns, min_len, max_len;
     uint32_t seed_q[2], seed_d[2];     /* per encoding (index = mk_encoding); 0 = tables not built yet */
     uint32_t n_seeds[2];               /* distinct seed codes */
-    uint32_t filter_log2_bits[2];      /* first-level filter, L2-resident flavour: log2 of its bits (else 0) */
+    uint32_t filter_log2_bits[2];      /* first-level filter, L2-resident plain bitmap (stride 16): log2 of its bits (else 0) */
     uint32_t filter_hashes[2];         /* bits tested per probe */
     uint64_t filter_bytes[2];          /* size of the first-level filter */
     uint32_t filter_in_smem[2];        /* 1: bitmap staged in shared memory, 0: L2-resident */
