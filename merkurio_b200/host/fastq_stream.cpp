@@ -157,7 +157,8 @@ void FastqChunkReader::run() {
                 }
                 consumed = p;
                 if (c->failed || eof || !c->recs.empty()) break;
-                // not even one whole record in a full buffer: grow it and keep reading
+                // not even one whole record in a full buffer: grow it and keep reading (offsets are 32-bit)
+                if (c->data.size() > ((size_t)1 << 30)) throw Error("FASTQ record larger than 1 GiB");
                 c->data.resize(c->data.size() * 2);
             }
             if (c->failed) eof = true;  // nothing after a malformed record is looked at
