@@ -318,11 +318,11 @@ int enqueue_sort(mk_engine* e, Workspace& ws, bool buckets) {
         unsigned long long* overflow = ws.counters.p + 3;
         mk::mk_bucket_count<<<e->sm_count * 2, 256, 0, ws.stream>>>(ws.raw_a.p, cnt, ws.hit_cap, shift, bcount);
         mk::mk_bucket_scan<<<1, 1024, 0, ws.stream>>>(bcount, bstart, bcursor, overflow);
-        mk::mk_bucket_scatter<<<e->sm_count * 2, 256, 0, ws.stream>>>(ws.raw_a.p, ws.raw_b.p, cnt, ws.hit_cap, shift, bcursor, overflow);
+        mk::mk_bucket_scatter<<<e->sm_count * 8, 256, 0, ws.stream>>>(ws.raw_a.p, ws.raw_b.p, cnt, ws.hit_cap, shift, bcursor, overflow);
         if (ws.mode == MK_MODE_ALL_HITS) {
-            mk::mk_bucket_sort<<<e->sm_count * 4, 256, 0, ws.stream>>>(ws.raw_b.p, bstart, overflow, ws.out.p, ws.d_off, dt.pat_off.p, len_tie_bits);
+            mk::mk_bucket_sort<<<e->sm_count * 7, 256, 0, ws.stream>>>(ws.raw_b.p, bstart, overflow, ws.out.p, ws.d_off, dt.pat_off.p, len_tie_bits);
         } else {
-            mk::mk_bucket_sort<<<e->sm_count * 4, 256, 0, ws.stream>>>(ws.raw_b.p, bstart, overflow, nullptr, nullptr, nullptr, 0);
+            mk::mk_bucket_sort<<<e->sm_count * 7, 256, 0, ws.stream>>>(ws.raw_b.p, bstart, overflow, nullptr, nullptr, nullptr, 0);
             mk::mk_heads_count<<<e->sm_count * 4, 256, 0, ws.stream>>>(ws.raw_b.p, cnt, ws.hit_cap, ws.heads.p);
             mk::mk_heads_scan<<<1, 1024, 0, ws.stream>>>(cnt, ws.hit_cap, ws.heads.p, ws.counters.p + 1);
             mk::mk_finalize_pairs<<<e->sm_count * 4, 256, 0, ws.stream>>>(ws.raw_b.p, ws.out.p, cnt, ws.hit_cap, ws.heads.p, dt.pat_off.p);

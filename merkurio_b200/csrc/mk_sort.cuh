@@ -216,9 +216,18 @@ __global__ void __launch_bounds__(256) mk_bucket_scatter(const RawHit* __restric
     if (*overflow) return;
     unsigned long long n = *count;
     if (n > cap) n = cap;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        RawHit h = in[i];
-        out[atomicAdd(&cursor[bucket_of(h.key, bm)], 1u)] = h;
+    // two hits per thread and step: the cursor atomics return a value (a full L2 round trip each), so the
+    // kernel lives on how many of them are in flight
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += 2 * stride) {
+        const uint64_t j = i + stride;
+        RawHit a = in[i], b;
+        if (j < n) b = in[j];
+        const uint32_t pa = atomicAdd(&cursor[bucket_of(a.key, bm)], 1u);
+        uint32_t pb = 0;
+        if (j < n) pb = atomicAdd(&cursor[bucket_of(b.key, bm)], 1u);
+        out[pa] = a;
+        if (j < n) out[pb] = b;
     }
 }
 
