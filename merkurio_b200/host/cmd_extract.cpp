@@ -2,10 +2,12 @@
 // (src/cmd_extract.rs:143-717); the per-record matcher calls are replaced by batches on the GPU.
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <memory>
 
 #include "commands.h"
 #include "device.h"
+#include "fasta_pipeline.h"
 #include "fastq_pipeline.h"
 #include "fastq_stream.h"
 #include "helpers.h"
@@ -59,14 +61,30 @@ FastxRecord to_record(const RecMeta& m) {
 
 // Records of the chunked FASTQ ingest carry a (chunk, span) reference instead of strings.
 std::string record_id(const RecMeta& m) {
-    if (!m.chunk) return m.a;
+    if (m.kind != 1) return m.a;
     const Chunk* ch = static_cast<const Chunk*>(m.chunk);
     const RecSpan& r = ch->recs[m.idx];
     return std::string(ch->id(r), r.id_len);
 }
 
 void write_record(OutFile& w, const RecMeta& m) {
-    if (!m.chunk) { w.write(to_record(m)); return; }
+    if (m.kind == 2) {  // FASTA pipeline: '>' id, the wrapped lines as they are in the file, a final line break
+        const FaRecord* rec = static_cast<const FaRecord*>(m.chunk);
+        const char* le = rec->crlf ? "\r\n" : "\n";
+        w.write_raw(">", 1);
+        w.write_raw(rec->id.data(), rec->id.size());
+        w.write_raw(le, std::strlen(le));
+        for (size_t i = 0; i < rec->raw.size(); ++i) {
+            const FaRecord::Range& r = rec->raw[i];
+            if (i) w.write_raw("\n", 1);  // chunks are cut at line breaks: exactly one '\n' lies between two ranges
+            uint32_t n = r.len;
+            if (i + 1 == rec->raw.size() && n && r.chunk->data[r.off + n - 1] == '\r') --n;  // the last line's '\r' is not part of raw_seq
+            w.write_raw(r.chunk->data.data() + r.off, n);
+        }
+        w.write_raw(le, std::strlen(le));
+        return;
+    }
+    if (m.kind != 1) { w.write(to_record(m)); return; }
     const Chunk* ch = static_cast<const Chunk*>(m.chunk);
     const RecSpan& r = ch->recs[m.idx];
     if (r.plain) { w.write_raw(ch->data.data() + r.start, r.end - r.start); return; }
@@ -262,11 +280,19 @@ void extract_records(CmdExtract args) {
             chunks1 = FastqPipeline::open_reader(args.in_fastx);
             if (paired) chunks2 = FastqPipeline::open_reader(*args.in_fastq_2);
         }
+        // single-file FASTA has its own pipeline (fasta_pipeline.h): records of any length, cut into pieces
+        const bool fasta_pipelined = !pipelined && !paired && !std::getenv("MERKURIO_NO_FASTA_PIPELINE") && looks_like_fasta(args.in_fastx);
+        std::unique_ptr<FastaChunkReader> fa_chunks;
+        if (fasta_pipelined) {
+            const size_t chunk_bytes = std::getenv("MERKURIO_CHUNK_BYTES") ? (size_t)std::strtoull(std::getenv("MERKURIO_CHUNK_BYTES"), nullptr, 10)
+                                                                           : (size_t)8 << 20;
+            fa_chunks.reset(new FastaChunkReader(args.in_fastx, chunk_bytes));
+        }
         // the record-by-record path (FASTA, and whatever the FASTQ pipeline does not take) reads ahead on its own
         // threads, also started before the engines
         const bool keep_text = !args.suppress_output;
         std::unique_ptr<PrefetchingFastxReader> ahead1, ahead2;
-        if (!pipelined) {
+        if (!pipelined && !fasta_pipelined) {
             reader->set_keep_raw(keep_text);
             ahead1.reset(new PrefetchingFastxReader(reader.get()));
             if (paired) {
@@ -274,7 +300,7 @@ void extract_records(CmdExtract args) {
                 ahead2.reset(new PrefetchingFastxReader(reader2.get()));
             }
         }
-        EngineSet engines(pattern_list, args.case_insensitive, pipelined ? 16 : 64);
+        EngineSet engines(pattern_list, args.case_insensitive, pipelined ? 16 : (fasta_pipelined ? 32 : 64));
         Scanner scanner(engines, MK_ENC_ASCII, mode, cb);
         auto feed = [&](FastxRecord& rec, uint8_t file) {
             RecMeta m;
@@ -297,6 +323,7 @@ void extract_records(CmdExtract args) {
                     const uint32_t r = u * F + f;
                     const BatchSeg& sg = b.locate((int)f, u, &cursor[f]);
                     RecMeta m;
+                    m.kind = 1;
                     m.chunk = sg.chunk.get();
                     m.idx = sg.first + (u - sg.rec0);
                     const RecSpan& sp = static_cast<const Chunk*>(sg.chunk.get())->recs[m.idx];
@@ -324,10 +351,36 @@ void extract_records(CmdExtract args) {
                 }
             }
         };
+        // FASTA pipeline: assemble the records from their pieces; every record goes through the per-record consumer
+        auto consume_fasta = [&](const PackedBatch& b, const mk_result& res) {
+            const FaBatchInfo& fi = FastaPipeline::info(b);
+            size_t hi = 0;
+            for (uint32_t r = 0; r < b.n_records; ++r) {
+                const FaPiece& pc = fi.pieces[r];
+                FaRecord& rec = *pc.rec;
+                if ((res.record_flags[r >> 6] >> (r & 63)) & 1) rec.found = true;
+                for (; hi < res.n_hits && res.hits[hi].record == r; ++hi) {
+                    const mk_hit& h = res.hits[hi];
+                    if (!pc.first && (uint64_t)h.start + h.len <= pc.own_from) continue;  // owned by the previous piece
+                    rec.hits.push_back(RecHit{pc.base + h.start, h.pattern, h.len});
+                }
+                if (!pc.last) continue;
+                RecMeta m;
+                m.kind = 2;
+                m.chunk = &rec;
+                m.a = rec.id;
+                m.len = (uint32_t)rec.len;
+                m.crlf = rec.crlf;
+                cb(m, rec.found, rec.hits);
+            }
+        };
         FastxRecord r1, r2;
-
         try {
-            if (pipelined) {
+            if (fasta_pipelined) {
+                reader.reset();
+                FastaPipeline pipe(engines, std::move(fa_chunks), mode, keep_text, consume_fasta);
+                pipe.run();
+            } else if (pipelined) {
                 reader.reset();
                 reader2.reset();
                 bulk_totals = true;

@@ -24,6 +24,7 @@ struct RecMeta {
     // batch being delivered keeps the chunk alive
     const void* chunk = nullptr;
     uint32_t idx = 0;
+    uint8_t kind = 0;  // 0: strings a / b / c; 1: FASTQ span (chunk = Chunk, idx); 2: FASTA record (chunk = FaRecord); 3: alignment span
 };
 
 struct RecHit {

@@ -41,6 +41,7 @@ struct PackedBatch {
     uint64_t n_bytes = 0;      // bytes used in seq
     uint64_t total_bases = 0;  // sum of the record lengths
     std::vector<BatchSeg> seg[2];  // per input file
+    std::shared_ptr<void> extra;   // format-specific description of the batch's records (FASTA: its pieces)
     // set on the last batch when the input ended with an error: raised after the batch is delivered
     std::vector<std::string> error_chain;
     // the record of file `f` with index i among the batch's records of that file

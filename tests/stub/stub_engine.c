@@ -1,0 +1,77 @@
+/* Test double of the C ABI (include/merkurio_cuda.h) for the CPU tier of the test-suite: it owns slot
+ * buffers in ordinary memory and reports NO hits for every batch. It is not a matcher and is never
+ * shipped or loaded by the product; tests preload it (LD_PRELOAD) to exercise the host's reader ->
+ * packer -> driver -> writer plumbing (batching, pieces of long records, chunk hand-over, error
+ * propagation, output formatting) on a machine without a GPU. */
+#include <stdlib.h>
+#include <string.h>
+
+#include "merkurio_cuda.h"
+
+struct mk_engine {
+    mk_config cfg;
+    uint8_t* seq[16];
+    uint64_t* off[16];
+    uint32_t* lens[16];
+    uint64_t* flags;
+    uint32_t n_records[16];
+    uint64_t n_units[16];
+};
+
+int mk_engine_create(const mk_patterns* p, const mk_config* c, mk_engine** out) {
+    (void)p;
+    mk_engine* e = calloc(1, sizeof *e);
+    e->cfg = *c;
+    for (uint32_t s = 0; s < c->n_slots && s < 16; ++s) {
+        e->seq[s] = calloc(c->max_batch_bytes + 64, 1);
+        e->off[s] = calloc((size_t)c->max_batch_records + 1, 8);
+        e->lens[s] = calloc((size_t)c->max_batch_records + 1, 4);
+    }
+    e->flags = calloc((size_t)c->max_batch_records / 64 + 2, 8);
+    *out = e;
+    return 0;
+}
+void mk_engine_destroy(mk_engine* e) {
+    if (!e) return;
+    for (int s = 0; s < 16; ++s) { free(e->seq[s]); free(e->off[s]); free(e->lens[s]); }
+    free(e->flags);
+    free(e);
+}
+int mk_engine_get_info(mk_engine* e, mk_engine_info* o) { (void)e; memset(o, 0, sizeof *o); return 0; }
+int mk_slot_buffers(mk_engine* e, uint32_t s, uint8_t** a, uint64_t** b, uint32_t** c) {
+    if (a) *a = e->seq[s];
+    if (b) *b = e->off[s];
+    if (c) *c = e->lens[s];
+    return 0;
+}
+int mk_scan_submit(mk_engine* e, uint32_t s, uint32_t n, uint64_t u, int l, mk_encoding enc, mk_mode m) {
+    (void)l; (void)enc; (void)m;
+    e->n_records[s] = n;
+    e->n_units[s] = u;
+    return 0;
+}
+int mk_scan_wait(mk_engine* e, uint32_t s, mk_result* r) {
+    memset(r, 0, sizeof *r);
+    r->record_flags = e->flags;  /* all zero: no record has a hit */
+    r->n_records = e->n_records[s];
+    r->bases_scanned = e->n_units[s];
+    return 0;
+}
+int mk_scan_host(mk_engine* e, uint32_t s, const uint8_t* a, const uint64_t* b, const uint32_t* c, uint32_t n, uint64_t u,
+                 mk_encoding enc, mk_mode m) {
+    (void)a; (void)b; (void)c;
+    return mk_scan_submit(e, s, n, u, 0, enc, m);
+}
+int mk_scan_device(mk_engine* e, const void* a, const uint64_t* b, const uint32_t* c, uint32_t n, uint64_t u, mk_encoding enc,
+                   mk_mode m, int f, mk_result* r) {
+    (void)e; (void)a; (void)b; (void)c; (void)n; (void)u; (void)enc; (void)m; (void)f;
+    memset(r, 0, sizeof *r);
+    return 0;
+}
+int mk_scan_device_submit(mk_engine* e, uint32_t s, const void* a, const uint64_t* b, const uint32_t* c, uint32_t n, uint64_t u,
+                          mk_encoding enc, mk_mode m, int f) {
+    (void)a; (void)b; (void)c; (void)f;
+    return mk_scan_submit(e, s, n, u, 0, enc, m);
+}
+const char* mk_last_error(void) { return ""; }
+const char* mk_version(void) { return "stub (reports no hits; tests only)"; }

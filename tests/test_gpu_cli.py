@@ -517,3 +517,39 @@ def test_tag_bam_to_bam_passthrough(tmp_path, flags):
     sam_lines = [ln for ln in c[2]["o.sam"].split(b"\n") if ln and not ln.startswith(b"@")]
     assert [r.line for r in ra] == sam_lines
     assert len(ra) == (4000 if not flags else sum(1 for ln in sam_lines)) and len(ra) > 300
+
+
+@pytest.mark.parametrize("logs", [False, True])
+def test_fasta_pipeline_equals_record_path_and_oracle(tmp_path, logs):
+    """Multi-line FASTA through the reader -> packer -> GPU pipeline with batches far smaller than the records:
+    every occurrence must be reported once, at its position in the record, also when it straddles two pieces."""
+    rng = np.random.default_rng(123)
+    pats = sorted({rng.choice(np.frombuffer(b"ACGT", np.uint8), size=int(k)).tobytes() for k in rng.integers(21, 64, size=30)})
+    recs = []
+    for i in range(12):
+        n = int(rng.integers(0, 3000)) if i % 3 else int(rng.integers(60000, 140000))
+        r = bytearray(rng.choice(np.frombuffer(b"ACGTNacgt", np.uint8), size=n).tobytes())
+        pos = 50
+        while pos + 70 < n:  # an occurrence every ~1 kb: some of them cross every kind of boundary
+            p = pats[int(rng.integers(len(pats)))]
+            r[pos:pos + len(p)] = p
+            pos += int(rng.integers(700, 1400))
+        recs.append(bytes(r))
+    fa = tmp_path / "g.fa"
+    _write_fasta(fa, recs, width=70)
+    kf = tmp_path / "k.txt"
+    kf.write_bytes(b"\n".join(pats) + b"\n")
+    log_args = ["-l", "@OUT@/x.log", "-j", "@OUT@/x.json"] if logs else []
+    env = {"MERKURIO_BATCH_BYTES": "30000", "MERKURIO_CHUNK_BYTES": "8000"}
+    args = ["extract", "-i", fa, "-f", kf, "-o", "@OUT@/x.fa", *log_args]
+    rc, err, files = _same_both_ways(tmp_path, args, "MERKURIO_NO_FASTA_PIPELINE", env)
+    assert rc == 0, err
+    # and against the oracle
+    (tmp_path / "ora").mkdir()
+    rm.extract_records(rm.CmdExtract(in_fastx=str(fa), kmer_file=str(kf), out_fastx=str(tmp_path / "ora" / "x.fa"),
+                                     out_log=str(tmp_path / "ora" / "x.log") if logs else None, json_log=str(tmp_path / "ora" / "x.json") if logs else None))
+    assert files["x.fa"] == (tmp_path / "ora" / "x.fa").read_bytes()
+    assert files["x.fa"].count(b">chr") >= 4
+    if logs:
+        assert_log_equal(files["x.log"], (tmp_path / "ora" / "x.log").read_bytes())
+        assert_json_equal(files["x.json"], (tmp_path / "ora" / "x.json").read_bytes())

@@ -1,0 +1,147 @@
+"""CPU tests of the host's ingest pipelines (reader -> packer -> driver -> writer) with a test double
+of the C ABI that reports no hits (tests/stub/stub_engine.c, preloaded): with `-v` every record is
+then written, so the output shows exactly what the pipelines read, how they cut batches and pieces,
+and what the writers emit. Each pipeline must agree byte for byte with the record-by-record path,
+whatever the chunk and batch sizes. (Matching itself is only ever tested on the GPU.)"""
+import gzip
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+QUERY = "ACGTACGTACGTACGTACGTACGTACGTAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAC"
+
+
+@pytest.fixture(scope="module")
+def exe():
+    from merkurio_b200.build import build_host
+    return str(build_host())
+
+
+@pytest.fixture(scope="module")
+def stub(tmp_path_factory):
+    out = tmp_path_factory.mktemp("stub") / "libstub_engine.so"
+    subprocess.run(["gcc", "-O1", "-shared", "-fPIC", "-I", str(ROOT / "include"), "-o", str(out), str(ROOT / "tests" / "stub" / "stub_engine.c")],
+                   check=True)
+    return str(out)
+
+
+def run(exe, stub, args, env=None):
+    e = dict(os.environ, LD_PRELOAD=stub)
+    e.update(env or {})
+    return subprocess.run([exe, *map(str, args)], capture_output=True, env=e)
+
+
+def log_body(p: Path) -> bytes:
+    return b"\n".join(p.read_bytes().split(b"\n")[4:])
+
+
+SIZES = [{}, {"MERKURIO_BATCH_BYTES": "20000", "MERKURIO_CHUNK_BYTES": "5000"},
+         {"MERKURIO_BATCH_BYTES": "17000", "MERKURIO_CHUNK_BYTES": "4096", "MERKURIO_SLOTS": "1"}]
+
+
+def fasta_text(rng, crlf=False, blanks=False, final_nl=True, width=60):
+    out = bytearray()
+    le = b"\r\n" if crlf else b"\n"
+    for i in range(40):
+        n = int(rng.integers(0, 9000)) if i % 7 else int(rng.integers(40000, 90000))
+        s = bytes(rng.choice(np.frombuffer(b"ACGTNacgt", dtype=np.uint8), size=n).tobytes())
+        out += b">rec%d some description" % i + le
+        for k in range(0, n, width):
+            out += s[k:k + width] + le
+            if blanks and rng.random() < 0.02:
+                out += le
+        if blanks and i % 5 == 0:
+            out += le + le
+    return bytes(out) if final_nl else bytes(out).rstrip(b"\r\n")
+
+
+@pytest.mark.parametrize("kw", [{}, {"crlf": True}, {"blanks": True}, {"final_nl": False}, {"width": 7},
+                                {"crlf": True, "blanks": True, "final_nl": False}], ids=lambda k: "-".join(k) or "plain")
+def test_fasta_pipeline_equals_record_path(exe, stub, tmp_path, kw):
+    rng = np.random.default_rng(3)
+    src = tmp_path / "g.fa"
+    src.write_bytes(fasta_text(rng, **kw))
+    results = []
+    for env in [{"MERKURIO_NO_FASTA_PIPELINE": "1"}] + SIZES:
+        o, lg = tmp_path / ("o%d.fa" % len(results)), tmp_path / ("l%d.log" % len(results))
+        r = run(exe, stub, ["extract", "-i", src, "-s", QUERY, "-v", "-o", o, "-l", lg], env)
+        assert r.returncode == 0, r.stderr
+        results.append((o.read_bytes(), log_body(lg)))
+    assert results[0][0].count(b">rec") == 40 and b"records searched: 40" in results[0][1]
+    for other in results[1:]:
+        assert other == results[0]
+
+
+def fastq_text(rng, n, prefix, crlf=False, odd=False):
+    out = bytearray()
+    le = b"\r\n" if crlf else b"\n"
+    for i in range(n):
+        L = int(rng.integers(0, 200))
+        s = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=L).tobytes())
+        plus = b"+" + (b"%s%d" % (prefix, i) if odd and i % 3 == 0 else b"")
+        out += b"@%s%d d=%d" % (prefix, i, i) + le + s + le + plus + le + b"F" * L + le
+        if odd and i % 11 == 0:
+            out += b"\n"
+    return bytes(out)
+
+
+@pytest.mark.parametrize("flavour", ["plain", "crlf", "odd", "gz", "truncated"])
+def test_fastq_pipeline_equals_record_path(exe, stub, tmp_path, flavour):
+    rng = np.random.default_rng(9)
+    d1 = fastq_text(rng, 3000, b"a", crlf=flavour == "crlf", odd=flavour == "odd")
+    d2 = fastq_text(rng, 3000, b"b", crlf=flavour == "crlf", odd=flavour == "odd")
+    if flavour == "truncated":
+        d2 = d2[: len(d2) // 2]
+    p1, p2 = tmp_path / "r1.fq", tmp_path / "r2.fq"
+    p1.write_bytes(gzip.compress(d1) if flavour == "gz" else d1)
+    p2.write_bytes(gzip.compress(d2) if flavour == "gz" else d2)
+    for paired in (False, True):
+        results = []
+        for env in [{"MERKURIO_NO_FASTQ_PIPELINE": "1"}] + SIZES:
+            d = tmp_path / ("out%d%d" % (paired, len(results)))
+            d.mkdir()
+            args = ["extract", "-i", p1, "-s", QUERY, "-v", "-o", d / "x.fastq", "-l", d / "x.log"] + (["-2", p2] if paired else [])
+            r = run(exe, stub, args, env)
+            files = {f.name: (log_body(f) if f.suffix == ".log" else f.read_bytes()) for f in sorted(d.iterdir())}
+            results.append((r.returncode, r.stderr, files))
+        assert (results[0][0] != 0) == (paired and flavour == "truncated")
+        # (the output takes the input's extension: x.fq, x_1.fq / x_2.fq)
+        assert sum(v.count(b"\n@a") for k, v in results[0][2].items() if k.endswith(".fq")) > 1000
+        for other in results[1:]:
+            assert other == results[0]
+
+
+@pytest.mark.parametrize("flags", [[], ["-v"], ["-l", "@/t.log", "-j", "@/t.json"]])
+def test_sam_pipeline_equals_record_path(exe, stub, tmp_path, flags):
+    from tests.test_cli_cpu import _sam_text
+    src = tmp_path / "in.sam"
+    src.write_bytes(_sam_text(3000, seed=5))
+    results = []
+    for env in [{"MERKURIO_NO_ALN_PIPELINE": "1"}] + SIZES:
+        d = tmp_path / ("o%d" % len(results))
+        d.mkdir()
+        r = run(exe, stub, ["tag", "-i", src, "-s", QUERY[:31], "-o", d / "t.sam"] + [f.replace("@", str(d)) for f in flags], env)
+        assert r.returncode == 0, r.stderr
+        files = {}
+        for f in sorted(d.iterdir()):
+            data = f.read_bytes()
+            if f.suffix == ".log":
+                data = log_body(f)
+            elif f.suffix == ".sam":
+                data = b"\n".join(ln for ln in data.split(b"\n") if not ln.startswith(b"@PG"))
+            elif f.suffix == ".json":
+                import json
+                j = json.loads(data)
+                j["meta_information"] = {k: v for k, v in j["meta_information"].items() if k not in ("timestamp", "command_line")}
+                data = json.dumps(j, sort_keys=True).encode()
+            files[f.name] = data
+        results.append(files)
+    # nothing matched: every record is kept and gets a tag (records that already had one keep the old field too)
+    assert results[0]["t.sam"].count(b"\tkm:Z:") == 3000 + 75
+    assert sum(1 for ln in results[0]["t.sam"].split(b"\n") if ln and not ln.startswith(b"@")) == 3000
+    for other in results[1:]:
+        assert other == results[0]
