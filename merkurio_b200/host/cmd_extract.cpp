@@ -448,8 +448,6 @@ void extract_records(CmdExtract args) {
         input_files["kmer_file"] = args.kmer_file ? Json::string(*args.kmer_file) : Json::null();
         input_files["record_file_1"] = Json::string(f1);
         input_files["record_file_2"] = paired ? Json::string(f2) : Json::null();
-        Json counts = Json::object();
-        for (size_t i = 0; i < pattern_list.size(); ++i) counts[pattern_list[i]] = Json::integer((int64_t)pattern_hit_counts[i]);
         Json cmdline = Json::array();
         for (auto& a : args.argv) cmdline.a.push_back(Json::string(a));
         Json meta = Json::object();
@@ -476,7 +474,7 @@ void extract_records(CmdExtract args) {
         pstats["number_of_distinct_records_with_a_hit_in_file_1"] = Json::integer((int64_t)nb_records_hit[0]);
         pstats["number_of_distinct_records_with_a_hit_in_file_2"] = paired ? Json::integer((int64_t)nb_records_hit[1]) : Json::null();
         pstats["number_of_extracted_records"] = Json::integer((int64_t)nb_records_extracted);
-        jl->finalize(meta, counts, summary, &pstats);
+        jl->finalize(meta, pattern_list, pattern_hit_counts, summary, &pstats);
     }
 }
 

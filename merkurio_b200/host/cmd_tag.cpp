@@ -309,8 +309,6 @@ void tag_records(CmdTag args) {
         Json input_files = Json::object();
         input_files["kmer_file"] = args.kmer_file ? Json::string(*args.kmer_file) : Json::null();
         input_files["record_file_1"] = Json::string(in_name);
-        Json counts = Json::object();
-        for (size_t i = 0; i < pattern_list.size(); ++i) counts[pattern_list[i]] = Json::integer((int64_t)pattern_hit_counts[i]);
         Json cmdline = Json::array();
         for (auto& a : args.argv) cmdline.a.push_back(Json::string(a));
         Json meta = Json::object();
@@ -331,7 +329,7 @@ void tag_records(CmdTag args) {
         summary["number_of_characters_searched"] = Json::integer((int64_t)nb_bases);
         summary["number_of_matches"] = Json::integer((int64_t)nb_hits_tot);
         summary["number_of_distinct_records_with_a_hit"] = Json::integer((int64_t)nb_records_hit);
-        jl->finalize(meta, counts, summary, nullptr);
+        jl->finalize(meta, pattern_list, pattern_hit_counts, summary, nullptr);
     }
 }
 

@@ -104,7 +104,8 @@ void JsonLogger::write_indented_value(const Json& v, int indent) {
     buf_ += v.pretty(indent);
     buf_ += '\n';
 }
-void JsonLogger::finalize(const Json& meta, const Json& counts, const Json& summary, const Json* paired) {
+void JsonLogger::finalize(const Json& meta, const std::vector<std::string>& patterns, const std::vector<uint64_t>& counts, const Json& summary,
+                          const Json* paired) {
     auto pop_nl = [&] { if (!buf_.empty() && buf_.back() == '\n') buf_.pop_back(); };
     buf_ += "  ],\n  \"meta_information\": ";
     write_indented_value(meta, 2); pop_nl();
@@ -112,8 +113,22 @@ void JsonLogger::finalize(const Json& meta, const Json& counts, const Json& summ
         buf_ += ",\n  \"paired_end_reads_statistics\": ";
         write_indented_value(*paired, 2); pop_nl();
     }
+    // written straight from the list (a million queries would otherwise go through a map and one big string)
     buf_ += ",\n  \"pattern_hit_counts\": ";
-    write_indented_value(counts, 2); pop_nl();
+    if (patterns.empty()) {
+        buf_ += "{}";
+    } else {
+        buf_ += "{\n";
+        for (size_t i = 0; i < patterns.size(); ++i) {
+            buf_ += "    ";
+            buf_ += json_escape(patterns[i]);
+            buf_ += ": ";
+            buf_ += std::to_string(counts[i]);
+            buf_ += i + 1 < patterns.size() ? ",\n" : "\n";
+            if (buf_.size() >= (1u << 20)) flush();
+        }
+        buf_ += "  }";
+    }
     buf_ += ",\n  \"summary_statistics\": ";
     write_indented_value(summary, 2); pop_nl();
     buf_ += "\n}\n";

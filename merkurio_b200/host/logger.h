@@ -63,8 +63,9 @@ public:
     JsonLogger(std::unique_ptr<Sink> sink, size_t buffer_size);
     void log_fields(const std::string& file, const std::string& record, const std::string& pattern, uint64_t index);
     void flush();
-    void finalize(const Json& meta_information, const Json& pattern_hit_counts, const Json& summary_statistics,
-                  const Json* paired_end_stats);
+    // patterns: the sorted unique query list (= the key order serde_json's sorted map gives), counts[i] its hits
+    void finalize(const Json& meta_information, const std::vector<std::string>& patterns, const std::vector<uint64_t>& counts,
+                  const Json& summary_statistics, const Json* paired_end_stats);
 private:
     void write_indented_value(const Json& v, int indent);
     std::unique_ptr<Sink> sink_;
