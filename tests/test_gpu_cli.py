@@ -340,6 +340,24 @@ def test_two_gpus_from_the_cli(ref_tree, tmp_path):
     got = json.loads((tmp_path / "m.json").read_bytes())
     want = json.loads((ew / "logs" / "mutant_extracted.stats.json").read_bytes())
     assert got["matching_records"] == want["matching_records"] and got["summary_statistics"] == want["summary_statistics"]
+    # FASTA pieces and SAM records dealt over two engines: same files as on one
+    rng = np.random.default_rng(5)
+    pats = sorted({rng.choice(np.frombuffer(b"ACGT", np.uint8), size=31).tobytes() for _ in range(20)})
+    recs = _rand_reads(rng, 6, 30000, 60000, pats, plant=1.0)
+    fa = tmp_path / "g.fa"
+    _write_fasta(fa, recs)
+    kf = tmp_path / "k.txt"
+    kf.write_bytes(b"\n".join(pats) + b"\n")
+    one = _outputs(tmp_path, "fa1", ["extract", "-i", fa, "-f", kf, "-r", "-o", "@OUT@/x.fa", "-l", "@OUT@/x.log"], {"MERKURIO_BATCH_BYTES": "25000"})
+    two = _outputs(tmp_path, "fa2", ["extract", "-i", fa, "-f", kf, "-r", "-o", "@OUT@/x.fa", "-l", "@OUT@/x.log"],
+                   {"MERKURIO_BATCH_BYTES": "25000", "MERKURIO_GPUS": "2"})
+    assert one[0] == two[0] == 0 and one[2]["x.fa"] == two[2]["x.fa"] and one[2]["x.fa"].count(b">chr") >= 1
+    assert _strip_volatile("x.log", one[2]["x.log"]) == _strip_volatile("x.log", two[2]["x.log"])
+    sam = ref_tree / "example-workflow" / "output" / "mutant_extracted.sorted.sam"
+    a = _outputs(tmp_path, "t1", ["tag", "-i", sam, "-f", ew / "data" / "significant_kmers.txt", "-r", "-o", "@OUT@/t.sam"], {"MERKURIO_BATCH_BYTES": "20000"})
+    b = _outputs(tmp_path, "t2", ["tag", "-i", sam, "-f", ew / "data" / "significant_kmers.txt", "-r", "-o", "@OUT@/t.sam"],
+                 {"MERKURIO_BATCH_BYTES": "20000", "MERKURIO_GPUS": "2"})
+    assert a[0] == b[0] == 0 and _strip_volatile("t.sam", a[2]["t.sam"]) == _strip_volatile("t.sam", b[2]["t.sam"])
 
 
 # ------------------------------------------------------------------ ingest pipelines vs the line-by-line readers
