@@ -351,7 +351,7 @@ int run(int argc, char** argv) {
                     if (ch->bam) {
                         std::string nm;
                         bam_body_to_sam(ch->data.data() + sp.off, sp.len, refs, &nm, &line, nullptr, nullptr);
-                        std::memcpy(packed.data(), ch->data.data() + sp.seq_off, packed.size());
+                        if (!packed.empty()) std::memcpy(packed.data(), ch->data.data() + sp.seq_off, packed.size());
                     } else {
                         line.assign(ch->data.data() + sp.off, sp.len);
                         for (uint32_t i = 0; i < sp.l_seq; ++i)
