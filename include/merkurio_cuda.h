@@ -142,6 +142,12 @@ int mk_scan_host(mk_engine* e, uint32_t slot, const uint8_t* h_seq, const uint64
                  const uint32_t* h_lens, uint32_t n_records, uint64_t n_units, mk_encoding enc,
                  mk_mode mode);
 
+/* mk_scan_host for records of one common length (fixed-length reads): record r occupies units
+ * [r * record_len, (r + 1) * record_len) of h_seq, so no offset array crosses the bus — the offsets are
+ * written on the device. For MK_ENC_BAM4 record_len must be even. */
+int mk_scan_host_uniform(mk_engine* e, uint32_t slot, const uint8_t* h_seq, uint32_t n_records,
+                         uint32_t record_len, mk_encoding enc, mk_mode mode);
+
 /* Synchronous scan of a batch that already sits in device memory (sequence decoded / generated on
  * the device, or the device-timed benchmark). d_seq must be 16-byte aligned and readable up to the
  * next multiple of 16 bytes plus 16. fetch != 0 also copies flags and hits to the host views. */

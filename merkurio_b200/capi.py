@@ -16,7 +16,7 @@ MK_MODE_FLAG, MK_MODE_PATTERN_SET, MK_MODE_ALL_HITS = 0, 1, 2
 
 EXPORTS = (
     "mk_engine_create", "mk_engine_destroy", "mk_engine_get_info", "mk_slot_buffers", "mk_scan_submit",
-    "mk_scan_wait", "mk_scan_host", "mk_scan_device", "mk_scan_device_submit", "mk_last_error", "mk_version",
+    "mk_scan_wait", "mk_scan_host", "mk_scan_device", "mk_scan_device_submit", "mk_scan_host_uniform", "mk_last_error", "mk_version",
 )
 
 
@@ -86,6 +86,8 @@ def load():
         L.mk_scan_device_submit.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int,
                                             C.c_int, C.c_int]
         L.mk_scan_device_submit.restype = C.c_int
+        L.mk_scan_host_uniform.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
+        L.mk_scan_host_uniform.restype = C.c_int
         L.mk_last_error.argtypes = []
         L.mk_last_error.restype = C.c_char_p
         L.mk_version.argtypes = []
@@ -216,6 +218,11 @@ class Engine:
         r = MkResult()
         _check(load().mk_scan_device(self._h, d_seq, d_off, d_lens, n_records, n_units, enc, mode, int(fetch), C.byref(r)))
         return ScanResult(r, copy=True)
+
+    def scan_host_uniform_async(self, slot: int, seq, n_records: int, record_len: int, enc: int, mode: int):
+        """mk_scan_host_uniform: fixed-length records, no offset array (caller keeps seq alive until wait)."""
+        sp = seq.ctypes.data if isinstance(seq, np.ndarray) else seq
+        _check(load().mk_scan_host_uniform(self._h, slot, sp, n_records, record_len, enc, mode))
 
     def scan_device_submit(self, slot: int, d_seq: int, d_off: int, n_records: int, n_units: int, mode: int = MK_MODE_FLAG,
                            enc: int = MK_ENC_ASCII, d_lens: Optional[int] = None, fetch: bool = False):

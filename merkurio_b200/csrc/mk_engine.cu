@@ -685,6 +685,34 @@ int mk_scan_host(mk_engine* e, uint32_t slot, const uint8_t* h_seq, const uint64
     return begin_batch(e, s->ws, s->d_seq.p, s->d_off.p, h_lens ? s->d_lens.p : nullptr, n_records, n_units, enc, mode, true);
 }
 
+namespace {
+__global__ void mk_uniform_offsets(unsigned long long* off, uint32_t n_records, uint32_t record_len) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n_records; i += (uint64_t)gridDim.x * blockDim.x)
+        off[i] = i * record_len;
+}
+}  // namespace
+
+int mk_scan_host_uniform(mk_engine* e, uint32_t slot, const uint8_t* h_seq, uint32_t n_records, uint32_t record_len, mk_encoding enc,
+                         mk_mode mode) {
+    Slot* s = nullptr;
+    int rc = get_slot(e, slot, &s);
+    if (rc) return rc;
+    if (s->ws.busy) return fail(MK_ERR_STATE, "slot %u still has a batch in flight", slot);
+    if (!h_seq) return fail(MK_ERR_INVALID, "null batch buffer");
+    if (enc == MK_ENC_BAM4 && (record_len & 1)) return fail(MK_ERR_INVALID, "BAM4 records of a common length must have an even length");
+    const uint64_t n_units = (uint64_t)n_records * record_len;
+    rc = check_batch(e, n_records, n_units, enc);
+    if (rc) return rc;
+    CU(cudaSetDevice(e->device));
+    const uint64_t bytes = enc == MK_ENC_ASCII ? n_units : n_units / 2;
+    cudaStream_t st = s->ws.stream;
+    if (bytes) CU(cudaMemcpyAsync(s->d_seq.p, h_seq, bytes, cudaMemcpyHostToDevice, st));
+    if (bytes % 16) CU(cudaMemsetAsync(s->d_seq.p + bytes, 0, 16 - bytes % 16, st));
+    mk_uniform_offsets<<<std::max(1u, std::min(1024u, (n_records + 256) / 256)), 256, 0, st>>>(s->d_off.p, n_records, record_len);
+    CU(cudaGetLastError());
+    return begin_batch(e, s->ws, s->d_seq.p, s->d_off.p, nullptr, n_records, n_units, enc, mode, true);
+}
+
 int mk_scan_submit(mk_engine* e, uint32_t slot, uint32_t n_records, uint64_t n_units, int use_lens, mk_encoding enc,
                    mk_mode mode) {
     Slot* s = nullptr;

@@ -62,6 +62,10 @@ int mk_scan_host(mk_engine* e, uint32_t s, const uint8_t* a, const uint64_t* b, 
     (void)a; (void)b; (void)c;
     return mk_scan_submit(e, s, n, u, 0, enc, m);
 }
+int mk_scan_host_uniform(mk_engine* e, uint32_t s, const uint8_t* a, uint32_t n, uint32_t len, mk_encoding enc, mk_mode m) {
+    (void)a;
+    return mk_scan_submit(e, s, n, (uint64_t)n * len, 0, enc, m);
+}
 int mk_scan_device(mk_engine* e, const void* a, const uint64_t* b, const uint32_t* c, uint32_t n, uint64_t u, mk_encoding enc,
                    mk_mode m, int f, mk_result* r) {
     (void)e; (void)a; (void)b; (void)c; (void)n; (void)u; (void)enc; (void)m; (void)f;

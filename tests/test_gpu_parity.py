@@ -462,3 +462,24 @@ def test_device_resident_batches_in_flight():
             np.testing.assert_array_equal(r.hits["start"], st)
             np.testing.assert_array_equal(r.hits["pattern"], pat)
             np.testing.assert_array_equal(r.flagged_records(), np.unique(rec))
+
+
+def test_fixed_length_batches_without_offsets():
+    """mk_scan_host_uniform: records of one common length, offsets generated on the device (ASCII and BAM4)."""
+    rng = np.random.default_rng(73)
+    pats = sorted({rand_seq(rng, 31) for _ in range(50)})
+    recs = planted_records(rng, pats, 3000, 150, 150, plant_p=0.2)
+    seq, off = pack_records(recs)
+    rec, st, pat = oracle_hits(pats, recs)
+    with capi.Engine(pats, n_slots=2, max_batch_bytes=int(seq.size) + 64, max_batch_records=len(recs)) as e:
+        e.scan_host_uniform_async(0, seq, len(recs), 150, capi.MK_ENC_ASCII, capi.MK_MODE_ALL_HITS)
+        r = e.wait(0)
+        np.testing.assert_array_equal(r.hits["record"], rec)
+        np.testing.assert_array_equal(r.hits["start"], st)
+        np.testing.assert_array_equal(r.hits["pattern"], pat)
+        packed, poff, lens = pack_bam4(recs)
+        e.scan_host_uniform_async(1, packed, len(recs), 150, capi.MK_ENC_BAM4, capi.MK_MODE_FLAG)
+        f = e.wait(1)
+        np.testing.assert_array_equal(f.flagged_records(), np.unique(rec))
+        with pytest.raises(capi.MkError):
+            e.scan_host_uniform_async(0, packed, 10, 151, capi.MK_ENC_BAM4, capi.MK_MODE_FLAG)
