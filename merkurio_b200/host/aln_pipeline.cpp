@@ -53,7 +53,7 @@ bool AlnPipeline::fill(PackedBatch& b) {
         b.n_bytes += nbytes;
         b.n_units += nbytes * 2;
         b.total_bases += r.l_seq;
-        b.add_to_seg(0, std::shared_ptr<const void>(cur_), (uint32_t)idx_, b.n_records);
+        b.add_to_seg(0, cur_, (uint32_t)idx_, b.n_records);
         b.n_records += 1;
         idx_ += 1;
     }

@@ -50,6 +50,7 @@ struct EngineSet {
     uint32_t n_slots = 3, max_records = 0, max_pattern_len = 0;
     uint64_t max_bytes = 0;
     double t_start = 0, t_setup = 0, t_wait = 0, t_deliver = 0;
+    double t_pack = 0, t_pack_wait = 0;  // packer thread: filling slots / waiting for a free slot
     uint64_t device_ns = 0, n_records = 0, n_bases = 0, n_batches = 0;
 };
 

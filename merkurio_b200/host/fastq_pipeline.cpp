@@ -64,7 +64,7 @@ bool FastqPipeline::fill(PackedBatch& b) {
         if (r.seq_len) std::memcpy(b.seq + b.n_units, c.seq(r), r.seq_len);
         b.n_units += r.seq_len;
         b.n_records += 1;
-        b.add_to_seg(f, std::shared_ptr<const void>(cur_[f]), (uint32_t)idx_[f], nrec[f]);
+        b.add_to_seg(f, cur_[f], (uint32_t)idx_[f], nrec[f]);
         nrec[f] += 1;
         idx_[f] += 1;
     };

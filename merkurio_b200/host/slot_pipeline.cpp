@@ -39,6 +39,7 @@ void SlotPipeline::pack() {
         begin();
         for (;;) {
             std::unique_ptr<PackedBatch> b;
+            const double t0 = now_s();
             {
                 std::unique_lock<std::mutex> lk(mu_);
                 cv_.wait(lk, [this] { return !free_.empty() || stop_; });
@@ -46,7 +47,10 @@ void SlotPipeline::pack() {
                 b = std::move(free_.front());
                 free_.pop_front();
             }
+            const double t1 = now_s();
             bool any = fill(*b);
+            es_.t_pack_wait += t1 - t0;
+            es_.t_pack += now_s() - t1;
             std::lock_guard<std::mutex> lk(mu_);
             if (any) packed_.push_back(std::move(b));
             else free_.push_front(std::move(b));

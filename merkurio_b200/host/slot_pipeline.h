@@ -53,10 +53,12 @@ struct PackedBatch {
         *cursor = c;
         return v[c];
     }
-    void add_to_seg(int f, const std::shared_ptr<const void>& chunk, uint32_t idx, uint32_t rec_index) {
+    // (the chunk's reference count is only touched when a new run of records starts)
+    template <class T>
+    void add_to_seg(int f, const std::shared_ptr<T>& chunk, uint32_t idx, uint32_t rec_index) {
         std::vector<BatchSeg>& v = seg[f];
         if (!v.empty() && v.back().chunk.get() == chunk.get() && v.back().first + v.back().count == idx) v.back().count += 1;
-        else v.push_back(BatchSeg{chunk, idx, 1, rec_index});
+        else v.push_back(BatchSeg{std::shared_ptr<const void>(chunk), idx, 1, rec_index});
     }
 };
 

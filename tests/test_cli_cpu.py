@@ -177,6 +177,8 @@ FASTQ_CASES = {
     "missing_plus": b"@r1\nACGT\n-\nIIII\n",
     "only_header": b"@r1\n",
     "long_record": b"@long\n" + b"ACGTTGCA" * 5000 + b"\n+\n" + b"I" * 40000 + b"\n@r2\nGG\n+\nII\n",
+    # longer than the reader's head room and than the stretch its indexer works on at a time
+    "very_long_record": b"@r0\nAC\n+\nII\n@long\n" + b"ACGTTGCA" * 50000 + b"\n+\n" + b"I" * 400000 + b"\n@r2\nGG\n+\nII\n@r3\nT\n+\nI",
 }
 
 
