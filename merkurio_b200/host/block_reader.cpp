@@ -1,0 +1,153 @@
+#include "block_reader.h"
+
+#include <chrono>
+#include <cstring>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
+
+#include "codecs.h"
+
+namespace mkh {
+
+void* big_alloc(size_t bytes) {
+    const size_t align = (size_t)2 << 20;
+    const size_t rounded = (bytes + align - 1) / align * align;
+    void* p = std::aligned_alloc(align, rounded);
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+    if (p) madvise(p, rounded, MADV_HUGEPAGE);  // advice only: failure changes nothing
+#endif
+    return p;
+}
+
+double steady_seconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+BlockReader::BlockReader(const std::string& path, size_t block_bytes, size_t head, size_t depth)
+    : path_(path), block_bytes_(std::max<size_t>(block_bytes, 4096)), head_(head), depth_(std::max<size_t>(depth, 1)) {
+    // open here so that a missing file fails in the caller's thread, with the caller's context
+    { std::unique_ptr<InputStream> probe = InputStream::open(path_); }
+    thread_ = std::thread([this] { run(); });
+}
+
+BlockReader::~BlockReader() {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    if (thread_.joinable()) thread_.join();
+}
+
+bool BlockReader::next(Block& b) {
+    std::unique_lock<std::mutex> lk(mu_);
+    if (b.data.capacity() && spare_.size() < depth_ + 2) spare_.push_back(std::move(b.data));
+    b.data = ByteBuf();
+    b.n = 0;
+    b.last = false;
+    cv_.wait(lk, [this] { return !ready_.empty() || done_; });
+    if (!ready_.empty()) {
+        b = std::move(ready_.front());
+        ready_.pop_front();
+        lk.unlock();
+        cv_.notify_all();
+        return true;
+    }
+    if (!io_error_.empty()) throw Error(io_error_);
+    return false;
+}
+
+void BlockReader::run() {
+    std::string error;
+    try {
+        std::unique_ptr<InputStream> src = InputStream::open(path_);
+        for (bool eof = false; !eof;) {
+            Block b;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!spare_.empty()) { b.data = std::move(spare_.back()); spare_.pop_back(); }
+            }
+            if (b.data.size() < head_ + block_bytes_) b.data.resize(head_ + block_bytes_);
+            const double t0 = steady_seconds();
+            while (!eof && b.n < block_bytes_) {
+                size_t got = src->read(b.data.data() + head_ + b.n, block_bytes_ - b.n);
+                if (got == 0) eof = true;
+                b.n += got;
+            }
+            b.last = eof;
+            const double dt = steady_seconds() - t0;
+            std::unique_lock<std::mutex> lk(mu_);
+            t_read_ += dt;
+            cv_.wait(lk, [this] { return ready_.size() < depth_ || stop_; });
+            if (stop_) return;
+            ready_.push_back(std::move(b));
+            lk.unlock();
+            cv_.notify_all();
+        }
+    } catch (const std::exception& e) {
+        error = e.what();
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        io_error_ = error;
+        done_ = true;
+    }
+    cv_.notify_all();
+}
+
+#if defined(__x86_64__)
+namespace {
+__attribute__((target("avx2"))) void line_breaks_avx2(const char* d, size_t from, size_t to, OffsetList& out) {
+    const __m256i nl = _mm256_set1_epi8('\n');
+    size_t p = from;
+    while (p + 32 <= to) {
+        const size_t stop = std::min(to, p + 4096) - 31;  // a stretch of at most 4 KiB: room for its line breaks up front
+        out.reserve(out.n + 4096);
+        uint32_t* w = out.p + out.n;
+        for (; p < stop; p += 32) {
+            uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(d + p)), nl));
+            while (m) {
+                *w++ = (uint32_t)(p + (unsigned)__builtin_ctz(m));
+                m &= m - 1;
+            }
+        }
+        out.n = (size_t)(w - out.p);
+    }
+    out.reserve(out.n + 32);
+    for (; p < to; ++p)
+        if (d[p] == '\n') out.p[out.n++] = (uint32_t)p;
+}
+}  // namespace
+#endif
+
+void find_line_breaks(const char* d, size_t from, size_t to, OffsetList& out) {
+    size_t p = from;
+#if defined(__x86_64__)
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) return line_breaks_avx2(d, from, to, out);
+    const __m128i nl = _mm_set1_epi8('\n');
+    while (p + 16 <= to) {
+        const size_t stop = std::min(to, p + 4096) - 15;
+        out.reserve(out.n + 4096);
+        uint32_t* w = out.p + out.n;
+        for (; p < stop; p += 16) {
+            uint32_t m = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i*>(d + p)), nl));
+            while (m) {
+                *w++ = (uint32_t)(p + (unsigned)__builtin_ctz(m));
+                m &= m - 1;
+            }
+        }
+        out.n = (size_t)(w - out.p);
+    }
+#endif
+    for (; p < to; ++p)
+        if (d[p] == '\n') {
+            out.reserve(out.n + 1);
+            out.p[out.n++] = (uint32_t)p;
+        }
+}
+
+}  // namespace mkh

@@ -1,0 +1,114 @@
+// First stage of the chunked readers (fastq_stream.h, fasta_pipeline.h): one thread that does nothing
+// but read (or inflate, codecs.h) the input into large blocks, so that locating the records of a block
+// (second stage, another thread) overlaps the read of the next one. Also the line-break scanner both
+// indexers use.
+#pragma once
+#include <algorithm>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdlib>
+#include <deque>
+#include <mutex>
+#include <new>
+#include <string>
+#include <memory>
+#include <thread>
+#include <utility>
+#include <vector>
+
+#include "common.h"
+
+namespace mkh {
+
+// Bytes that are not zero-filled when a buffer is sized (the reader overwrites them anyway; zero-filling
+// 8 MB per new block cost as much as reading it from the page cache).
+void* big_alloc(size_t bytes);  // 2 MB aligned, madvise(MADV_HUGEPAGE) where the system offers it; free() releases it
+
+template <class T>
+struct DefaultInitAllocator : std::allocator<T> {
+    template <class U> struct rebind { using other = DefaultInitAllocator<U>; };
+    DefaultInitAllocator() = default;
+    template <class U> DefaultInitAllocator(const DefaultInitAllocator<U>&) {}
+    // large buffers: 2 MB aligned and marked for transparent huge pages (512 x fewer page faults on first touch)
+    T* allocate(size_t n) {
+        const size_t bytes = n * sizeof(T);
+        if (bytes < kHugeFrom) return static_cast<T*>(::operator new(bytes));
+        void* p = big_alloc(bytes);
+        if (!p) throw std::bad_alloc();
+        return static_cast<T*>(p);
+    }
+    void deallocate(T* p, size_t n) {
+        if (n * sizeof(T) < kHugeFrom) ::operator delete(p);
+        else std::free(p);
+    }
+    static constexpr size_t kHugeFrom = (size_t)1 << 20;
+    template <class U> void construct(U* p) { ::new (static_cast<void*>(p)) U; }
+    template <class U, class... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+};
+using ByteBuf = std::vector<char, DefaultInitAllocator<char>>;
+
+class BlockReader {
+public:
+    // n bytes of the file at data[head, head + n); the head room is the indexer's (it puts the unfinished
+    // record or line of the block before there).
+    struct Block {
+        ByteBuf data;
+        size_t n = 0;
+        bool last = false;  // the file ends with this block
+    };
+    BlockReader(const std::string& path, size_t block_bytes, size_t head, size_t depth = 3);
+    ~BlockReader();
+    BlockReader(const BlockReader&) = delete;
+    // The next block in file order, swapped into b (whatever b.data held before is reused as a buffer).
+    // False after the last block; an I/O error is rethrown here once the blocks before it are out.
+    bool next(Block& b);
+    size_t head() const { return head_; }
+    size_t block_bytes() const { return block_bytes_; }
+    double seconds_reading() {
+        std::lock_guard<std::mutex> lk(mu_);
+        return t_read_;
+    }
+
+private:
+    void run();
+    std::string path_;
+    size_t block_bytes_, head_, depth_;
+    std::thread thread_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<Block> ready_;
+    std::vector<ByteBuf> spare_;
+    bool done_ = false, stop_ = false;
+    std::string io_error_;
+    double t_read_ = 0;
+};
+
+// Growable array of offsets without value initialisation (the scanner appends through a raw pointer).
+struct OffsetList {
+    uint32_t* p = nullptr;
+    size_t n = 0, cap = 0;
+    OffsetList() = default;
+    OffsetList(const OffsetList&) = delete;
+    OffsetList& operator=(const OffsetList&) = delete;
+    ~OffsetList() { std::free(p); }
+    void reserve(size_t want) {
+        if (want <= cap) return;
+        size_t c = std::max(want, cap * 2);
+        void* q = std::realloc(p, c * sizeof(uint32_t));
+        if (!q) throw std::bad_alloc();
+        p = static_cast<uint32_t*>(q);
+        cap = c;
+    }
+    void clear() { n = 0; }
+    size_t size() const { return n; }
+    uint32_t operator[](size_t i) const { return p[i]; }
+};
+
+// Offsets of every '\n' in d[from, to), appended to out in ascending order. One vector compare per 32
+// (16) bytes instead of a memchr call per line: FASTA / FASTQ lines are short, so the per-call cost of
+// memchr was most of the indexing time.
+void find_line_breaks(const char* d, size_t from, size_t to, OffsetList& out);
+
+double steady_seconds();
+
+}  // namespace mkh

@@ -1,5 +1,7 @@
 #include "fasta_pipeline.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "codecs.h"
@@ -14,7 +16,7 @@ struct FastaChunkReader::Shared {
 
 FastaChunkReader::FastaChunkReader(const std::string& path, size_t chunk_bytes, size_t depth)
     : path_(path), chunk_bytes_(std::max<size_t>(chunk_bytes, 4096)), depth_(std::max<size_t>(depth, 1)), pool_(new Shared) {
-    { std::unique_ptr<InputStream> probe = InputStream::open(path_); }  // a missing file fails in the caller's thread
+    blocks_.reset(new BlockReader(path_, chunk_bytes_, kHead));  // a missing file fails here, in the caller's thread
     thread_ = std::thread([this] { run(); });
 }
 
@@ -25,6 +27,7 @@ FastaChunkReader::~FastaChunkReader() {
     }
     cv_.notify_all();
     if (thread_.joinable()) thread_.join();
+    blocks_.reset();
 }
 
 std::shared_ptr<FaChunk> FastaChunkReader::next() {
@@ -41,13 +44,20 @@ std::shared_ptr<FaChunk> FastaChunkReader::next() {
     return nullptr;
 }
 
+// The indexing thread: lines of each block the reading thread (blocks_) hands over. An unfinished last
+// line is carried over to the front of the next block.
 void FastaChunkReader::run() {
+    double t_index = 0, t_starved = 0, t_blocked = 0;
     try {
-        std::unique_ptr<InputStream> src = InputStream::open(path_);
         std::vector<char> carry;
-        bool eof = false;
         std::shared_ptr<Shared> pool = pool_;
-        while (!eof) {
+        BlockReader::Block rb;
+        OffsetList nl;
+        for (bool eof = false; !eof;) {
+            const double t_w0 = steady_seconds();
+            if (!blocks_->next(rb)) break;  // (an I/O error is thrown by next() after the blocks before it)
+            const double t_i0 = steady_seconds();
+            t_starved += t_i0 - t_w0;
             std::unique_ptr<FaChunk> up;
             {
                 std::lock_guard<std::mutex> lk(pool->mu);
@@ -55,35 +65,49 @@ void FastaChunkReader::run() {
             }
             if (!up) up.reset(new FaChunk);
             FaChunk* c = up.get();
+            c->data.swap(rb.data);  // the chunk's previous buffer goes back to the reader with the next call
+            eof = rb.last;
             c->lines.clear();
-            c->last = false;
-            if (c->data.size() < chunk_bytes_ + carry.size()) c->data.resize(chunk_bytes_ + carry.size());
-            size_t have = carry.size();
-            if (have) std::memcpy(c->data.data(), carry.data(), have);
-            carry.clear();
-            size_t p = 0;
-            for (;;) {
-                while (!eof && have < c->data.size()) {
-                    size_t n = src->read(c->data.data() + have, c->data.size() - have);
-                    if (n == 0) eof = true;
-                    have += n;
-                }
-                const char* d = c->data.data();
-                while (p < have) {
-                    const char* nl = static_cast<const char*>(std::memchr(d + p, '\n', have - p));
-                    size_t e;
-                    if (nl) e = (size_t)(nl - d);
-                    else if (eof) e = have;  // an unterminated last line (p < have: it is not empty)
-                    else break;
-                    c->lines.push_back(FaLine{(uint32_t)p, (uint32_t)(e - p), (uint8_t)(e > p && d[p] == '>')});
-                    p = nl ? e + 1 : have;
-                }
-                if (eof || !c->lines.empty()) break;
-                if (c->data.size() > ((size_t)1 << 30)) throw Error("FASTA line longer than 1 GiB");
-                c->data.resize(c->data.size() * 2);  // one line longer than the buffer
+            size_t begin, have;
+            if (carry.size() <= kHead) {
+                begin = kHead - carry.size();
+                have = kHead + rb.n;
+                if (!carry.empty()) std::memcpy(c->data.data() + begin, carry.data(), carry.size());
+            } else {
+                // a line longer than the head room (offsets are 32-bit)
+                if (carry.size() > ((size_t)1 << 30)) throw Error("FASTA line longer than 1 GiB");
+                ByteBuf joined(kHead + carry.size() + std::max(rb.n, chunk_bytes_));
+                std::memcpy(joined.data() + kHead, carry.data(), carry.size());
+                std::memcpy(joined.data() + kHead + carry.size(), c->data.data() + kHead, rb.n);
+                c->data.swap(joined);
+                begin = kHead;
+                have = kHead + carry.size() + rb.n;
             }
-            if (p < have) carry.assign(c->data.data() + p, c->data.data() + have);
+            carry.clear();
+            // line breaks are located a stretch at a time, the lines noted while the stretch is still in the cache
+            const char* d = c->data.data();
+            size_t p = begin;
+            for (size_t scanned = begin; scanned < have;) {
+                const size_t upto = std::min(have, scanned + kStretch);
+                nl.clear();
+                find_line_breaks(d, scanned, upto, nl);
+                scanned = upto;
+                const size_t base = c->lines.size();
+                c->lines.resize(base + nl.n);
+                FaLine* w = c->lines.data() + base;
+                for (size_t i = 0; i < nl.n; ++i) {
+                    const size_t e = nl.p[i];
+                    w[i] = FaLine{(uint32_t)p, (uint32_t)(e - p), (uint8_t)(e > p && d[p] == '>')};
+                    p = e + 1;
+                }
+            }
+            if (eof && p < have) {  // an unterminated last line (it is not empty)
+                c->lines.push_back(FaLine{(uint32_t)p, (uint32_t)(have - p), (uint8_t)(d[p] == '>')});
+                p = have;
+            }
+            if (p < have) carry.assign(d + p, d + have);
             c->last = eof;
+            t_index += steady_seconds() - t_i0;
             if (c->lines.empty()) {
                 std::lock_guard<std::mutex> lk(pool->mu);
                 pool->free_list.push_back(std::move(up));
@@ -94,8 +118,10 @@ void FastaChunkReader::run() {
                 std::lock_guard<std::mutex> lk(pool->mu);
                 if (pool->free_list.size() < 24) pool->free_list.push_back(std::move(back));
             });
+            const double t_b0 = steady_seconds();
             std::unique_lock<std::mutex> lk(mu_);
             cv_.wait(lk, [this] { return ready_.size() < depth_ || stop_; });
+            t_blocked += steady_seconds() - t_b0;
             if (stop_) return;
             ready_.push_back(std::move(sp));
             lk.unlock();
@@ -105,6 +131,9 @@ void FastaChunkReader::run() {
         std::lock_guard<std::mutex> lk(mu_);
         io_error_ = e.what();
     }
+    if (std::getenv("MERKURIO_TIMING"))
+        std::fprintf(stderr, "[merkurio] FASTA reader %s: read %.3f s | index %.3f s, waiting for input %.3f s, blocked on the packer %.3f s\n",
+                     path_.c_str(), blocks_->seconds_reading(), t_index, t_starved, t_blocked);
     {
         std::lock_guard<std::mutex> lk(mu_);
         done_ = true;

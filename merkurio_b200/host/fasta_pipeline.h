@@ -1,6 +1,6 @@
 // FASTA input of `extract` on the slot pipeline (slot_pipeline.h): replaces needletail's FASTA reader
-// and the per-record loop of src/cmd_extract.rs:321-406 for (multi-line) FASTA. A reader thread
-// indexes the lines of 8 MB chunks in place; the packer copies the sequence lines — line breaks
+// and the per-record loop of src/cmd_extract.rs:321-406 for (multi-line) FASTA. One thread reads 8 MB blocks
+// (block_reader.h), a second one indexes their lines in place; the packer copies the sequence lines — line breaks
 // dropped, exactly what record.seq() hands the reference's matchers — straight into the pinned slots.
 // A record larger than what is left of a slot continues in the next batch as a further *piece* that
 // starts with the last (longest pattern - 1) bases again, so that every occurrence lies inside one
@@ -18,7 +18,7 @@ struct FaLine {
 };
 
 struct FaChunk {
-    std::vector<char> data;
+    ByteBuf data;
     std::vector<FaLine> lines;
     bool last = false;
 };
@@ -31,10 +31,13 @@ public:
 
 private:
     struct Shared;
-    void run();
+    static constexpr size_t kHead = 64u << 10;      // room in front of a block for the line its predecessor left unfinished
+    static constexpr size_t kStretch = 128u << 10;  // bytes indexed at a time
+    void run();  // the indexing thread; the reading thread is blocks_'s
     std::string path_;
     size_t chunk_bytes_, depth_;
     std::shared_ptr<Shared> pool_;
+    std::unique_ptr<BlockReader> blocks_;
     std::thread thread_;
     std::mutex mu_;
     std::condition_variable cv_;

@@ -4,9 +4,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#if defined(__x86_64__)
-#include <immintrin.h>
-#endif
 
 #include "codecs.h"
 
@@ -24,66 +21,11 @@ private:
     std::unique_ptr<InputStream> in_;
 };
 
-inline double dbg_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-
 struct Line {
     uint32_t off, len;  // without line break and without a trailing '\r'
     bool cr, nl;        // had "\r" before the break / ended with '\n'
     uint32_t next;      // offset of the following line
 };
-
-// Offsets of every '\n' in d[from, to), appended to out in ascending order. One vector compare per 32
-// (16) bytes instead of a memchr call per line: FASTQ lines are short, so the per-call cost of memchr
-// was most of the indexing time.
-#if defined(__x86_64__)
-__attribute__((target("avx2"))) void newlines_avx2(const char* d, size_t from, size_t to, OffsetList& out) {
-    const __m256i nl = _mm256_set1_epi8('\n');
-    size_t p = from;
-    while (p + 32 <= to) {
-        const size_t stop = std::min(to, p + 4096) - 31;  // a stretch of at most 4 KiB: room for its line breaks up front
-        out.reserve(out.n + 4096);
-        uint32_t* w = out.p + out.n;
-        for (; p < stop; p += 32) {
-            uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(d + p)), nl));
-            while (m) {
-                *w++ = (uint32_t)(p + (unsigned)__builtin_ctz(m));
-                m &= m - 1;
-            }
-        }
-        out.n = (size_t)(w - out.p);
-    }
-    out.reserve(out.n + 32);
-    for (; p < to; ++p)
-        if (d[p] == '\n') out.p[out.n++] = (uint32_t)p;
-}
-#endif
-
-void newlines(const char* d, size_t from, size_t to, OffsetList& out) {
-    size_t p = from;
-#if defined(__x86_64__)
-    static const bool have_avx2 = __builtin_cpu_supports("avx2");
-    if (have_avx2) return newlines_avx2(d, from, to, out);
-    const __m128i nl = _mm_set1_epi8('\n');
-    while (p + 16 <= to) {
-        const size_t stop = std::min(to, p + 4096) - 15;
-        out.reserve(out.n + 4096);
-        uint32_t* w = out.p + out.n;
-        for (; p < stop; p += 16) {
-            uint32_t m = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i*>(d + p)), nl));
-            while (m) {
-                *w++ = (uint32_t)(p + (unsigned)__builtin_ctz(m));
-                m &= m - 1;
-            }
-        }
-        out.n = (size_t)(w - out.p);
-    }
-#endif
-    for (; p < to; ++p)
-        if (d[p] == '\n') {
-            out.reserve(out.n + 1);
-            out.p[out.n++] = (uint32_t)p;
-        }
-}
 
 // The line starting at p, where nl[k] is the first line break at or after p (nl holds every '\n' of
 // d[0, len)); k moves past the line. Returns false if the line is not complete yet (no '\n' and more
@@ -127,9 +69,7 @@ struct FastqChunkReader::Shared {
 
 FastqChunkReader::FastqChunkReader(const std::string& path, size_t chunk_bytes, size_t depth)
     : path_(path), chunk_bytes_(std::max<size_t>(chunk_bytes, 4096)), depth_(std::max<size_t>(depth, 1)), pool_(new Shared) {
-    // open here so that a missing file fails in the caller's thread, with the caller's context
-    { RawSource probe(path_); }
-    io_thread_ = std::thread([this] { read_blocks(); });
+    blocks_.reset(new BlockReader(path_, chunk_bytes_, kHead));  // a missing file fails here, in the caller's thread
     thread_ = std::thread([this] { run(); });
 }
 
@@ -139,8 +79,8 @@ FastqChunkReader::~FastqChunkReader() {
         stop_ = true;
     }
     cv_.notify_all();
-    if (io_thread_.joinable()) io_thread_.join();
     if (thread_.joinable()) thread_.join();
+    blocks_.reset();
 }
 
 std::shared_ptr<Chunk> FastqChunkReader::next() {
@@ -157,69 +97,26 @@ std::shared_ptr<Chunk> FastqChunkReader::next() {
     return nullptr;
 }
 
-// First stage: the file's bytes (read or inflated) in blocks of chunk_bytes_, each placed kHead bytes into
-// its buffer so that the indexer can put the unfinished record of the block before in front of it.
-void FastqChunkReader::read_blocks() {
-    std::string error;
-    try {
-        RawSource src(path_);
-        std::shared_ptr<Shared> pool = pool_;
-        for (bool eof = false; !eof;) {
-            std::unique_ptr<Chunk> up;  // a recycled buffer, or a new one
-            {
-                std::lock_guard<std::mutex> lk(pool->mu);
-                if (!pool->free_list.empty()) { up = std::move(pool->free_list.back()); pool->free_list.pop_back(); }
-            }
-            if (!up) up.reset(new Chunk);
-            if (up->data.size() < kHead + chunk_bytes_) up->data.resize(kHead + chunk_bytes_);
-            const double t0 = dbg_now();
-            size_t have = 0;
-            while (!eof && have < chunk_bytes_) {
-                size_t n = src.read(up->data.data() + kHead + have, chunk_bytes_ - have);
-                if (n == 0) eof = true;
-                have += n;
-            }
-            t_read_ += dbg_now() - t0;
-            std::unique_lock<std::mutex> lk(mu_);
-            cv_.wait(lk, [this] { return raw_.size() < 3 || stop_; });
-            if (stop_) return;
-            raw_.push_back(RawBlock{std::move(up), have, eof});
-            lk.unlock();
-            cv_.notify_all();
-        }
-    } catch (const std::exception& e) {
-        error = e.what();
-    }
-    {
-        std::lock_guard<std::mutex> lk(mu_);
-        if (!error.empty()) io_error_ = error;
-        io_done_ = true;
-    }
-    cv_.notify_all();
-}
-
 // Second stage: index the 4-line records of each block. Bytes after the last whole record of a block are
 // carried over to the front of the next one.
 void FastqChunkReader::run() {
     try {
         std::vector<char> carry;
         std::shared_ptr<Shared> pool = pool_;
+        BlockReader::Block rb;
         for (bool eof = false; !eof;) {
-            RawBlock rb;
+            const double t_w0 = steady_seconds();
+            if (!blocks_->next(rb)) break;  // (an I/O error is thrown by next() after the blocks before it)
+            const double t_i0 = steady_seconds();
+            t_starved_ += t_i0 - t_w0;
+            std::unique_ptr<Chunk> up;  // a recycled chunk, or a new one
             {
-                const double t_w0 = dbg_now();
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [this] { return !raw_.empty() || io_done_ || stop_; });
-                t_starved_ += dbg_now() - t_w0;
-                if (stop_) return;
-                if (raw_.empty()) break;  // the reader failed: io_error_ is reported once the chunks before it are consumed
-                rb = std::move(raw_.front());
-                raw_.pop_front();
+                std::lock_guard<std::mutex> lk(pool->mu);
+                if (!pool->free_list.empty()) { up = std::move(pool->free_list.back()); pool->free_list.pop_back(); }
             }
-            cv_.notify_all();
-            const double t_i0 = dbg_now();
-            std::unique_ptr<Chunk> up = std::move(rb.chunk);
+            if (!up) up.reset(new Chunk);
             Chunk* c = up.get();
+            c->data.swap(rb.data);  // the chunk's previous buffer goes back to the reader with the next call
             eof = rb.last;
             c->recs.clear();
             c->nl.clear();
@@ -232,7 +129,7 @@ void FastqChunkReader::run() {
             } else {
                 // a record longer than the head room (offsets are 32-bit)
                 if (carry.size() > ((size_t)1 << 30)) throw Error("FASTQ record larger than 1 GiB");
-                std::vector<char> joined(kHead + carry.size() + std::max(rb.n, chunk_bytes_));
+                ByteBuf joined(kHead + carry.size() + std::max(rb.n, chunk_bytes_));
                 std::memcpy(joined.data() + kHead, carry.data(), carry.size());
                 std::memcpy(joined.data() + kHead + carry.size(), c->data.data() + kHead, rb.n);
                 c->data.swap(joined);
@@ -248,7 +145,7 @@ void FastqChunkReader::run() {
             bool stuck = false;       // malformed or truncated: nothing more to parse in this block
             for (size_t scanned = begin; !stuck && (scanned < have || (eof && p < have));) {
                 const size_t upto = std::min(have, scanned + kStretch);
-                newlines(d, scanned, upto, c->nl);
+                find_line_breaks(d, scanned, upto, c->nl);
                 scanned = upto;
                 const bool last = eof && scanned == have;  // only then a line without '\n' is complete
                 for (;;) {
@@ -296,7 +193,7 @@ void FastqChunkReader::run() {
             if (c->failed) eof = true;  // nothing after a malformed record is looked at
             else if (p < have) carry.assign(d + p, d + have);
             c->len = p;
-            t_index_ += dbg_now() - t_i0;
+            t_index_ += steady_seconds() - t_i0;
             if (c->recs.empty() && !c->failed) {
                 std::lock_guard<std::mutex> lk(pool->mu);
                 pool->free_list.push_back(std::move(up));
@@ -308,10 +205,10 @@ void FastqChunkReader::run() {
                 std::lock_guard<std::mutex> lk(pool->mu);
                 if (pool->free_list.size() < 16) pool->free_list.push_back(std::move(back));
             });
-            const double t_w0 = dbg_now();
+            const double t_b0 = steady_seconds();
             std::unique_lock<std::mutex> lk(mu_);
             cv_.wait(lk, [this] { return ready_.size() < depth_ || stop_; });
-            t_blocked_ += dbg_now() - t_w0;
+            t_blocked_ += steady_seconds() - t_b0;
             if (stop_) return;
             ready_.push_back(std::move(sp));
             lk.unlock();
@@ -323,7 +220,7 @@ void FastqChunkReader::run() {
     }
     if (std::getenv("MERKURIO_TIMING"))
         std::fprintf(stderr, "[merkurio] FASTQ reader %s: read %.3f s | index %.3f s, waiting for input %.3f s, blocked on the packer %.3f s\n",
-                     path_.c_str(), t_read_, t_index_, t_starved_, t_blocked_);
+                     path_.c_str(), blocks_->seconds_reading(), t_index_, t_starved_, t_blocked_);
     {
         std::lock_guard<std::mutex> lk(mu_);
         done_ = true;

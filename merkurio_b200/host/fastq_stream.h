@@ -7,10 +7,7 @@
 // FASTA and anything unusual stays on FastxReader (io.h). Results are identical to FastxReader's by
 // construction of the span rules below (tests/test_cli_cpu.py and tests/test_gpu_cli.py compare both).
 #pragma once
-#include <algorithm>
 #include <condition_variable>
-#include <cstdlib>
-#include <new>
 #include <cstdint>
 #include <deque>
 #include <memory>
@@ -19,6 +16,7 @@
 #include <thread>
 #include <vector>
 
+#include "block_reader.h"
 #include "common.h"
 
 namespace mkh {
@@ -34,29 +32,8 @@ struct RecSpan {
     uint8_t plain;     // bytes [start, end) are exactly "@id\nseq\n+\nqual\n": the writer copies them
 };
 
-// Growable array of offsets without value initialisation (the indexer appends through a raw pointer).
-struct OffsetList {
-    uint32_t* p = nullptr;
-    size_t n = 0, cap = 0;
-    OffsetList() = default;
-    OffsetList(const OffsetList&) = delete;
-    OffsetList& operator=(const OffsetList&) = delete;
-    ~OffsetList() { std::free(p); }
-    void reserve(size_t want) {
-        if (want <= cap) return;
-        size_t c = std::max(want, cap * 2);
-        void* q = std::realloc(p, c * sizeof(uint32_t));
-        if (!q) throw std::bad_alloc();
-        p = static_cast<uint32_t*>(q);
-        cap = c;
-    }
-    void clear() { n = 0; }
-    size_t size() const { return n; }
-    uint32_t operator[](size_t i) const { return p[i]; }
-};
-
 struct Chunk {
-    std::vector<char> data;
+    ByteBuf data;
     size_t len = 0;
     std::vector<RecSpan> recs;
     OffsetList nl;  // offsets of the line breaks of data[0, len...), scratch of the indexer
@@ -80,26 +57,20 @@ public:
 
 private:
     struct Shared;  // free list of chunk buffers; outlives the reader while chunks are still referenced
-    struct RawBlock {
-        std::unique_ptr<Chunk> chunk;  // n bytes of the file at data[kHead, kHead + n)
-        size_t n = 0;
-        bool last = false;
-    };
-    static constexpr size_t kHead = 64u << 10;  // room in front of a block for the record its predecessor left unfinished
+    static constexpr size_t kHead = 64u << 10;      // room in front of a block for the record its predecessor left unfinished
     static constexpr size_t kStretch = 128u << 10;  // bytes indexed at a time (stays in the core's cache)
-    void read_blocks();  // thread 1: read / inflate
-    void run();          // thread 2: index
+    void run();  // the indexing thread; the reading thread is blocks_'s
     std::string path_;
     size_t chunk_bytes_, depth_;
     std::shared_ptr<Shared> pool_;
-    std::thread io_thread_, thread_;
+    std::unique_ptr<BlockReader> blocks_;
+    std::thread thread_;
     std::mutex mu_;
     std::condition_variable cv_;
-    std::deque<RawBlock> raw_;
     std::deque<std::shared_ptr<Chunk>> ready_;
-    bool io_done_ = false, done_ = false, stop_ = false;
+    bool done_ = false, stop_ = false;
     std::string io_error_;
-    double t_read_ = 0, t_index_ = 0, t_starved_ = 0, t_blocked_ = 0;  // MERKURIO_TIMING
+    double t_index_ = 0, t_starved_ = 0, t_blocked_ = 0;  // MERKURIO_TIMING
 };
 
 }  // namespace mkh
