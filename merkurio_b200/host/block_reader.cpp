@@ -26,6 +26,13 @@ void* big_alloc(size_t bytes) {
 
 double steady_seconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+size_t prefetch_depth(size_t chunk_bytes, int n_files) {
+    size_t budget = (size_t)1024 << 20;
+    if (const char* mb = std::getenv("MERKURIO_PREFETCH_MB")) budget = (size_t)std::strtoull(mb, nullptr, 10) << 20;
+    const size_t per_chunk = std::max<size_t>(chunk_bytes, 4096) + ((size_t)64 << 10);  // block + head room
+    return std::min<size_t>(std::max<size_t>(budget / (size_t)std::max(n_files, 1) / per_chunk, 4), 4096);
+}
+
 BlockReader::BlockReader(const std::string& path, size_t block_bytes, size_t head, size_t depth)
     : path_(path), block_bytes_(std::max<size_t>(block_bytes, 4096)), head_(head), depth_(std::max<size_t>(depth, 1)) {
     // open here so that a missing file fails in the caller's thread, with the caller's context

@@ -111,4 +111,8 @@ void find_line_breaks(const char* d, size_t from, size_t to, OffsetList& out);
 
 double steady_seconds();
 
+// How many chunks of chunk_bytes a chunked reader may hold ready: MERKURIO_PREFETCH_MB (default 1024) shared
+// by the input files. The readers start before the engines, so this is what is read during CUDA start-up.
+size_t prefetch_depth(size_t chunk_bytes, int n_files);
+
 }  // namespace mkh

@@ -277,8 +277,8 @@ void extract_records(CmdExtract args) {
                                (!paired || looks_like_fastq(*args.in_fastq_2));
         std::unique_ptr<FastqChunkReader> chunks1, chunks2;
         if (pipelined) {
-            chunks1 = FastqPipeline::open_reader(args.in_fastx);
-            if (paired) chunks2 = FastqPipeline::open_reader(*args.in_fastq_2);
+            chunks1 = FastqPipeline::open_reader(args.in_fastx, paired ? 2 : 1);
+            if (paired) chunks2 = FastqPipeline::open_reader(*args.in_fastq_2, 2);
         }
         // single-file FASTA has its own pipeline (fasta_pipeline.h): records of any length, cut into pieces
         const bool fasta_pipelined = !pipelined && !paired && !std::getenv("MERKURIO_NO_FASTA_PIPELINE") && looks_like_fasta(args.in_fastx);
@@ -286,7 +286,7 @@ void extract_records(CmdExtract args) {
         if (fasta_pipelined) {
             const size_t chunk_bytes = std::getenv("MERKURIO_CHUNK_BYTES") ? (size_t)std::strtoull(std::getenv("MERKURIO_CHUNK_BYTES"), nullptr, 10)
                                                                            : (size_t)8 << 20;
-            fa_chunks.reset(new FastaChunkReader(args.in_fastx, chunk_bytes));
+            fa_chunks.reset(new FastaChunkReader(args.in_fastx, chunk_bytes, prefetch_depth(chunk_bytes, 1)));
         }
         // the record-by-record path (FASTA, and whatever the FASTQ pipeline does not take) reads ahead on its own
         // threads, also started before the engines

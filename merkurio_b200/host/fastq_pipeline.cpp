@@ -10,11 +10,11 @@ const char* kParseError = "Error during FASTQ/A record parsing.";
 const char* kSecondCtx = "Error during FASTQ record parsing of second file. Do the two input files contain the same number of records?";
 }  // namespace
 
-std::unique_ptr<FastqChunkReader> FastqPipeline::open_reader(const std::string& path) {
+std::unique_ptr<FastqChunkReader> FastqPipeline::open_reader(const std::string& path, int n_files) {
     const size_t chunk_bytes = std::getenv("MERKURIO_CHUNK_BYTES") ? (size_t)std::strtoull(std::getenv("MERKURIO_CHUNK_BYTES"), nullptr, 10)
                                                                    : (size_t)8 << 20;
-    // up to 16 chunks are read ahead while the engines start up
-    return std::unique_ptr<FastqChunkReader>(new FastqChunkReader(path, chunk_bytes, 16));
+    // read ahead (by byte budget) while the engines start up
+    return std::unique_ptr<FastqChunkReader>(new FastqChunkReader(path, chunk_bytes, prefetch_depth(chunk_bytes, n_files)));
 }
 
 FastqPipeline::FastqPipeline(EngineSet& engines, std::unique_ptr<FastqChunkReader> reader1, std::unique_ptr<FastqChunkReader> reader2,

@@ -14,7 +14,7 @@ public:
     FastqPipeline(EngineSet& engines, std::unique_ptr<FastqChunkReader> reader1, std::unique_ptr<FastqChunkReader> reader2, mk_mode mode,
                   BatchConsumer consumer);
     ~FastqPipeline() override;
-    static std::unique_ptr<FastqChunkReader> open_reader(const std::string& path);
+    static std::unique_ptr<FastqChunkReader> open_reader(const std::string& path, int n_files = 1);
 
 protected:
     void begin() override;
