@@ -1,5 +1,5 @@
-// Chunked SAM / BAM ingest for the tag feeder: a reader thread pulls the (inflated) bytes that follow
-// the header into large buffers and indexes the alignment records in place; the packer thread then
+// Chunked SAM / BAM ingest for the tag feeder: one thread pulls the (inflated) bytes that follow the
+// header into large blocks (block_reader.h), a second one indexes the alignment records in place; the packer thread then
 // copies (BAM) or packs (SAM text) the sequences into the pinned batches. Replaces the per-record
 // `bam` crate readers of src/cmd_tag.rs:504-531,561-586. Records are kept as they are in the file: a
 // SAM line, or a BAM record body that is turned into SAM text only if the record is written.
@@ -12,6 +12,7 @@
 #include <thread>
 #include <vector>
 
+#include "block_reader.h"
 #include "io.h"
 
 namespace mkh {
@@ -23,7 +24,7 @@ struct AlnSpan {
 };
 
 struct AlnChunk {
-    std::vector<char> data;
+    ByteBuf data;
     std::vector<AlnSpan> recs;
     bool bam = false;
     std::string error;  // non-empty: the input is malformed right after recs.back()
@@ -40,10 +41,12 @@ public:
 
 private:
     struct Shared;
-    void run();
+    static constexpr size_t kHead = 64u << 10;  // room in front of a block for the record its predecessor left unfinished
+    void run();  // the indexing thread; the reading thread is blocks_'s
     std::unique_ptr<AlnReader> reader_;
     size_t chunk_bytes_, depth_;
     std::shared_ptr<Shared> pool_;
+    std::unique_ptr<BlockReader> blocks_;
     std::thread thread_;
     std::mutex mu_;
     std::condition_variable cv_;

@@ -40,6 +40,11 @@ BlockReader::BlockReader(const std::string& path, size_t block_bytes, size_t hea
     thread_ = std::thread([this] { run(); });
 }
 
+BlockReader::BlockReader(ReadFn read, size_t block_bytes, size_t head, size_t depth)
+    : read_(std::move(read)), block_bytes_(std::max<size_t>(block_bytes, 4096)), head_(head), depth_(std::max<size_t>(depth, 1)) {
+    thread_ = std::thread([this] { run(); });
+}
+
 BlockReader::~BlockReader() {
     {
         std::lock_guard<std::mutex> lk(mu_);
@@ -70,7 +75,12 @@ bool BlockReader::next(Block& b) {
 void BlockReader::run() {
     std::string error;
     try {
-        std::unique_ptr<InputStream> src = InputStream::open(path_);
+        std::unique_ptr<InputStream> src;
+        if (!read_) {
+            src = InputStream::open(path_);
+            InputStream* in = src.get();
+            read_ = [in](char* dst, size_t n) { return in->read(dst, n); };
+        }
         for (bool eof = false; !eof;) {
             Block b;
             {
@@ -80,7 +90,7 @@ void BlockReader::run() {
             if (b.data.size() < head_ + block_bytes_) b.data.resize(head_ + block_bytes_);
             const double t0 = steady_seconds();
             while (!eof && b.n < block_bytes_) {
-                size_t got = src->read(b.data.data() + head_ + b.n, block_bytes_ - b.n);
+                size_t got = read_(b.data.data() + head_ + b.n, block_bytes_ - b.n);
                 if (got == 0) eof = true;
                 b.n += got;
             }
@@ -105,17 +115,22 @@ void BlockReader::run() {
     cv_.notify_all();
 }
 
-#if defined(__x86_64__)
 namespace {
-__attribute__((target("avx2"))) void line_breaks_avx2(const char* d, size_t from, size_t to, OffsetList& out) {
-    const __m256i nl = _mm256_set1_epi8('\n');
+#if defined(__x86_64__)
+// TWO: also match the second byte
+template <bool TWO>
+__attribute__((target("avx2"))) void scan_avx2(const char* d, size_t from, size_t to, char c1, char c2, OffsetList& out) {
+    const __m256i v1 = _mm256_set1_epi8(c1), v2 = _mm256_set1_epi8(c2);
     size_t p = from;
     while (p + 32 <= to) {
-        const size_t stop = std::min(to, p + 4096) - 31;  // a stretch of at most 4 KiB: room for its line breaks up front
+        const size_t stop = std::min(to, p + 4096) - 31;  // a stretch of at most 4 KiB: room for its matches up front
         out.reserve(out.n + 4096);
         uint32_t* w = out.p + out.n;
         for (; p < stop; p += 32) {
-            uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(d + p)), nl));
+            const __m256i x = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(d + p));
+            __m256i eq = _mm256_cmpeq_epi8(x, v1);
+            if (TWO) eq = _mm256_or_si256(eq, _mm256_cmpeq_epi8(x, v2));
+            uint32_t m = (uint32_t)_mm256_movemask_epi8(eq);
             while (m) {
                 *w++ = (uint32_t)(p + (unsigned)__builtin_ctz(m));
                 m &= m - 1;
@@ -125,23 +140,26 @@ __attribute__((target("avx2"))) void line_breaks_avx2(const char* d, size_t from
     }
     out.reserve(out.n + 32);
     for (; p < to; ++p)
-        if (d[p] == '\n') out.p[out.n++] = (uint32_t)p;
+        if (d[p] == c1 || (TWO && d[p] == c2)) out.p[out.n++] = (uint32_t)p;
 }
-}  // namespace
 #endif
 
-void find_line_breaks(const char* d, size_t from, size_t to, OffsetList& out) {
+template <bool TWO>
+void scan_bytes(const char* d, size_t from, size_t to, char c1, char c2, OffsetList& out) {
     size_t p = from;
 #if defined(__x86_64__)
     static const bool have_avx2 = __builtin_cpu_supports("avx2");
-    if (have_avx2) return line_breaks_avx2(d, from, to, out);
-    const __m128i nl = _mm_set1_epi8('\n');
+    if (have_avx2) return scan_avx2<TWO>(d, from, to, c1, c2, out);
+    const __m128i v1 = _mm_set1_epi8(c1), v2 = _mm_set1_epi8(c2);
     while (p + 16 <= to) {
         const size_t stop = std::min(to, p + 4096) - 15;
         out.reserve(out.n + 4096);
         uint32_t* w = out.p + out.n;
         for (; p < stop; p += 16) {
-            uint32_t m = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i*>(d + p)), nl));
+            const __m128i x = _mm_loadu_si128(reinterpret_cast<const __m128i*>(d + p));
+            __m128i eq = _mm_cmpeq_epi8(x, v1);
+            if (TWO) eq = _mm_or_si128(eq, _mm_cmpeq_epi8(x, v2));
+            uint32_t m = (uint32_t)_mm_movemask_epi8(eq);
             while (m) {
                 *w++ = (uint32_t)(p + (unsigned)__builtin_ctz(m));
                 m &= m - 1;
@@ -151,10 +169,14 @@ void find_line_breaks(const char* d, size_t from, size_t to, OffsetList& out) {
     }
 #endif
     for (; p < to; ++p)
-        if (d[p] == '\n') {
+        if (d[p] == c1 || (TWO && d[p] == c2)) {
             out.reserve(out.n + 1);
             out.p[out.n++] = (uint32_t)p;
         }
 }
+}  // namespace
+
+void find_line_breaks(const char* d, size_t from, size_t to, OffsetList& out) { scan_bytes<false>(d, from, to, '\n', '\n', out); }
+void find_breaks_and_tabs(const char* d, size_t from, size_t to, OffsetList& out) { scan_bytes<true>(d, from, to, '\n', '\t', out); }
 
 }  // namespace mkh

@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <new>
 #include <string>
@@ -57,6 +58,9 @@ public:
         bool last = false;  // the file ends with this block
     };
     BlockReader(const std::string& path, size_t block_bytes, size_t head, size_t depth = 3);
+    // The same over an input that is already open: read(dst, n) returns up to n bytes, 0 at the end.
+    using ReadFn = std::function<size_t(char*, size_t)>;
+    BlockReader(ReadFn read, size_t block_bytes, size_t head, size_t depth = 3);
     ~BlockReader();
     BlockReader(const BlockReader&) = delete;
     // The next block in file order, swapped into b (whatever b.data held before is reused as a buffer).
@@ -72,6 +76,7 @@ public:
 private:
     void run();
     std::string path_;
+    ReadFn read_;
     size_t block_bytes_, head_, depth_;
     std::thread thread_;
     std::mutex mu_;
@@ -108,6 +113,8 @@ struct OffsetList {
 // (16) bytes instead of a memchr call per line: FASTA / FASTQ lines are short, so the per-call cost of
 // memchr was most of the indexing time.
 void find_line_breaks(const char* d, size_t from, size_t to, OffsetList& out);
+// The same for every '\n' and every '\t' (SAM lines and their fields).
+void find_breaks_and_tabs(const char* d, size_t from, size_t to, OffsetList& out);
 
 double steady_seconds();
 
