@@ -6,7 +6,10 @@ namespace mkh {
 
 AlnPipeline::AlnPipeline(EngineSet& engines, std::unique_ptr<AlnChunkReader> reader, mk_mode mode, BatchConsumer consumer)
     : SlotPipeline(engines, MK_ENC_BAM4, mode, std::move(consumer)), rd_(std::move(reader)) {
-    for (int c = 0; c < 256; ++c) pair_lut_[c] = nibble_of_sam_char((char)c);
+    for (int c = 0; c < 256; ++c) code_lut_[c] = nibble_of_sam_char((char)c);
+    pair_lut_.resize(65536);
+    for (int hi = 0; hi < 256; ++hi)
+        for (int lo = 0; lo < 256; ++lo) pair_lut_[(size_t)(hi << 8 | lo)] = (uint8_t)((code_lut_[lo] << 4) | code_lut_[hi]);
 }
 
 AlnPipeline::~AlnPipeline() { stop_packer(); }
@@ -47,8 +50,9 @@ bool AlnPipeline::fill(PackedBatch& b) {
         } else {
             const uint8_t* s = reinterpret_cast<const uint8_t*>(src);
             uint32_t i = 0;
-            for (; i + 1 < r.l_seq; i += 2) *dst++ = (uint8_t)((pair_lut_[s[i]] << 4) | pair_lut_[s[i + 1]]);
-            if (i < r.l_seq) *dst = (uint8_t)(pair_lut_[s[i]] << 4);
+            const uint8_t* lut = pair_lut_.data();  // one look-up per packed byte
+            for (; i + 1 < r.l_seq; i += 2) *dst++ = lut[(size_t)s[i] | (size_t)s[i + 1] << 8];
+            if (i < r.l_seq) *dst = (uint8_t)(code_lut_[s[i]] << 4);
         }
         b.n_bytes += nbytes;
         b.n_units += nbytes * 2;

@@ -20,7 +20,8 @@ private:
     std::unique_ptr<AlnChunkReader> rd_;
     std::shared_ptr<AlnChunk> cur_;
     size_t idx_ = 0;
-    uint8_t pair_lut_[256];  // SAM character -> BAM code
+    uint8_t code_lut_[256];               // SAM character -> BAM code
+    std::vector<uint8_t> pair_lut_;       // two SAM characters (first in the low byte) -> one packed byte
 };
 
 }  // namespace mkh

@@ -129,6 +129,7 @@ if args.config == "cfg5":
         m = [ln for ln in pr.stderr.splitlines() if ln.startswith("[merkurio] engine setup")]
         setups.append(float(m[-1].split()[3]) if m else 0.0)
         print(f"run {len(runs)}: {runs[-1]:.3f} s  {m[-1] if m else ''}", file=sys.stderr, flush=True)
+        stage_lines = [ln for ln in pr.stderr.splitlines() if ln.startswith("[merkurio]")]
     log = json.loads((tmp / "log.json").read_bytes())
     got = {(h["record_id"], int(h["position"]), h["pattern"]) for h in log["matching_records"]}
     missing = sum(1 for q, wh in zip(queries, where) if wh is not None and ("chr%d synthetic" % wh[0], wh[1], q.decode()) not in got)
@@ -137,7 +138,7 @@ if args.config == "cfg5":
     steady = min(r - s_ for r, s_ in zip(runs, setups))
     res = {"config": "cfg5", "scale": args.scale, "bases": int(lens.sum()), "queries": len(queries), "input_bytes": in_bytes, "hits_logged": len(got),
            "sampled_queries_missing": missing, "wall_s": wall, "runs_s": runs, "engine_setup_s": setups, "gbases_per_s": int(lens.sum()) / wall / 1e9,
-           "gbases_per_s_after_setup": int(lens.sum()) / steady / 1e9, "host_cores": os.cpu_count(), "generate_s": t_gen, "cmd": " ".join(cmd[1:])}
+           "gbases_per_s_after_setup": int(lens.sum()) / steady / 1e9, "host_cores": os.cpu_count(), "generate_s": t_gen, "cmd": " ".join(cmd[1:]), "stages_last_run": stage_lines}
     print(json.dumps(res))
     if args.out:
         Path(args.out).write_text(json.dumps(res, indent=1) + "\n")
@@ -220,6 +221,7 @@ for _ in range(3):
     m = [ln for ln in pr.stderr.splitlines() if ln.startswith("[merkurio] engine setup")]
     setups.append(float(m[-1].split()[3]) if m else 0.0)
     print(f"run {len(runs)}: {runs[-1]:.3f} s  {m[-1] if m else ''}", file=sys.stderr, flush=True)
+    stage_lines = [ln for ln in pr.stderr.splitlines() if ln.startswith("[merkurio]")]  # reader / packer / driver timings of the last run
 best = int(np.argmin(runs))
 wall = runs[best]
 steady = min(r - s for r, s in zip(runs, setups))
@@ -269,7 +271,7 @@ res = {"config": args.config, "reads": n * mult, "input_bytes": in_bytes, "gz": 
        "wall_s": wall, "runs_s": runs, "engine_setup_s": setups, "records_per_s": n * mult / wall,
        "records_per_s_after_setup": n * mult / steady, "gbases_per_s_after_setup": n * mult * L / steady / 1e9, "gbases_per_s": n * mult * L / wall / 1e9,
        "input_gb_per_s": in_bytes / wall / 1e9, "extracted_checked": len(want), "host_cores": os.cpu_count(),
-       "generate_s": t_gen, "cmd": " ".join(cmd[1:])}
+       "generate_s": t_gen, "cmd": " ".join(cmd[1:]), "stages_last_run": stage_lines}
 print(json.dumps(res))
 if args.out:
     Path(args.out).write_text(json.dumps(res, indent=1) + "\n")
