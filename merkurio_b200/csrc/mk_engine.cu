@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <future>
@@ -591,19 +592,27 @@ int mk_engine_create(const mk_patterns* patterns, const mk_config* config, mk_en
         for (int enc = 0; enc < 2; ++enc)
             e->tables[enc].pending = std::async(std::launch::async, [ps, enc] { return mk::build_tables(*ps, enc); });
     }
+    // MERKURIO_TIMING / MK_TIMING: where the start-up time goes (driver initialisation, context, allocations)
+    const bool timing = std::getenv("MERKURIO_TIMING") || std::getenv("MK_TIMING");
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_c0 = now();
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0)
         return fail(MK_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
                     ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
     if (config->device < 0 || config->device >= ndev) return fail(MK_ERR_INVALID, "device %d out of range", config->device);
+    const double t_c1 = now();
     CU(cudaSetDevice(config->device));
+    CU(cudaFree(nullptr));  // the context is created here
+    const double t_c2 = now();
     e->device = config->device;
     e->cfg = *config;
     CU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device));
     CU(e->tie_rank.upload(e->ps.tie_rank));
     int rc = init_workspace(e->direct);
     if (rc) return rc;
+    const double t_c3 = now();
     for (uint32_t s = 0; s < config->n_slots; ++s) {
         std::unique_ptr<Slot> sl(new (std::nothrow) Slot);
         if (!sl) return fail(MK_ERR_NOMEM, "out of memory");
@@ -617,6 +626,9 @@ int mk_engine_create(const mk_patterns* patterns, const mk_config* config, mk_en
         // the lens buffers are allocated on first use (only BAM batches carry explicit lengths)
         e->slots.push_back(std::move(sl));
     }
+    if (timing)
+        std::fprintf(stderr, "[merkurio] engine start-up on device %d: driver %.3f s, context %.3f s, workspace %.3f s, %u slots (pinned + device) %.3f s\n",
+                     config->device, t_c1 - t_c0, t_c2 - t_c1, t_c3 - t_c2, config->n_slots, now() - t_c3);
     *out = e.release();
     return MK_OK;
 }

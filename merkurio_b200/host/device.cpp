@@ -16,6 +16,17 @@ static double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// MERKURIO_TIMING: when this process image was loaded, and a line at the very end of exit() (registered
+// before the CUDA runtime registers its own handler, so it runs after the context has been torn down).
+static const double g_loaded_at = now_s();
+bool g_leave_engines_to_process_exit = false;
+
+static void report_process_time() { std::fprintf(stderr, "[merkurio] process: %.3f s from load to the end of exit()\n", now_s() - g_loaded_at); }
+
+void report_process_time_if_asked() {
+    if (std::getenv("MERKURIO_TIMING")) report_process_time();
+}
+
 static uint64_t env_u64(const char* name, uint64_t dflt) {
     const char* s = std::getenv(name);
     if (!s || !*s) return dflt;
@@ -24,6 +35,11 @@ static uint64_t env_u64(const char* name, uint64_t dflt) {
 
 EngineSet::EngineSet(const std::vector<std::string>& patterns, bool case_insensitive, uint32_t default_batch_mb) {
     t_start = now_s();
+    if (std::getenv("MERKURIO_TIMING")) {
+        static bool once = false;
+        if (!once) { once = true; std::atexit(report_process_time); }
+        std::fprintf(stderr, "[merkurio] process: engines requested %.3f s after load\n", t_start - g_loaded_at);
+    }
     std::string blob;
     std::vector<uint32_t> off{0};
     for (auto& p : patterns) {
@@ -56,11 +72,14 @@ EngineSet::EngineSet(const std::vector<std::string>& patterns, bool case_insensi
 }
 
 EngineSet::~EngineSet() {
-    for (mk_engine* e : engines) mk_engine_destroy(e);
+    const double t_d0 = now_s();
+    if (!g_leave_engines_to_process_exit)
+        for (mk_engine* e : engines) mk_engine_destroy(e);
+    const double t_destroy = now_s() - t_d0;
     if (std::getenv("MERKURIO_TIMING"))
         std::fprintf(stderr, "[merkurio] engine setup %.3f s, %llu batches, %llu records, %.3f Gbases, waited %.3f s for the GPU, "
-                     "device time %.3f s, delivering results %.3f s, packer %.3f s busy (incl. waiting for input) + %.3f s waiting for a slot, total %.3f s\n", t_setup, (unsigned long long)n_batches,
-                     (unsigned long long)n_records, (double)n_bases / 1e9, t_wait, (double)device_ns / 1e9, t_deliver, t_pack, t_pack_wait, now_s() - t_start);
+                     "device time %.3f s, delivering results %.3f s, packer %.3f s busy (incl. waiting for input) + %.3f s waiting for a slot, pipeline %.3f s, engine teardown %.3f s, total %.3f s\n", t_setup, (unsigned long long)n_batches,
+                     (unsigned long long)n_records, (double)n_bases / 1e9, t_wait, (double)device_ns / 1e9, t_deliver, t_pack, t_pack_wait, t_run, t_destroy, now_s() - t_start);
 }
 
 void EngineSet::wait(int engine, uint32_t slot, mk_result* out) {

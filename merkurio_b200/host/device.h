@@ -14,6 +14,11 @@
 
 namespace mkh {
 
+// Set by main() for the one-command-per-process case: ~EngineSet leaves the engines (device and pinned
+// memory, streams, context) to the end of the process instead of releasing them one by one.
+extern bool g_leave_engines_to_process_exit;
+void report_process_time_if_asked();  // MERKURIO_TIMING: the line exit() would have printed
+
 // What the command keeps per input record until its result arrives.
 struct RecMeta {
     std::string a, b, c;  // extract: id, raw sequence text, quality — tag: name, SAM line
@@ -50,6 +55,7 @@ struct EngineSet {
     uint32_t n_slots = 3, max_records = 0, max_pattern_len = 0;
     uint64_t max_bytes = 0;
     double t_start = 0, t_setup = 0, t_wait = 0, t_deliver = 0;
+    double t_run = 0;  // SlotPipeline::run from its first to its last statement
     double t_pack = 0, t_pack_wait = 0;  // packer thread: filling slots / waiting for a free slot
     uint64_t device_ns = 0, n_records = 0, n_bases = 0, n_batches = 0;
 };

@@ -66,6 +66,7 @@ void SlotPipeline::pack() {
 }
 
 void SlotPipeline::run() {
+    const double t_run0 = now_s();
     packer_ = std::thread([this] { pack(); });
     std::deque<std::unique_ptr<PackedBatch>> inflight;
     std::vector<std::string> error_chain;
@@ -116,6 +117,7 @@ void SlotPipeline::run() {
         if (done) break;
     }
     if (packer_.joinable()) packer_.join();
+    es_.t_run += now_s() - t_run0;
     if (!packer_error_.empty()) throw Error(packer_error_);
     if (!error_chain.empty()) {
         Error e(error_chain.back());
