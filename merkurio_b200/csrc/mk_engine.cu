@@ -10,6 +10,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mk_scan.cuh"
@@ -598,13 +599,28 @@ int mk_engine_create(const mk_patterns* patterns, const mk_config* config, mk_en
     const double t_c0 = now();
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
+    // On a box without the persistence daemon the GPU is re-initialised when the previous process has just
+    // released the last context; a process starting at that moment can be turned away once. Anything but
+    // "there is no device / no driver" is tried again a few times before it is reported.
+    for (int attempt = 0; attempt < 4 && ce != cudaSuccess && ce != cudaErrorNoDevice && ce != cudaErrorInsufficientDriver; ++attempt) {
+        cudaGetLastError();
+        std::this_thread::sleep_for(std::chrono::milliseconds(250));
+        ce = cudaGetDeviceCount(&ndev);
+    }
     if (ce != cudaSuccess || ndev == 0)
         return fail(MK_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
                     ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
     if (config->device < 0 || config->device >= ndev) return fail(MK_ERR_INVALID, "device %d out of range", config->device);
     const double t_c1 = now();
-    CU(cudaSetDevice(config->device));
-    CU(cudaFree(nullptr));  // the context is created here
+    ce = cudaSetDevice(config->device);
+    if (ce == cudaSuccess) ce = cudaFree(nullptr);  // the context is created here
+    for (int attempt = 0; attempt < 4 && ce != cudaSuccess; ++attempt) {
+        cudaGetLastError();
+        std::this_thread::sleep_for(std::chrono::milliseconds(250));
+        ce = cudaSetDevice(config->device);
+        if (ce == cudaSuccess) ce = cudaFree(nullptr);
+    }
+    if (ce != cudaSuccess) return fail(MK_ERR_CUDA, "creating a CUDA context on device %d failed: %s", config->device, cudaGetErrorString(ce));
     const double t_c2 = now();
     e->device = config->device;
     e->cfg = *config;

@@ -455,7 +455,7 @@ def test_fastq_pipeline_equals_record_path(tmp_path, flavour, logs):
     (tmp_path / "se").mkdir()
     rc, err, files = _same_both_ways(tmp_path / "se", ["extract", "-i", p1, "-f", kf, "-r", "-o", "@OUT@/x.fastq", *log_args],
                                      "MERKURIO_NO_FASTQ_PIPELINE", env)
-    assert (rc != 0) == (flavour == "truncated")
+    assert (rc != 0) == (flavour == "truncated"), err
     assert files["x.fastq"].count(b"\n@a") > 50
     # paired, also inverted
     for extra, tag in (([], "pe"), (["-v"], "pev")):
@@ -464,7 +464,7 @@ def test_fastq_pipeline_equals_record_path(tmp_path, flavour, logs):
         (tmp_path / tag).mkdir()
         rc, err, files = _same_both_ways(tmp_path / tag, ["extract", "-i", p1, "-2", p2, "-f", kf, "-r", "-o", "@OUT@/x.fastq", *extra, *log_args],
                                          "MERKURIO_NO_FASTQ_PIPELINE", env)
-        assert (rc != 0) == (flavour in ("truncated", "bad_second_file"))
+        assert (rc != 0) == (flavour in ("truncated", "bad_second_file")), (tag, err)
         assert set(files) >= {"x_1.fastq", "x_2.fastq"}
 
 
@@ -497,7 +497,7 @@ def test_aln_pipeline_equals_record_path(tmp_path, kind, flags):
         src.write_bytes(data[: len(data) // 2].rsplit(b"\t", 4)[0] + b"\n" + data[len(data) // 2:])
     env = {"MERKURIO_BATCH_BYTES": "50000", "MERKURIO_CHUNK_BYTES": "40000"}
     rc, err, files = _same_both_ways(tmp_path, ["tag", "-i", src, "-o", "@OUT@/t.sam", "-f", kf, "-r", *flags], "MERKURIO_NO_ALN_PIPELINE", env)
-    assert (rc != 0) == (kind == "sam_truncated")
+    assert (rc != 0) == (kind == "sam_truncated"), err
     if rc == 0:
         assert files["t.sam"].count(b"\tkm:Z:") > 100
 
