@@ -12,7 +12,9 @@
 //   * the pattern bytes used by the exact verify step (case-folded under -I).
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -215,7 +217,15 @@ inline bool cuckoo_build(const std::vector<SeedKey>& keys, uint32_t log2_buckets
     uint32_t nb = 1u << log2_buckets, mask = nb - 1;
     std::vector<SeedSlot> slots((size_t)nb * kBucketSlots, SeedSlot{0, kEmptySlot});
     std::mt19937 rng(0x5EEDu + log2_buckets);
-    for (const SeedKey& kv : keys) {
+    const size_t kAhead = 24;  // the table is far larger than the cache: fetch the buckets of the keys to come
+    for (size_t ki = 0; ki < keys.size(); ++ki) {
+        if (ki + kAhead < keys.size()) {
+            const SeedKey& nx = keys[ki + kAhead];
+            const uint32_t hk = mk_group_key(nx.code, nx.group ? 1u : 0u);
+            __builtin_prefetch(&slots[(size_t)mk_hash_b1(hk, mask) * kBucketSlots], 1);
+            __builtin_prefetch(&slots[(size_t)mk_hash_b2(hk, mask) * kBucketSlots], 1);
+        }
+        const SeedKey& kv = keys[ki];
         SeedSlot cur{kv.code, kv.first | (kv.group ? kGroupBit : 0u)};
         bool placed = false;
         uint32_t from = UINT32_MAX;
@@ -263,15 +273,24 @@ inline double blocked_fp32(double nn, uint32_t nblocks32) {
     return fp;
 }
 
+#ifdef MK_TABLE_TIMING
+#define TBT_INIT double tbt_t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+#define TBT(name) { double n_ = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); std::fprintf(stderr, "  %s %.3f\n", name, n_ - tbt_t0); tbt_t0 = n_; }
+#else
+#define TBT_INIT
+#define TBT(name)
+#endif
 inline Tables build_tables(const PatternSet& ps, int enc) {
     Tables t;
+    TBT_INIT
     t.enc = enc;
     const uint32_t n = ps.n;
     // compare form of the patterns
     t.pat_off = ps.off;
     t.pat_bytes.resize(ps.bytes.size());
     t.pat_live.assign(n, 1);
-    for (uint32_t p = 0; p < n; ++p) {
+    if (enc == 0 && !ps.case_insensitive && !ps.bytes.empty()) std::memcpy(t.pat_bytes.data(), ps.bytes.data(), ps.bytes.size());
+    else for (uint32_t p = 0; p < n; ++p) {
         for (uint32_t i = ps.off[p]; i < ps.off[p + 1]; ++i) {
             uint8_t c = ps.bytes[i];
             if (enc == 0) {
@@ -289,13 +308,28 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
     choose_geometry(ps.min_len, &t.q, &t.d);
     t.perm = (t.d == 16);
 
-    // (group, code, pattern, j) of every indexed seed, and the distinct keys with their first posting
-    struct Trip { uint32_t code, pid, j, grp; };
-    std::vector<Trip> trips;
+    // Every indexed seed as one 64-bit word: group (bit 63) | code (bits 31..62) | pattern (bits 4..30) | offset j
+    // (bits 0..3), sorted — i.e. by (group, code, pattern, j) — and the distinct keys with their first posting.
+    // The words are generated in (pattern, j) order, so a stable LSD radix sort over the 33 key bits is enough
+    // (8-bit digits; std::sort of 8 M seeds was most of the 7 s a million queries took to index).
+    std::vector<uint64_t> trips, trips_tmp;
     std::vector<SeedKey> keys;
+    auto t_grp = [](uint64_t v) { return (uint32_t)(v >> 63); };
+    auto t_code = [](uint64_t v) { return (uint32_t)(v >> 31); };
+    auto t_pid = [](uint64_t v) { return (uint32_t)(v >> 4) & 0x7FFFFFFu; };
+    auto t_j = [](uint64_t v) { return (uint32_t)v & 15u; };
     // stride 8 / 4 (BAM4: 8 only) can use the window layout of mk_scan_win if the filter fits shared memory
     bool win_layout = (enc == 0 ? (t.d == 8 || t.d == 4) : t.d == 8) && !std::getenv("MK_NO_WIN_SCAN");
     if (win_layout) window_masks(enc, t.q, &t.win_mask0, &t.win_mask1);
+    // ordered code byte b (bases 4b .. 4b+3, first base in the two highest bits) -> its fields in the permuted
+    // packing of mk_pack_ascii_perm (base t: byte lane t % 4, 2-bit field t / 4)
+    uint32_t perm_lut[4][256];
+    for (uint32_t b = 0; b < 4; ++b)
+        for (uint32_t v = 0; v < 256; ++v) {
+            uint32_t w = 0;
+            for (uint32_t i = 0; i < 4; ++i) w |= ((v >> (6 - 2 * i)) & 3u) << (8 * i + 2 * b);
+            perm_lut[b][v] = w;
+        }
     auto index_seeds = [&](uint32_t long_min_len) {
         trips.clear();
         keys.clear();
@@ -304,28 +338,62 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
             if (!t.pat_live[p]) continue;
             const uint8_t* sym = t.pat_bytes.data() + t.pat_off[p];
             const bool lng = long_min_len && ps.len(p) >= long_min_len;
+            const uint64_t tag = (uint64_t)(lng ? 1u : 0u) << 63 | (uint64_t)p << 4;
+            if (enc == 0) {
+                // ASCII: every layout is a function of the 2-bit classes, so the d seeds of a pattern come from
+                // one rolling code (ordered packing) and, for the permuted / window layouts, four table look-ups
+                const uint32_t qq = t.perm ? 16u : win_layout ? std::min(t.q, 16u) : (lng ? 16u : t.q);
+                const uint32_t keep = qq == 16 ? 0xFFFFFFFFu : (1u << (2 * qq)) - 1u;
+                uint32_t c = 0;
+                for (uint32_t i = 0; i + 1 < qq; ++i) c = (c << 2) | sym_class(0, sym[i]);
+                for (uint32_t j = 0; j < t.d; ++j) {
+                    c = ((c << 2) | sym_class(0, sym[j + qq - 1])) & keep;
+                    uint32_t code = c;
+                    if (t.perm || win_layout) {
+                        const uint32_t top = c << (32 - 2 * qq);  // first base in the two highest bits
+                        code = perm_lut[0][top >> 24] | perm_lut[1][(top >> 16) & 255] | perm_lut[2][(top >> 8) & 255] | perm_lut[3][top & 255];
+                    }
+                    trips.push_back(tag | (uint64_t)code << 31 | j);
+                }
+                continue;
+            }
             for (uint32_t j = 0; j < t.d; ++j) {
                 uint32_t code = t.perm ? seed_code_perm(enc, sym + j)
                               : win_layout ? seed_code_win(enc, sym + j, t.q, t.win_mask0, t.win_mask1)
                                            : seed_code_ord(enc, sym + j, lng ? 16u : t.q);
-                trips.push_back({code, p, j, lng ? 1u : 0u});
+                trips.push_back(tag | (uint64_t)code << 31 | j);
             }
         }
-        std::sort(trips.begin(), trips.end(), [](const Trip& a, const Trip& b) {
-            if (a.grp != b.grp) return a.grp < b.grp;
-            if (a.code != b.code) return a.code < b.code;
-            if (a.pid != b.pid) return a.pid < b.pid;
-            return a.j < b.j;
-        });
         if (trips.size() >= (size_t)kInlineBit) throw std::runtime_error("too many seeds for the posting index");
-        auto same_key = [](const Trip& a, const Trip& b) { return a.grp == b.grp && a.code == b.code; };
+        if (trips.size() < 4096) {
+            std::sort(trips.begin(), trips.end());
+        } else {
+            trips_tmp.resize(trips.size());
+            // 8-bit digits: 256 write streams stay in the cache (2048 did not); a pass whose digit is the same in
+            // every word (the group bit of a single-group index, the empty top bits of short seeds) is skipped
+            for (int shift = 31; shift < 64; shift += 8) {
+                size_t count[256] = {0};
+                for (uint64_t v : trips) ++count[(v >> shift) & 255];
+                bool one_digit = false;
+                for (size_t c : count) one_digit |= (c == trips.size());
+                if (one_digit) continue;
+                size_t at = 0;
+                for (size_t& c : count) { size_t k = c; c = at; at += k; }
+                for (uint64_t v : trips) trips_tmp[count[(v >> shift) & 255]++] = v;
+                trips.swap(trips_tmp);
+            }
+        }
+        const uint64_t key_bits = ~(uint64_t)0 << 31;
+        keys.reserve(trips.size());
         for (size_t i = 0; i < trips.size(); ++i)
-            if (i == 0 || !same_key(trips[i - 1], trips[i])) {
-                const bool single = i + 1 == trips.size() || !same_key(trips[i], trips[i + 1]);
-                keys.push_back({trips[i].code, single ? (kInlineBit | (trips[i].pid << 4) | trips[i].j) : (uint32_t)i, trips[i].grp});
+            if (i == 0 || ((trips[i - 1] ^ trips[i]) & key_bits)) {
+                const bool single = i + 1 == trips.size() || ((trips[i] ^ trips[i + 1]) & key_bits);
+                keys.push_back({t_code(trips[i]), single ? (kInlineBit | (t_pid(trips[i]) << 4) | t_j(trips[i])) : (uint32_t)i, t_grp(trips[i])});
             }
     };
+    TBT("pat_bytes");
     index_seeds(0);
+    TBT("index1");
 
     // first-level filter flavour: blocked Bloom in shared memory while it stays selective
     uint32_t nblocks = MK_BLOOM_MIN_BLOCKS;
@@ -342,6 +410,7 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
     if (win_layout && !want_smem) {  // the L2-resident flavours use the ordered packing
         win_layout = false;
         index_seeds(0);
+    TBT("index2");
     }
     t.win = win_layout;
 
@@ -352,15 +421,17 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
         t.q2 = 16;
         t.long_min_len = t.d + 15;
         index_seeds(t.long_min_len);
+    TBT("index3");
     }
 
     t.postings.resize(trips.size());
     for (size_t i = 0; i < trips.size(); ++i) {
-        bool last = (i + 1 == trips.size()) || trips[i + 1].grp != trips[i].grp || trips[i + 1].code != trips[i].code;
-        t.postings[i] = make_posting(trips[i].pid, trips[i].j, last);
+        bool last = (i + 1 == trips.size()) || ((trips[i + 1] ^ trips[i]) >> 31) != 0;
+        t.postings[i] = make_posting(t_pid(trips[i]), t_j(trips[i]), last);
     }
     if (t.postings.empty()) t.postings.push_back(make_posting(0, 0, true));  // keep device pointers non-null
     t.n_seeds = (uint32_t)keys.size();
+    TBT("postings");
 
     // cuckoo table (4-slot buckets) at <= 80 % load, grown until the insertion succeeds
     uint32_t lb = 1;
@@ -369,6 +440,7 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
         if (++lb > 28) throw std::runtime_error("seed table does not fit");
     }
 
+    TBT("cuckoo");
     const double nn = (double)t.n_seeds;
     if (want_smem) {
         t.filter_in_smem = true;
@@ -411,7 +483,12 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
         t.filter_blocks = (uint32_t)std::min<uint64_t>(nb, 1u << 27) & ~1u;
         t.filter.assign((size_t)t.filter_blocks * 2, 0);
         const uint32_t sshift = 32u - 2u * t.q;
-        for (auto& kv : keys) {
+        for (size_t ki = 0; ki < keys.size(); ++ki) {
+            if (ki + 24 < keys.size()) {  // the filter is far larger than the cache
+                const SeedKey& nx = keys[ki + 24];
+                __builtin_prefetch(&t.filter[2 * (size_t)mk_dual_block(nx.group ? (nx.code >> sshift) : nx.code, t.filter_blocks)], 1);
+            }
+            const SeedKey& kv = keys[ki];
             uint32_t short_code = kv.group ? (kv.code >> sshift) : kv.code;
             uint32_t blk = mk_dual_block(short_code, t.filter_blocks), lo, hi;
             mk_bloom_masks_g(kv.group ? mk_dual_g_long(kv.code) : mk_dual_g_short(short_code), &lo, &hi);
@@ -431,6 +508,7 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
             t.filter[h >> 5] |= 1u << (h & 31);
         }
     }
+    TBT("filter");
     return t;
 }
 

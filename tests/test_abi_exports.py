@@ -1,6 +1,7 @@
 """CPU tests of the boundary: libmerkurio_cuda.so loads without a GPU and exports exactly the entry
 points include/merkurio_cuda.h declares; without a device it fails loudly (no CPU path)."""
 import ctypes
+import os
 import re
 from pathlib import Path
 
@@ -55,3 +56,19 @@ def test_product_does_not_touch_the_oracle():
                 continue  # builds the checker, does not use it
             assert "oracle" not in txt.lower() or "mk_oracle" not in txt, p
             assert "refmodel" not in txt, p
+
+
+def test_table_builder_output_is_unchanged(tmp_path):
+    """mk::build_tables is host code that only the GPU suite exercises end to end; its output for seeded
+    query lists (perm / window / ordered / dual-key layouts, -I, queries with N, both encodings) must stay
+    byte-identical to the digests recorded when that suite last ran against it."""
+    import subprocess
+    exe = tmp_path / "table_digest"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", str(ROOT / "merkurio_b200" / "csrc"), "-I", str(ROOT / "include"), "-o", str(exe),
+                    str(ROOT / "tests" / "stub" / "table_digest.cpp")], check=True)
+    env = {k: v for k, v in os.environ.items() if not k.startswith("MK_")}
+    got = subprocess.run([str(exe), "9"], check=True, capture_output=True, env=env).stdout.decode().splitlines()
+    want = (ROOT / "tests" / "golden" / "table_digests.txt").read_text().splitlines()
+    assert len(got) == len(want) == 18
+    for g, w in zip(got, want):
+        assert g == w
