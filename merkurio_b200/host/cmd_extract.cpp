@@ -420,6 +420,7 @@ void extract_records(CmdExtract args) {
     }
     writer.flush();
     writer2.flush();
+    const double t_sum0 = steady_seconds();
 
     size_t nb_patterns_found = 0;
     for (uint64_t c : pattern_hit_counts) nb_patterns_found += c > 0;
@@ -429,7 +430,18 @@ void extract_records(CmdExtract args) {
         std::snprintf(pct, sizeof pct, "%.2f", (double)nb_patterns_found / (double)pattern_hit_counts.size() * 100.0);
         logger.write_header("#\n#Number of patterns found: " + std::to_string(nb_patterns_found) + "/" + std::to_string(pattern_hit_counts.size()) + " (" + pct + " %)\n");
         logger.write_header("#Pattern\tCount\n");
-        for (size_t i = 0; i < pattern_list.size(); ++i) logger.write_header("#" + pattern_list[i] + "\t" + std::to_string(pattern_hit_counts[i]) + "\n");
+        if (logger.active()) {  // a million queries: one write per MiB, not per line
+            std::string block;
+            for (size_t i = 0; i < pattern_list.size(); ++i) {
+                block += '#';
+                block += pattern_list[i];
+                block += '\t';
+                block += std::to_string(pattern_hit_counts[i]);
+                block += '\n';
+                if (block.size() >= (1u << 20)) { logger.write_header(block); block.clear(); }
+            }
+            if (!block.empty()) logger.write_header(block);
+        }
         logger.write_header("#\n#Total number of records searched: " + std::to_string(nb_records_tot) + "\n");
         logger.write_header("#Total number of characters searched: " + std::to_string(nb_bases) + "\n");
         logger.write_header("#Total number of hits: " + std::to_string(nb_hits_tot[0] + nb_hits_tot[1]) + "\n");
@@ -476,6 +488,7 @@ void extract_records(CmdExtract args) {
         pstats["number_of_extracted_records"] = Json::integer((int64_t)nb_records_extracted);
         jl->finalize(meta, pattern_list, pattern_hit_counts, summary, &pstats);
     }
+    if (std::getenv("MERKURIO_TIMING")) std::fprintf(stderr, "[merkurio] summaries of the logs: %.3f s\n", steady_seconds() - t_sum0);
 }
 
 }  // namespace mkh

@@ -7,6 +7,7 @@
 #include <ctime>
 #include <fstream>
 #include <sstream>
+#include <thread>
 
 namespace mkh {
 
@@ -102,18 +103,35 @@ std::vector<std::string> read_kmers_from_file(const std::string& path) {
         Error inner(path_exists(path) ? "Permission denied (os error 13)" : "No such file or directory (os error 2)");
         throw inner.with_context(path_exists(path) ? "Error reading file: " + path : "File not found.");
     }
-    std::stringstream ss;
-    ss << in.rdbuf();
-    std::string content = ss.str();
+    in.seekg(0, std::ios::end);
+    const std::streamoff size = in.tellg();
+    std::string content;
+    if (size > 0) {
+        content.resize((size_t)size);
+        in.seekg(0, std::ios::beg);
+        in.read(&content[0], size);
+        content.resize((size_t)std::max<std::streamsize>(in.gcount(), 0));
+    } else {  // not seekable (a pipe): read it as a stream
+        in.clear();
+        std::stringstream ss;
+        ss << in.rdbuf();
+        content = ss.str();
+    }
     std::vector<std::string> kmers;
+    kmers.reserve((size_t)std::count(content.begin(), content.end(), '\n') + 1);
     size_t pos = 0;
     while (pos < content.size()) {  // str::lines(): split on '\n', strip one trailing '\r'
-        size_t nl = content.find('\n', pos);
-        std::string line = content.substr(pos, nl == std::string::npos ? std::string::npos : nl - pos);
-        pos = nl == std::string::npos ? content.size() : nl + 1;
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        if (line.empty() || line[0] == '#' || line[0] == '>') continue;
-        kmers.push_back(trim(line));
+        const char* nlp = static_cast<const char*>(std::memchr(content.data() + pos, '\n', content.size() - pos));
+        size_t end = nlp ? (size_t)(nlp - content.data()) : content.size();
+        const size_t next = nlp ? end + 1 : content.size();
+        if (end > pos && content[end - 1] == '\r') --end;
+        if (end > pos && content[pos] != '#' && content[pos] != '>') {
+            size_t a = pos, b = end;  // trim() in place: one allocation per line
+            while (a < b && is_rust_whitespace((unsigned char)content[a])) ++a;
+            while (b > a && is_rust_whitespace((unsigned char)content[b - 1])) --b;
+            kmers.emplace_back(content.data() + a, b - a);
+        }
+        pos = next;
     }
     if (kmers.empty()) throw Error("No k-mers found in the file.");
     return kmers;
@@ -173,10 +191,33 @@ std::vector<std::string> parse_pattern_list(const std::optional<std::string>& km
     }
     if (canonical_) for (auto& p : pats) p = canonical(p);
     pats.erase(std::remove_if(pats.begin(), pats.end(), [](const std::string& s) { return s.empty(); }), pats.end());
-    std::sort(pats.begin(), pats.end(), [](const std::string& a, const std::string& b) {
+    auto bytewise = [](const std::string& a, const std::string& b) {
         int c = std::memcmp(a.data(), b.data(), std::min(a.size(), b.size()));
         return c != 0 ? c < 0 : a.size() < b.size();
-    });
+    };
+    // large lists (cfg5: a million queries): runs sorted on several threads, then merged pairwise
+    const size_t n_threads = pats.size() < 100000 ? 1 : std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), 8);
+    if (n_threads == 1) {
+        std::sort(pats.begin(), pats.end(), bytewise);
+    } else {
+        std::vector<size_t> cut(n_threads + 1);
+        for (size_t i = 0; i <= n_threads; ++i) cut[i] = pats.size() * i / n_threads;
+        {
+            std::vector<std::thread> th;
+            for (size_t i = 0; i < n_threads; ++i)
+                th.emplace_back([&, i] { std::sort(pats.begin() + (std::ptrdiff_t)cut[i], pats.begin() + (std::ptrdiff_t)cut[i + 1], bytewise); });
+            for (auto& t : th) t.join();
+        }
+        for (size_t width = 1; width < n_threads; width *= 2) {
+            std::vector<std::thread> th;
+            for (size_t i = 0; i + width < n_threads; i += 2 * width)
+                th.emplace_back([&, i, width] {
+                    std::inplace_merge(pats.begin() + (std::ptrdiff_t)cut[i], pats.begin() + (std::ptrdiff_t)cut[i + width],
+                                       pats.begin() + (std::ptrdiff_t)cut[std::min(i + 2 * width, n_threads)], bytewise);
+                });
+            for (auto& t : th) t.join();
+        }
+    }
     pats.erase(std::unique(pats.begin(), pats.end()), pats.end());
     if (pats.empty()) throw Error("No k-mers found in file or provided sequence.");
     return pats;

@@ -1,5 +1,7 @@
 #include "logger.h"
 
+#include <charconv>
+
 #include "common.h"
 
 namespace mkh {
@@ -120,10 +122,21 @@ void JsonLogger::finalize(const Json& meta, const std::vector<std::string>& patt
     } else {
         buf_ += "{\n";
         for (size_t i = 0; i < patterns.size(); ++i) {
+            const std::string& p = patterns[i];
+            bool plain = true;  // nothing to escape (every query of ordinary input): no temporary string
+            for (unsigned char c : p) plain &= (c >= 0x20 && c != '"' && c != '\\');
             buf_ += "    ";
-            buf_ += json_escape(patterns[i]);
+            if (plain) {
+                buf_ += '"';
+                buf_ += p;
+                buf_ += '"';
+            } else {
+                buf_ += json_escape(p);
+            }
             buf_ += ": ";
-            buf_ += std::to_string(counts[i]);
+            char digits[24];
+            auto r = std::to_chars(digits, digits + sizeof digits, counts[i]);
+            buf_.append(digits, r.ptr);
             buf_ += i + 1 < patterns.size() ? ",\n" : "\n";
             if (buf_.size() >= (1u << 20)) flush();
         }
