@@ -18,9 +18,11 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mk_codes.h"
@@ -330,11 +332,9 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
             for (uint32_t i = 0; i < 4; ++i) w |= ((v >> (6 - 2 * i)) & 3u) << (8 * i + 2 * b);
             perm_lut[b][v] = w;
         }
-    auto index_seeds = [&](uint32_t long_min_len) {
-        trips.clear();
-        keys.clear();
-        trips.reserve((size_t)n * t.d);
-        for (uint32_t p = 0; p < n; ++p) {
+    // the seeds of patterns [p0, p1), d words per live pattern, written to out
+    auto seeds_of = [&](uint32_t p0, uint32_t p1, uint32_t long_min_len, uint64_t* out) {
+        for (uint32_t p = p0; p < p1; ++p) {
             if (!t.pat_live[p]) continue;
             const uint8_t* sym = t.pat_bytes.data() + t.pat_off[p];
             const bool lng = long_min_len && ps.len(p) >= long_min_len;
@@ -353,7 +353,7 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
                         const uint32_t top = c << (32 - 2 * qq);  // first base in the two highest bits
                         code = perm_lut[0][top >> 24] | perm_lut[1][(top >> 16) & 255] | perm_lut[2][(top >> 8) & 255] | perm_lut[3][top & 255];
                     }
-                    trips.push_back(tag | (uint64_t)code << 31 | j);
+                    *out++ = tag | (uint64_t)code << 31 | j;
                 }
                 continue;
             }
@@ -361,25 +361,70 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
                 uint32_t code = t.perm ? seed_code_perm(enc, sym + j)
                               : win_layout ? seed_code_win(enc, sym + j, t.q, t.win_mask0, t.win_mask1)
                                            : seed_code_ord(enc, sym + j, lng ? 16u : t.q);
-                trips.push_back(tag | (uint64_t)code << 31 | j);
+                *out++ = tag | (uint64_t)code << 31 | j;
             }
         }
-        if (trips.size() >= (size_t)kInlineBit) throw std::runtime_error("too many seeds for the posting index");
+    };
+    size_t n_live = 0;
+    for (uint32_t p = 0; p < n; ++p) n_live += t.pat_live[p] ? 1 : 0;
+    // large query sets: a few threads generate and sort (both encodings are usually built at the same time)
+    const size_t n_threads = n_live * t.d < ((size_t)1 << 20) ? 1 : std::min<size_t>(4, std::max(1u, std::thread::hardware_concurrency() / 2));
+    auto on_threads = [&](const std::function<void(size_t)>& job) {
+        if (n_threads == 1) return job(0);
+        std::vector<std::thread> th;
+        for (size_t w = 0; w < n_threads; ++w) th.emplace_back(job, w);
+        for (auto& x : th) x.join();
+    };
+    auto index_seeds = [&](uint32_t long_min_len) {
+        keys.clear();
+        if (n_live * t.d >= (size_t)kInlineBit) throw std::runtime_error("too many seeds for the posting index");
+        trips.resize(n_live * t.d);
+        {
+            // pattern ranges of equal size; where each range's words start follows from the live patterns before it
+            std::vector<uint32_t> cut(n_threads + 1);
+            std::vector<size_t> first(n_threads + 1, 0);
+            for (size_t w = 0; w <= n_threads; ++w) cut[w] = (uint32_t)((uint64_t)n * w / n_threads);
+            for (size_t w = 0; w < n_threads; ++w) {
+                size_t live = 0;
+                for (uint32_t p = cut[w]; p < cut[w + 1]; ++p) live += t.pat_live[p] ? 1 : 0;
+                first[w + 1] = first[w] + live * t.d;
+            }
+            on_threads([&](size_t w) { seeds_of(cut[w], cut[w + 1], long_min_len, trips.data() + first[w]); });
+        }
         if (trips.size() < 4096) {
             std::sort(trips.begin(), trips.end());
         } else {
             trips_tmp.resize(trips.size());
             // 8-bit digits: 256 write streams stay in the cache (2048 did not); a pass whose digit is the same in
-            // every word (the group bit of a single-group index, the empty top bits of short seeds) is skipped
+            // every word (the group bit of a single-group index, the empty top bits of short seeds) is skipped.
+            // Each thread counts and scatters one contiguous slice; slices keep their order inside a digit (stable).
+            const size_t total = trips.size();
+            std::vector<size_t> count(n_threads * 256);
             for (int shift = 31; shift < 64; shift += 8) {
-                size_t count[256] = {0};
-                for (uint64_t v : trips) ++count[(v >> shift) & 255];
+                const uint64_t* src = trips.data();
+                uint64_t* dst = trips_tmp.data();
+                on_threads([&](size_t w) {
+                    size_t* c = count.data() + w * 256;
+                    std::fill(c, c + 256, (size_t)0);
+                    for (size_t i = total * w / n_threads, e = total * (w + 1) / n_threads; i < e; ++i) ++c[(src[i] >> shift) & 255];
+                });
                 bool one_digit = false;
-                for (size_t c : count) one_digit |= (c == trips.size());
-                if (one_digit) continue;
                 size_t at = 0;
-                for (size_t& c : count) { size_t k = c; c = at; at += k; }
-                for (uint64_t v : trips) trips_tmp[count[(v >> shift) & 255]++] = v;
+                for (size_t dg = 0; dg < 256; ++dg) {
+                    size_t of_digit = 0;
+                    for (size_t w = 0; w < n_threads; ++w) {
+                        const size_t k = count[w * 256 + dg];
+                        count[w * 256 + dg] = at;
+                        at += k;
+                        of_digit += k;
+                    }
+                    one_digit |= (of_digit == total);
+                }
+                if (one_digit) continue;
+                on_threads([&](size_t w) {
+                    size_t* c = count.data() + w * 256;
+                    for (size_t i = total * w / n_threads, e = total * (w + 1) / n_threads; i < e; ++i) dst[c[(src[i] >> shift) & 255]++] = src[i];
+                });
                 trips.swap(trips_tmp);
             }
         }
@@ -407,17 +452,20 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
     bool want_smem = blocked_fp((double)keys.size(), nblocks) <= 0.25;
     if (force && std::strcmp(force, "l2") == 0) want_smem = false;
     if (force && std::strcmp(force, "smem") == 0) want_smem = true;
+    // Seed sets too large for shared memory with a stride below 16 are indexed once more below, with 16-base seeds
+    // for the patterns that are long enough
+    const bool long_seeds = !want_smem && t.d < 16 && t.d >= 2 && t.q < 16 && ps.max_len >= t.d + 15 && !std::getenv("MK_NO_LONG_SEEDS");
     if (win_layout && !want_smem) {  // the L2-resident flavours use the ordered packing
         win_layout = false;
-        index_seeds(0);
-    TBT("index2");
+        if (!long_seeds) index_seeds(0);
+        TBT("index2");
     }
     t.win = win_layout;
 
     // Seed sets too large for shared memory with a stride below 16: give every pattern that is long
     // enough a 16-base seed (far fewer text positions carry one of those than one of the q-base seeds)
     // (stride >= 2: the scan flags candidates in bit 0 of their position)
-    if (!want_smem && t.d < 16 && t.d >= 2 && t.q < 16 && ps.max_len >= t.d + 15 && !std::getenv("MK_NO_LONG_SEEDS")) {
+    if (long_seeds) {
         t.q2 = 16;
         t.long_min_len = t.d + 15;
         index_seeds(t.long_min_len);

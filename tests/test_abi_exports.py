@@ -64,7 +64,7 @@ def test_table_builder_output_is_unchanged(tmp_path):
     byte-identical to the digests recorded when that suite last ran against it."""
     import subprocess
     exe = tmp_path / "table_digest"
-    subprocess.run(["g++", "-O2", "-std=c++17", "-I", str(ROOT / "merkurio_b200" / "csrc"), "-I", str(ROOT / "include"), "-o", str(exe),
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-I", str(ROOT / "merkurio_b200" / "csrc"), "-I", str(ROOT / "include"), "-o", str(exe),
                     str(ROOT / "tests" / "stub" / "table_digest.cpp")], check=True)
     env = {k: v for k, v in os.environ.items() if not k.startswith("MK_")}
     got = subprocess.run([str(exe), "9"], check=True, capture_output=True, env=env).stdout.decode().splitlines()
