@@ -148,7 +148,7 @@ template <bool TWO>
 void scan_bytes(const char* d, size_t from, size_t to, char c1, char c2, OffsetList& out) {
     size_t p = from;
 #if defined(__x86_64__)
-    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    static const bool have_avx2 = __builtin_cpu_supports("avx2") && !std::getenv("MERKURIO_NO_AVX2");  // (the switch: tests of the SSE2 path)
     if (have_avx2) return scan_avx2<TWO>(d, from, to, c1, c2, out);
     const __m128i v1 = _mm_set1_epi8(c1), v2 = _mm_set1_epi8(c2);
     while (p + 16 <= to) {
