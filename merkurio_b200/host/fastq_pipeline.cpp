@@ -27,8 +27,13 @@ FastqPipeline::FastqPipeline(EngineSet& engines, std::unique_ptr<FastqChunkReade
 FastqPipeline::~FastqPipeline() { stop_packer(); }
 
 void FastqPipeline::begin() {
-    cur_[0] = rd_[0]->next();
-    if (paired_) cur_[1] = rd_[1]->next();
+    for (int f = 0; f < (paired_ ? 2 : 1); ++f) {
+        try {
+            cur_[f] = rd_[f]->next();
+        } catch (const Error& e) {  // surfaces in fill(), where the error gets the record path's context
+            read_error_[f] = e.what();
+        }
+    }
 }
 
 // Fill one slot with as many whole records (pairs) as fit. Runs on the packer thread.
@@ -47,12 +52,22 @@ bool FastqPipeline::fill(PackedBatch& b) {
         b.error_chain = std::move(chain);
         input_done_ = true;
     };
-    // step file f to its next record; false at its end (cur_[f] == nullptr) or on a malformed record
-    auto advance = [&](int f, bool* malformed) {
+    // step file f to its next record; false at its end (cur_[f] == nullptr), on a malformed record or when the
+    // input cannot be read any further (*why: what the record-by-record reader would have thrown there)
+    auto advance = [&](int f, bool* malformed, std::string* why) {
         *malformed = false;
+        if (!read_error_[f].empty()) { *malformed = true; *why = read_error_[f]; return false; }
         while (cur_[f] && idx_[f] == cur_[f]->recs.size()) {
-            if (cur_[f]->failed) { *malformed = true; return false; }
-            cur_[f] = rd_[f]->next();
+            if (cur_[f]->failed) { *malformed = true; *why = kParseError; return false; }
+            try {
+                cur_[f] = rd_[f]->next();
+            } catch (const Error& e) {  // decompression / read error: reported like a parse error, with its own text
+                cur_[f] = nullptr;
+                read_error_[f] = e.what();
+                *malformed = true;
+                *why = read_error_[f];
+                return false;
+            }
             idx_[f] = 0;
         }
         return (bool)cur_[f];
@@ -70,15 +85,16 @@ bool FastqPipeline::fill(PackedBatch& b) {
     };
     for (;;) {
         bool bad = false;
-        if (!advance(0, &bad)) {
+        std::string why;
+        if (!advance(0, &bad, &why)) {
             if (bad) {
-                fail(paired_ ? std::vector<std::string>{"Error during FASTQ record parsing of first file.", kParseError}
-                             : std::vector<std::string>{kParseError, kParseError});
+                fail(paired_ ? std::vector<std::string>{"Error during FASTQ record parsing of first file.", why}
+                             : std::vector<std::string>{kParseError, why});
             } else {
                 if (paired_) {  // file 1 is exhausted: file 2 must be, too
                     bool bad2 = false;
-                    if (advance(1, &bad2)) fail({"The two input files have a different number of records. Please provide valid paired-end read files."});
-                    else if (bad2) fail({kParseError});
+                    if (advance(1, &bad2, &why)) fail({"The two input files have a different number of records. Please provide valid paired-end read files."});
+                    else if (bad2) fail({why});
                 }
                 input_done_ = true;
             }
@@ -87,8 +103,8 @@ bool FastqPipeline::fill(PackedBatch& b) {
         uint64_t need = cur_[0]->recs[idx_[0]].seq_len;
         if (paired_) {
             bool bad2 = false;
-            if (!advance(1, &bad2)) {
-                fail(bad2 ? std::vector<std::string>{kSecondCtx, kParseError} : std::vector<std::string>{kSecondCtx});
+            if (!advance(1, &bad2, &why)) {
+                fail(bad2 ? std::vector<std::string>{kSecondCtx, why} : std::vector<std::string>{kSecondCtx});
                 break;
             }
             need += cur_[1]->recs[idx_[1]].seq_len;

@@ -25,6 +25,7 @@ private:
     std::unique_ptr<FastqChunkReader> rd_[2];
     std::shared_ptr<Chunk> cur_[2];
     size_t idx_[2] = {0, 0};
+    std::string read_error_[2];  // what the reader of file f threw (decompression / read error); reported by fill()
 };
 
 }  // namespace mkh

@@ -115,6 +115,32 @@ def test_fastq_pipeline_equals_record_path(exe, stub, tmp_path, flavour):
             assert other == results[0]
 
 
+def test_fastq_pipeline_reports_read_errors_like_the_record_path(exe, stub, tmp_path):
+    """A gzip stream that breaks half way (flipped bytes): both paths stop with the same status and the same
+    chain of messages — the decompression error under the context of the file it came from. (How many records
+    are written before the error depends on the read-buffer sizes, like in the reference; not compared.)"""
+    rng = np.random.default_rng(10)
+    good = gzip.compress(fastq_text(rng, 3000, b"a"))
+    bad = bytearray(good)
+    bad[len(bad) // 2] ^= 0xFF
+    bad[len(bad) // 2 + 1] ^= 0x55
+    pg, pb = tmp_path / "good.fq.gz", tmp_path / "bad.fq.gz"
+    pg.write_bytes(good)
+    pb.write_bytes(bytes(bad))
+    for case, (files, ctx) in enumerate((([pb], b"Error during FASTQ/A record parsing."), ([pb, pg], b"parsing of first file"),
+                                         ([pg, pb], b"parsing of second file"))):
+        seen = []
+        for env in [{"MERKURIO_NO_FASTQ_PIPELINE": "1"}] + SIZES:
+            d = tmp_path / ("e%d_%d" % (case, len(seen)))
+            d.mkdir()
+            args = ["extract", "-i", files[0], "-s", QUERY, "-v", "-o", d / "x.fastq"] + (["-2", files[1]] if len(files) > 1 else [])
+            r = run(exe, stub, args, env)
+            seen.append((r.returncode, r.stderr))
+        assert seen[0][0] == 1 and ctx in seen[0][1] and b"Caused by:" in seen[0][1] and b"decompressing" in seen[0][1]
+        for other in seen[1:]:
+            assert other == seen[0]
+
+
 @pytest.mark.parametrize("flags", [[], ["-v"], ["-l", "@/t.log", "-j", "@/t.json"]])
 def test_sam_pipeline_equals_record_path(exe, stub, tmp_path, flags):
     from tests.test_cli_cpu import _sam_text
