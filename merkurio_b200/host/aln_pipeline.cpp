@@ -14,7 +14,13 @@ AlnPipeline::AlnPipeline(EngineSet& engines, std::unique_ptr<AlnChunkReader> rea
 
 AlnPipeline::~AlnPipeline() { stop_packer(); }
 
-void AlnPipeline::begin() { cur_ = rd_->next(); }
+void AlnPipeline::begin() {
+    try {
+        cur_ = rd_->next();
+    } catch (const Error& e) {  // raised by the first fill(), with the record path's context
+        begin_error_ = e.what();
+    }
+}
 
 bool AlnPipeline::fill(PackedBatch& b) {
     b.n_records = 0;
@@ -23,6 +29,12 @@ bool AlnPipeline::fill(PackedBatch& b) {
     b.seg[1].clear();
     b.error_chain.clear();
     if (input_done_) return false;
+    if (!begin_error_.empty()) {
+        b.error_chain = {std::string("Error during ") + (rd_->is_bam() ? "BAM" : "SAM") + " record parsing: " + begin_error_};
+        b.off[0] = 0;
+        input_done_ = true;
+        return true;
+    }
     const uint64_t cap = es_.max_bytes;
     const uint32_t max_rec = es_.max_records;
     for (;;) {
@@ -32,7 +44,16 @@ bool AlnPipeline::fill(PackedBatch& b) {
                 input_done_ = true;
                 break;
             }
-            cur_ = rd_->next();
+            try {
+                cur_ = rd_->next();
+            } catch (const Error& e) {
+                // read / decompression error: what has been packed so far still goes out, then the error is raised
+                // with the record path's context
+                cur_ = nullptr;
+                b.error_chain = {std::string("Error during ") + (rd_->is_bam() ? "BAM" : "SAM") + " record parsing: " + e.what()};
+                input_done_ = true;
+                break;
+            }
             idx_ = 0;
         }
         if (input_done_) break;

@@ -20,6 +20,7 @@ private:
     std::unique_ptr<AlnChunkReader> rd_;
     std::shared_ptr<AlnChunk> cur_;
     size_t idx_ = 0;
+    std::string begin_error_;             // what the reader threw before the first chunk
     uint8_t code_lut_[256];               // SAM character -> BAM code
     std::vector<uint8_t> pair_lut_;       // two SAM characters (first in the low byte) -> one packed byte
 };

@@ -84,13 +84,16 @@ void BgzfReader::worker() {
             seen = generation_;
         }
         std::string err;
-        try {
-            for (size_t i; (i = next_.fetch_add(1)) < blocks_.size();) inflate_block(blocks_[i]);
-        } catch (const std::exception& e) {
-            err = e.what();
+        size_t bad = SIZE_MAX;
+        for (size_t i; (i = next_.fetch_add(1)) < blocks_.size();) {
+            try {
+                inflate_block(blocks_[i]);
+            } catch (const std::exception& e) {
+                if (i < bad) { bad = i; err = e.what(); }
+            }
         }
         std::lock_guard<std::mutex> lk(mu_);
-        if (!err.empty() && error_.empty()) error_ = err;
+        if (bad < first_bad_) { first_bad_ = bad; error_ = err; }
         ++finished_workers_;
         cv_done_.notify_all();
     }
@@ -99,6 +102,8 @@ void BgzfReader::worker() {
 // Read the next stretch of whole blocks and inflate them (all threads, this one included).
 bool BgzfReader::refill() {
     out_pos_ = out_len_ = 0;
+    // the blocks in front of a broken one were handed out by the round before
+    if (!pending_error_.empty()) throw Error(pending_error_);
     while (!eof_ && in_have_ < kInChunk) {
         ssize_t n = ::read(fd_, in_.data() + in_have_, in_.size() - in_have_);
         if (n < 0) {
@@ -112,14 +117,25 @@ bool BgzfReader::refill() {
     size_t p = 0, out_total = 0;
     while (p < in_have_) {
         long bs = bgzf_block_size(in_.data() + p, in_have_ - p);
-        if (bs < 0) throw Error("Error while decompressing the input (not a BGZF block)");
-        if (bs == 0 || p + (size_t)bs > in_have_) {
-            if (eof_) throw Error("unexpected end of file");
+        // a broken block: the whole blocks in front of it are still inflated and handed out (the reference reads
+        // block by block and fails at the record it cannot read), the error follows with the next round
+        const char* broken = nullptr;
+        if (bs < 0) broken = "Error while decompressing the input (not a BGZF block)";
+        else if (bs == 0 || p + (size_t)bs > in_have_) {
+            if (!eof_) break;
+            broken = "unexpected end of file";
+        }
+        size_t isize = 0;
+        if (!broken) {
+            const unsigned char* t = in_.data() + p + bs - 4;
+            isize = t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
+            if (isize > (1u << 16)) broken = "corrupt BGZF block";
+        }
+        if (broken) {
+            if (blocks_.empty()) throw Error(broken);
+            pending_error_ = broken;
             break;
         }
-        const unsigned char* t = in_.data() + p + bs - 4;
-        const size_t isize = t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
-        if (isize > (1u << 16)) throw Error("corrupt BGZF block");
         blocks_.push_back(Block{p, (size_t)bs, out_total, isize});
         out_total += isize;
         p += (size_t)bs;
@@ -130,21 +146,31 @@ bool BgzfReader::refill() {
     {
         std::lock_guard<std::mutex> lk(mu_);
         finished_workers_ = 0;
+        first_bad_ = SIZE_MAX;
+        error_.clear();
         ++generation_;
     }
     cv_work_.notify_all();
     std::string err;
-    try {
-        for (size_t i; (i = next_.fetch_add(1)) < blocks_.size();) inflate_block(blocks_[i]);
-    } catch (const std::exception& e) {
-        err = e.what();
+    size_t bad = SIZE_MAX;
+    for (size_t i; (i = next_.fetch_add(1)) < blocks_.size();) {
+        try {
+            inflate_block(blocks_[i]);
+        } catch (const std::exception& e) {
+            if (i < bad) { bad = i; err = e.what(); }
+        }
     }
     {
         std::unique_lock<std::mutex> lk(mu_);
         cv_done_.wait(lk, [&] { return finished_workers_ == threads_.size(); });
-        if (err.empty()) err = error_;
+        if (first_bad_ < bad) { bad = first_bad_; err = error_; }
     }
-    if (!err.empty()) throw Error(err);
+    if (bad != SIZE_MAX) {
+        // the first block that does not inflate: what precedes it is good
+        if (blocks_[bad].out_off == 0) throw Error(err);
+        pending_error_ = err;
+        out_total = blocks_[bad].out_off;
+    }
     // keep the partial block at the end for the next round
     std::memmove(in_.data(), in_.data() + p, in_have_ - p);
     in_have_ -= p;

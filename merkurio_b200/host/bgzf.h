@@ -45,7 +45,9 @@ private:
     std::atomic<size_t> next_{0};
     size_t finished_workers_ = 0;
     bool stop_ = false;
-    std::string error_;
+    std::string error_;          // of the lowest-numbered block a worker could not inflate in this round
+    size_t first_bad_ = SIZE_MAX;  // its index
+    std::string pending_error_;  // raised by the next round: the blocks in front of the broken one go out first
 };
 
 }  // namespace mkh

@@ -89,12 +89,19 @@ void BlockReader::run() {
             }
             if (b.data.size() < head_ + block_bytes_) b.data.resize(head_ + block_bytes_);
             const double t0 = steady_seconds();
-            while (!eof && b.n < block_bytes_) {
-                size_t got = read_(b.data.data() + head_ + b.n, block_bytes_ - b.n);
-                if (got == 0) eof = true;
-                b.n += got;
+            try {
+                while (!eof && b.n < block_bytes_) {
+                    size_t got = read_(b.data.data() + head_ + b.n, block_bytes_ - b.n);
+                    if (got == 0) eof = true;
+                    b.n += got;
+                }
+            } catch (const std::exception& e) {
+                // what was read before the error still goes out (as a block that is not the last one: its
+                // unfinished record is not a truncation), the error after it
+                error = e.what();
+                if (b.n == 0) break;
             }
-            b.last = eof;
+            b.last = eof && error.empty();
             const double dt = steady_seconds() - t0;
             std::unique_lock<std::mutex> lk(mu_);
             t_read_ += dt;
@@ -103,6 +110,7 @@ void BlockReader::run() {
             ready_.push_back(std::move(b));
             lk.unlock();
             cv_.notify_all();
+            if (!error.empty()) break;
         }
     } catch (const std::exception& e) {
         error = e.what();

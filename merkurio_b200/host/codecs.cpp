@@ -47,7 +47,9 @@ public:
     }
     ~GzipStream() override { gzclose(gz_); }
     size_t read(char* dst, size_t n) override {
-        int got = gzread(gz_, dst, (unsigned)std::min<size_t>(n, 1u << 30));
+        // at most 256 KiB per call: gzread reports a broken stream with -1 for the whole call, so that much of
+        // the good data in front of the damage is lost at most (the caller asks again for the rest)
+        int got = gzread(gz_, dst, (unsigned)std::min<size_t>(n, 256u << 10));
         if (got < 0) throw Error("Error while decompressing the input");
         return (size_t)got;
     }

@@ -115,12 +115,13 @@ def test_fastq_pipeline_equals_record_path(exe, stub, tmp_path, flavour):
             assert other == results[0]
 
 
-def test_fastq_pipeline_reports_read_errors_like_the_record_path(exe, stub, tmp_path):
+@pytest.mark.parametrize("n_reads,level", [(3000, 9), (40000, 1)])
+def test_fastq_pipeline_reports_read_errors_like_the_record_path(exe, stub, tmp_path, n_reads, level):
     """A gzip stream that breaks half way (flipped bytes): both paths stop with the same status and the same
-    chain of messages — the decompression error under the context of the file it came from. (How many records
-    are written before the error depends on the read-buffer sizes, like in the reference; not compared.)"""
+    chain of messages — the decompression error under the context of the file it came from — after writing the
+    same records."""
     rng = np.random.default_rng(10)
-    good = gzip.compress(fastq_text(rng, 3000, b"a"))
+    good = gzip.compress(fastq_text(rng, n_reads, b"a"), compresslevel=level)
     bad = bytearray(good)
     bad[len(bad) // 2] ^= 0xFF
     bad[len(bad) // 2 + 1] ^= 0x55
@@ -135,8 +136,13 @@ def test_fastq_pipeline_reports_read_errors_like_the_record_path(exe, stub, tmp_
             d.mkdir()
             args = ["extract", "-i", files[0], "-s", QUERY, "-v", "-o", d / "x.fastq"] + (["-2", files[1]] if len(files) > 1 else [])
             r = run(exe, stub, args, env)
-            seen.append((r.returncode, r.stderr))
-        assert seen[0][0] == 1 and ctx in seen[0][1] and b"Caused by:" in seen[0][1] and b"decompressing" in seen[0][1]
+            seen.append((r.returncode, r.stderr, {f.name: f.read_bytes() for f in sorted(d.iterdir())}))
+        # (flipped bytes either break the deflate stream or decode to garbage that no longer parses)
+        assert seen[0][0] == 1 and ctx in seen[0][1] and b"Caused by:" in seen[0][1]
+        if n_reads == 3000:
+            assert b"decompressing" in seen[0][1]
+        else:  # the records in front of the damage (less zlib's last buffer) were written, by both paths alike
+            assert sum(v.count(b"\n@a") for v in seen[0][2].values()) > 500
         for other in seen[1:]:
             assert other == seen[0]
 
@@ -171,3 +177,35 @@ def test_sam_pipeline_equals_record_path(exe, stub, tmp_path, flags):
     assert sum(1 for ln in results[0]["t.sam"].split(b"\n") if ln and not ln.startswith(b"@")) == 3000
     for other in results[1:]:
         assert other == results[0]
+
+
+@pytest.mark.parametrize("damage", ["truncated", "flipped"])
+def test_bam_pipeline_stops_where_the_record_path_stops(exe, stub, tmp_path, damage):
+    """A BAM file that breaks off / has a corrupt BGZF block three quarters in: both paths write every record
+    in front of the broken block (the reference reads block by block) and fail with the same message."""
+    from tests.test_cli_cpu import _sam_text
+    sam = tmp_path / "in.sam"
+    sam.write_bytes(_sam_text(60000, seed=8))
+    bam = tmp_path / "in.bam"
+    r = run(exe, stub, ["tag", "-i", sam, "-s", QUERY[:31], "-o", bam])
+    assert r.returncode == 0, r.stderr
+    data = bytearray(bam.read_bytes())
+    at = len(data) * 3 // 4
+    if damage == "truncated":
+        del data[at:]
+    else:
+        data[at] ^= 0xFF
+        data[at + 1] ^= 0x55
+    broken = tmp_path / "broken.bam"
+    broken.write_bytes(bytes(data))
+    seen = []
+    for env in [{"MERKURIO_NO_ALN_PIPELINE": "1"}, {}, {"MERKURIO_BATCH_BYTES": "20000", "MERKURIO_CHUNK_BYTES": "5000"}]:
+        out = tmp_path / ("o%d.sam" % len(seen))
+        r = run(exe, stub, ["tag", "-i", broken, "-s", QUERY[:31], "-o", out], env)
+        body = b"\n".join(ln for ln in out.read_bytes().split(b"\n") if not ln.startswith(b"@PG"))
+        seen.append((r.returncode, r.stderr, body))
+    assert seen[0][0] == 1 and b"Error during BAM record parsing: " in seen[0][1]
+    n_written = sum(1 for ln in seen[0][2].split(b"\n") if ln and not ln.startswith(b"@"))
+    assert 30000 < n_written < 60000
+    for other in seen[1:]:
+        assert other == seen[0]
