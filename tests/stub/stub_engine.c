@@ -2,7 +2,13 @@
  * buffers in ordinary memory and reports NO hits for every batch. It is not a matcher and is never
  * shipped or loaded by the product; tests preload it (LD_PRELOAD) to exercise the host's reader ->
  * packer -> driver -> writer plumbing (batching, pieces of long records, chunk hand-over, error
- * propagation, output formatting) on a machine without a GPU. */
+ * propagation, output formatting) on a machine without a GPU.
+ *
+ * MK_STUB_FLAG_FIRST=<base> (A, C, G or T) makes it pretend instead: every record that starts with that
+ * base and is at least as long as the first query gets its flag bit and, outside FLAG mode, one made-up
+ * "hit" of the first query at position 0. Nothing is compared with the queries — the point is only that
+ * the host's paths (which cut their batches differently) must then agree on which records are written,
+ * tagged and logged, flagged and unflagged ones mixed. */
 #include <stdlib.h>
 #include <string.h>
 
@@ -16,6 +22,11 @@ struct mk_engine {
     uint64_t* flags;
     uint32_t n_records[16];
     uint64_t n_units[16];
+    int use_lens[16];
+    mk_encoding enc[16];
+    mk_mode mode[16];
+    uint32_t first_len;  /* length of query 0 */
+    mk_hit* hits;
 };
 
 int mk_engine_create(const mk_patterns* p, const mk_config* c, mk_engine** out) {
@@ -28,6 +39,8 @@ int mk_engine_create(const mk_patterns* p, const mk_config* c, mk_engine** out) 
         e->lens[s] = calloc((size_t)c->max_batch_records + 1, 4);
     }
     e->flags = calloc((size_t)c->max_batch_records / 64 + 2, 8);
+    e->hits = calloc((size_t)c->max_batch_records + 1, sizeof(mk_hit));
+    e->first_len = p && p->n ? p->off[1] - p->off[0] : 0;
     *out = e;
     return 0;
 }
@@ -35,6 +48,7 @@ void mk_engine_destroy(mk_engine* e) {
     if (!e) return;
     for (int s = 0; s < 16; ++s) { free(e->seq[s]); free(e->off[s]); free(e->lens[s]); }
     free(e->flags);
+    free(e->hits);
     free(e);
 }
 int mk_engine_get_info(mk_engine* e, mk_engine_info* o) { (void)e; memset(o, 0, sizeof *o); return 0; }
@@ -45,9 +59,11 @@ int mk_slot_buffers(mk_engine* e, uint32_t s, uint8_t** a, uint64_t** b, uint32_
     return 0;
 }
 int mk_scan_submit(mk_engine* e, uint32_t s, uint32_t n, uint64_t u, int l, mk_encoding enc, mk_mode m) {
-    (void)l; (void)enc; (void)m;
     e->n_records[s] = n;
     e->n_units[s] = u;
+    e->use_lens[s] = l;
+    e->enc[s] = enc;
+    e->mode[s] = m;
     return 0;
 }
 int mk_scan_wait(mk_engine* e, uint32_t s, mk_result* r) {
@@ -55,6 +71,26 @@ int mk_scan_wait(mk_engine* e, uint32_t s, mk_result* r) {
     r->record_flags = e->flags;  /* all zero: no record has a hit */
     r->n_records = e->n_records[s];
     r->bases_scanned = e->n_units[s];
+    memset(e->flags, 0, ((size_t)e->cfg.max_batch_records / 64 + 2) * 8);
+    const char* want = getenv("MK_STUB_FLAG_FIRST");
+    if (want && *want) {
+        const uint8_t nib = *want == 'A' ? 1 : *want == 'C' ? 2 : *want == 'G' ? 4 : 8;
+        uint64_t nh = 0;
+        for (uint32_t i = 0; i < e->n_records[s]; ++i) {
+            const uint64_t at = e->off[s][i];
+            const uint64_t len = e->use_lens[s] ? e->lens[s][i] : e->off[s][i + 1] - at;
+            if (len == 0 || len < e->first_len) continue;
+            const int starts = e->enc[s] == MK_ENC_ASCII ? e->seq[s][at] == (uint8_t)*want : (e->seq[s][at / 2] >> 4) == nib;
+            if (!starts) continue;
+            e->flags[i >> 6] |= (uint64_t)1 << (i & 63);
+            if (e->mode[s] != MK_MODE_FLAG) {
+                mk_hit h = {i, 0, 0, e->first_len};
+                e->hits[nh++] = h;
+            }
+        }
+        r->hits = nh ? e->hits : NULL;
+        r->n_hits = nh;
+    }
     return 0;
 }
 int mk_scan_host(mk_engine* e, uint32_t s, const uint8_t* a, const uint64_t* b, const uint32_t* c, uint32_t n, uint64_t u,

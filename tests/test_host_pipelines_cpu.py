@@ -209,3 +209,86 @@ def test_bam_pipeline_stops_where_the_record_path_stops(exe, stub, tmp_path, dam
     assert 30000 < n_written < 60000
     for other in seen[1:]:
         assert other == seen[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# The same comparisons with flagged and unflagged records mixed: the test double then flags every record that
+# starts with a given base (tests/stub/stub_engine.c, MK_STUB_FLAG_FIRST) and, with logs on, reports a made-up
+# hit for it. Which records those are does not depend on how a path cuts its batches, so every path must
+# write, tag and log the same ones.
+@pytest.mark.parametrize("extra", [[], ["-v"], ["-l", "@/x.log", "-j", "@/x.json"], ["-v", "-l", "@/x.log"]], ids=lambda e: "_".join(e).replace("@/", "") or "plain")
+@pytest.mark.parametrize("flavour", ["plain", "odd"])
+def test_fastq_paths_agree_on_flagged_records(exe, stub, tmp_path, flavour, extra):
+    rng = np.random.default_rng(12)
+    d1 = fastq_text(rng, 2500, b"a", odd=flavour == "odd")
+    d2 = fastq_text(rng, 2500, b"b", odd=flavour == "odd")
+    p1, p2 = tmp_path / "r1.fq", tmp_path / "r2.fq"
+    p1.write_bytes(d1)
+    p2.write_bytes(d2)
+    for paired in (False, True):
+        results = []
+        for env in [{"MERKURIO_NO_FASTQ_PIPELINE": "1"}] + SIZES:
+            d = tmp_path / ("out%d%d" % (paired, len(results)))
+            d.mkdir()
+            args = ["extract", "-i", p1, "-s", QUERY[:25], "-o", d / "x.fastq"] + [a.replace("@", str(d)) for a in extra] + (["-2", p2] if paired else [])
+            r = run(exe, stub, args, dict(env, MK_STUB_FLAG_FIRST="G"))
+            assert r.returncode == 0, r.stderr
+            files = {}
+            for f in sorted(d.iterdir()):
+                data = f.read_bytes()
+                if f.suffix == ".log":
+                    data = log_body(f)
+                elif f.suffix == ".json":
+                    import json
+                    j = json.loads(data)
+                    j["meta_information"] = {k: v for k, v in j["meta_information"].items() if k not in ("timestamp", "command_line")}
+                    data = json.dumps(j, sort_keys=True).encode()
+                files[f.name] = data
+            results.append(files)
+        written = sum(v.count(b"\n@a") for k, v in results[0].items() if k.endswith(".fq"))
+        assert 200 < written < 2300  # some records, not all of them
+        for other in results[1:]:
+            assert other == results[0]
+
+
+@pytest.mark.parametrize("flags", [["-m"], ["-v"], [], ["-m", "-l", "@/t.log", "-j", "@/t.json"]], ids=lambda e: "_".join(e).replace("@/", "") or "keep_all")
+@pytest.mark.parametrize("bam", [False, True])
+def test_tag_paths_agree_on_flagged_records(exe, stub, tmp_path, flags, bam):
+    from tests.test_cli_cpu import _sam_text
+    src = tmp_path / "in.sam"
+    src.write_bytes(_sam_text(3000, seed=6))
+    if bam:
+        r = run(exe, stub, ["tag", "-i", src, "-s", QUERY[:25], "-o", tmp_path / "in.bam"])
+        assert r.returncode == 0, r.stderr
+        src = tmp_path / "in.bam"
+    results = []
+    for env in [{"MERKURIO_NO_ALN_PIPELINE": "1"}] + SIZES:
+        d = tmp_path / ("o%d" % len(results))
+        d.mkdir()
+        r = run(exe, stub, ["tag", "-i", src, "-s", QUERY[:25], "-o", d / "t.sam"] + [f.replace("@", str(d)) for f in flags], dict(env, MK_STUB_FLAG_FIRST="C"))
+        assert r.returncode == 0, r.stderr
+        files = {}
+        for f in sorted(d.iterdir()):
+            data = f.read_bytes()
+            if f.suffix == ".log":
+                data = log_body(f)
+            elif f.suffix == ".sam":
+                data = b"\n".join(ln for ln in data.split(b"\n") if not ln.startswith(b"@PG"))
+            elif f.suffix == ".json":
+                import json
+                j = json.loads(data)
+                j["meta_information"] = {k: v for k, v in j["meta_information"].items() if k not in ("timestamp", "command_line")}
+                data = json.dumps(j, sort_keys=True).encode()
+            files[f.name] = data
+        results.append(files)
+    kept = sum(1 for ln in results[0]["t.sam"].split(b"\n") if ln and not ln.startswith(b"@"))
+    # (a record that came with a km tag keeps the old field; the new one, last on the line, merges both lists)
+    tagged = sum(1 for ln in results[0]["t.sam"].split(b"\n") if b"\tkm:Z:" in ln and QUERY[:25].encode() in ln.rsplit(b"\tkm:Z:", 1)[1])
+    if flags[:1] == ["-m"]:
+        assert kept == tagged and 300 < tagged < 2000
+    elif flags[:1] == ["-v"]:
+        assert tagged == 0 and 1000 < kept < 2700
+    else:
+        assert kept == 3000 and 300 < tagged < 2000
+    for other in results[1:]:
+        assert other == results[0]
