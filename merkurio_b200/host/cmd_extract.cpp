@@ -33,6 +33,11 @@ struct OutFile {
         if (buf.size() >= (1u << 20)) flush();
     }
     void write_raw(const char* p, size_t n) {
+        if (n >= (256u << 10)) {  // a long run of records: straight to the file, not through the buffer
+            flush();
+            if (f) std::fwrite(p, 1, n, f);
+            return;
+        }
         buf.append(p, n);
         if (buf.size() >= (1u << 20)) flush();
     }
@@ -336,6 +341,29 @@ void extract_records(CmdExtract args) {
                     cb(m, found, hits);
                 }
             };
+            if (args.invert_match && !logging_active && !paired && !args.suppress_output) {
+                // -v without logs writes nearly every record: runs of unflagged records that lie back to back in one
+                // chunk, already in the writer's form, are copied in one piece (what on_single would do one by one)
+                auto flagged = [&](uint32_t r) { return (res.record_flags[r >> 6] >> (r & 63)) & 1; };
+                size_t at = 0;
+                for (uint32_t u = 0; u < n_units;) {
+                    if (flagged(u)) { ++u; continue; }
+                    const BatchSeg& sg = b.locate(0, u, &at);
+                    const Chunk* ch = static_cast<const Chunk*>(sg.chunk.get());
+                    const RecSpan& first = ch->recs[sg.first + (u - sg.rec0)];
+                    if (!first.plain) { deliver(u); ++u; continue; }
+                    uint32_t end = first.end, v = u + 1;
+                    for (const uint32_t seg_end = sg.rec0 + sg.count; v < seg_end && !flagged(v); ++v) {
+                        const RecSpan& next = ch->recs[sg.first + (v - sg.rec0)];
+                        if (!next.plain || next.start != end) break;
+                        end = next.end;
+                    }
+                    writer.write_raw(ch->data.data() + first.start, end - first.start);
+                    nb_records_extracted += v - u;
+                    u = v;
+                }
+                return;
+            }
             if (args.invert_match) {
                 for (uint32_t u = 0; u < n_units; ++u) deliver(u);
                 return;
