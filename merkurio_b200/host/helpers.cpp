@@ -89,13 +89,6 @@ std::string identify_uncompressed_type(const std::string& path) {
 
 static bool is_rust_whitespace(unsigned char c) { return c == ' ' || (c >= 0x09 && c <= 0x0D); }
 
-static std::string trim(const std::string& s) {
-    size_t a = 0, b = s.size();
-    while (a < b && is_rust_whitespace((unsigned char)s[a])) ++a;
-    while (b > a && is_rust_whitespace((unsigned char)s[b - 1])) --b;
-    return s.substr(a, b - a);
-}
-
 std::vector<std::string> read_kmers_from_file(const std::string& path) {
     if (path_is_dir(path)) throw Error("K-mer file path '" + path + "' is a directory, not a file.");
     std::ifstream in(path, std::ios::binary);
