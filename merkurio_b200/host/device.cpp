@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace mkh {
 
@@ -56,7 +57,12 @@ EngineSet::EngineSet(const std::vector<std::string>& patterns, bool case_insensi
     max_records = (uint32_t)std::min<uint64_t>(max_bytes / 32 + 1024, 1u << 26);
     n_slots = (uint32_t)env_u64("MERKURIO_SLOTS", 3);
     if (n_slots < 1) n_slots = 1;
-    for (int g = 0; g < std::max(n_gpus, 1); ++g) {
+    // one engine per GPU; with several GPUs they are created side by side (a CUDA context takes a second or
+    // more to create, one after the other that is most of an 8-GPU run)
+    const int n_engines = std::max(n_gpus, 1);
+    engines.assign((size_t)n_engines, nullptr);
+    std::vector<std::string> failed((size_t)n_engines);
+    auto create = [&](int g) {
         mk_config cfg{};
         cfg.device = g;
         cfg.case_insensitive = case_insensitive ? 1 : 0;
@@ -65,9 +71,22 @@ EngineSet::EngineSet(const std::vector<std::string>& patterns, bool case_insensi
         cfg.max_batch_bytes = max_bytes;
         cfg.hit_capacity = 0;
         mk_engine* e = nullptr;
-        check(mk_engine_create(&mp, &cfg, &e));
-        engines.push_back(e);
+        if (mk_engine_create(&mp, &cfg, &e) != 0) failed[(size_t)g] = std::string("GPU matching engine: ") + mk_last_error();  // (thread-local text)
+        engines[(size_t)g] = e;
+    };
+    if (n_engines == 1) {
+        create(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < n_engines; ++g) th.emplace_back(create, g);
+        for (auto& t : th) t.join();
     }
+    for (int g = 0; g < n_engines; ++g)
+        if (!failed[(size_t)g].empty()) {
+            for (mk_engine* e : engines) mk_engine_destroy(e);
+            engines.clear();
+            throw Error(failed[(size_t)g]);
+        }
     t_setup = now_s() - t_start;
 }
 

@@ -40,7 +40,9 @@ def log_body(p: Path) -> bytes:
 
 
 SIZES = [{}, {"MERKURIO_BATCH_BYTES": "20000", "MERKURIO_CHUNK_BYTES": "5000"},
-         {"MERKURIO_BATCH_BYTES": "17000", "MERKURIO_CHUNK_BYTES": "4096", "MERKURIO_SLOTS": "1"}]
+         {"MERKURIO_BATCH_BYTES": "17000", "MERKURIO_CHUNK_BYTES": "4096", "MERKURIO_SLOTS": "1"},
+         # batches dealt over two engines (created side by side), results consumed in batch order
+         {"MERKURIO_GPUS": "2", "MERKURIO_BATCH_BYTES": "30000", "MERKURIO_CHUNK_BYTES": "9000"}]
 
 
 def fasta_text(rng, crlf=False, blanks=False, final_nl=True, width=60):
