@@ -72,6 +72,10 @@ def revcomp_rows(a: np.ndarray) -> np.ndarray:
 
 tmp = Path(args.dir or tempfile.mkdtemp(prefix="mk_cli_"))
 tmp.mkdir(parents=True, exist_ok=True)
+if not args.dir:  # gigabytes of synthetic input: do not leave them in /tmp for whatever runs next on the box
+    import atexit
+    import shutil
+    atexit.register(shutil.rmtree, tmp, ignore_errors=True)
 if args.config == "cfg5":
     rng = np.random.default_rng(5)
     total = int(3_000_000_000 * args.scale)
