@@ -191,6 +191,60 @@ private:
     bool eof_ = false, done_ = false;
 };
 
+// ---- zstd (libzstd.so.1) -------------------------------------------------------------------------
+// needletail's "compression" feature (the reference's Cargo.toml:26) reads Zstandard input as well
+// (magic 28 B5 2F FD). Streaming API of libzstd, stable since 1.0: buffers are {pointer, size, position}.
+struct zstd_in { const void* src; size_t size, pos; };
+struct zstd_out { void* dst; size_t size, pos; };
+
+class ZstdStream : public InputStream {
+public:
+    explicit ZstdStream(int fd) : fd_(fd), in_(1 << 20) {
+        lib_ = dlopen("libzstd.so.1", RTLD_NOW);
+        if (!lib_) { ::close(fd_); throw Error("zstd input needs libzstd.so.1, which is not installed"); }
+        auto create = (void* (*)())load_symbol(lib_, "ZSTD_createDStream", "libzstd");
+        auto init = (size_t (*)(void*))load_symbol(lib_, "ZSTD_initDStream", "libzstd");
+        run_ = (size_t (*)(void*, zstd_out*, zstd_in*))load_symbol(lib_, "ZSTD_decompressStream", "libzstd");
+        is_error_ = (unsigned (*)(size_t))load_symbol(lib_, "ZSTD_isError", "libzstd");
+        free_ = (size_t (*)(void*))load_symbol(lib_, "ZSTD_freeDStream", "libzstd");
+        ds_ = create();
+        if (!ds_ || is_error_(init(ds_))) { ::close(fd_); throw Error("ZSTD_createDStream failed"); }
+        buf_ = zstd_in{in_.data(), 0, 0};
+    }
+    ~ZstdStream() override {
+        if (ds_) free_(ds_);
+        ::close(fd_);
+    }
+    size_t read(char* dst, size_t n) override {
+        zstd_out out{dst, n, 0};
+        while (out.pos == 0) {
+            if (buf_.pos == buf_.size && !eof_) {
+                size_t got = read_fd(fd_, in_.data(), in_.size());
+                if (got == 0) eof_ = true;
+                buf_ = zstd_in{in_.data(), got, 0};
+            }
+            const bool no_input = buf_.pos == buf_.size;
+            if (no_input && !mid_frame_) break;  // the end of the input, between two frames
+            // (without input the call only hands out what the decoder still holds)
+            const size_t rc = run_(ds_, &out, &buf_);  // 0: a frame is complete (more frames may follow)
+            if (is_error_(rc)) throw Error("Error while decompressing the input (zstd)");
+            mid_frame_ = rc != 0;
+            if (no_input && out.pos == 0) throw Error("Error while decompressing the input (truncated zstd stream)");
+        }
+        return out.pos;
+    }
+private:
+    int fd_;
+    void* lib_ = nullptr;
+    void* ds_ = nullptr;
+    size_t (*run_)(void*, zstd_out*, zstd_in*) = nullptr;
+    unsigned (*is_error_)(size_t) = nullptr;
+    size_t (*free_)(void*) = nullptr;
+    std::vector<char> in_;
+    zstd_in buf_{nullptr, 0, 0};
+    bool eof_ = false, mid_frame_ = false;
+};
+
 }  // namespace
 
 std::unique_ptr<InputStream> InputStream::open(const std::string& path) {
@@ -205,6 +259,7 @@ std::unique_ptr<InputStream> InputStream::open(const std::string& path) {
     if (n >= 3 && m[0] == 'B' && m[1] == 'Z' && m[2] == 'h') return std::unique_ptr<InputStream>(new Bzip2Stream(fd));
     if (n >= 6 && m[0] == 0xFD && m[1] == '7' && m[2] == 'z' && m[3] == 'X' && m[4] == 'Z' && m[5] == 0x00)
         return std::unique_ptr<InputStream>(new XzStream(fd));
+    if (n >= 4 && m[0] == 0x28 && m[1] == 0xB5 && m[2] == 0x2F && m[3] == 0xFD) return std::unique_ptr<InputStream>(new ZstdStream(fd));
     return std::unique_ptr<InputStream>(new PlainStream(fd));
 }
 

@@ -300,6 +300,7 @@ int run(int argc, char** argv) {
         } else {
             if (!looks_like_fastq(path)) { std::fputs("#not-fastq\n", stdout); return 0; }
             FastqChunkReader cr(path, argc > 4 ? (size_t)std::strtoull(argv[4], nullptr, 10) : (size_t)16 << 20);
+            try {
             while (std::shared_ptr<Chunk> ch = cr.next()) {
                 for (const RecSpan& sp : ch->recs) {
                     FastxRecord r;
@@ -317,6 +318,9 @@ int run(int argc, char** argv) {
                     }
                 }
                 if (ch->failed) out += "#error\tError during FASTQ/A record parsing.\n";
+            }
+            } catch (const Error& e) {  // read / decompression error: reported like the line reader's
+                out += std::string("#error\t") + e.what() + "\n";
             }
         }
         std::fwrite(out.data(), 1, out.size(), stdout);

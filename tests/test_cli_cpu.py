@@ -361,13 +361,19 @@ def test_chunked_bam_reader_equals_record_reader(exe, ref_tree, tmp_path):
             assert got.stdout == want.stdout, (src.name, chunk)
 
 
-@pytest.mark.parametrize("codec", ["gz", "bz2", "bz2_multi", "xz", "xz_multi"])
+@pytest.mark.parametrize("codec", ["gz", "bz2", "bz2_multi", "xz", "xz_multi", "zstd", "zstd_multi"])
 def test_compressed_inputs_are_recognised_by_their_magic_bytes(exe, tmp_path, codec):
-    """needletail opens .gz / .bz2 / .xz by content, not by name (README.md:39): same records as the plain file."""
+    """needletail opens .gz / .bz2 / .xz / .zst by content, not by name (README.md:39; its "compression" feature,
+    Cargo.toml:26, includes zstd): same records as the plain file."""
     import bz2
     import gzip
     import lzma
     import numpy as np
+    if codec.startswith("zstd"):
+        pa = pytest.importorskip("pyarrow")  # the only zstd encoder at hand
+        zstd = lambda d: pa.compress(d, codec="zstd", asbytes=True)
+    else:
+        zstd = None
     rng = np.random.default_rng(13)
     recs = []
     for i in range(6000):
@@ -377,7 +383,8 @@ def test_compressed_inputs_are_recognised_by_their_magic_bytes(exe, tmp_path, co
     data = b"".join(recs)
     half = data.index(b"\n@r3000\n") + 1
     packed = {"gz": gzip.compress(data), "bz2": bz2.compress(data), "bz2_multi": bz2.compress(data[:half]) + bz2.compress(data[half:]),
-              "xz": lzma.compress(data), "xz_multi": lzma.compress(data[:half]) + lzma.compress(data[half:])}[codec]
+              "xz": lzma.compress(data), "xz_multi": lzma.compress(data[:half]) + lzma.compress(data[half:]),
+              "zstd": zstd and zstd(data), "zstd_multi": zstd and zstd(data[:half]) + zstd(data[half:])}[codec]
     plain = tmp_path / "p.fastq"
     plain.write_bytes(data)
     comp = tmp_path / "reads.fastq.dat"  # the name says nothing
@@ -395,7 +402,8 @@ def test_compressed_inputs_are_recognised_by_their_magic_bytes(exe, tmp_path, co
     # FASTA through the same streams
     fa = b"".join(b">s%d\n%s\n" % (i, b"ACGTTGCA" * 20) for i in range(500))
     (tmp_path / "g.fa").write_bytes(fa)
-    (tmp_path / "g.fa.z").write_bytes({"gz": gzip.compress, "bz2": bz2.compress, "bz2_multi": bz2.compress, "xz": lzma.compress, "xz_multi": lzma.compress}[codec](fa))
+    (tmp_path / "g.fa.z").write_bytes({"gz": gzip.compress, "bz2": bz2.compress, "bz2_multi": bz2.compress, "xz": lzma.compress, "xz_multi": lzma.compress,
+                                       "zstd": zstd, "zstd_multi": zstd}[codec](fa))
     a = subprocess.run([exe, "records", str(tmp_path / "g.fa"), "generic"], capture_output=True).stdout
     b = subprocess.run([exe, "records", str(tmp_path / "g.fa.z"), "generic"], capture_output=True).stdout
     assert a == b and a.count(b"#id\t") == 500
