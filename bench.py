@@ -9,10 +9,18 @@ A step is one pass of the scan over one batch = the whole per-GPU data set (100 
 resident in HBM, far larger than the 126 MB L2 so no flush is needed). `value` is the whole-job
 Gbases/s with inputs resident; `e2e` is the same workload pushed through the C ABI from pinned host
 memory (H2D of every batch and D2H of the flags inside the timed region). Rank 0 prints one JSON line.
+
+Beside the headline the line carries (N = 1 only, each can be switched off):
+  sustained   >= 2 s of back-to-back cfg2 passes with per-pass device times and the clocks seen meanwhile
+  configs     cfg3 / cfg4 / cfg5 at BASELINE size: device time, dominant kernel, fraction of the HBM peak,
+              and parity with the oracle on a sample of the same data
+  e2e_file    file -> file: the host binary `merkurio extract` on a FASTQ on tmpfs, wall clock, with the
+              single-threaded oracle matcher timed on the same reads
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -37,47 +45,94 @@ def log(*a):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock, power and throttle reasons of one GPU while a timed region runs: NVML (pynvml) polled from a
+    thread every 10 ms; `nvidia-smi -lms` as the fallback when NVML cannot be loaded."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+    SMI_Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.rows = []
-        self.proc = None
-        self.gpu = gpu_index
+    def __init__(self, torch_device_index: int):
+        self.rows = []  # (t, sm_mhz, power_w, reason bitmask)
+        self.max_mhz = None
+        self.source = None
+        self._stop = threading.Event()
+        self._th = None
+        self._proc = None
+        self._idx = torch_device_index
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self._idx).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self._idx]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self._idx
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
+            nv, h = self._nvml_handle()
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.source = "nvml"
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        try:
+                            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.rows.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                          nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons)))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.01)
+            self._th = threading.Thread(target=poll, daemon=True)
+            self._th.start()
+            return
+        except Exception as e:  # no NVML: nvidia-smi
+            log(f"[bench] NVML unavailable ({e!r}); sampling clocks with nvidia-smi")
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", "-i", str(self._idx), f"--query-gpu={self.SMI_Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
+
+            def read():
+                for line in self._proc.stdout:
+                    f = [x.strip() for x in line.split(",")]
+                    try:
+                        mask = sum(bit for bit, v in zip((0x8, 0x40, 0x20, 0x4), f[3:7]) if v.lower().startswith("active"))
+                        self.rows.append((time.perf_counter(), float(f[0]), float(f[2]), mask))
+                        self.max_mhz = float(f[1])
+                    except (ValueError, IndexError):
+                        continue
+            self._th = threading.Thread(target=read, daemon=True)
+            self._th.start()
         except OSError:
-            self.proc = None
+            self.source = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
-
-    def stop(self, t0: float, t1: float) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.05] or [r for _, r in self.rows[-3:]]
-        sm, mx, reasons = [], [], set()
+    def window(self, t0: float, t1: float) -> dict:
+        """Summary of the samples taken in [t0, t1] (perf_counter times)."""
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        if not rows:  # a region shorter than the sampling period: the nearest samples around it
+            rows = sorted(self.rows, key=lambda r: abs(r[0] - (t0 + t1) / 2))[:3]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"], "samples": 0, "source": self.source}
+        mask = 0
         for r in rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            mask |= r[3]
+        sm = [r[1] for r in rows]
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": self.max_mhz, "power_w_max": float(max(r[2] for r in rows)),
+                "reasons": sorted(name for bit, name in self.REASONS.items() if mask & bit), "samples": len(rows), "source": self.source}
+
+    def stop(self):
+        self._stop.set()
+        if self._proc:
+            self._proc.terminate()
 
 
 def measured_peak_gbs():
@@ -88,6 +143,31 @@ def measured_peak_gbs():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def csrc_digest() -> str:
+    """sha256 over the CUDA sources and the C ABI header: what an ncu capture of a kernel is valid for."""
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "merkurio_b200" / "csrc").glob("*")) + [ROOT / "include" / "merkurio_cuda.h"]:
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel: str, workload_key: str):
+    """DRAM bytes (read + write) of one launch of `kernel` from the committed ncu summary, or (None, why) when that
+    capture was taken from other sources than the ones that are running now."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if not p.exists():
+        return None, "no profiles/ncu_traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        e = d["kernels"][kernel][workload_key]
+    except Exception:
+        return None, f"profiles/ncu_traffic.json has no entry for {kernel} / {workload_key}"
+    if e.get("csrc_sha16") != csrc_digest():
+        return None, f"stale: captured at csrc {e.get('csrc_sha16')}, running {csrc_digest()}"
+    return int(e["dram_bytes_read"]) + int(e["dram_bytes_write"]), f"{e['source']} (csrc {e['csrc_sha16']})"
 
 
 def workload_name(n_reads, read_len, n_queries):
@@ -145,6 +225,115 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def bench_config(name: str, steps: int, peak: float, oracle_check: bool = True):
+    """One of cfg3 / cfg4 / cfg5 at BASELINE size: device-timed passes over the resident batch, the dominant (scan)
+    kernel against the HBM peak, and parity: oracle on a sample of the same data + size-independent properties."""
+    import torch
+    from merkurio_b200 import capi
+    from merkurio_b200.synth import workloads as wlm
+    from oracle import checks
+
+    t_gen = time.perf_counter()
+    if name in ("cfg3", "cfg4"):
+        wl = wlm.reads_workload(name)
+    else:
+        wl = wlm.genome_workload(1.0, upper_queries=(name == "cfg5"))
+    t_gen = time.perf_counter() - t_gen
+    entry = {"config": wl.name, "records": wl.n_records, "bases": wl.n_units, "patterns": len(wl.pats),
+             "encoding": "BAM4" if wl.enc == capi.MK_ENC_BAM4 else "ASCII",
+             "mode": {capi.MK_MODE_FLAG: "FLAG", capi.MK_MODE_PATTERN_SET: "PATTERN_SET", capi.MK_MODE_ALL_HITS: "ALL_HITS"}[wl.mode],
+             "generate_s": t_gen}
+    with capi.Engine(wl.pats, n_slots=0, hit_capacity=wl.hit_capacity) as eng:
+        t0 = time.perf_counter()
+        wl.scan(eng)  # first pass: waits for the seed tables (built on host threads while the engine starts)
+        entry["table_build_and_first_pass_s"] = time.perf_counter() - t0
+        for _ in range(3):
+            wl.scan(eng)
+        scan, dev, ver = [], [], []
+        for _ in range(steps):
+            r = wl.scan(eng)
+            scan.append(r.scan_ns / 1e6)
+            dev.append(r.device_ns / 1e6)
+            ver.append(r.verify_ns / 1e6)
+        full = wl.scan(eng, fetch=True)
+        info = eng.info()
+        enc = wl.enc
+        scan_ms, dev_ms = float(np.median(scan)), float(np.median(dev))
+        entry.update(
+            device_ms=dev_ms, device_ms_min=float(min(dev)), kernel=eng.scan_kernel(enc),
+            kernel_ms=scan_ms, verify_ms=float(np.median(ver)), sort_and_rest_ms=dev_ms - scan_ms - float(np.median(ver)),
+            algorithmic_bytes=int(wl.algorithmic_bytes), achieved_gbs=wl.algorithmic_bytes / scan_ms / 1e6,
+            frac=wl.algorithmic_bytes / scan_ms / 1e6 / peak, frac_whole_pass=wl.algorithmic_bytes / dev_ms / 1e6 / peak,
+            gbases_per_s=wl.n_units / dev_ms / 1e6, n_hits=int(full.n_hits), candidates=int(full.n_candidates), rescans=int(full.n_rescans),
+            seed_q=int(info.seed_q[enc]), seed_d=int(info.seed_d[enc]), seeds=int(info.n_seeds[enc]), filter_in_smem=int(info.filter_in_smem[enc]),
+            filter_bytes=int(info.filter_bytes[enc]), table_bytes=int(info.table_bytes[enc]), steps=steps)
+        # parity
+        t0 = time.perf_counter()
+        if wl.syn is not None:
+            entry["oracle_sample"] = f"first 200000 reads, Aho-Corasick (oracle/mk_oracle.c), bit-exact {entry['mode']}"
+            entry["oracle_sample_hits"] = checks.reads_sample_equal(full, wl, 200_000)
+            entry["oracle_sample_equal"] = True
+            if wl.mode == capi.MK_MODE_ALL_HITS:
+                entry["hits_reverified"] = checks.reverify_hits(wl.d_seq, wl.d_off, full.hits, wl.pats, wl.enc == capi.MK_ENC_BAM4)
+        else:
+            assert info.filter_in_smem[enc] == 0, "cfg5 must run through the L2-resident filter path"
+            entry["hits_reverified"] = checks.reverify_hits(wl.d_seq, wl.d_off, full.hits, wl.pats, False)
+            entry["expected_queries_missing"] = checks.genome_expected_found(full, wl)
+            entry["lower_case_frac"], entry["n_frac"] = wl.extra["lower_case_frac"], wl.extra["n_frac"]
+            assert entry["hits_reverified"] and entry["expected_queries_missing"] == 0
+            if name == "cfg5" and oracle_check:
+                entry["oracle_sample"] = ("hits of the full run (same engine, all queries, L2 dual-key filter) inside the first 4 Mbp of record 0 "
+                                          "vs the oracle's Aho-Corasick automaton of all queries over that slice")
+                entry["oracle_sample_hits"] = checks.genome_slice_equal(full, wl, 4_000_000)
+                entry["oracle_sample_equal"] = True
+        entry["check_s"] = time.perf_counter() - t0
+    del wl, full
+    torch.cuda.empty_cache()
+    return entry
+
+
+def bench_e2e_file(args):
+    """File -> file: `merkurio extract -i reads.fastq -f q.txt -r -o out.fastq` (the host binary, its own process, CUDA
+    start-up included) on a synthetic FASTQ on tmpfs, via scripts/bench_cli.py (which also checks the extracted set
+    against the oracle), and the oracle's single-threaded Aho-Corasick any-hit scan of the same reads beside it."""
+    from merkurio_b200 import patterns as pt
+    from merkurio_b200.synth import Synth
+    from oracle import refmodel as rm
+    n = args.file_reads
+    shm = Path("/dev/shm") if Path("/dev/shm").is_dir() else Path("/tmp")
+    d = shm / f"mk_bench_file_{os.getpid()}"
+    out_json = d / "cli.json"
+    try:
+        d.mkdir(parents=True, exist_ok=True)
+        pr = subprocess.run([sys.executable, str(ROOT / "scripts" / "bench_cli.py"), "--config", "cfg2", "--reads", str(n), "--dir", str(d), "--out", str(out_json)],
+                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+        if pr.returncode != 0:
+            return {"error": pr.stderr[-400:]}
+        res = json.loads(out_json.read_text())
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
+    # the reference's matcher on the same reads, one thread, no parsing and no output (it can only be faster than the reference)
+    m = min(n, args.file_ref_reads)
+    syn = Synth(SEED, n, 150, K_MER, 1000)
+    pats = pt.parse_pattern_list(syn.query_list(), reverse_complement_=True)
+    seq, off = syn.host_reads(0, m)
+    ac = rm.AhoCorasick(pats)
+    t0 = time.perf_counter()
+    ac.scan_batch(seq, off, 1, False)
+    t_ref = time.perf_counter() - t0
+    best = int(np.argmin(res["runs_s"]))
+    wall, startup = res["runs_s"][best], res["engine_setup_s"][best]
+    return {"workload": f"cfg2 shape, {n} reads x 150 bp FASTQ ({res['input_bytes'] / 1e9:.2f} GB) on {shm}, extract -f q.txt -r -o out.fastq",
+            "records_per_s": n / wall, "records_per_s_after_cuda_startup": n / (wall - startup),
+            "gbases_per_s": n * 150 / wall / 1e9, "wall_s": wall, "cuda_startup_s": startup, "runs_s": res["runs_s"], "cuda_startup_of_runs_s": res["engine_setup_s"],
+            "extracted_set_equals_oracle": True, "host_cores": res["host_cores"],
+            "reference_matcher_single_thread": {"records_per_s": m / t_ref, "gbases_per_s": m * 150 / t_ref / 1e9, "reads": m, "kind": "port",
+                                                "what": "oracle Aho-Corasick any-hit scan of the same reads in memory: no parsing, no output"},
+            "speedup_vs_reference_matcher": (n / wall) / (m / t_ref), "stages_last_run": res.get("stages_last_run", [])}
+
+
+# ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
 
@@ -156,15 +345,28 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the matching engine has no CPU path")
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dctx = Dist("nccl", torch.device("cuda", local))  # barrier / max-over-ranks only: no data-path collective
-    rank, world = dctx.rank, dctx.world
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
     def barrier():
         torch.cuda.synchronize()
         dctx.barrier()
 
+    # file -> file first: the host binary is its own process with its own CUDA start-up, which is slower (and varies more)
+    # while another process holds a context and tens of GB on the same GPU — so before this process creates its context
+    e2e_file = None
+    if rank == 0 and world == 1 and not args.no_e2e_file:
+        try:
+            e2e_file = bench_e2e_file(args)
+        except Exception as ex:
+            e2e_file = {"error": repr(ex)[:300]}
+        log(f"[bench] e2e_file: {json.dumps({k: v for k, v in e2e_file.items() if k != 'stages_last_run'})}")
+    torch.cuda.set_device(local)
+    dctx = Dist("nccl", torch.device("cuda", local))  # barrier / max-over-ranks only: no data-path collective
+    assert (rank, world) == (dctx.rank, dctx.world)
     max_over_ranks, sum_over_ranks = dctx.max, dctx.sum
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # well before the first timed region
 
     n_reads, L = args.reads, args.read_len
     n_bytes = n_reads * L
@@ -213,10 +415,6 @@ def run_ours(args):
     flagged_resident = int(np.bitwise_count(fl.flags).sum())
     resident_flags = fl.flags.copy()
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
     barrier()
     t0 = time.perf_counter()
     scan_ns, dev_ns, ver_ns, n_cand = [], [], [], 0
@@ -227,22 +425,39 @@ def run_ours(args):
         n_cand = r.n_candidates
     barrier()
     t1 = time.perf_counter()
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    clocks = sampler.window(t0, t1) if rank == 0 else None
     elapsed = max_over_ranks(t1 - t0)
     value = world * n_bytes * args.steps / elapsed / 1e9
     scan_ms = float(np.mean(scan_ns)) / 1e6
     dev_ms_max = max_over_ranks(float(np.mean(dev_ns)) / 1e6)
+
+    # ---- sustained: seconds of back-to-back passes (thermal / power evidence for the burst figure) -------
+    sustained = None
+    if args.sustained_s > 0:
+        k_sus = max(int(args.sustained_s * 1e3 / max(dev_ms_max, 0.1)) + 1, args.steps)
+        barrier()
+        t0s = time.perf_counter()
+        rs = run_steps(k_sus)
+        barrier()
+        t1s = time.perf_counter()
+        el = max_over_ranks(t1s - t0s)
+        dms = np.array([x.device_ns for x in rs], dtype=np.float64) / 1e6
+        sms = np.array([x.scan_ns for x in rs], dtype=np.float64) / 1e6
+        sustained = {"steps": k_sus, "seconds": el, "value": world * n_bytes * k_sus / el / 1e9, "unit": UNIT,
+                     "device_ms_median": float(np.median(dms)), "device_ms_min": float(dms.min()), "device_ms_max": float(dms.max()),
+                     "device_ms_last_tenth_median": float(np.median(dms[-max(k_sus // 10, 1):])),
+                     "scan_ms_median": float(np.median(sms)),
+                     "scan_gbs_median": (n_bytes + (n_reads + 7) // 8) / float(np.median(sms)) / 1e6,
+                     "clocks": sampler.window(t0s, t1s) if rank == 0 else None}
 
     # ---- end to end through the C ABI from pinned host memory ---------------------------------
     e2e = None
     if not args.no_e2e:
         h_seq = torch.empty(n_bytes + 64, dtype=torch.uint8, pin_memory=True)
         h_seq.copy_(d_seq)
-        rel_off = torch.empty(batch_reads + 1, dtype=torch.int64, pin_memory=True)
-        rel_off.copy_(torch.arange(batch_reads + 1, dtype=torch.int64) * L)
         torch.cuda.synchronize()
         n_batches = (n_reads + batch_reads - 1) // batch_reads
-        base_ptr, off_ptr = h_seq.data_ptr(), rel_off.data_ptr()
+        base_ptr = h_seq.data_ptr()
 
         def e2e_pass(collect=None):
             flagged, pending = 0, []
@@ -279,11 +494,31 @@ def run_ours(args):
         barrier()
         t1e = time.perf_counter()
         el = max_over_ranks(t1e - t0e)
+        # the ceiling of that leg: the same pinned buffer copied to the device by bare cudaMemcpyAsync calls of the same
+        # size, on every rank at once (what the host's memory and PCIe fabric give N concurrent streams)
+        d_tmp = torch.empty(batch_reads * L, dtype=torch.uint8, device="cuda")
+        st = torch.cuda.Stream()
+        def h2d_pass():
+            with torch.cuda.stream(st):
+                for b in range(n_batches):
+                    nb = min(batch_reads, n_reads - b * batch_reads) * L
+                    d_tmp[:nb].copy_(h_seq[b * batch_reads * L: b * batch_reads * L + nb], non_blocking=True)
+            st.synchronize()
+        h2d_pass()
+        barrier()
+        t0c = time.perf_counter()
+        h2d_pass()
+        barrier()
+        ceil_s = max_over_ranks(time.perf_counter() - t0c)
+        ceiling = world * n_bytes / ceil_s / 1e9
+        del d_tmp
         e2e = {"value": world * n_bytes * args.e2e_steps / el / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(world * n_bytes),
                "d2h_bytes_per_step": int(world * n_batches * ((batch_reads + 63) // 64 * 8 + 16)),
                "steps": args.e2e_steps, "ms_per_step": el / args.e2e_steps * 1e3,
                "records_per_s": world * n_reads * args.e2e_steps / el,
+               "h2d_ceiling_gb_per_s": ceiling, "frac_of_h2d_ceiling": (world * n_bytes * args.e2e_steps / el / 1e9) / ceiling,
+               "h2d_ceiling_how": f"bare cudaMemcpyAsync of the same {n_batches} x {batch_reads * L} byte pieces from the same pinned buffer, all {world} ranks at once",
                "path": f"mk_scan_host_uniform/mk_scan_wait, {args.slots} slots, batches of {batch_reads} reads from pinned host memory"}
         del h_seq
 
@@ -311,15 +546,32 @@ def run_ours(args):
                "sample": f"first {sample} reads of the workload, Aho-Corasick DFA any-hit scan (oracle/mk_oracle.c), {cores} threads; "
                          f"single thread on {one} reads: {one * L / t_one / 1e9:.3f} Gbases/s",
                "single_thread_value": one * L / t_one / 1e9, "flags_equal_device": True}
+        del h, ac
 
     total_flagged = sum_over_ranks(float(flagged_resident))
+    peak, peak_src = measured_peak_gbs()
+    eng.close()
+    del d_seq, d_off
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs and the file -> file run (rank 0, N == 1) ------------------------
+    configs = None
+    if rank == 0 and world == 1:
+        if not args.no_configs:
+            configs = []
+            for name in args.configs.split(","):
+                t0c = time.perf_counter()
+                try:
+                    configs.append(bench_config(name.strip(), args.config_steps, peak))
+                except Exception as ex:  # reported, never hidden: a failed parity check must show in the line
+                    configs.append({"config": name, "error": repr(ex)[:300], "oracle_sample_equal": False})
+                log(f"[bench] {name}: {time.perf_counter() - t0c:.1f} s  {json.dumps({k: v for k, v in configs[-1].items() if k in ('kernel_ms', 'device_ms', 'frac', 'n_hits', 'oracle_sample_equal', 'error')})}")
+
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
         algo_bytes = n_bytes + (n_reads + 7) // 8  # sequence bytes + flag bitmap; offsets are only read for hits
         achieved = algo_bytes / (scan_ms / 1e3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of mk_scan_d16 from the ncu --set full capture of exactly this
-        # workload (profiles/r1_ncu_full_cfg2.txt: 15.001007 GB read + 14.089984 MB written); null for any other size
-        traffic = 15_001_007_000 + 14_089_984 if (n_reads, L, args.queries) == (100_000_000, 150, 1000) else None
+        kernel = "mk_scan_d16<ASCII, smem filter, U=4, T=896>"
+        traffic, traffic_source = ncu_traffic("mk_scan_d16", f"cfg2:{n_reads}x{L}:{args.queries}")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -330,15 +582,15 @@ def run_ours(args):
                        "l2": "per-step input (15 GB) is far larger than the 126 MB L2; no flush needed",
                        "timing": "wall clock around K passes between barriers, two in flight (mk_scan_device_submit / mk_scan_wait on alternating slots); device_ms_per_step is the CUDA-event time of one pass on its stream",
                        "records_flagged": int(total_flagged)},
-            "device_ms_per_step": dev_ms_max, "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps * world,
+            "device_ms_per_step": dev_ms_max, "clocks": clocks, "sustained": sustained, "e2e": e2e, "gpu_launches": 2 * args.steps * world,
             "kernels_per_step": {"mk_scan_d16": 1, "mk_verify_candidates": 1, "verify_ms": float(np.mean(ver_ns)) / 1e6, "candidates": int(n_cand)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "mk_scan_d16<ASCII, smem filter, U=4, T=896>", "kernel_ms": scan_ms, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_source, "kernel": kernel, "kernel_ms": scan_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(algo_bytes)},
-            "cpu_baseline": cpu,
+            "cpu_baseline": cpu, "configs": configs, "e2e_file": e2e_file, "csrc_sha16": csrc_digest(),
         }
         emit(line)
-    eng.close()
+    sampler.stop()
     dctx.close()
     return 0
 
@@ -373,6 +625,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-reads", type=int, default=16_000_000)
     ap.add_argument("--ref-sample-reads", type=int, default=8_000_000)
+    ap.add_argument("--sustained-s", type=float, default=2.5, help="seconds of back-to-back passes for the `sustained` entry (0: skip)")
+    ap.add_argument("--configs", default="cfg3,cfg4,cfg5,cfg5_verbatim_case", help="the other BASELINE configs measured into `configs` (N = 1)")
+    ap.add_argument("--config-steps", type=int, default=10)
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-e2e-file", action="store_true")
+    ap.add_argument("--file-reads", type=int, default=12_000_000, help="reads of the FASTQ of the file -> file run")
+    ap.add_argument("--file-ref-reads", type=int, default=4_000_000, help="reads the single-threaded oracle matcher is timed on")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] note: fewer than 3 warm-up steps requested; using 3")

@@ -118,12 +118,48 @@ typedef struct {
     uint32_t filter_in_smem[2];        /* 1: bitmap staged in shared memory, 0: L2-resident */
     uint64_t table_bytes[2];           /* cuckoo seed table + postings + pattern bytes */
     uint32_t sm_count;
-    uint32_t reserved;
+    uint32_t features;                 /* MK_FEATURE_* of the ASCII tables in bits 0..7, of the BAM4 tables in bits 8..15 */
 } mk_engine_info;
+#define MK_FEATURE_DUAL8 1u            /* stride-8 scan with the L2-resident dual-key filter (large query sets) */
+#define MK_FEATURE_GATE 2u             /* the query alphabet allows an alphabet gate (windows holding a byte no pattern contains are not probed) */
+
+/* Layout contract with bindings in other languages (the #[repr(C)] structs): sizes and offsets
+ * on the LP64 targets this library is built for. A change here is an ABI break. */
+#if defined(__cplusplus)
+#define MK_STATIC_ASSERT(c, m) static_assert(c, m)
+#else
+#define MK_STATIC_ASSERT(c, m) _Static_assert(c, m)
+#endif
+#include <stddef.h>
+MK_STATIC_ASSERT(sizeof(mk_patterns) == 24 && offsetof(mk_patterns, off) == 8 && offsetof(mk_patterns, n) == 16, "mk_patterns layout");
+MK_STATIC_ASSERT(sizeof(mk_config) == 32 && offsetof(mk_config, n_slots) == 8 && offsetof(mk_config, max_batch_records) == 12 &&
+                 offsetof(mk_config, max_batch_bytes) == 16 && offsetof(mk_config, hit_capacity) == 24, "mk_config layout");
+MK_STATIC_ASSERT(sizeof(mk_hit) == 16 && offsetof(mk_hit, start) == 4 && offsetof(mk_hit, pattern) == 8 && offsetof(mk_hit, len) == 12, "mk_hit layout");
+MK_STATIC_ASSERT(sizeof(mk_result) == 96 && offsetof(mk_result, n_records) == 8 && offsetof(mk_result, hits) == 16 && offsetof(mk_result, n_hits) == 24 &&
+                 offsetof(mk_result, bases_scanned) == 32 && offsetof(mk_result, device_ns) == 40 && offsetof(mk_result, scan_ns) == 48 &&
+                 offsetof(mk_result, verify_ns) == 56 && offsetof(mk_result, n_candidates) == 64 && offsetof(mk_result, n_rescans) == 72 &&
+                 offsetof(mk_result, d_record_flags) == 80 && offsetof(mk_result, d_hits) == 88, "mk_result layout");
+MK_STATIC_ASSERT(sizeof(mk_engine_info) == 104 && offsetof(mk_engine_info, seed_q) == 12 && offsetof(mk_engine_info, filter_bytes) == 56 &&
+                 offsetof(mk_engine_info, filter_in_smem) == 72 && offsetof(mk_engine_info, table_bytes) == 80 && offsetof(mk_engine_info, sm_count) == 96 &&
+                 offsetof(mk_engine_info, features) == 100, "mk_engine_info layout");
 
 int mk_engine_create(const mk_patterns* patterns, const mk_config* config, mk_engine** out);
 void mk_engine_destroy(mk_engine* e);
 int mk_engine_get_info(mk_engine* e, mk_engine_info* out);
+/* Name and flavour of the scan kernel the tables of `enc` run on ("" until a batch of that encoding was scanned);
+ * the string is valid until the calling thread's next call. For logs and the roofline report. */
+const char* mk_engine_scan_kernel(mk_engine* e, mk_encoding enc);
+
+/* Build once, upload N times: the host side of a query set (what AhoCorasick::builder()...build(list) returns in the
+ * reference, src/cmd_extract.rs:259-277) as its own object, from which one engine per GPU is created. The seed
+ * tables are built once, on host threads, while the callers create their CUDA contexts; every engine uploads its
+ * own device copy. mk_engine_create(patterns, config) == mk_tables_create + mk_engine_create_shared +
+ * mk_tables_destroy. The engines keep the tables alive: mk_tables_destroy may be called right after the last
+ * mk_engine_create_shared. Engines of one mk_tables may be created from different threads at the same time. */
+typedef struct mk_tables mk_tables;
+int mk_tables_create(const mk_patterns* patterns, int case_insensitive, mk_tables** out);
+int mk_engine_create_shared(mk_tables* tables, const mk_config* config, mk_engine** out);
+void mk_tables_destroy(mk_tables* t);
 
 /* Slot staging (pinned host memory the caller fills in place). lens_pinned may be NULL if the
  * caller never passes explicit lengths (that buffer is allocated by the first call that asks for it). */

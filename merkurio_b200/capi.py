@@ -17,6 +17,7 @@ MK_MODE_FLAG, MK_MODE_PATTERN_SET, MK_MODE_ALL_HITS = 0, 1, 2
 EXPORTS = (
     "mk_engine_create", "mk_engine_destroy", "mk_engine_get_info", "mk_slot_buffers", "mk_scan_submit",
     "mk_scan_wait", "mk_scan_host", "mk_scan_device", "mk_scan_device_submit", "mk_scan_host_uniform", "mk_last_error", "mk_version",
+    "mk_engine_scan_kernel", "mk_tables_create", "mk_engine_create_shared", "mk_tables_destroy",
 )
 
 
@@ -43,7 +44,7 @@ class MkEngineInfo(C.Structure):
                 ("filter_log2_bits", C.c_uint32 * 2), ("filter_hashes", C.c_uint32 * 2),
                 ("filter_bytes", C.c_uint64 * 2),
                 ("filter_in_smem", C.c_uint32 * 2), ("table_bytes", C.c_uint64 * 2),
-                ("sm_count", C.c_uint32), ("reserved", C.c_uint32)]
+                ("sm_count", C.c_uint32), ("features", C.c_uint32)]
 
 
 HIT_DTYPE = np.dtype([("record", "<u4"), ("start", "<u4"), ("pattern", "<u4"), ("len", "<u4")])
@@ -88,6 +89,14 @@ def load():
         L.mk_scan_device_submit.restype = C.c_int
         L.mk_scan_host_uniform.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
         L.mk_scan_host_uniform.restype = C.c_int
+        L.mk_engine_scan_kernel.argtypes = [C.c_void_p, C.c_int]
+        L.mk_engine_scan_kernel.restype = C.c_char_p
+        L.mk_tables_create.argtypes = [C.POINTER(MkPatterns), C.c_int, C.POINTER(C.c_void_p)]
+        L.mk_tables_create.restype = C.c_int
+        L.mk_engine_create_shared.argtypes = [C.c_void_p, C.POINTER(MkConfig), C.POINTER(C.c_void_p)]
+        L.mk_engine_create_shared.restype = C.c_int
+        L.mk_tables_destroy.argtypes = [C.c_void_p]
+        L.mk_tables_destroy.restype = None
         L.mk_last_error.argtypes = []
         L.mk_last_error.restype = C.c_char_p
         L.mk_version.argtypes = []
@@ -173,6 +182,10 @@ class Engine:
         out = MkEngineInfo()
         _check(load().mk_engine_get_info(self._h, C.byref(out)))
         return out
+
+    def scan_kernel(self, enc: int = MK_ENC_ASCII) -> str:
+        """Name of the scan kernel of that encoding's tables ("" before the first batch)."""
+        return load().mk_engine_scan_kernel(self._h, enc).decode()
 
     # -- pinned slot path (mk_slot_buffers / mk_scan_submit / mk_scan_wait) ------------------------
     def slot_arrays(self, slot: int):

@@ -147,6 +147,17 @@ MK_HD void mk_bloom_masks_g(uint32_t g, uint32_t* lo, uint32_t* hi) {
 MK_HD uint32_t mk_dual_block(uint32_t short_code, uint32_t nblocks) { return mk_bloom_block(short_code, nblocks); }
 MK_HD uint32_t mk_dual_g_short(uint32_t short_code) { return short_code * MK_BLOOM_MUL * MK_BLOOM_MUL2; }
 MK_HD uint32_t mk_dual_g_long(uint32_t code16) { return (code16 ^ (code16 >> 15)) * MK_DUAL_MUL_LONG; }
+// mk_scan_dual8's flavour of the dual-key filter: 3 bits per key (two in the low word of the block, one in the high
+// word) taken from the top bits of one product, so that a test is three shifts-by-register and one AND — this
+// kernel is bound by its integer instructions as much as by its gathers (profiles/r2_cfg5_experiments/).
+#define MK_DUAL3_MUL_SHORT 0x85EBCA77u
+#define MK_DUAL3_MUL_LONG 0xCC9E2D51u
+MK_HD uint32_t mk_dual3_g_short(uint32_t short_code) { return short_code * MK_DUAL3_MUL_SHORT; }
+MK_HD uint32_t mk_dual3_g_long(uint32_t code16) { return code16 * MK_DUAL3_MUL_LONG; }
+MK_HD void mk_dual3_masks(uint32_t g, uint32_t* lo, uint32_t* hi) {
+    *lo = (1u << (g >> 27)) | (1u << ((g >> 22) & 31));
+    *hi = 1u << ((g >> 17) & 31);
+}
 // key of the cuckoo seed table: the group is folded into the hashed value
 MK_HD uint32_t mk_group_key(uint32_t code, uint32_t group) { return group ? (code ^ 0x3C6EF372u) : code; }
 // Shared-memory flavour with 32-bit blocks and 3 bits per key (small seed sets): one LDS.32 per probe.

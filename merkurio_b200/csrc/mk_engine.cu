@@ -6,8 +6,10 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <future>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -74,14 +76,13 @@ struct PinBuf {
 
 struct DeviceTables {
     bool built = false;
-    mk::Tables host;
-    std::future<mk::Tables> pending;  // large pattern sets: built on a host thread while CUDA starts up
+    const mk::Tables* host = nullptr;  // owned by the engine's mk_tables
     DevBuf<uint32_t> filter, filter2, postings, pat_off;
     DevBuf<mk::SeedSlot> slots;
     DevBuf<uint8_t> pat_bytes;
     uint64_t bytes() const {
-        return host.slots.size() * sizeof(mk::SeedSlot) + host.postings.size() * 4 + host.pat_bytes.size() +
-               host.pat_off.size() * 4 + host.filter.size() * 4 + host.filter2.size() * 4;
+        return host->slots.size() * sizeof(mk::SeedSlot) + host->postings.size() * 4 + host->pat_bytes.size() +
+               host->pat_off.size() * 4 + host->filter.size() * 4 + host->filter2.size() * 4;
     }
 };
 
@@ -135,12 +136,46 @@ struct Slot {
 
 }  // namespace
 
+// The host side of a query set: pattern bytes and the seed tables of both encodings, built once (on demand, on
+// host threads for large sets) and shared by every engine created from it — one engine per GPU uploads its own
+// device copy. Reference-counted: the engines hold it alive after mk_tables_destroy.
+struct mk_tables {
+    mk::PatternSet ps;
+    std::mutex mu;
+    mk::Tables host[2];
+    bool built[2] = {false, false};
+    std::future<mk::Tables> pending[2];
+    std::atomic<int> refs{1};
+
+    void start_async() {  // large query sets take seconds to index: start now, whichever encoding will be scanned
+        for (int enc = 0; enc < 2; ++enc)
+            pending[enc] = std::async(std::launch::async, [this, enc] { return mk::build_tables(ps, enc); });
+    }
+    // the tables of one encoding (thread-safe; throws what the builder throws)
+    const mk::Tables* get(int enc) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!built[enc]) {
+            if (pending[enc].valid()) host[enc] = pending[enc].get();
+            else host[enc] = mk::build_tables(ps, enc);
+            built[enc] = true;
+        }
+        return &host[enc];
+    }
+    void release() {
+        if (refs.fetch_sub(1) == 1) {
+            for (auto& f : pending) if (f.valid()) f.wait();
+            delete this;
+        }
+    }
+};
+
 struct mk_engine {
     int device = 0;
     int sm_count = 0;
     mk_config cfg{};
-    mk::PatternSet ps;
+    mk_tables* tab = nullptr;
     DeviceTables tables[2];
+    ~mk_engine() { if (tab) tab->release(); }
     DevBuf<uint32_t> tie_rank;
     std::vector<std::unique_ptr<Slot>> slots;
     Workspace direct;  // mk_scan_device
@@ -214,7 +249,28 @@ ScanLaunch pick_by_d(uint32_t d) {
     }
 }
 
-ScanLaunch pick_kernel(int enc, uint32_t d, bool smemf, bool win = false, bool f32 = false) {
+// Stride 8, ASCII, L2-resident dual-key filter (large query sets). MK_DUAL_SHAPE picks another launch shape
+// (tuning runs only).
+ScanLaunch pick_dual8(bool gate) {
+    // measured (cfg5, upper-case queries, scan ms): U=2 T=1024: 1.06, U=4 T=768: 1.08, U=4 T=512: 1.14
+    static const int shape = std::getenv("MK_DUAL_SHAPE") ? std::atoi(std::getenv("MK_DUAL_SHAPE")) : 1;
+    switch (shape) {
+        case 0: return gate ? ScanLaunch{mk::mk_scan_dual8<4, 512, true>, 512, 4 * 32} : ScanLaunch{mk::mk_scan_dual8<4, 512, false>, 512, 4 * 32};
+        case 2: return gate ? ScanLaunch{mk::mk_scan_dual8<4, 768, true>, 768, 4 * 32} : ScanLaunch{mk::mk_scan_dual8<4, 768, false>, 768, 4 * 32};
+        case 3: return gate ? ScanLaunch{mk::mk_scan_dual8<2, 512, true>, 512, 2 * 32} : ScanLaunch{mk::mk_scan_dual8<2, 512, false>, 512, 2 * 32};
+        default: return gate ? ScanLaunch{mk::mk_scan_dual8<2, 1024, true>, 1024, 2 * 32} : ScanLaunch{mk::mk_scan_dual8<2, 1024, false>, 1024, 2 * 32};
+    }
+}
+
+// The scan kernel of a table set
+ScanLaunch pick_kernel(int enc, uint32_t d, bool smemf, bool win = false, bool f32 = false);
+ScanLaunch pick_kernel(const mk::Tables& t) {
+    if (t.dual_perm) return pick_dual8(t.gate_mask != 0);
+    return pick_kernel(t.enc, t.d, t.filter_in_smem, t.win, t.filter32);
+}
+size_t scan_smem_bytes(const mk::Tables& t) { return t.filter_in_smem ? t.filter.size() * 4 : 0; }
+
+ScanLaunch pick_kernel(int enc, uint32_t d, bool smemf, bool win, bool f32) {
     if (f32) {  // shared-memory filter with 32-bit blocks (small seed sets)
         if (win) {
             if (enc == MK_ENC_ASCII && d == 8) return {mk::mk_scan_win<MK_ENC_ASCII, 8, 4, 896, true>, 896, 4 * 32};
@@ -276,25 +332,21 @@ int ensure_tables(mk_engine* e, int enc) {
     DeviceTables& dt = e->tables[enc];
     if (dt.built) return MK_OK;
     try {
-        if (dt.pending.valid()) dt.host = dt.pending.get();
-        else dt.host = mk::build_tables(e->ps, enc);
-        // the tables of the other encoding are only needed if that encoding shows up: drop a pending build
-        DeviceTables& other = e->tables[1 - enc];
-        if (other.pending.valid()) { other.pending.wait(); other.pending = std::future<mk::Tables>(); }
+        dt.host = e->tab->get(enc);
     } catch (const std::bad_alloc&) {
         return fail(MK_ERR_NOMEM, "out of host memory while building the seed tables");
     } catch (const std::exception& ex) {
         return fail(MK_ERR_INVALID, "table build failed: %s", ex.what());
     }
-    CU(dt.filter.upload(dt.host.filter));
-    if (!dt.host.filter2.empty()) CU(dt.filter2.upload(dt.host.filter2));
-    CU(dt.postings.upload(dt.host.postings));
-    CU(dt.pat_off.upload(dt.host.pat_off));
-    CU(dt.slots.upload(dt.host.slots));
-    CU(dt.pat_bytes.upload(dt.host.pat_bytes));
-    ScanLaunch k = pick_kernel(enc, dt.host.d, dt.host.filter_in_smem, dt.host.win, dt.host.filter32);
-    if (dt.host.filter_in_smem)
-        CU(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(dt.host.filter.size() * 4)));
+    CU(dt.filter.upload(dt.host->filter));
+    if (!dt.host->filter2.empty()) CU(dt.filter2.upload(dt.host->filter2));
+    CU(dt.postings.upload(dt.host->postings));
+    CU(dt.pat_off.upload(dt.host->pat_off));
+    CU(dt.slots.upload(dt.host->slots));
+    CU(dt.pat_bytes.upload(dt.host->pat_bytes));
+    ScanLaunch k = pick_kernel(*dt.host);
+    if (scan_smem_bytes(*dt.host))
+        CU(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(*dt.host)));
     dt.built = true;
     return MK_OK;
 }
@@ -304,14 +356,14 @@ int ensure_tables(mk_engine* e, int enc) {
 int enqueue_sort(mk_engine* e, Workspace& ws, bool buckets) {
     DeviceTables& dt = e->tables[ws.enc];
     const uint32_t key_bits = ws.key_bits;
-    const uint32_t len_tie_bits = e->ps.len_bits + e->ps.tie_bits;
+    const uint32_t len_tie_bits = e->tab->ps.len_bits + e->tab->ps.tie_bits;
     const unsigned long long* cnt = ws.counters.p;
     ws.used_buckets = buckets;
     if (buckets) {
         // the largest key of the batch: ALL_HITS (end <= n_units | len field | tie), PATTERN_SET (record | pattern)
         const unsigned long long max_key = ws.mode == MK_MODE_ALL_HITS
                                                ? ((((unsigned long long)ws.n_units + 1) << len_tie_bits) - 1)
-                                               : ((((unsigned long long)ws.n_records) << mk::bits_for(e->ps.n ? e->ps.n - 1 : 0)) - 1);
+                                               : ((((unsigned long long)ws.n_records) << mk::bits_for(e->tab->ps.n ? e->tab->ps.n - 1 : 0)) - 1);
         const mk::BucketMap shift = mk::make_bucket_map(max_key);
         (void)key_bits;
         uint32_t* bcount = ws.buckets.p;
@@ -353,17 +405,34 @@ int enqueue_sort(mk_engine* e, Workspace& ws, bool buckets) {
     return MK_OK;
 }
 
+// Candidate positions travel from the scan to the verify kernel as 32-bit grid indices (position / pos_mul):
+// vector index * seeds per vector for the stride-16 scan, vector index * windows per vector for the window
+// scans, the base position itself for the ordered scan. A batch whose last index does not fit is refused
+// (MK_ERR_CAPACITY) instead of being verified at wrapped positions; INTEGRATION.md lists the limits.
+int check_position_range(const mk::Tables& t, mk_encoding enc, uint64_t n_units) {
+    const uint64_t seq_bytes = enc == MK_ENC_ASCII ? n_units : (n_units + 1) / 2;
+    const uint64_t n_vec = (seq_bytes + 15) / 16;
+    if (n_vec > 0xFFFFFFF0ull) return fail(MK_ERR_CAPACITY, "batch larger than 64 GiB of sequence");
+    uint64_t per_vec;  // grid indices per 16-byte vector
+    if (t.d == 16) per_vec = enc == MK_ENC_ASCII ? 1 : 2;
+    else if (t.win) per_vec = (enc == MK_ENC_ASCII ? 16 : 32) / t.d;
+    else return n_units >= (1ull << 32) ? fail(MK_ERR_CAPACITY, "batches of 2^32 bases or more need patterns of at least 31 bases; split the batch") : MK_OK;
+    if (n_vec * per_vec >= (1ull << 32))
+        return fail(MK_ERR_CAPACITY, "batch of %llu bases exceeds the 32-bit candidate index of this query set (seed stride %u: at most %llu bases per batch); split the batch",
+                    (unsigned long long)n_units, t.d, (unsigned long long)(((1ull << 32) / per_vec - 1) * (enc == MK_ENC_ASCII ? 16 : 32)));
+    return MK_OK;
+}
+
 // Enqueue the device work of one batch on ws.stream (no host synchronisation).
 int enqueue(mk_engine* e, Workspace& ws) {
     DeviceTables& dt = e->tables[ws.enc];
-    const mk::Tables& t = dt.host;
+    const mk::Tables& t = *dt.host;
     const uint64_t seq_bytes = ws.enc == MK_ENC_ASCII ? ws.n_units : (ws.n_units + 1) / 2;
     const size_t flag_words32 = ((size_t)ws.n_records + 63) / 64 * 2;
 
     mk::ScanParams P{};
     P.text = reinterpret_cast<const uint4*>(ws.d_seq);
     P.n_units = ws.n_units;
-    if ((seq_bytes + 15) / 16 > 0xFFFFFFF0ull) return fail(MK_ERR_CAPACITY, "batch larger than 64 GiB of sequence");
     P.n_vec = (uint32_t)((seq_bytes + 15) / 16);
     P.off = ws.d_off;
     P.lens = ws.d_lens;
@@ -381,11 +450,15 @@ int enqueue(mk_engine* e, Workspace& ws) {
     P.pat_off = dt.pat_off.p;
     P.tie_rank = e->tie_rank.p;
     P.q = t.q;
-    P.short_shift = (t.perm || t.win) ? 0u : 32u - 2u * t.q;
+    P.short_shift = (t.perm || t.win || t.dual_perm) ? 0u : 32u - 2u * t.q;
     P.win_mask0 = t.win_mask0;
     P.win_mask1 = t.win_mask1;
     P.has_long = t.q2 ? 1u : 0u;
-    P.case_insensitive = e->ps.case_insensitive ? 1 : 0;
+    P.case_insensitive = e->tab->ps.case_insensitive ? 1 : 0;
+    P.short_mask = t.dual_perm ? t.win_mask0 : 0xFFFFFFFFu;
+    P.pos_flags2 = t.dual_perm ? 1u : 0u;
+    P.gate_mask = t.gate_mask;
+    P.gate_val = t.gate_val;
     P.cand = ws.cand.p;
     P.cand_capacity = ws.cand_cap;
     P.cand_count = ws.counters.p + 2;
@@ -395,10 +468,10 @@ int enqueue(mk_engine* e, Workspace& ws) {
     P.hit_capacity = ws.hit_cap;
     P.hit_count = ws.counters.p;
     P.mode = ws.mode;
-    P.len_bits = e->ps.len_bits;
-    P.tie_bits = e->ps.tie_bits;
-    P.pat_bits = mk::bits_for(e->ps.n ? e->ps.n - 1 : 0);
-    P.max_len = e->ps.max_len;
+    P.len_bits = e->tab->ps.len_bits;
+    P.tie_bits = e->tab->ps.tie_bits;
+    P.pat_bits = mk::bits_for(e->tab->ps.n ? e->tab->ps.n - 1 : 0);
+    P.max_len = e->tab->ps.max_len;
 
     uint32_t key_bits;
     if (ws.mode == MK_MODE_ALL_HITS) key_bits = mk::bits_for(ws.n_units) + P.len_bits + P.tie_bits;
@@ -406,19 +479,19 @@ int enqueue(mk_engine* e, Workspace& ws) {
     if (ws.mode != MK_MODE_FLAG && key_bits > 64)
         return fail(MK_ERR_CAPACITY, "batch too large for the 64-bit hit sort key (%u bits)", key_bits);
 
-    if (t.d != 16 && !t.win && ws.n_units >= (1ull << 32))
-        return fail(MK_ERR_CAPACITY, "batches of 2^32 bases or more need patterns of at least 31 bases; split the batch");
+    int rc_pos = check_position_range(t, ws.enc, ws.n_units);
+    if (rc_pos) return rc_pos;
+    // device_ns is the device work of the batch: clearing the flags and counters belongs to it
+    CU(cudaEventRecord(ws.ev_begin, ws.stream));
     CU(cudaMemsetAsync(ws.flags.p, 0, flag_words32 * 4, ws.stream));
     CU(cudaMemsetAsync(ws.counters.p, 0, 8 * sizeof(unsigned long long), ws.stream));
-    CU(cudaEventRecord(ws.ev_begin, ws.stream));
     if (P.n_vec > 0 && ws.n_records > 0) {
-        ScanLaunch k = pick_kernel(ws.enc, t.d, t.filter_in_smem, t.win, t.filter32);
+        ScanLaunch k = pick_kernel(t);
         const uint64_t warps = k.threads / 32;
         uint64_t tiles = ((uint64_t)P.n_vec + k.tile_vecs - 1) / k.tile_vecs;
         uint64_t want = (tiles + warps - 1) / warps;
         int grid = (int)std::min<uint64_t>((uint64_t)e->sm_count, std::max<uint64_t>(want, 1));
-        size_t smem = t.filter_in_smem ? t.filter.size() * 4 : 0;
-        k.fn<<<grid, k.threads, smem, ws.stream>>>(P);
+        k.fn<<<grid, k.threads, scan_smem_bytes(t), ws.stream>>>(P);
         CU(cudaEventRecord(ws.ev_scan, ws.stream));
         if (ws.enc == MK_ENC_ASCII) mk::mk_verify_candidates<MK_ENC_ASCII><<<e->sm_count * 8, 256, 0, ws.stream>>>(P);
         else mk::mk_verify_candidates<MK_ENC_BAM4><<<e->sm_count * 8, 256, 0, ws.stream>>>(P);
@@ -446,6 +519,8 @@ int begin_batch(mk_engine* e, Workspace& ws, const void* d_seq, const unsigned l
     if (mode != MK_MODE_FLAG && mode != MK_MODE_PATTERN_SET && mode != MK_MODE_ALL_HITS)
         return fail(MK_ERR_INVALID, "unknown mode %d", (int)mode);
     int rc = ensure_tables(e, enc);
+    if (rc) return rc;
+    rc = check_position_range(*e->tables[enc].host, enc, n_units);  // before anything is sized for the batch
     if (rc) return rc;
     ws.d_seq = d_seq; ws.d_off = d_off; ws.d_lens = d_lens;
     ws.n_records = n_records; ws.n_units = n_units; ws.enc = enc; ws.mode = mode; ws.fetch = fetch;
@@ -568,9 +643,7 @@ extern "C" {
 const char* mk_last_error(void) { return g_err.c_str(); }
 const char* mk_version(void) { return "merkurio-b200 0.1.0 (sm_100a)"; }
 
-int mk_engine_create(const mk_patterns* patterns, const mk_config* config, mk_engine** out) {
-    if (!patterns || !config || !out) return fail(MK_ERR_INVALID, "null argument");
-    *out = nullptr;
+static int check_patterns(const mk_patterns* patterns) {
     if (patterns->n == 0) return fail(MK_ERR_NO_PATTERNS, "No k-mers found in file or provided sequence.");
     if (!patterns->bytes || !patterns->off) return fail(MK_ERR_INVALID, "null pattern storage");
     if (patterns->n > mk::kMaxPatternId) return fail(MK_ERR_INVALID, "too many patterns (%u)", patterns->n);
@@ -578,21 +651,53 @@ int mk_engine_create(const mk_patterns* patterns, const mk_config* config, mk_en
         if (patterns->off[p + 1] < patterns->off[p]) return fail(MK_ERR_INVALID, "pattern offsets must be non-decreasing");
         if (patterns->off[p + 1] == patterns->off[p]) return fail(MK_ERR_EMPTY_PATTERN, "Pattern is empty.");
     }
-    std::unique_ptr<mk_engine> e(new (std::nothrow) mk_engine);
-    if (!e) return fail(MK_ERR_NOMEM, "out of memory");
+    return MK_OK;
+}
+
+int mk_tables_create(const mk_patterns* patterns, int case_insensitive, mk_tables** out) {
+    if (!patterns || !out) return fail(MK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int rc = check_patterns(patterns);
+    if (rc) return rc;
+    std::unique_ptr<mk_tables> t(new (std::nothrow) mk_tables);
+    if (!t) return fail(MK_ERR_NOMEM, "out of memory");
     try {
-        e->ps = mk::make_pattern_set(patterns->bytes, patterns->off, patterns->n, config->case_insensitive != 0);
+        t->ps = mk::make_pattern_set(patterns->bytes, patterns->off, patterns->n, case_insensitive != 0);
     } catch (const std::bad_alloc&) {
         return fail(MK_ERR_NOMEM, "out of host memory");
     }
-    // Large query sets take seconds to index (sort + cuckoo insertion): do it on host threads now, while
-    // the CUDA context is created below (also seconds on a multi-GPU box). Which encoding the caller
-    // will scan is not known yet, so both are prepared; the unused one is dropped at the first scan.
-    if (patterns->n >= 50000 && !std::getenv("MK_NO_ASYNC_TABLES")) {
-        const mk::PatternSet* ps = &e->ps;
-        for (int enc = 0; enc < 2; ++enc)
-            e->tables[enc].pending = std::async(std::launch::async, [ps, enc] { return mk::build_tables(*ps, enc); });
-    }
+    // Large query sets take seconds to index (sort + cuckoo insertion): do it on host threads now, while the
+    // caller creates CUDA contexts (also seconds on a multi-GPU box). Which encoding will be scanned is not
+    // known yet, so both are prepared.
+    if (patterns->n >= 50000 && !std::getenv("MK_NO_ASYNC_TABLES")) t->start_async();
+    *out = t.release();
+    return MK_OK;
+}
+
+void mk_tables_destroy(mk_tables* t) {
+    if (t) t->release();
+}
+
+int mk_engine_create(const mk_patterns* patterns, const mk_config* config, mk_engine** out) {
+    if (!patterns || !config || !out) return fail(MK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    mk_tables* t = nullptr;
+    int rc = mk_tables_create(patterns, config->case_insensitive, &t);
+    if (rc) return rc;
+    rc = mk_engine_create_shared(t, config, out);
+    mk_tables_destroy(t);  // the engine holds its own reference
+    return rc;
+}
+
+int mk_engine_create_shared(mk_tables* tables, const mk_config* config, mk_engine** out) {
+    if (!tables || !config || !out) return fail(MK_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if ((config->case_insensitive != 0) != tables->ps.case_insensitive)
+        return fail(MK_ERR_INVALID, "mk_config.case_insensitive differs from the value the tables were created with");
+    std::unique_ptr<mk_engine> e(new (std::nothrow) mk_engine);
+    if (!e) return fail(MK_ERR_NOMEM, "out of memory");
+    tables->refs.fetch_add(1);
+    e->tab = tables;
     // MERKURIO_TIMING / MK_TIMING: where the start-up time goes (driver initialisation, context, allocations)
     const bool timing = std::getenv("MERKURIO_TIMING") || std::getenv("MK_TIMING");
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -625,7 +730,7 @@ int mk_engine_create(const mk_patterns* patterns, const mk_config* config, mk_en
     e->device = config->device;
     e->cfg = *config;
     CU(cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, e->device));
-    CU(e->tie_rank.upload(e->ps.tie_rank));
+    CU(e->tie_rank.upload(e->tab->ps.tie_rank));
     int rc = init_workspace(e->direct);
     if (rc) return rc;
     const double t_c3 = now();
@@ -659,23 +764,47 @@ void mk_engine_destroy(mk_engine* e) {
 int mk_engine_get_info(mk_engine* e, mk_engine_info* out) {
     if (!e || !out) return fail(MK_ERR_INVALID, "null argument");
     *out = mk_engine_info{};
-    out->n_patterns = e->ps.n;
-    out->min_len = e->ps.min_len;
-    out->max_len = e->ps.max_len;
+    out->n_patterns = e->tab->ps.n;
+    out->min_len = e->tab->ps.min_len;
+    out->max_len = e->tab->ps.max_len;
     out->sm_count = (uint32_t)e->sm_count;
+    for (int enc = 0; enc < 2; ++enc)
+        if (e->tables[enc].built) {
+            const mk::Tables& t = *e->tables[enc].host;
+            out->features |= ((t.dual_perm ? MK_FEATURE_DUAL8 : 0u) | (t.gate_mask ? MK_FEATURE_GATE : 0u)) << (8 * enc);
+        }
     for (int enc = 0; enc < 2; ++enc) {
         const DeviceTables& dt = e->tables[enc];
         if (!dt.built) continue;
-        out->seed_q[enc] = dt.host.q;
-        out->seed_d[enc] = dt.host.d;
-        out->n_seeds[enc] = dt.host.n_seeds;
-        out->filter_log2_bits[enc] = dt.host.filter_in_smem ? 0 : dt.host.filter_log2_bits;
-        out->filter_bytes[enc] = dt.host.filter.size() * 4;
-        out->filter_hashes[enc] = dt.host.filter_hashes;
-        out->filter_in_smem[enc] = dt.host.filter_in_smem ? 1 : 0;
+        out->seed_q[enc] = dt.host->q;
+        out->seed_d[enc] = dt.host->d;
+        out->n_seeds[enc] = dt.host->n_seeds;
+        out->filter_log2_bits[enc] = dt.host->filter_in_smem ? 0 : dt.host->filter_log2_bits;
+        out->filter_bytes[enc] = dt.host->filter.size() * 4;
+        out->filter_hashes[enc] = dt.host->filter_hashes;
+        out->filter_in_smem[enc] = dt.host->filter_in_smem ? 1 : 0;
         out->table_bytes[enc] = dt.bytes();
     }
     return MK_OK;
+}
+
+const char* mk_engine_scan_kernel(mk_engine* e, mk_encoding enc) {
+    thread_local std::string name;
+    name.clear();
+    if (!e || (enc != MK_ENC_ASCII && enc != MK_ENC_BAM4) || !e->tables[enc].built) return "";
+    const mk::Tables& t = *e->tables[enc].host;
+    const char* en = enc == MK_ENC_ASCII ? "ASCII" : "BAM4";
+    char buf[160];
+    if (t.dual_perm)
+        std::snprintf(buf, sizeof buf, "mk_scan_dual8<%s, stride 8, L2 dual-key filter%s>", en, t.gate_mask ? ", alphabet gate" : "");
+    else if (t.d == 16)
+        std::snprintf(buf, sizeof buf, "mk_scan_d16<%s, %s>", en, t.filter_in_smem ? (t.filter32 ? "smem filter 32-bit blocks" : "smem filter 64-bit blocks") : "L2 bitmap");
+    else if (t.win)
+        std::snprintf(buf, sizeof buf, "mk_scan_win<%s, stride %u, smem filter %s>", en, t.d, t.filter32 ? "32-bit blocks" : "64-bit blocks");
+    else
+        std::snprintf(buf, sizeof buf, "mk_scan_ord<%s, stride %u, %s>", en, t.d, t.filter_in_smem ? "smem filter" : (t.filter_dual ? "L2 dual-key filter" : "L2 bitmap"));
+    name = buf;
+    return name.c_str();
 }
 
 int mk_slot_buffers(mk_engine* e, uint32_t slot, uint8_t** seq_pinned, uint64_t** off_pinned, uint32_t** lens_pinned) {

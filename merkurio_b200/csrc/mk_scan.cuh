@@ -51,6 +51,9 @@ struct ScanParams {
     uint32_t win_mask0, win_mask1;  // mk_scan_win: the q bases of a window that form the seed (ASCII: code bits; BAM4: the two words)
     uint32_t has_long;              // 1: patterns of the long group are keyed by the whole 16-base window
     int case_insensitive;
+    uint32_t short_mask;            // candidate code -> short seed code: (code >> short_shift) & short_mask
+    uint32_t pos_flags2;            // 1: bit 1 of a candidate position says "only the short key passed" (mk_scan_dual8)
+    uint32_t gate_mask, gate_val;   // alphabet gate (mk_scan_dual8): byte b with (b ^ gate_val) & gate_mask != 0 occurs in no pattern (per byte lane)
     // candidates: seeds that passed both filters, handed from the scan to the verify kernel
     uint2* cand;                    // {seed position / pos_mul, seed code}
     unsigned long long cand_capacity;
@@ -322,13 +325,17 @@ __device__ __forceinline__ void verify_postings(const ScanParams& P, uint64_t po
 // scans (its q-base prefix is the short key, the whole window the long key).
 template <int ENC>
 __device__ __forceinline__ void verify_seed(const ScanParams& P, uint64_t pos, uint32_t code, HitSink& sink) {
-    bool long_only = false;
-    if (P.has_long) {  // bit 0 of the position is a flag of the scan (the stride is even)
+    bool long_only = false, short_only = false;
+    if (P.pos_flags2) {  // mk_scan_dual8 (stride 8): bits 0..1 of the position say which single key passed, if only one did
+        long_only = pos & 1u;
+        short_only = pos & 2u;
+        pos &= ~3ull;
+    } else if (P.has_long) {  // bit 0 of the position is a flag of the scan (the stride is even)
         long_only = pos & 1u;
         pos &= ~1ull;
     }
-    uint32_t f_long = P.has_long ? seed_lookup(P, code, 1u) : kEmptySlot;
-    uint32_t f_short = long_only ? kEmptySlot : seed_lookup(P, code >> P.short_shift, 0u);
+    uint32_t f_long = (P.has_long && !short_only) ? seed_lookup(P, code, 1u) : kEmptySlot;
+    uint32_t f_short = long_only ? kEmptySlot : seed_lookup(P, (code >> P.short_shift) & P.short_mask, 0u);
     if (f_long != kEmptySlot) verify_postings<ENC>(P, pos, f_long, sink);
     if (f_short != kEmptySlot) verify_postings<ENC>(P, pos, f_short, sink);
 }
@@ -717,6 +724,165 @@ __global__ void __launch_bounds__(kScanThreads, 1) mk_scan_ord(const __grid_cons
                 }
             }
         }
+    }
+    queue_flush(P, wq, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// D == 8, ASCII, L2-resident dual-key filter: query sets far too large for shared memory (BASELINE cfg5: a
+// million queries of 21..63 bases, 8 million seeds). Two things bound this kernel, and it is written around both:
+//   * gathers: every probe is a lane-divergent 8-byte load, and an SM retires about one of those per cycle whatever
+//     the path (global, texture or distributed shared memory: scripts/micro/gather_bench.cu,
+//     profiles/r2_gather_bench.txt) against ten per cycle from its own shared memory, which 8 million keys do not
+//     fit. The alphabet gate removes the probes that cannot succeed: a window whose first q bytes hold a byte that
+//     occurs in no pattern (lower-case soft-masked spans against an upper-case k-mer list, N runs, ...) cannot
+//     start a seed — exact, tested on the raw bytes, one OR-chain per tile in the common all-clean case.
+//   * integer instructions (the first version ran at 84 % of the ALU pipe: profiles/r2_cfg5_experiments/): keys in
+//     the permuted window layout (8 instead of 22 operations per packed unit, a window is two shifts and a select),
+//     3-bit filter entries addressed by the top bits of one product (a test is six shifts and an AND), multiplies
+//     instead of shift-or wherever the two are the same (they issue on the other pipe), tiles without a live window
+//     left after the gate are dropped before anything is packed.
+// Same tile loop as the other scans (two tiles in flight per lane), all gathers of a tile issued before the first
+// one is consumed, candidates queued with one shared-memory atomic per lane that holds any.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dual3_test(uint2 w, uint32_t g) {  // bit 0: all three bits of the key are set
+    return __funnelshift_r(w.x, 0u, g >> 27) & __funnelshift_r(w.x, 0u, g >> 22) & __funnelshift_r(w.y, 0u, g >> 17);
+}
+
+template <int U, bool GATE>
+__device__ __forceinline__ void process_tile_dual8(const ScanParams& P, const uint4 (&v)[U], const uint4& halo, uint32_t v0,
+                                                   WarpQueue& wq, uint32_t lane) {
+    constexpr int K = 2 * U;
+    const uint32_t nblocks = P.filter_blocks, has_long = P.has_long, smask = P.win_mask0;
+    // gate: bit k of `dead` = window k holds a byte no pattern contains within its first 12 (<= q) bytes
+    uint32_t dead = 0;
+    if (GATE) {
+        const uint32_t M = P.gate_mask, V = P.gate_val;
+        uint32_t acc = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc |= (v[u].x ^ V) | (v[u].y ^ V) | (v[u].z ^ V) | (v[u].w ^ V);
+        if (lane == 31) acc |= (halo.x ^ V);  // the bytes the last window of the tile reaches into
+        if (__any_sync(0xFFFFFFFFu, (acc & M) != 0)) {
+            // rare: a span of foreign bytes (soft-masked, N, ...) starts, ends or runs through this tile
+            uint32_t head_votes[U + 1], tail_bad = 0;
+#pragma unroll
+            for (int u = 0; u <= U; ++u) {
+                const uint4& x = (u < U) ? v[u] : halo;
+                const bool head = ((x.x ^ V) & M) != 0;  // bytes 0..3: what the window that starts 8 bytes earlier sees of this vector
+                if (u < U) {
+                    head_votes[u] = __ballot_sync(0xFFFFFFFFu, head);
+                    if ((((x.x ^ V) | (x.y ^ V) | (x.z ^ V)) & M) != 0) dead |= 1u << (2 * u);  // bytes 0..11
+                    if ((((x.z ^ V) | (x.w ^ V)) & M) != 0) tail_bad |= 1u << u;                // bytes 8..15
+                } else {
+                    head_votes[u] = head ? 1u : 0u;  // lane 31's halo vector
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t next_head = (lane == 31) ? (head_votes[u + 1] & 1u) : ((head_votes[u] >> (lane + 1)) & 1u);
+                if (((tail_bad >> u) & 1u) | next_head) dead |= 2u << (2 * u);
+            }
+            if (__all_sync(0xFFFFFFFFu, dead == (1u << K) - 1u)) return;  // nothing in this tile can match
+        }
+    }
+    uint32_t c[U + 1];
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = mk_pack_ascii_perm(v[u].x, v[u].y, v[u].z, v[u].w);
+    c[U] = mk_pack_ascii_perm(halo.x, halo.y, halo.z, halo.w);  // meaningful in lane 31 only
+    uint32_t win[K];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint32_t from_next_lane = __shfl_down_sync(0xFFFFFFFFu, c[u], 1);
+        const uint32_t from_next_row = (u + 1 < U) ? __shfl_sync(0xFFFFFFFFu, c[u + 1], 0) : c[U];
+        const uint32_t succ = (lane == 31) ? from_next_row : from_next_lane;
+        win[2 * u] = c[u];
+        win[2 * u + 1] = ((c[u] >> 4) & 0x0F0F0F0Fu) | ((succ << 4) & 0xF0F0F0F0u);  // the window 8 bases into the unit
+    }
+    // all gathers of the tile, then the tests
+    uint2 blk[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        blk[k] = make_uint2(0, 0);
+        if (!GATE || !((dead >> k) & 1u)) blk[k] = __ldg(reinterpret_cast<const uint2*>(P.filter) + mk_dual_block(win[k] & smask, nblocks));
+    }
+    uint32_t pass = 0, only = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const uint32_t sh = dual3_test(blk[k], mk_dual3_g_short(win[k] & smask));
+        const uint32_t lg = has_long ? dual3_test(blk[k], mk_dual3_g_long(win[k])) : 0u;
+        pass += ((sh | lg) & 1u) * (1u << k);        // disjoint bits: a multiply-add is an OR (and issues on the other pipe)
+        only += ((lg ^ sh) & 1u) * ((sh & 1u) + 1u) * (1u << (2 * k));  // 2-bit field k: 1 = only the long key passed, 2 = only the short key
+    }
+    const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, __popc(pass));
+    if (total == 0) return;
+    // candidate = {base position | which single key passed (bits 0..1), 16-base window}; positions are multiples of 8
+    const uint32_t pos0 = v0 * 16u;
+    if (wq.count + total <= kQueueCap) {
+        if (pass) {
+            uint32_t idx = atomicAdd(wq.cnt, __popc(pass));
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if ((pass >> k) & 1u) wq.slot[idx++] = make_uint2((pos0 + (k / 2) * 512u + (k % 2) * 8u) | ((only >> (2 * k)) & 3u), win[k]);
+        }
+        __syncwarp();
+        wq.count += total;
+        if (wq.count >= 32) {
+            do queue_drain32(P, wq, lane); while (wq.count >= 32);
+            if (lane == 0) *wq.cnt = wq.count;
+            __syncwarp();
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            queue_push(P, wq, lane, (pass >> k) & 1u, (pos0 + (k / 2) * 512u + (k % 2) * 8u) | ((only >> (2 * k)) & 3u), win[k]);
+        if (lane == 0) *wq.cnt = wq.count;
+        __syncwarp();
+    }
+}
+
+template <int U, int T, bool GATE>
+__global__ void __launch_bounds__(T, 1) mk_scan_dual8(const __grid_constant__ ScanParams P) {
+    constexpr int kWarps = T / 32;
+    __shared__ uint2 s_queue[kWarps][kQueueCap];
+    __shared__ uint32_t s_qcount[kWarps];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t pol = make_evict_first_policy();
+    const uint32_t nwarps = gridDim.x * kWarps;
+    const uint32_t full_tiles = P.n_vec / (U * 32);
+    WarpQueue wq{s_queue[threadIdx.x >> 5], 0, &s_qcount[threadIdx.x >> 5]};
+    if (lane == 0) *wq.cnt = 0;
+    __syncwarp();
+    uint32_t t = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const uint32_t warp0 = t;
+    const size_t stride = (size_t)nwarps * (U * 32);
+    const uint4* p = P.text + (size_t)t * (U * 32) + lane;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    auto load_halo = [&](uint32_t tt) {  // first vector of the tile after tile `tt` (lane 31 only; zero past the end of the text)
+        const uint64_t hv = ((uint64_t)tt + 1) * (U * 32);
+        return (lane == 31 && hv < P.n_vec) ? ld_stream(P.text + hv, pol) : zero;
+    };
+
+    uint4 a[U], b[U], ha = zero, hb = zero;
+    if (t < full_tiles) { load_rows<U, false>(p, pol, a); ha = load_halo(t); }
+    while (t < full_tiles) {
+        uint32_t tn = t + nwarps;
+        if (tn < full_tiles) { load_rows<U, false>(p + stride, pol, b); hb = load_halo(tn); }
+        process_tile_dual8<U, GATE>(P, a, ha, t * (U * 32) + lane, wq, lane);
+        t = tn;
+        p += stride;
+        if (t >= full_tiles) break;
+        tn = t + nwarps;
+        if (tn < full_tiles) { load_rows<U, false>(p + stride, pol, a); ha = load_halo(tn); }
+        process_tile_dual8<U, GATE>(P, b, hb, t * (U * 32) + lane, wq, lane);
+        t = tn;
+        p += stride;
+    }
+    // ragged last tile (bounds-checked loads; nothing follows it)
+    if (P.n_vec % (U * 32) != 0 && warp0 == full_tiles % nwarps) {
+        const uint32_t v0 = full_tiles * (U * 32) + lane;
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = (v0 + u * 32 < P.n_vec) ? ld_stream(P.text + v0 + u * 32, pol) : zero;
+        process_tile_dual8<U, GATE>(P, a, zero, v0, wq, lane);
     }
     queue_flush(P, wq, lane);
 }

@@ -54,6 +54,10 @@ struct Tables {
     bool win = false;   // D == 8 / 4 with the shared-memory filter: seeds are masked 16-base windows in the permuted packing
     uint32_t win_mask0 = 0xFFFFFFFFu, win_mask1 = 0xFFFFFFFFu;
     bool filter_dual = false;  // L2-resident 64-bit blocked filter probed with both keys (stride < 16)
+    bool dual_perm = false;    // dual-key flavour for mk_scan_dual8 (ASCII, stride 8): keys in the permuted window layout, 3-bit filter entries
+    // Alphabet gate: a text byte b with (b ^ gate_val) & gate_mask != 0 occurs in no pattern (after -I folding),
+    // so a seed window that holds one inside its first q bytes cannot belong to a match. 0: no such bit exists.
+    uint32_t gate_mask = 0, gate_val = 0;
     uint32_t n_seeds = 0;
     // first-level filter
     uint32_t filter_log2_bits = 0, filter_hashes = 1;
@@ -349,7 +353,7 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
                 for (uint32_t j = 0; j < t.d; ++j) {
                     c = ((c << 2) | sym_class(0, sym[j + qq - 1])) & keep;
                     uint32_t code = c;
-                    if (t.perm || win_layout) {
+                    if (t.perm || win_layout || t.dual_perm) {
                         const uint32_t top = c << (32 - 2 * qq);  // first base in the two highest bits
                         code = perm_lut[0][top >> 24] | perm_lut[1][(top >> 16) & 255] | perm_lut[2][(top >> 8) & 255] | perm_lut[3][top & 255];
                     }
@@ -455,9 +459,13 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
     // Seed sets too large for shared memory with a stride below 16 are indexed once more below, with 16-base seeds
     // for the patterns that are long enough
     const bool long_seeds = !want_smem && t.d < 16 && t.d >= 2 && t.q < 16 && ps.max_len >= t.d + 15 && !std::getenv("MK_NO_LONG_SEEDS");
-    if (win_layout && !want_smem) {  // the L2-resident flavours use the ordered packing
+    // stride 8, ASCII, L2-resident filter: mk_scan_dual8 takes its keys in the permuted window layout (the short key
+    // is the window with the bases after the q-th masked away); the other L2-resident flavours use the ordered packing
+    t.dual_perm = !want_smem && enc == 0 && t.d == 8 && t.q >= 12 && !std::getenv("MK_NO_DUAL8");
+    if (t.dual_perm) window_masks(enc, t.q, &t.win_mask0, &t.win_mask1);
+    if (win_layout && !want_smem) {
         win_layout = false;
-        if (!long_seeds) index_seeds(0);
+        if (!long_seeds && !t.dual_perm) index_seeds(0);  // (with dual_perm the codes of the first pass are already right)
         TBT("index2");
     }
     t.win = win_layout;
@@ -526,7 +534,9 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
         t.filter_in_smem = false;
         t.filter_dual = true;
         t.filter_hashes = 4;
-        uint64_t nb = std::max<uint64_t>(1u << 15, (uint64_t)t.n_seeds / 2);
+        // bits per key: 32 (4-bit entries); 48 for mk_scan_dual8's 3-bit entries (cfg5: 3.1 M candidates at 32, 2.2 M at 48,
+        // same scan time, verification 0.27 -> 0.21 ms)
+        uint64_t nb = std::max<uint64_t>(1u << 15, t.dual_perm ? (uint64_t)t.n_seeds * 3 / 4 : (uint64_t)t.n_seeds / 2);
         if (const char* bk = std::getenv("MK_DUAL_BITS_PER_KEY")) nb = std::max<uint64_t>(1u << 15, (uint64_t)t.n_seeds * (uint64_t)std::atoi(bk) / 64);
         t.filter_blocks = (uint32_t)std::min<uint64_t>(nb, 1u << 27) & ~1u;
         t.filter.assign((size_t)t.filter_blocks * 2, 0);
@@ -534,12 +544,13 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
         for (size_t ki = 0; ki < keys.size(); ++ki) {
             if (ki + 24 < keys.size()) {  // the filter is far larger than the cache
                 const SeedKey& nx = keys[ki + 24];
-                __builtin_prefetch(&t.filter[2 * (size_t)mk_dual_block(nx.group ? (nx.code >> sshift) : nx.code, t.filter_blocks)], 1);
+                __builtin_prefetch(&t.filter[2 * (size_t)mk_dual_block(nx.group ? (t.dual_perm ? (nx.code & t.win_mask0) : (nx.code >> sshift)) : nx.code, t.filter_blocks)], 1);
             }
             const SeedKey& kv = keys[ki];
-            uint32_t short_code = kv.group ? (kv.code >> sshift) : kv.code;
+            uint32_t short_code = kv.group ? (t.dual_perm ? (kv.code & t.win_mask0) : (kv.code >> sshift)) : kv.code;
             uint32_t blk = mk_dual_block(short_code, t.filter_blocks), lo, hi;
-            mk_bloom_masks_g(kv.group ? mk_dual_g_long(kv.code) : mk_dual_g_short(short_code), &lo, &hi);
+            if (t.dual_perm) mk_dual3_masks(kv.group ? mk_dual3_g_long(kv.code) : mk_dual3_g_short(short_code), &lo, &hi);
+            else mk_bloom_masks_g(kv.group ? mk_dual_g_long(kv.code) : mk_dual_g_short(short_code), &lo, &hi);
             t.filter[2 * (size_t)blk] |= lo;
             t.filter[2 * (size_t)blk + 1] |= hi;
         }
@@ -557,6 +568,18 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
         }
     }
     TBT("filter");
+    if (enc == 0 && !std::getenv("MK_NO_GATE")) {
+        // bits that are the same in every byte a pattern can match
+        bool in_set[256] = {false};
+        for (size_t i = 0; i < ps.bytes.size(); ++i) in_set[t.pat_bytes[i]] = true;  // compare form: folded under -I
+        if (ps.case_insensitive)
+            for (int b = 'a'; b <= 'z'; ++b) if (in_set[b]) in_set[b - 0x20] = true;
+        uint32_t all_and = 0xFF, all_or = 0;
+        for (int b = 0; b < 256; ++b) if (in_set[b]) { all_and &= (uint32_t)b; all_or |= (uint32_t)b; }
+        const uint32_t constant = (all_and | ~all_or) & 0xFF;  // bits that are 1 everywhere or 0 everywhere
+        t.gate_mask = constant * 0x01010101u;
+        t.gate_val = (all_and & constant) * 0x01010101u;
+    }
     return t;
 }
 

@@ -161,7 +161,7 @@ void BamWriter::compress_pending() {
     work();
     for (auto& t : pool) t.join();
     if (!error.empty()) throw Error(error);
-    for (auto& o : out) std::fwrite(o.data(), 1, o.size(), f_);
+    for (auto& o : out) write_all(f_, o.data(), o.size());
     pending_.clear();
 }
 
@@ -170,9 +170,15 @@ void BamWriter::close() {
     flush_block();
     compress_pending();
     static const uint8_t eof[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    std::fwrite(eof, 1, sizeof eof, f_);
-    std::fclose(f_);
+    FILE* f = f_;
     f_ = nullptr;
+    try {
+        write_all(f, eof, sizeof eof);
+    } catch (...) {
+        std::fclose(f);
+        throw;
+    }
+    close_checked(f);
 }
 
 void BamWriter::write_bam_record(const char* body, size_t len, const std::string& tag, const std::string& value) {

@@ -35,19 +35,24 @@ struct OutFile {
     void write_raw(const char* p, size_t n) {
         if (n >= (256u << 10)) {  // a long run of records: straight to the file, not through the buffer
             flush();
-            if (f) std::fwrite(p, 1, n, f);
+            if (f) write_all(f, p, n);
             return;
         }
         buf.append(p, n);
         if (buf.size() >= (1u << 20)) flush();
     }
-    void flush() {
-        if (f && !buf.empty()) std::fwrite(buf.data(), 1, buf.size(), f);
-        buf.clear();
-        if (f) std::fflush(f);
+    void flush() {  // throws on a write error (full disk, closed pipe): see write_all
+        std::string pending;
+        pending.swap(buf);  // the bytes count as handed over even if the write fails: the destructor must not try again
+        if (f && !pending.empty()) write_all(f, pending.data(), pending.size());
+        if (f) flush_checked(f);
+    }
+    void close() {  // end of a successful run: the last bytes and the close itself are checked
+        flush();
+        if (f && owned) { FILE* g = f; f = nullptr; close_checked(g); }
     }
     ~OutFile() {
-        flush();
+        try { flush(); } catch (...) {}
         if (f && owned) std::fclose(f);
     }
 };
@@ -127,6 +132,9 @@ void extract_records(CmdExtract args) {
         f2 = path_file_name(*args.in_fastq_2);
     }
     const bool paired = args.in_fastq_2.has_value();
+    // what the readers open: the inputs themselves, or seekable copies of inputs that can be read only once
+    const std::string in1 = spool_if_not_seekable(args.in_fastx);
+    const std::string in2 = paired ? spool_if_not_seekable(*args.in_fastq_2) : std::string();
     const bool logging_active = log_sink || args.json_log;
     BufferedLogger logger(std::move(log_sink), 8192);
     std::unique_ptr<JsonLogger> jl;
@@ -146,7 +154,7 @@ void extract_records(CmdExtract args) {
 
     std::unique_ptr<FastxReader> reader, reader2;
     try {
-        reader.reset(new FastxReader(args.in_fastx));
+        reader.reset(new FastxReader(in1));
     } catch (const Error& e) {
         throw e.with_context("Invalid FASTQ/A input path or file: " + rust_debug_string(args.in_fastx));
     }
@@ -162,7 +170,7 @@ void extract_records(CmdExtract args) {
         writer.open(path, "Error writing to output file; no such directory: ");
     } else {
         try {
-            reader2.reset(new FastxReader(*args.in_fastq_2));
+            reader2.reset(new FastxReader(in2));
         } catch (const Error& e) {
             throw e.with_context("Invalid second FASTQ input path or file: Some(" + rust_debug_string(*args.in_fastq_2) + ")");
         }
@@ -278,20 +286,20 @@ void extract_records(CmdExtract args) {
         // 4-line FASTQ (plain or gzip) goes through the reader -> packer -> GPU pipeline (fastq_pipeline.h);
         // this thread then only looks at the records the device flagged. The readers start first: the
         // input is read and indexed while CUDA starts up.
-        const bool pipelined = !std::getenv("MERKURIO_NO_FASTQ_PIPELINE") && looks_like_fastq(args.in_fastx) &&
-                               (!paired || looks_like_fastq(*args.in_fastq_2));
+        const bool pipelined = !std::getenv("MERKURIO_NO_FASTQ_PIPELINE") && looks_like_fastq(in1) &&
+                               (!paired || looks_like_fastq(in2));
         std::unique_ptr<FastqChunkReader> chunks1, chunks2;
         if (pipelined) {
-            chunks1 = FastqPipeline::open_reader(args.in_fastx, paired ? 2 : 1);
-            if (paired) chunks2 = FastqPipeline::open_reader(*args.in_fastq_2, 2);
+            chunks1 = FastqPipeline::open_reader(in1, paired ? 2 : 1);
+            if (paired) chunks2 = FastqPipeline::open_reader(in2, 2);
         }
         // single-file FASTA has its own pipeline (fasta_pipeline.h): records of any length, cut into pieces
-        const bool fasta_pipelined = !pipelined && !paired && !std::getenv("MERKURIO_NO_FASTA_PIPELINE") && looks_like_fasta(args.in_fastx);
+        const bool fasta_pipelined = !pipelined && !paired && !std::getenv("MERKURIO_NO_FASTA_PIPELINE") && looks_like_fasta(in1);
         std::unique_ptr<FastaChunkReader> fa_chunks;
         if (fasta_pipelined) {
             const size_t chunk_bytes = std::getenv("MERKURIO_CHUNK_BYTES") ? (size_t)std::strtoull(std::getenv("MERKURIO_CHUNK_BYTES"), nullptr, 10)
                                                                            : (size_t)8 << 20;
-            fa_chunks.reset(new FastaChunkReader(args.in_fastx, chunk_bytes, prefetch_depth(chunk_bytes, 1)));
+            fa_chunks.reset(new FastaChunkReader(in1, chunk_bytes, prefetch_depth(chunk_bytes, 1)));
         }
         // the record-by-record path (FASTA, and whatever the FASTQ pipeline does not take) reads ahead on its own
         // threads, also started before the engines
@@ -446,8 +454,8 @@ void extract_records(CmdExtract args) {
         }
         scanner.finish();
     }
-    writer.flush();
-    writer2.flush();
+    writer.close();
+    writer2.close();
     const double t_sum0 = steady_seconds();
 
     size_t nb_patterns_found = 0;

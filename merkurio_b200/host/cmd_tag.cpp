@@ -96,7 +96,7 @@ void tag_records(CmdTag args) {
     set_decompression_threads(std::max(decompression_threads(), args.threads));
     std::unique_ptr<AlnReader> reader;
     try {
-        reader.reset(new AlnReader(args.in_file, in_ext == "bam"));
+        reader.reset(new AlnReader(spool_if_not_seekable(args.in_file), in_ext == "bam"));
     } catch (const Error& e) {
         throw e.with_context(std::string("Error reading ") + (in_ext == "bam" ? "BAM" : "SAM") + " file: " + rust_debug_string(args.in_file));
     }
@@ -124,9 +124,10 @@ void tag_records(CmdTag args) {
     }
     std::string obuf;
     auto flush_out = [&] {
-        if (!obuf.empty()) std::fwrite(obuf.data(), 1, obuf.size(), out);
-        obuf.clear();
-        std::fflush(out);
+        std::string pending;
+        pending.swap(obuf);
+        write_all(out, pending.data(), pending.size());  // throws: "Error writing record to output file" (src/cmd_tag.rs:494-496)
+        flush_checked(out);
     };
     if (!bam_out) for (auto& h : header) { obuf += h; obuf += '\n'; }
 
@@ -282,12 +283,17 @@ void tag_records(CmdTag args) {
         scanner.finish();
         }
     } catch (...) {
-        flush_out();
+        try { flush_out(); } catch (...) {}  // the error on its way out is the one to report
         if (out_owned) std::fclose(out);
         throw;
     }
-    flush_out();
-    if (out_owned) std::fclose(out);
+    try {
+        flush_out();
+    } catch (...) {
+        if (out_owned) std::fclose(out);
+        throw;
+    }
+    if (out_owned) close_checked(out);
     if (bam_out) bam_out->close();
 
     size_t nb_patterns_found = 0;

@@ -38,23 +38,51 @@ private:
     int fd_;
 };
 
+// gzip (also concatenated members, as `cat a.gz b.gz` and bgzip produce) through zlib's inflate. Not gzread: that
+// function reports an incomplete stream only from gzclose() (Z_BUF_ERROR), so a file cut short — a FASTA cut anywhere,
+// a FASTQ cut on a record boundary — would be taken for a complete, shorter input. Here the end of the file inside a
+// member is an error, like in the bzip2 / xz / zstd streams below.
 class GzipStream : public InputStream {
 public:
-    explicit GzipStream(int fd) {
-        gz_ = gzdopen(fd, "rb");
-        if (!gz_) { ::close(fd); throw Error("cannot open the gzip stream"); }
-        gzbuffer(gz_, 1 << 20);
+    explicit GzipStream(int fd) : fd_(fd), in_(1 << 20) {
+        std::memset(&z_, 0, sizeof z_);
+        if (inflateInit2(&z_, 15 + 16) != Z_OK) { ::close(fd_); throw Error("cannot open the gzip stream"); }
     }
-    ~GzipStream() override { gzclose(gz_); }
+    ~GzipStream() override {
+        inflateEnd(&z_);
+        ::close(fd_);
+    }
     size_t read(char* dst, size_t n) override {
-        // at most 256 KiB per call: gzread reports a broken stream with -1 for the whole call, so that much of
-        // the good data in front of the damage is lost at most (the caller asks again for the rest)
-        int got = gzread(gz_, dst, (unsigned)std::min<size_t>(n, 256u << 10));
-        if (got < 0) throw Error("Error while decompressing the input");
-        return (size_t)got;
+        if (done_) return 0;
+        // at most 256 KiB per call: a broken stream is reported for the whole call, so that much of the good data in
+        // front of the damage is lost at most (the caller asks again for the rest)
+        const unsigned want = (unsigned)std::min<size_t>(n, 256u << 10);
+        z_.next_out = reinterpret_cast<Bytef*>(dst);
+        z_.avail_out = want;
+        while (z_.avail_out == want) {
+            if (z_.avail_in == 0 && !eof_) {
+                size_t got = read_fd(fd_, in_.data(), in_.size());
+                if (got == 0) eof_ = true;
+                z_.next_in = reinterpret_cast<Bytef*>(in_.data());
+                z_.avail_in = (unsigned)got;
+            }
+            if (between_members_) {
+                if (z_.avail_in == 0) { done_ = true; break; }  // clean end of the file
+                if (inflateReset(&z_) != Z_OK) throw Error("Error while decompressing the input (gzip)");
+                between_members_ = false;
+            }
+            if (z_.avail_in == 0 && eof_) throw Error("Error while decompressing the input (truncated gzip stream)");
+            const int rc = inflate(&z_, Z_NO_FLUSH);
+            if (rc == Z_STREAM_END) between_members_ = true;
+            else if (rc != Z_OK && rc != Z_BUF_ERROR) throw Error("Error while decompressing the input (gzip)");
+        }
+        return want - z_.avail_out;
     }
 private:
-    gzFile gz_;
+    int fd_;
+    z_stream z_;
+    std::vector<char> in_;
+    bool eof_ = false, done_ = false, between_members_ = false;
 };
 
 class BgzfStream : public InputStream {

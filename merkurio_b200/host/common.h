@@ -1,6 +1,7 @@
 // Shared host utilities: anyhow-style errors, Rust-compatible path helpers.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -32,6 +33,15 @@ public:
 private:
     std::vector<std::string> chain_;
 };
+
+// --- record output: every write is checked -------------------------------------------------------
+// A full disk, a quota or a closed pipe must end the run with an error and a non-zero status instead of a truncated
+// output file: the reference propagates record-write failures ("Error writing record to output file",
+// src/cmd_tag.rs:494-496; extract unwraps the result of record.write, src/cmd_extract.rs:403,603-604). Only its
+// loggers ignore write errors (src/logger.rs), and so do ours.
+void write_all(FILE* f, const void* p, size_t n);  // fwrite, throws Error on a short write
+void flush_checked(FILE* f);                       // fflush, throws Error
+void close_checked(FILE* f);                       // fclose, throws Error
 
 // --- std::path::Path semantics the reference relies on -----------------------------------------
 std::string path_file_name(const std::string& path);                        // Path::file_name

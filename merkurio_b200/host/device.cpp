@@ -49,7 +49,24 @@ EngineSet::EngineSet(const std::vector<std::string>& patterns, bool case_insensi
         max_pattern_len = std::max<uint32_t>(max_pattern_len, (uint32_t)p.size());
     }
     mk_patterns mp{reinterpret_cast<const uint8_t*>(blob.data()), off.data(), (uint32_t)patterns.size()};
-    int n_gpus = (int)env_u64("MERKURIO_GPUS", 1);
+    // MERKURIO_GPUS=N: one engine on each of the devices 0..N-1. MERKURIO_DEVICES=a,b,...: one engine per entry on
+    // exactly those devices (an ordinal may repeat: "0,0" drives two engines on one GPU, which is how the
+    // round-robin deal and the in-order merge are tested on a single-GPU box).
+    std::vector<int> devices;
+    if (const char* dl = std::getenv("MERKURIO_DEVICES")) {
+        for (const char* c = dl; *c;) {
+            char* end = nullptr;
+            long v = std::strtol(c, &end, 10);
+            if (end == c || v < 0) throw Error(std::string("MERKURIO_DEVICES: cannot read the device list '") + dl + "'");
+            devices.push_back((int)v);
+            c = (*end == ',') ? end + 1 : end;
+            if (*end && *end != ',') throw Error(std::string("MERKURIO_DEVICES: cannot read the device list '") + dl + "'");
+        }
+    }
+    if (devices.empty()) {
+        const int n_gpus = std::max((int)env_u64("MERKURIO_GPUS", 1), 1);
+        for (int g = 0; g < n_gpus; ++g) devices.push_back(g);
+    }
     max_bytes = env_u64("MERKURIO_BATCH_MB", default_batch_mb) << 20;
     if (uint64_t b = env_u64("MERKURIO_BATCH_BYTES", 0)) max_bytes = b;  // tests: tiny batches, many pieces
     if (max_bytes < (uint64_t)4 * max_pattern_len + 16384) max_bytes = (uint64_t)4 * max_pattern_len + 16384;
@@ -57,21 +74,24 @@ EngineSet::EngineSet(const std::vector<std::string>& patterns, bool case_insensi
     max_records = (uint32_t)std::min<uint64_t>(max_bytes / 32 + 1024, 1u << 26);
     n_slots = (uint32_t)env_u64("MERKURIO_SLOTS", 3);
     if (n_slots < 1) n_slots = 1;
-    // one engine per GPU; with several GPUs they are created side by side (a CUDA context takes a second or
-    // more to create, one after the other that is most of an 8-GPU run)
-    const int n_engines = std::max(n_gpus, 1);
+    // The seed tables are built once (mk_tables_create starts that on host threads) and shared by all engines,
+    // which are created side by side: a CUDA context takes a second or more to create, one after the other that
+    // is most of an 8-GPU run.
+    mk_tables* tables = nullptr;
+    check(mk_tables_create(&mp, case_insensitive ? 1 : 0, &tables));
+    const int n_engines = (int)devices.size();
     engines.assign((size_t)n_engines, nullptr);
     std::vector<std::string> failed((size_t)n_engines);
     auto create = [&](int g) {
         mk_config cfg{};
-        cfg.device = g;
+        cfg.device = devices[(size_t)g];
         cfg.case_insensitive = case_insensitive ? 1 : 0;
         cfg.n_slots = n_slots;
         cfg.max_batch_records = max_records;
         cfg.max_batch_bytes = max_bytes;
         cfg.hit_capacity = 0;
         mk_engine* e = nullptr;
-        if (mk_engine_create(&mp, &cfg, &e) != 0) failed[(size_t)g] = std::string("GPU matching engine: ") + mk_last_error();  // (thread-local text)
+        if (mk_engine_create_shared(tables, &cfg, &e) != 0) failed[(size_t)g] = std::string("GPU matching engine: ") + mk_last_error();  // (thread-local text)
         engines[(size_t)g] = e;
     };
     if (n_engines == 1) {
@@ -81,6 +101,7 @@ EngineSet::EngineSet(const std::vector<std::string>& patterns, bool case_insensi
         for (int g = 0; g < n_engines; ++g) th.emplace_back(create, g);
         for (auto& t : th) t.join();
     }
+    mk_tables_destroy(tables);  // the engines hold their own references
     for (int g = 0; g < n_engines; ++g)
         if (!failed[(size_t)g].empty()) {
             for (mk_engine* e : engines) mk_engine_destroy(e);

@@ -1,5 +1,8 @@
 #include "helpers.h"
 
+#include <cerrno>
+#include <cstring>
+
 #include <sys/stat.h>
 
 #include <algorithm>
@@ -17,6 +20,20 @@ const char* const kVersion = "1.0.0";  // crate_version!() of the reference tree
 // ---------------------------------------------------------------------------------------------
 // paths
 // ---------------------------------------------------------------------------------------------
+static Error write_error() {
+    const int e = errno;
+    return Error(std::string(std::strerror(e)) + " (os error " + std::to_string(e) + ")").with_context("Error writing record to output file");
+}
+void write_all(FILE* f, const void* p, size_t n) {
+    if (n && std::fwrite(p, 1, n, f) != n) throw write_error();
+}
+void flush_checked(FILE* f) {
+    if (std::fflush(f) != 0) throw write_error();
+}
+void close_checked(FILE* f) {
+    if (std::fclose(f) != 0) throw write_error();
+}
+
 std::string path_file_name(const std::string& path) {
     std::string p = path;
     while (p.size() > 1 && p.back() == '/') p.pop_back();

@@ -1,9 +1,11 @@
 #include "io.h"
 
 #include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <charconv>
 #include <condition_variable>
 #include <cstdlib>
@@ -11,6 +13,7 @@
 #include <deque>
 #include <mutex>
 #include <thread>
+#include <vector>
 
 namespace mkh {
 
@@ -18,6 +21,33 @@ const char kNibbleChars[17] = "=ACMGRSVTWYHKDBN";
 
 // ---------------------------------------------------------------------------------------------
 static int g_decompression_threads = 0;
+std::string spool_if_not_seekable(const std::string& path) {
+    struct stat st;
+    if (::stat(path.c_str(), &st) != 0 || S_ISREG(st.st_mode) || S_ISDIR(st.st_mode)) return path;
+    const int in = ::open(path.c_str(), O_RDONLY);
+    if (in < 0) return path;
+    const char* dir = std::getenv("TMPDIR");
+    std::string tmpl = std::string(dir && *dir ? dir : "/tmp") + "/merkurio-input-XXXXXX";
+    const int out = ::mkstemp(&tmpl[0]);
+    if (out < 0) { ::close(in); throw Error("cannot create a temporary file for the input stream " + path + ": " + std::strerror(errno)); }
+    ::unlink(tmpl.c_str());
+    std::vector<char> buf(4 << 20);
+    for (;;) {
+        ssize_t got = ::read(in, buf.data(), buf.size());
+        if (got < 0 && errno == EINTR) continue;
+        if (got < 0) { ::close(in); ::close(out); throw Error("read failed: " + std::string(std::strerror(errno))); }
+        if (got == 0) break;
+        for (ssize_t done = 0; done < got;) {
+            ssize_t w = ::write(out, buf.data() + done, (size_t)(got - done));
+            if (w < 0 && errno == EINTR) continue;
+            if (w < 0) { ::close(in); ::close(out); throw Error("cannot spool the input stream " + path + ": " + std::strerror(errno)); }
+            done += w;
+        }
+    }
+    ::close(in);
+    return "/proc/self/fd/" + std::to_string(out);  // `out` stays open for the rest of the process
+}
+
 void set_decompression_threads(int n) { g_decompression_threads = std::max(n, 1); }
 int decompression_threads() {
     if (g_decompression_threads > 0) return g_decompression_threads;

@@ -19,6 +19,13 @@ namespace mkh {
 void set_decompression_threads(int n);
 int decompression_threads();
 
+// Inputs are opened more than once (format sniffing by content, then the reader the format calls for; BGZF detection
+// reads the head of the file with pread). A FIFO, a process substitution (`-i <(zcat x.fq.gz)`) or /dev/stdin can be
+// read only once: such an input is copied into an unlinked temporary file first and the path of that copy
+// (/proc/self/fd/N) is returned; regular files and paths that cannot be opened come back unchanged (the reader then
+// raises the usual error). The reference opens its input once and sniffs from the stream (needletail).
+std::string spool_if_not_seekable(const std::string& path);
+
 class ByteSource {
 public:
     explicit ByteSource(const std::string& path);

@@ -44,6 +44,22 @@ int mk_engine_create(const mk_patterns* p, const mk_config* c, mk_engine** out) 
     *out = e;
     return 0;
 }
+/* shared tables: the stub only remembers the length of query 0 */
+struct mk_tables { uint32_t first_len; int case_insensitive; };
+int mk_tables_create(const mk_patterns* p, int ci, mk_tables** out) {
+    mk_tables* t = calloc(1, sizeof *t);
+    t->first_len = p && p->n ? p->off[1] - p->off[0] : 0;
+    t->case_insensitive = ci;
+    *out = t;
+    return 0;
+}
+void mk_tables_destroy(mk_tables* t) { free(t); }
+int mk_engine_create_shared(mk_tables* t, const mk_config* c, mk_engine** out) {
+    int rc = mk_engine_create(NULL, c, out);
+    if (rc == 0) (*out)->first_len = t->first_len;
+    return rc;
+}
+const char* mk_engine_scan_kernel(mk_engine* e, mk_encoding enc) { (void)e; (void)enc; return "stub"; }
 void mk_engine_destroy(mk_engine* e) {
     if (!e) return;
     for (int s = 0; s < 16; ++s) { free(e->seq[s]); free(e->off[s]); free(e->lens[s]); }

@@ -1,8 +1,11 @@
 """CPU tests of the C++ host (merkurio_b200/host): query-list preprocessing, algorithm choice and
 flag rules against the oracle and the reference's own helper tests (src/helpers.rs:218-568,
 src/main.rs:60-293). Nothing here needs a GPU — these paths run before any engine is created."""
+import gzip
 import os
+import random
 import subprocess
+import zlib
 from pathlib import Path
 
 import pytest
@@ -361,7 +364,7 @@ def test_chunked_bam_reader_equals_record_reader(exe, ref_tree, tmp_path):
             assert got.stdout == want.stdout, (src.name, chunk)
 
 
-@pytest.mark.parametrize("codec", ["gz", "bz2", "bz2_multi", "xz", "xz_multi", "zstd", "zstd_multi"])
+@pytest.mark.parametrize("codec", ["gz", "gz_multi", "bz2", "bz2_multi", "xz", "xz_multi", "zstd", "zstd_multi"])
 def test_compressed_inputs_are_recognised_by_their_magic_bytes(exe, tmp_path, codec):
     """needletail opens .gz / .bz2 / .xz / .zst by content, not by name (README.md:39; its "compression" feature,
     Cargo.toml:26, includes zstd): same records as the plain file."""
@@ -382,7 +385,7 @@ def test_compressed_inputs_are_recognised_by_their_magic_bytes(exe, tmp_path, co
         recs.append(b"@r%d\n%s\n+\n%s\n" % (i, s, b"I" * n))
     data = b"".join(recs)
     half = data.index(b"\n@r3000\n") + 1
-    packed = {"gz": gzip.compress(data), "bz2": bz2.compress(data), "bz2_multi": bz2.compress(data[:half]) + bz2.compress(data[half:]),
+    packed = {"gz": gzip.compress(data), "gz_multi": gzip.compress(data[:half]) + gzip.compress(data[half:]), "bz2": bz2.compress(data), "bz2_multi": bz2.compress(data[:half]) + bz2.compress(data[half:]),
               "xz": lzma.compress(data), "xz_multi": lzma.compress(data[:half]) + lzma.compress(data[half:]),
               "zstd": zstd and zstd(data), "zstd_multi": zstd and zstd(data[:half]) + zstd(data[half:])}[codec]
     plain = tmp_path / "p.fastq"
@@ -402,7 +405,7 @@ def test_compressed_inputs_are_recognised_by_their_magic_bytes(exe, tmp_path, co
     # FASTA through the same streams
     fa = b"".join(b">s%d\n%s\n" % (i, b"ACGTTGCA" * 20) for i in range(500))
     (tmp_path / "g.fa").write_bytes(fa)
-    (tmp_path / "g.fa.z").write_bytes({"gz": gzip.compress, "bz2": bz2.compress, "bz2_multi": bz2.compress, "xz": lzma.compress, "xz_multi": lzma.compress,
+    (tmp_path / "g.fa.z").write_bytes({"gz": gzip.compress, "gz_multi": gzip.compress, "bz2": bz2.compress, "bz2_multi": bz2.compress, "xz": lzma.compress, "xz_multi": lzma.compress,
                                        "zstd": zstd, "zstd_multi": zstd}[codec](fa))
     a = subprocess.run([exe, "records", str(tmp_path / "g.fa"), "generic"], capture_output=True).stdout
     b = subprocess.run([exe, "records", str(tmp_path / "g.fa.z"), "generic"], capture_output=True).stdout
@@ -470,3 +473,27 @@ def test_chunked_sam_reader_fuzz(exe, tmp_path):
         got = subprocess.run([exe, "alnrecords", str(p), "chunked", str(int(rng.integers(4096, 9000)))], capture_output=True, env=env)
         assert got.returncode == 0, got.stderr
         assert got.stdout == want.stdout, trial
+
+
+def test_truncated_gzip_is_an_error_wherever_it_is_cut(exe, tmp_path):
+    """zlib's gzread reports an incomplete stream only from gzclose(): a FASTA cut anywhere, or a FASTQ cut where the
+    decompressed bytes happen to end on a record boundary, must not pass for a complete, shorter input."""
+    rng = random.Random(9)
+    fa = b"".join(b">s%d\n%s\n" % (i, bytes(rng.choice(b"ACGT") for _ in range(120))) for i in range(3000))
+    z = gzip.compress(fa)
+    (tmp_path / "cut.fa.gz").write_bytes(z[: len(z) * 2 // 3])
+    r = subprocess.run([exe, "records", str(tmp_path / "cut.fa.gz"), "generic"], capture_output=True)  # (the chunked reader of this command is FASTQ only)
+    assert r.returncode != 0 or b"#error" in r.stdout
+    # FASTQ: stored (uncompressed) deflate blocks, cut right after a block that ends on a record boundary
+    rec = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, b"ACGT" * 25, b"I" * 100) for i in range(2000))
+    co = zlib.compressobj(0, zlib.DEFLATED, 31)
+    cut_at = rec.index(b"@r1000\n")
+    first = co.compress(rec[:cut_at]) + co.flush(zlib.Z_FULL_FLUSH)  # ends on a record boundary, no trailer
+    (tmp_path / "cut.fastq.gz").write_bytes(first)
+    for how in ("generic", "chunked"):
+        r = subprocess.run([exe, "records", str(tmp_path / "cut.fastq.gz"), how], capture_output=True)
+        assert r.returncode != 0 or b"#error" in r.stdout, how
+    # the complete stream of the same object is fine
+    (tmp_path / "ok.fastq.gz").write_bytes(first + co.compress(rec[cut_at:]) + co.flush())
+    r = subprocess.run([exe, "records", str(tmp_path / "ok.fastq.gz"), "generic"], capture_output=True)
+    assert r.returncode == 0 and r.stdout.count(b"#id\t") == 2000

@@ -138,69 +138,56 @@ def test_cfg4_full_size_bam4_properties():
     torch.cuda.empty_cache()
 
 
-def test_cfg5_shape_properties():
-    """cfg5 at 1/10 scale (300 Mbp in 24 records, 100 k queries of 21-63 bases, 1 % with N, soft-masked
-    and N spans in the text): the L2-resident dual-key filter path with records far larger than a tile."""
-    import torch
-    from merkurio_b200 import capi, patterns as pt
-    from oracle import refmodel as rm
-    rng = np.random.default_rng(5)
-    total = 300_000_000
-    lens = (rng.dirichlet(np.ones(24) * 3) * total).astype(np.int64) + 1000
-    total = int(lens.sum())
-    off = np.zeros(25, dtype=np.int64)
-    off[1:] = np.cumsum(lens)
-    g = torch.Generator(device="cuda").manual_seed(55)
-    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device="cuda")
-    d_seq = torch.zeros(total + 64, dtype=torch.uint8, device="cuda")
-    d_seq[:total] = lut[torch.randint(0, 4, (total,), generator=g, device="cuda", dtype=torch.uint8).long()]
-    pos = 0
-    while pos < total:  # 30 % lower case, 2 % N
-        e = min(total, pos + int(rng.integers(2000, 200000)))
-        kind = rng.random()
-        if kind < 0.30:
-            d_seq[pos:e] |= 0x20
-        elif kind < 0.32:
-            d_seq[pos:e] = 78
-        pos = e
-    nq = 100_000
-    ql = rng.integers(21, 64, size=nq)
-    chrom = rng.choice(24, size=nq, p=lens / lens.sum())
-    qs = off[chrom] + (rng.random(nq) * (lens[chrom] - ql)).astype(np.int64)
-    idx = torch.from_numpy(qs).cuda()[:, None] + torch.arange(63, device="cuda")[None, :]
-    qmat = d_seq[idx.clamp_(max=total - 1)].cpu().numpy()
-    keep = ((qmat == 78) & (np.arange(63)[None, :] < ql[:, None])).sum(axis=1) <= 2
-    qmat, ql, chrom, qs = qmat[keep], ql[keep], chrom[keep], qs[keep]
-    queries = [qmat[i, :ql[i]].tobytes() for i in range(len(ql))]
-    altered = set(rng.choice(len(queries), size=len(queries) // 100, replace=False).tolist())
-    for i in altered:
-        b = bytearray(queries[i])
-        b[int(rng.integers(len(b)))] = 78
-        queries[i] = bytes(b)
-    pats = pt.parse_pattern_list(queries)
-    pid_of = {p: i for i, p in enumerate(pats)}
-    d_off = torch.from_numpy(off).cuda()
-    with capi.Engine(pats, n_slots=0, hit_capacity=1 << 19) as e:
-        r = e.scan_device(d_seq.data_ptr(), d_off.data_ptr(), 24, total, capi.MK_MODE_ALL_HITS, fetch=True)
+def _cfg5_checks(wl, expect_min_hits):
+    """cfg5 through ONE engine (all queries, the L2-resident dual-key filter): report order, every hit re-verified,
+    every query that still equals the text at its sampling position reported there, flags == records of the hit
+    list, idempotence — and the hits inside the first 4 Mbp of record 0 against the oracle's Aho-Corasick automaton
+    of the SAME full query set over that slice."""
+    from merkurio_b200 import capi
+    from oracle import checks
+    with capi.Engine(wl.pats, n_slots=0, hit_capacity=wl.hit_capacity) as e:
+        r = wl.scan(e, fetch=True)
         info = e.info()
         assert info.filter_in_smem[0] == 0 and info.seed_d[0] == 8  # the L2-resident filter, stride 8
+        assert "dual-key" in e.scan_kernel(capi.MK_ENC_ASCII)
         hits = r.hits
+        assert r.n_hits == len(hits) >= expect_min_hits
         key = (hits["record"].astype(np.uint64) << np.uint64(40)) | ((hits["start"].astype(np.uint64) + hits["len"]) << np.uint64(8)) | (np.uint64(255) - hits["len"].astype(np.uint64))
         assert np.all(key[1:] >= key[:-1])  # (record, end, longer pattern first)
-        _reverify(d_seq, d_off, hits, pats, False)
-        found = set(zip(hits["record"].tolist(), hits["start"].tolist(), hits["pattern"].tolist()))
-        for i, q in enumerate(queries):
-            if i not in altered:
-                assert (int(chrom[i]), int(qs[i] - off[chrom[i]]), pid_of[q]) in found
+        assert checks.reverify_hits(wl.d_seq, wl.d_off, hits, wl.pats, False)
+        assert checks.genome_expected_found(r, wl) == 0
         assert np.array_equal(np.nonzero(_flag_bits(r.flags, 24))[0], np.unique(hits["record"]))
-        # oracle parity on the first 3 Mbp of record 0 with the queries sampled from it
-        sl = min(3_000_000, int(lens[0]))
-        sub = pt.parse_pattern_list([q for q, c, s_ in zip(queries, chrom, qs) if c == 0 and s_ + 63 < sl])
-    text = d_seq[:sl].cpu().numpy()
-    rec, st, pat = rm.AhoCorasick(sub).batch_hits(text, np.array([0, sl], dtype=np.uint64))
-    with capi.Engine(sub, n_slots=0) as e2:
-        o2 = torch.tensor([0, sl], dtype=torch.int64, device="cuda")
-        r2 = e2.scan_device(d_seq.data_ptr(), o2.data_ptr(), 1, sl, capi.MK_MODE_ALL_HITS, fetch=True)
-    assert len(st) > 100 and np.array_equal(r2.hits["start"], st) and np.array_equal(r2.hits["pattern"], pat)
-    del d_seq
+        r2 = wl.scan(e, fetch=True)
+        assert np.array_equal(r2.hits, hits)  # idempotent, order included
+        n_slice = checks.genome_slice_equal(r, wl, 4_000_000)  # same engine, same pattern set
+        assert n_slice > 100
+    return r
+
+
+def test_cfg5_full_size_same_engine():
+    """BASELINE cfg5 at full size: 3.0 Gbp in 24 records, ~980 k queries of 21-63 bases (upper case, 1 % with N)
+    against text with 30 % lower-case soft-masked spans (which must not match) and 2 % N."""
+    import torch
+    from merkurio_b200.synth import workloads as wlm
+    wl = wlm.genome_workload(1.0, upper_queries=True)
+    assert len(wl.pats) > 900_000 and wl.n_units > 2_900_000_000
+    r = _cfg5_checks(wl, 500_000)
+    # upper-case queries never match inside a soft-masked span: no hit may hold a lower-case text byte
+    h = r.hits[:: max(len(r.hits) // 200_000, 1)]
+    st = torch.from_numpy((wl.extra["off"][h["record"]] + h["start"]).astype(np.int64)).cuda()
+    ln = torch.from_numpy(h["len"].astype(np.int64)).cuda()
+    first, last = wl.d_seq[st], wl.d_seq[st + ln - 1]
+    assert bool(((first < 97) & (last < 97)).all().item())
+    del wl
+    torch.cuda.empty_cache()
+
+
+def test_cfg5_verbatim_case_tenth_scale():
+    """cfg5 at 1/10 scale with the queries kept as sampled (a query from a soft-masked span is lower case and matches
+    there): lower-case and mixed-case patterns through the same path, the alphabet gate finding nothing to skip."""
+    import torch
+    from merkurio_b200.synth import workloads as wlm
+    wl = wlm.genome_workload(0.1, upper_queries=False)
+    _cfg5_checks(wl, 90_000)
+    del wl
     torch.cuda.empty_cache()

@@ -294,3 +294,51 @@ def test_tag_paths_agree_on_flagged_records(exe, stub, tmp_path, flags, bam):
         assert kept == 3000 and 300 < tagged < 2000
     for other in results[1:]:
         assert other == results[0]
+
+
+def test_truncated_gzip_fasta_and_write_errors_end_the_run(exe, stub, tmp_path):
+    """(a) a gzip FASTA cut short is an error in the FASTA pipeline and in the record path alike (zlib's
+    gzread would have reported it from gzclose() only); (b) a record writer that cannot write (/dev/full) ends the run
+    with "Error writing record to output file" and a non-zero status instead of a truncated file and status 0."""
+    rng = np.random.default_rng(21)
+    z = gzip.compress(fasta_text(rng))
+    cut = tmp_path / "cut.fa.gz"
+    cut.write_bytes(z[: len(z) * 2 // 3])
+    for env in ({}, {"MERKURIO_NO_FASTA_PIPELINE": "1"}):
+        r = run(exe, stub, ["extract", "-i", cut, "-s", QUERY, "-v", "-o", tmp_path / "o.fa"], env)
+        assert r.returncode != 0 and b"decompress" in r.stderr, (env, r.stderr)
+    ok = tmp_path / "ok.fa.gz"
+    ok.write_bytes(z)
+    assert run(exe, stub, ["extract", "-i", ok, "-s", QUERY, "-v", "-o", tmp_path / "o2.fa"]).returncode == 0
+    if os.path.exists("/dev/full"):
+        os.symlink("/dev/full", tmp_path / "full.fa")  # (-o keeps the name: its extension is already the input's)
+        for env in ({}, {"MERKURIO_NO_FASTA_PIPELINE": "1"}):
+            r = run(exe, stub, ["extract", "-i", ok, "-s", QUERY, "-v", "-o", tmp_path / "full.fa"], env)
+            assert r.returncode != 0 and b"Error writing record to output file" in r.stderr, (env, r.stderr)
+        sam = tmp_path / "x.sam"
+        sam.write_bytes(b"@HD\tVN:1.6\n" + b"".join(b"r%d\t4\t*\t0\t0\t*\t*\t0\t0\t%s\t*\n" % (i, b"ACGT" * 30) for i in range(20000)))
+        os.symlink("/dev/full", tmp_path / "full.sam")
+        r = run(exe, stub, ["tag", "-i", sam, "-s", QUERY, "-o", tmp_path / "full.sam"])
+        assert r.returncode != 0 and b"Error writing record to output file" in r.stderr, r.stderr
+
+
+def test_input_that_can_be_read_only_once(exe, stub, tmp_path):
+    """a FIFO (process substitution, /dev/stdin) is read exactly once — plain and gzip FASTQ through a
+    named pipe give the output of the same data in a file."""
+    import threading
+    rng = np.random.default_rng(33)
+    data = fastq_text(rng, 3000, b"a")
+    src = tmp_path / "r.fastq"
+    src.write_bytes(data)
+    want_o = tmp_path / "want.fastq"
+    assert run(exe, stub, ["extract", "-i", src, "-s", QUERY, "-v", "-o", want_o]).returncode == 0
+    for payload, name in ((data, "p.fastq"), (gzip.compress(data), "z.fastq")):
+        fifo = tmp_path / name
+        os.mkfifo(fifo)
+        t = threading.Thread(target=lambda: open(fifo, "wb").write(payload))
+        t.start()
+        got_o = tmp_path / ("got_" + name)
+        r = run(exe, stub, ["extract", "-i", fifo, "-s", QUERY, "-v", "-o", got_o])
+        t.join()
+        assert r.returncode == 0, r.stderr
+        assert got_o.read_bytes() == want_o.read_bytes(), name
