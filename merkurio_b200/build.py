@@ -50,12 +50,15 @@ def cuda_sources():
     return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "merkurio_cuda.h"]
 
 
-def build_cuda(force: bool = False, verbose: bool = False, ptxas_v: bool = False) -> Path:
-    """libmerkurio_cuda.so: kernels + C ABI (include/merkurio_cuda.h)."""
+def build_cuda(force: bool = False, verbose: bool = False, ptxas_v: bool = False, debug_checks: bool = False) -> Path:
+    """libmerkurio_cuda.so: kernels + C ABI (include/merkurio_cuda.h). debug_checks: libmerkurio_cuda_dbg.so with
+    device-side asserts on every computed index (-DMK_DEBUG_CHECKS); load it with MK_CUDA_LIB=<path> (capi.py)."""
     LIBDIR.mkdir(exist_ok=True)
-    out = LIBDIR / "libmerkurio_cuda.so"
+    out = LIBDIR / ("libmerkurio_cuda_dbg.so" if debug_checks else "libmerkurio_cuda.so")
     if force or _stale(out, cuda_sources()):
         cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-I", ROOT / "include", "-o", out, CSRC / "mk_engine.cu"]
+        if debug_checks:
+            cmd += ["-DMK_DEBUG_CHECKS"]
         if ptxas_v:
             cmd += ["-Xptxas", "-v"]
         if os.environ.get("MK_TUNE_BUILD"):  # every launch shape scripts/tune_scan.py sweeps

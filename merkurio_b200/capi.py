@@ -9,10 +9,14 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libmerkurio_cuda.so"
+import os
+
+# MK_CUDA_LIB: another build of the same library (the -DMK_DEBUG_CHECKS build with device-side asserts)
+LIB_PATH = Path(os.environ.get("MK_CUDA_LIB") or Path(__file__).resolve().parent / "lib" / "libmerkurio_cuda.so")
 
 MK_ENC_ASCII, MK_ENC_BAM4 = 0, 1
 MK_MODE_FLAG, MK_MODE_PATTERN_SET, MK_MODE_ALL_HITS = 0, 1, 2
+MK_FEATURE_DUAL8, MK_FEATURE_GATE = 1, 2  # mk_engine_info.features (ASCII tables: bits 0..7, BAM4: bits 8..15)
 
 EXPORTS = (
     "mk_engine_create", "mk_engine_destroy", "mk_engine_get_info", "mk_slot_buffers", "mk_scan_submit",

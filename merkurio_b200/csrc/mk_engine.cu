@@ -472,6 +472,8 @@ int enqueue(mk_engine* e, Workspace& ws) {
     P.tie_bits = e->tab->ps.tie_bits;
     P.pat_bits = mk::bits_for(e->tab->ps.n ? e->tab->ps.n - 1 : 0);
     P.max_len = e->tab->ps.max_len;
+    P.n_patterns = e->tab->ps.n;
+    P.n_postings = (uint32_t)t.postings.size();
 
     uint32_t key_bits;
     if (ws.mode == MK_MODE_ALL_HITS) key_bits = mk::bits_for(ws.n_units) + P.len_bits + P.tie_bits;
@@ -641,7 +643,13 @@ int check_batch(mk_engine* e, uint32_t n_records, uint64_t n_units, mk_encoding 
 extern "C" {
 
 const char* mk_last_error(void) { return g_err.c_str(); }
-const char* mk_version(void) { return "merkurio-b200 0.1.0 (sm_100a)"; }
+const char* mk_version(void) {
+#ifdef MK_DEBUG_CHECKS
+    return "merkurio-b200 0.2.0 (sm_100a, device-side debug checks)";
+#else
+    return "merkurio-b200 0.2.0 (sm_100a)";
+#endif
+}
 
 static int check_patterns(const mk_patterns* patterns) {
     if (patterns->n == 0) return fail(MK_ERR_NO_PATTERNS, "No k-mers found in file or provided sequence.");

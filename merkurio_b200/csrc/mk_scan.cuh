@@ -16,6 +16,17 @@
 #include "mk_codes.h"
 #include "mk_tables.h"
 
+// -DMK_DEBUG_CHECKS (merkurio_b200.build.build_cuda(debug_checks=True) -> libmerkurio_cuda_dbg.so): device-side
+// asserts on every index the kernels compute for shared-memory queues, filters, tables and lists. compute-sanitizer
+// is closed on the GPU pool this was developed on, so the parity suite is run against this build instead
+// (profiles/sanitizer/README.md). Compiled out otherwise.
+#ifdef MK_DEBUG_CHECKS
+#include <cassert>
+#define MK_ASSERT(c) assert(c)
+#else
+#define MK_ASSERT(c) ((void)0)
+#endif
+
 namespace mk {
 
 struct RawHit {
@@ -66,6 +77,7 @@ struct ScanParams {
     unsigned long long* hit_count;
     int mode;
     uint32_t len_bits, tie_bits, pat_bits, max_len;
+    uint32_t n_patterns, n_postings;  // bounds for the debug checks
 };
 
 constexpr int kScanThreads = 1024;
@@ -101,6 +113,7 @@ template <int FMODE>
 __device__ __forceinline__ uint32_t filter_probe(const uint32_t* __restrict__ f, uint32_t code, uint32_t lb) {
     if (FMODE == kFilterSmem) {
         uint32_t h = code * MK_BLOOM_MUL;
+        MK_ASSERT(__umulhi(h, lb) < lb);
         uint2 w = reinterpret_cast<const uint2*>(f)[__umulhi(h, lb)];
         uint32_t g = h * MK_BLOOM_MUL2;
         // shifts by a register use its low 5 bits (SHF.R.W), so the bit positions need no masking
@@ -130,6 +143,7 @@ __device__ __forceinline__ uint32_t bloom_test(uint2 w, uint32_t g) {
 __device__ __forceinline__ uint32_t dual_probe(const uint32_t* __restrict__ f, uint32_t win, uint32_t short_shift,
                                                uint32_t nblocks, uint32_t has_long) {
     uint32_t sc = win >> short_shift;
+    MK_ASSERT(mk_dual_block(sc, nblocks) < nblocks);
     uint2 w = __ldg(reinterpret_cast<const uint2*>(f) + mk_dual_block(sc, nblocks));
     uint32_t pass = bloom_test(w, mk_dual_g_short(sc));           // bit 0: short key present
     if (has_long) pass |= bloom_test(w, mk_dual_g_long(win)) << 1;  // bit 1: long key present
@@ -207,6 +221,7 @@ __device__ __forceinline__ uint32_t seed_lookup(const ScanParams& P, uint32_t co
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         uint32_t b = h == 0 ? mk_hash_b1(hk, P.bucket_mask) : mk_hash_b2(hk, P.bucket_mask);
+        MK_ASSERT(b <= P.bucket_mask);
         const uint4* bp = reinterpret_cast<const uint4*>(P.slots + (size_t)b * kBucketSlots);
         uint4 lo = __ldg(bp), hi = __ldg(bp + 1);
         if (lo.x == code && lo.y != kEmptySlot && (lo.y >> 31) == group) return lo.y & ~kGroupBit;
@@ -257,6 +272,7 @@ __device__ __forceinline__ void sink_flush(const ScanParams& P, HitSink& sink, u
 template <int ENC>
 __device__ __forceinline__ void verify_one(const ScanParams& P, uint64_t pos, uint32_t pid, uint32_t j, HitSink& sink) {
     if (pos < j) return;
+    MK_ASSERT(pid < P.n_patterns && pos < P.n_units + 16);
     const uint8_t* text = reinterpret_cast<const uint8_t*>(P.text);
     const uint64_t s = pos - j;
     const uint32_t po = __ldg(P.pat_off + pid);
@@ -289,6 +305,7 @@ __device__ __forceinline__ void verify_one(const ScanParams& P, uint64_t pos, ui
     }
     if (!eq || s < P.off[0]) return;
     const uint32_t r = find_record(P.off, P.n_records, s);
+    MK_ASSERT(r < P.n_records && P.off[r] <= s);
     const uint64_t rend = P.lens ? P.off[r] + P.lens[r] : P.off[r + 1];
     if (s + L > rend) return;
     // test before set: with few long records (chromosomes) every hit lands on the same word
@@ -315,6 +332,7 @@ __device__ __forceinline__ void verify_postings(const ScanParams& P, uint64_t po
         return;
     }
     for (uint32_t i = first;; ++i) {
+        MK_ASSERT(i < P.n_postings);
         const uint32_t e = __ldg(P.postings + i);
         verify_one<ENC>(P, pos, e >> 5, (e >> 1) & 15u, sink);
         if (e & 1u) break;
@@ -384,6 +402,7 @@ __device__ __forceinline__ void emit_candidates(const ScanParams& P, bool mine, 
 }
 
 __device__ __forceinline__ void queue_drain32(const ScanParams& P, WarpQueue& wq, uint32_t lane) {
+    MK_ASSERT(wq.count >= 32 && wq.count <= kQueueCap);
     wq.count -= 32;
     uint2 e = wq.slot[wq.count + lane];
     __syncwarp();
@@ -406,6 +425,7 @@ __device__ __forceinline__ void queue_push(const ScanParams& P, WarpQueue& wq, u
                                            uint32_t code) {
     uint32_t m = __ballot_sync(0xFFFFFFFFu, mine);
     if (m) {
+        MK_ASSERT(wq.count + __popc(m) <= kQueueCap);
         if (mine) wq.slot[wq.count + __popc(m & ((1u << lane) - 1u))] = make_uint2(unit, code);
         wq.count += __popc(m);
         __syncwarp();
@@ -439,6 +459,7 @@ __device__ __forceinline__ void process_tile(const ScanParams& P, const uint32_t
         // atomic each; no per-seed warp votes
         if (pass) {
             uint32_t idx = atomicAdd(wq.cnt, __popc(pass));
+            MK_ASSERT(idx + __popc(pass) <= kQueueCap);
 #pragma unroll
             for (int k = 0; k < U * SPV; ++k) {
                 const int u = k / SPV;
@@ -544,6 +565,7 @@ __device__ __forceinline__ void push_tile_candidates(const ScanParams& P, WarpQu
     if (wq.count + total <= kQueueCap) {
         if (pass) {
             uint32_t idx = atomicAdd(wq.cnt, __popc(pass));
+            MK_ASSERT(idx + __popc(pass) <= kQueueCap);
 #pragma unroll
             for (int k = 0; k < K; ++k)
                 if ((pass >> k) & 1u) wq.slot[idx++] = make_uint2(unit0 + (k / per_row) * unit_row_stride + (k % per_row), code[k]);
@@ -803,6 +825,7 @@ __device__ __forceinline__ void process_tile_dual8(const ScanParams& P, const ui
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         blk[k] = make_uint2(0, 0);
+        MK_ASSERT(mk_dual_block(win[k] & smask, nblocks) < nblocks);
         if (!GATE || !((dead >> k) & 1u)) blk[k] = __ldg(reinterpret_cast<const uint2*>(P.filter) + mk_dual_block(win[k] & smask, nblocks));
     }
     uint32_t pass = 0, only = 0;
@@ -820,6 +843,7 @@ __device__ __forceinline__ void process_tile_dual8(const ScanParams& P, const ui
     if (wq.count + total <= kQueueCap) {
         if (pass) {
             uint32_t idx = atomicAdd(wq.cnt, __popc(pass));
+            MK_ASSERT(idx + __popc(pass) <= kQueueCap);
 #pragma unroll
             for (int k = 0; k < K; ++k)
                 if ((pass >> k) & 1u) wq.slot[idx++] = make_uint2((pos0 + (k / 2) * 512u + (k % 2) * 8u) | ((only >> (2 * k)) & 3u), win[k]);
@@ -908,6 +932,7 @@ __global__ void __launch_bounds__(kVerifyThreads) mk_verify_candidates(const __g
     for (unsigned long long base = (unsigned long long)blockIdx.x * kVerifyThreads + w * 32; base < n; base += stride) {
         unsigned long long i = base + lane;
         if (i < n) {
+            MK_ASSERT(i < P.cand_capacity);
             uint2 e = P.cand[i];
             verify_seed<ENC>(P, (uint64_t)e.x * P.pos_mul, e.y, sink);
         }

@@ -12,6 +12,15 @@
 #include "../../include/merkurio_cuda.h"
 #include "mk_scan.cuh"
 
+#ifndef MK_ASSERT
+#ifdef MK_DEBUG_CHECKS
+#include <cassert>
+#define MK_ASSERT(c) assert(c)
+#else
+#define MK_ASSERT(c) ((void)0)
+#endif
+#endif
+
 namespace mk {
 
 constexpr int kSortBlocks = 256;
@@ -171,7 +180,10 @@ __global__ void __launch_bounds__(256) mk_bucket_count(const RawHit* __restrict_
     unsigned long long n = *count;
     if (n > cap) n = cap;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    {
+        MK_ASSERT(bucket_of(in[i].key, bm) < (uint32_t)kBuckets);
         atomicAdd(&bucket_count[bucket_of(in[i].key, bm)], 1u);
+    }
 }
 
 // one block: bucket_start = exclusive scan of bucket_count (kBuckets + 1 entries), cursor = copy of it,
@@ -226,6 +238,7 @@ __global__ void __launch_bounds__(256) mk_bucket_scatter(const RawHit* __restric
         const uint32_t pa = atomicAdd(&cursor[bucket_of(a.key, bm)], 1u);
         uint32_t pb = 0;
         if (j < n) pb = atomicAdd(&cursor[bucket_of(b.key, bm)], 1u);
+        MK_ASSERT(pa < n && (j >= n || pb < n));
         out[pa] = a;
         if (j < n) out[pb] = b;
     }

@@ -502,7 +502,9 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
         t.filter_in_smem = true;
         // small seed sets: 32-bit blocks are as selective and cost half the shared-memory traffic per probe
         // (k = 19..30, 2 000 patterns: 6.4 -> 7.0 TB/s); larger sets need the 64-bit blocks' lower false-positive rate
-        t.filter32 = (t.perm || t.win) && blocked_fp32((double)keys.size(), 2 * nblocks) <= 0.004 && !std::getenv("MK_NO_FILTER32");
+        double f32_max_fp = 0.004;
+        if (const char* mf = std::getenv("MK_F32_MAX_FP")) f32_max_fp = std::atof(mf);  // tuning override
+        t.filter32 = (t.perm || t.win) && blocked_fp32((double)keys.size(), 2 * nblocks) <= f32_max_fp && !std::getenv("MK_NO_FILTER32");
 #ifdef MK_TUNE_BUILD
         t.filter32 = false;  // the launch-shape sweep only builds the 64-bit flavour
 #endif

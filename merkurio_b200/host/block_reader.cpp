@@ -33,8 +33,12 @@ size_t prefetch_depth(size_t chunk_bytes, int n_files) {
     return std::min<size_t>(std::max<size_t>(budget / (size_t)std::max(n_files, 1) / per_chunk, 4), 4096);
 }
 
-BlockReader::BlockReader(const std::string& path, size_t block_bytes, size_t head, size_t depth)
-    : path_(path), block_bytes_(std::max<size_t>(block_bytes, 4096)), head_(head), depth_(std::max<size_t>(depth, 1)) {
+void find_line_breaks(const char* d, size_t from, size_t to, OffsetList& out);
+
+BlockReader::BlockReader(const std::string& path, size_t block_bytes, size_t head, size_t depth, bool scan_lines)
+    : path_(path), block_bytes_(std::max<size_t>(block_bytes, 4096)), head_(head), depth_(std::max<size_t>(depth, 1)), scan_lines_(scan_lines) {
+    helpers_ = std::getenv("MERKURIO_READ_THREADS") ? std::max(1, std::atoi(std::getenv("MERKURIO_READ_THREADS")))
+                                                    : (int)std::max(1u, std::min(4u, std::thread::hardware_concurrency() / 4));
     // open here so that a missing file fails in the caller's thread, with the caller's context
     { std::unique_ptr<InputStream> probe = InputStream::open(path_); }
     thread_ = std::thread([this] { run(); });
@@ -79,7 +83,8 @@ void BlockReader::run() {
         if (!read_) {
             src = InputStream::open(path_);
             InputStream* in = src.get();
-            read_ = [in](char* dst, size_t n) { return in->read(dst, n); };
+            const int rt = helpers_;  // concurrent preads of one block of an uncompressed regular file
+            read_ = [in, rt](char* dst, size_t n) { return in->read_parallel(dst, n, rt); };
         }
         for (bool eof = false; !eof;) {
             Block b;
@@ -102,6 +107,25 @@ void BlockReader::run() {
                 if (b.n == 0) break;
             }
             b.last = eof && error.empty();
+            b.nl.clear();
+            b.has_nl = false;
+            if (scan_lines_ && b.n > 0 && head_ + b.n < ((size_t)1 << 32)) {
+                // line breaks of the block, a slice per helper thread, concatenated in order
+                const int K = (b.n >= ((size_t)1 << 20)) ? helpers_ : 1;
+                const char* d = b.data.data();
+                if (K == 1) {
+                    find_line_breaks(d, head_, head_ + b.n, b.nl);
+                } else {
+                    std::vector<OffsetList> part((size_t)K);
+                    auto job = [&](int t) { find_line_breaks(d, head_ + b.n * (size_t)t / (size_t)K, head_ + b.n * (size_t)(t + 1) / (size_t)K, part[(size_t)t]); };
+                    std::vector<std::thread> th;
+                    for (int t = 1; t < K; ++t) th.emplace_back(job, t);
+                    job(0);
+                    for (auto& x : th) x.join();
+                    for (auto& pl : part) b.nl.append(pl);
+                }
+                b.has_nl = true;
+            }
             const double dt = steady_seconds() - t0;
             std::unique_lock<std::mutex> lk(mu_);
             t_read_ += dt;

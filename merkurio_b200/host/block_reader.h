@@ -7,6 +7,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <deque>
 #include <functional>
 #include <mutex>
@@ -48,6 +49,38 @@ struct DefaultInitAllocator : std::allocator<T> {
 };
 using ByteBuf = std::vector<char, DefaultInitAllocator<char>>;
 
+// Growable array of offsets without value initialisation (the scanner appends through a raw pointer).
+struct OffsetList {
+    uint32_t* p = nullptr;
+    size_t n = 0, cap = 0;
+    OffsetList() = default;
+    OffsetList(const OffsetList&) = delete;
+    OffsetList& operator=(const OffsetList&) = delete;
+    OffsetList(OffsetList&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+    OffsetList& operator=(OffsetList&& o) noexcept {
+        if (this != &o) { std::free(p); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = o.cap = 0; }
+        return *this;
+    }
+    void append(const OffsetList& o) {
+        if (!o.n) return;
+        reserve(n + o.n);
+        std::memcpy(p + n, o.p, o.n * sizeof(uint32_t));
+        n += o.n;
+    }
+    ~OffsetList() { std::free(p); }
+    void reserve(size_t want) {
+        if (want <= cap) return;
+        size_t c = std::max(want, cap * 2);
+        void* q = std::realloc(p, c * sizeof(uint32_t));
+        if (!q) throw std::bad_alloc();
+        p = static_cast<uint32_t*>(q);
+        cap = c;
+    }
+    void clear() { n = 0; }
+    size_t size() const { return n; }
+    uint32_t operator[](size_t i) const { return p[i]; }
+};
+
 class BlockReader {
 public:
     // n bytes of the file at data[head, head + n); the head room is the indexer's (it puts the unfinished
@@ -56,8 +89,12 @@ public:
         ByteBuf data;
         size_t n = 0;
         bool last = false;  // the file ends with this block
+        // scan_lines: the offsets (in data) of every '\n' of data[head, head + n), found by the reading stage on its
+        // helper threads while the bytes are still in their caches
+        OffsetList nl;
+        bool has_nl = false;
     };
-    BlockReader(const std::string& path, size_t block_bytes, size_t head, size_t depth = 3);
+    BlockReader(const std::string& path, size_t block_bytes, size_t head, size_t depth = 3, bool scan_lines = false);
     // The same over an input that is already open: read(dst, n) returns up to n bytes, 0 at the end.
     using ReadFn = std::function<size_t(char*, size_t)>;
     BlockReader(ReadFn read, size_t block_bytes, size_t head, size_t depth = 3);
@@ -78,6 +115,8 @@ private:
     std::string path_;
     ReadFn read_;
     size_t block_bytes_, head_, depth_;
+    bool scan_lines_ = false;
+    int helpers_ = 1;  // MERKURIO_READ_THREADS: concurrent preads of one block (uncompressed regular files), line-break scans
     std::thread thread_;
     std::mutex mu_;
     std::condition_variable cv_;
@@ -86,27 +125,6 @@ private:
     bool done_ = false, stop_ = false;
     std::string io_error_;
     double t_read_ = 0;
-};
-
-// Growable array of offsets without value initialisation (the scanner appends through a raw pointer).
-struct OffsetList {
-    uint32_t* p = nullptr;
-    size_t n = 0, cap = 0;
-    OffsetList() = default;
-    OffsetList(const OffsetList&) = delete;
-    OffsetList& operator=(const OffsetList&) = delete;
-    ~OffsetList() { std::free(p); }
-    void reserve(size_t want) {
-        if (want <= cap) return;
-        size_t c = std::max(want, cap * 2);
-        void* q = std::realloc(p, c * sizeof(uint32_t));
-        if (!q) throw std::bad_alloc();
-        p = static_cast<uint32_t*>(q);
-        cap = c;
-    }
-    void clear() { n = 0; }
-    size_t size() const { return n; }
-    uint32_t operator[](size_t i) const { return p[i]; }
 };
 
 // Offsets of every '\n' in d[from, to), appended to out in ascending order. One vector compare per 32

@@ -2,12 +2,15 @@
 
 #include <dlfcn.h>
 #include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 
 #include <cerrno>
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "bgzf.h"
@@ -31,11 +34,54 @@ size_t read_fd(int fd, void* dst, size_t n) {
 
 class PlainStream : public InputStream {
 public:
-    explicit PlainStream(int fd) : fd_(fd) {}
+    explicit PlainStream(int fd) : fd_(fd) {
+        struct stat st;
+        regular_ = ::fstat(fd_, &st) == 0 && S_ISREG(st.st_mode);
+    }
     ~PlainStream() override { ::close(fd_); }
-    size_t read(char* dst, size_t n) override { return read_fd(fd_, dst, n); }
+    size_t read(char* dst, size_t n) override {
+        size_t got = read_fd(fd_, dst, n);
+        pos_ += got;
+        return got;
+    }
+    size_t read_parallel(char* dst, size_t n, int threads) override {
+        if (!regular_ || threads <= 1 || n < ((size_t)1 << 20)) return read(dst, n);
+        // slices of the range [pos_, pos_ + n), each read with pread until it is full or the file ends
+        const size_t slice = (n / (size_t)threads + 4095) & ~(size_t)4095;
+        std::vector<size_t> got((size_t)threads, 0);
+        std::vector<int> err((size_t)threads, 0);
+        auto job = [&](int t) {
+            const size_t lo = std::min(n, slice * (size_t)t), hi = (t == threads - 1) ? n : std::min(n, slice * (size_t)(t + 1));
+            size_t done = 0;
+            while (lo + done < hi) {
+                ssize_t r = ::pread(fd_, dst + lo + done, hi - lo - done, (off_t)(pos_ + lo + done));
+                if (r < 0 && errno == EINTR) continue;
+                if (r < 0) { err[(size_t)t] = errno; break; }
+                if (r == 0) break;  // end of the file
+                done += (size_t)r;
+            }
+            got[(size_t)t] = done;
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < threads; ++t) th.emplace_back(job, t);
+        job(0);
+        for (auto& x : th) x.join();
+        size_t total = 0;
+        for (int t = 0; t < threads; ++t) {
+            if (err[(size_t)t]) throw Error(std::string("read failed: ") + std::strerror(err[(size_t)t]));
+            const size_t lo = std::min(n, slice * (size_t)t), hi = (t == threads - 1) ? n : std::min(n, slice * (size_t)(t + 1));
+            total += got[(size_t)t];
+            if (got[(size_t)t] < hi - lo) break;  // the file ended inside this slice: nothing valid follows
+        }
+        pos_ += total;
+        // keep the descriptor's own offset in step (read() continues from it)
+        ::lseek(fd_, (off_t)pos_, SEEK_SET);
+        return total;
+    }
 private:
     int fd_;
+    bool regular_ = false;
+    uint64_t pos_ = 0;
 };
 
 // gzip (also concatenated members, as `cat a.gz b.gz` and bgzip produce) through zlib's inflate. Not gzread: that

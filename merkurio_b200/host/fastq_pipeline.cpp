@@ -76,7 +76,7 @@ bool FastqPipeline::fill(PackedBatch& b) {
         const Chunk& c = *cur_[f];
         const RecSpan& r = c.recs[idx_[f]];
         b.off[b.n_records] = b.n_units;
-        if (r.seq_len) std::memcpy(b.seq + b.n_units, c.seq(r), r.seq_len);
+        if (r.seq_len) copies_.push_back(CopyPool::Copy{c.seq(r), b.n_units, r.seq_len});
         b.n_units += r.seq_len;
         b.n_records += 1;
         b.add_to_seg(f, cur_[f], (uint32_t)idx_[f], nrec[f]);
@@ -117,6 +117,8 @@ bool FastqPipeline::fill(PackedBatch& b) {
     }
     b.off[b.n_records] = b.n_units;
     b.n_bytes = b.total_bases = b.n_units;
+    copy_pool_.run(b.seq, copies_);  // the chunks the copies read from are held by b.seg
+    copies_.clear();
     return b.n_records > 0 || !b.error_chain.empty();
 }
 

@@ -26,6 +26,7 @@ private:
     std::shared_ptr<Chunk> cur_[2];
     size_t idx_[2] = {0, 0};
     std::string read_error_[2];  // what the reader of file f threw (decompression / read error); reported by fill()
+    std::vector<CopyPool::Copy> copies_;  // the sequence copies of the batch being filled (carried out by copy_pool_)
 };
 
 }  // namespace mkh

@@ -69,7 +69,7 @@ struct FastqChunkReader::Shared {
 
 FastqChunkReader::FastqChunkReader(const std::string& path, size_t chunk_bytes, size_t depth)
     : path_(path), chunk_bytes_(std::max<size_t>(chunk_bytes, 4096)), depth_(std::max<size_t>(depth, 1)), pool_(new Shared) {
-    blocks_.reset(new BlockReader(path_, chunk_bytes_, kHead));  // a missing file fails here, in the caller's thread
+    blocks_.reset(new BlockReader(path_, chunk_bytes_, kHead, 3, true));  // a missing file fails here, in the caller's thread
     thread_ = std::thread([this] { run(); });
 }
 
@@ -122,6 +122,9 @@ void FastqChunkReader::run() {
             c->nl.clear();
             c->failed = false;
             size_t begin, have;
+            // the reading stage has located the line breaks of its block already (BlockReader scan_lines); only those of
+            // the bytes carried over are missing — unless the block had to be moved (an over-long record)
+            const bool pre = rb.has_nl && carry.size() <= kHead;
             if (carry.size() <= kHead) {
                 begin = kHead - carry.size();
                 have = kHead + rb.n;
@@ -143,9 +146,13 @@ void FastqChunkReader::run() {
             const OffsetList& nl = c->nl;
             size_t p = begin, k = 0;  // nl[k]: the first line break at or after p
             bool stuck = false;       // malformed or truncated: nothing more to parse in this block
+            if (pre) {
+                find_line_breaks(d, begin, kHead, c->nl);
+                c->nl.append(rb.nl);
+            }
             for (size_t scanned = begin; !stuck && (scanned < have || (eof && p < have));) {
-                const size_t upto = std::min(have, scanned + kStretch);
-                find_line_breaks(d, scanned, upto, c->nl);
+                const size_t upto = pre ? have : std::min(have, scanned + kStretch);
+                if (!pre) find_line_breaks(d, scanned, upto, c->nl);
                 scanned = upto;
                 const bool last = eof && scanned == have;  // only then a line without '\n' is complete
                 for (;;) {

@@ -1,6 +1,9 @@
 #include "slot_pipeline.h"
 
+#include <algorithm>
 #include <chrono>
+#include <cstdlib>
+#include <cstring>
 
 namespace mkh {
 
@@ -8,8 +11,69 @@ namespace {
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 }  // namespace
 
+static int pack_threads() {
+    if (const char* s = std::getenv("MERKURIO_PACK_THREADS")) return std::max(1, std::atoi(s));
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(4u, hw / 4));
+}
+
+CopyPool::CopyPool(int threads) {
+    for (int t = 1; t < threads; ++t) workers_.emplace_back([this, t] { work((size_t)t); });
+}
+
+CopyPool::~CopyPool() {
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& w : workers_) w.join();
+}
+
+void CopyPool::copy_range(uint8_t* base, const Copy* c, size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; ++i) std::memcpy(base + c[i].dst, c[i].src, c[i].len);
+}
+
+void CopyPool::work(size_t me) {
+    uint64_t seen = 0;
+    for (;;) {
+        uint8_t* base;
+        const Copy* list;
+        size_t n;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+            if (stop_) return;
+            seen = generation_;
+            base = base_; list = list_; n = n_;
+        }
+        const size_t parts = workers_.size() + 1;
+        copy_range(base, list, n * me / parts, n * (me + 1) / parts);
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_cv_.notify_one();
+    }
+}
+
+void CopyPool::run(uint8_t* base, const std::vector<Copy>& list) {
+    const size_t n = list.size(), parts = workers_.size() + 1;
+    if (workers_.empty() || n < 4096) {  // not worth a hand-over
+        copy_range(base, list.data(), 0, n);
+        return;
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        base_ = base; list_ = list.data(); n_ = n;
+        pending_ = workers_.size();
+        ++generation_;
+    }
+    cv_.notify_all();
+    copy_range(base, list.data(), 0, n / parts);  // the packer thread takes the first range itself
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+}
+
 SlotPipeline::SlotPipeline(EngineSet& engines, mk_encoding enc, mk_mode mode, BatchConsumer consumer)
-    : es_(engines), enc_(enc), mode_(mode), consumer_(std::move(consumer)) {
+    : es_(engines), enc_(enc), mode_(mode), copy_pool_(pack_threads()), consumer_(std::move(consumer)) {
     // every slot of every engine, in the order the batches will use them
     const size_t G = es_.engines.size();
     for (uint32_t s = 0; s < es_.n_slots; ++s)

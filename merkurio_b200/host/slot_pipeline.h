@@ -64,6 +64,37 @@ struct PackedBatch {
 
 using BatchConsumer = std::function<void(const PackedBatch&, const mk_result&)>;
 
+// Helper threads of the packer. Deciding which records go into a batch, and where, is one cheap sequential pass
+// over the record index (it has to be: a batch closes when the slot is full); copying the sequence bytes — most of
+// the packer's time — is not, so fill() notes the copies and the pool carries them out on MERKURIO_PACK_THREADS
+// threads (default: 4 or a quarter of the cores, the packer thread included), each a contiguous range of the list.
+class CopyPool {
+public:
+    struct Copy {
+        const char* src;
+        uint64_t dst;  // offset in the slot's sequence buffer
+        uint32_t len;
+    };
+    explicit CopyPool(int threads);
+    ~CopyPool();
+    CopyPool(const CopyPool&) = delete;
+    void run(uint8_t* base, const std::vector<Copy>& list);  // returns when every copy is done
+    int threads() const { return (int)workers_.size() + 1; }
+
+private:
+    void work(size_t me);
+    static void copy_range(uint8_t* base, const Copy* c, size_t lo, size_t hi);
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    uint64_t generation_ = 0;
+    size_t pending_ = 0;
+    bool stop_ = false;
+    uint8_t* base_ = nullptr;
+    const Copy* list_ = nullptr;
+    size_t n_ = 0;
+};
+
 class SlotPipeline {
 public:
     SlotPipeline(EngineSet& engines, mk_encoding enc, mk_mode mode, BatchConsumer consumer);
@@ -83,6 +114,7 @@ protected:
     mk_encoding enc_;
     mk_mode mode_;
     bool input_done_ = false;
+    CopyPool copy_pool_;
 
 private:
     void pack();

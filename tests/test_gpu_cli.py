@@ -328,13 +328,17 @@ def test_tag_bam_output_random(tmp_path):
     assert len(again) == len(want) and all(a.startswith(w) for a, w in zip(again, want))
 
 
-def test_two_gpus_from_the_cli(ref_tree, tmp_path):
+@pytest.mark.parametrize("n_engines", [2, 3])
+def test_several_engines_from_the_cli(ref_tree, tmp_path, n_engines):
+    """The host's multi-GPU path: one engine per device, batches dealt round-robin, results merged in batch order, the
+    seed tables built once and uploaded per engine (mk_tables_create / mk_engine_create_shared). On a box with fewer
+    GPUs than engines the engines share device 0 (MERKURIO_DEVICES=0,0,...): the deal and the merge are the same."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+    multi = ({"MERKURIO_GPUS": str(n_engines)} if torch.cuda.device_count() >= n_engines
+             else {"MERKURIO_DEVICES": ",".join(["0"] * n_engines)})
     ew = ref_tree / "example-workflow"
     run("extract", "-i", ew / "data" / "mutant_R1.fastq", "-2", ew / "data" / "mutant_R2.fastq", "-f", ew / "data" / "significant_kmers.txt",
-        "-r", "-o", tmp_path / "m", "-j", tmp_path / "m.json", env={"MERKURIO_GPUS": "2", "MERKURIO_BATCH_BYTES": "300000"})
+        "-r", "-o", tmp_path / "m", "-j", tmp_path / "m.json", env=dict(multi, MERKURIO_BATCH_BYTES="300000", MERKURIO_TIMING="1"))
     assert (tmp_path / "m_1.fastq").read_bytes() == (ew / "output" / "mutant_extracted_1.fastq").read_bytes()
     assert (tmp_path / "m_2.fastq").read_bytes() == (ew / "output" / "mutant_extracted_2.fastq").read_bytes()
     got = json.loads((tmp_path / "m.json").read_bytes())
@@ -350,13 +354,13 @@ def test_two_gpus_from_the_cli(ref_tree, tmp_path):
     kf.write_bytes(b"\n".join(pats) + b"\n")
     one = _outputs(tmp_path, "fa1", ["extract", "-i", fa, "-f", kf, "-r", "-o", "@OUT@/x.fa", "-l", "@OUT@/x.log"], {"MERKURIO_BATCH_BYTES": "25000"})
     two = _outputs(tmp_path, "fa2", ["extract", "-i", fa, "-f", kf, "-r", "-o", "@OUT@/x.fa", "-l", "@OUT@/x.log"],
-                   {"MERKURIO_BATCH_BYTES": "25000", "MERKURIO_GPUS": "2"})
+                   dict(multi, MERKURIO_BATCH_BYTES="25000"))
     assert one[0] == two[0] == 0 and one[2]["x.fa"] == two[2]["x.fa"] and one[2]["x.fa"].count(b">chr") >= 1
     assert _strip_volatile("x.log", one[2]["x.log"]) == _strip_volatile("x.log", two[2]["x.log"])
     sam = ref_tree / "example-workflow" / "output" / "mutant_extracted.sorted.sam"
     a = _outputs(tmp_path, "t1", ["tag", "-i", sam, "-f", ew / "data" / "significant_kmers.txt", "-r", "-o", "@OUT@/t.sam"], {"MERKURIO_BATCH_BYTES": "20000"})
     b = _outputs(tmp_path, "t2", ["tag", "-i", sam, "-f", ew / "data" / "significant_kmers.txt", "-r", "-o", "@OUT@/t.sam"],
-                 {"MERKURIO_BATCH_BYTES": "20000", "MERKURIO_GPUS": "2"})
+                 dict(multi, MERKURIO_BATCH_BYTES="20000"))
     assert a[0] == b[0] == 0 and _strip_volatile("t.sam", a[2]["t.sam"]) == _strip_volatile("t.sam", b[2]["t.sam"])
 
 

@@ -483,3 +483,42 @@ def test_fixed_length_batches_without_offsets():
         np.testing.assert_array_equal(f.flagged_records(), np.unique(rec))
         with pytest.raises(capi.MkError):
             e.scan_host_uniform_async(0, packed, 10, 151, capi.MK_ENC_BAM4, capi.MK_MODE_FLAG)
+
+
+@pytest.mark.parametrize("kmin", [19, 20, 21, 22, 23, 26, 30])
+@pytest.mark.parametrize("foreign", [b"n", b"N", b"\x00", b"acgt"])
+def test_dual8_alphabet_gate_edges(monkeypatch, kmin, foreign):
+    """mk_scan_dual8 (stride 8, L2-resident dual-key filter) with its alphabet gate: bytes that occur in no pattern sit
+    directly in front of, directly behind and at every distance from occurrences, for every seed length q = 12..16
+    and every alignment of an occurrence to the 8-base grid. The gate may only drop windows that cannot match."""
+    monkeypatch.setenv("MK_FILTER_MODE", "l2")
+    rng = np.random.default_rng(kmin * 7 + len(foreign))
+    pats = sorted({rand_seq(rng, int(k)) for k in rng.integers(kmin, kmin + 30, size=300)} | {rand_seq(rng, kmin) for _ in range(20)})
+    pieces = []
+    for i in range(1500):
+        p = pats[int(rng.integers(len(pats)))]
+        gap = int(rng.integers(0, 40))
+        x = bytes([foreign[int(rng.integers(len(foreign)))]])
+        kind = i % 4
+        if kind == 0:    # foreign byte right behind and right in front of occurrences
+            pieces += [p, x, p, x * int(rng.integers(1, 20))]
+        elif kind == 1:  # clean text of any length between occurrences: every alignment to the grid
+            pieces += [p, rand_seq(rng, gap)]
+        elif kind == 2:  # an occurrence spoiled by one foreign byte anywhere inside it (no hit)
+            b = bytearray(p)
+            b[int(rng.integers(len(b)))] = x[0]
+            pieces += [bytes(b), rand_seq(rng, gap), p]
+        else:            # long foreign spans (whole tiles without a live window) with occurrences at their edges
+            pieces += [x * int(rng.integers(100, 5000)), p, x * int(rng.integers(1, 3)), p]
+    text = b"".join(pieces)
+    cuts = sorted(set(rng.integers(0, len(text), size=6).tolist()) | {0, len(text)})
+    recs = [text[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    with capi.Engine(pats, max_batch_bytes=len(text) + 64, max_batch_records=len(recs)) as e:
+        r = check_batch(pats, recs, engine=e)
+        assert "mk_scan_dual8" in e.scan_kernel(capi.MK_ENC_ASCII) and r.n_hits > 2000
+        gate = bool(e.info().features & capi.MK_FEATURE_GATE)
+        assert gate == (foreign != b"acgt" or True)  # upper-case ACGT patterns: bit 5 (and others) are constant, so a gate always exists
+    if foreign == b"acgt":  # -I: the folded alphabet holds both cases, the lower-case text matches and must not be gated away
+        with capi.Engine(pats, case_insensitive=True, max_batch_bytes=len(text) + 64, max_batch_records=len(recs)) as e:
+            r2 = check_batch(pats, recs, case_insensitive=True, engine=e)
+            assert r2.n_hits >= r.n_hits

@@ -141,8 +141,8 @@ def test_fastq_pipeline_reports_read_errors_like_the_record_path(exe, stub, tmp_
             seen.append((r.returncode, r.stderr, {f.name: f.read_bytes() for f in sorted(d.iterdir())}))
         # (flipped bytes either break the deflate stream or decode to garbage that no longer parses)
         assert seen[0][0] == 1 and ctx in seen[0][1] and b"Caused by:" in seen[0][1]
-        if n_reads == 3000:
-            assert b"decompressing" in seen[0][1]
+        if n_reads == 3000:  # (which of the two depends on how far inflate gets before it meets an invalid code)
+            assert b"decompressing" in seen[0][1] or seen[0][1].count(b"record parsing") >= 1
         else:  # the records in front of the damage (less zlib's last buffer) were written, by both paths alike
             assert sum(v.count(b"\n@a") for v in seen[0][2].values()) > 500
         for other in seen[1:]:
