@@ -262,13 +262,40 @@ ScanLaunch pick_dual8(bool gate) {
     }
 }
 
+// MK_TMA=1|2|3 (experiment, see mk_scan_d16_tma): tiles staged by bulk copies; 1: U=2 T=896, 2: U=4 T=512, 3: U=2 T=512.
+// The shapes are bounded by shared memory: filter (128-160 KiB) + candidate queues + 2 stages of U x 512 bytes per warp.
+int tma_shape() {
+    static const int v = std::getenv("MK_TMA") ? std::atoi(std::getenv("MK_TMA")) : 0;
+    return v;
+}
+bool use_tma(const mk::Tables& t) { return tma_shape() > 0 && t.d == 16 && t.filter_in_smem; }
+template <int ENC, bool B32>
+ScanLaunch pick_tma() {
+    switch (tma_shape()) {
+        case 2: return {mk::mk_scan_d16_tma<ENC, 4, 512, B32>, 512, 4 * 32};
+        case 3: return {mk::mk_scan_d16_tma<ENC, 2, 512, B32>, 512, 2 * 32};
+        default: return {mk::mk_scan_d16_tma<ENC, 2, 896, B32>, 896, 2 * 32};
+    }
+}
+
 // The scan kernel of a table set
 ScanLaunch pick_kernel(int enc, uint32_t d, bool smemf, bool win = false, bool f32 = false);
 ScanLaunch pick_kernel(const mk::Tables& t) {
     if (t.dual_perm) return pick_dual8(t.gate_mask != 0);
+    if (use_tma(t)) {
+        if (t.enc == MK_ENC_ASCII) return t.filter32 ? pick_tma<MK_ENC_ASCII, true>() : pick_tma<MK_ENC_ASCII, false>();
+        return t.filter32 ? pick_tma<MK_ENC_BAM4, true>() : pick_tma<MK_ENC_BAM4, false>();
+    }
     return pick_kernel(t.enc, t.d, t.filter_in_smem, t.win, t.filter32);
 }
-size_t scan_smem_bytes(const mk::Tables& t) { return t.filter_in_smem ? t.filter.size() * 4 : 0; }
+size_t scan_smem_bytes(const mk::Tables& t) {
+    if (!t.filter_in_smem) return 0;
+    if (use_tma(t)) {
+        const ScanLaunch k = pick_kernel(t);
+        return ((t.filter.size() * 4 + 127) & ~(size_t)127) + (size_t)(k.threads / 32) * 2 * (size_t)(k.tile_vecs * 16);
+    }
+    return t.filter.size() * 4;
+}
 
 ScanLaunch pick_kernel(int enc, uint32_t d, bool smemf, bool win, bool f32) {
     if (f32) {  // shared-memory filter with 32-bit blocks (small seed sets)
@@ -803,7 +830,9 @@ const char* mk_engine_scan_kernel(mk_engine* e, mk_encoding enc) {
     const mk::Tables& t = *e->tables[enc].host;
     const char* en = enc == MK_ENC_ASCII ? "ASCII" : "BAM4";
     char buf[160];
-    if (t.dual_perm)
+    if (use_tma(t))
+        std::snprintf(buf, sizeof buf, "mk_scan_d16_tma<%s, bulk-copy staged tiles, shape %d>", en, tma_shape());
+    else if (t.dual_perm)
         std::snprintf(buf, sizeof buf, "mk_scan_dual8<%s, stride 8, L2 dual-key filter%s>", en, t.gate_mask ? ", alphabet gate" : "");
     else if (t.d == 16)
         std::snprintf(buf, sizeof buf, "mk_scan_d16<%s, %s>", en, t.filter_in_smem ? (t.filter32 ? "smem filter 32-bit blocks" : "smem filter 64-bit blocks") : "L2 bitmap");

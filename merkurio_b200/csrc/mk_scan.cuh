@@ -272,7 +272,7 @@ __device__ __forceinline__ void sink_flush(const ScanParams& P, HitSink& sink, u
 template <int ENC>
 __device__ __forceinline__ void verify_one(const ScanParams& P, uint64_t pos, uint32_t pid, uint32_t j, HitSink& sink) {
     if (pos < j) return;
-    MK_ASSERT(pid < P.n_patterns && pos < P.n_units + 16);
+    MK_ASSERT(pid < P.n_patterns);  // (pos may lie past the text: the zero padding of a ragged last tile looks like poly-A and is dropped below)
     const uint8_t* text = reinterpret_cast<const uint8_t*>(P.text);
     const uint64_t s = pos - j;
     const uint32_t po = __ldg(P.pat_off + pid);
@@ -544,6 +544,105 @@ __global__ void __launch_bounds__(T, 1) mk_scan_d16(const __grid_constant__ Scan
 #pragma unroll
         for (int u = 0; u < U; ++u) a[u] = (v0 + u * 32 < P.n_vec) ? ld_stream(P.text + v0 + u * 32, pol16) : make_uint4(0, 0, 0, 0);
         process_tile<ENC, FMODE, U, false, B32>(P, filt, lb, a, v0, wq, lane);
+    }
+    queue_flush(P, wq, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Experiment (MK_TMA=1, not the default — measured slower, profiles/r2_tma_experiment.txt): the stride-16 scan with its
+// tiles staged through shared memory by the bulk-copy engine (TMA: cp.async.bulk.shared::cluster.global, completion on
+// an mbarrier) instead of 16-byte register loads. One lane per warp issues one bulk copy per tile (U x 512 contiguous
+// bytes) into one of the warp's two stages; the lanes wait on the stage's mbarrier and fetch their vectors with
+// LDS.128. The register double buffer goes away (fewer registers, no load instructions in the lanes), but every text
+// byte now crosses shared memory twice (written by the copy engine, read by LDS) in a kernel whose shared-memory
+// filter probes already keep L1TEX busy, and the stages take shared memory from the filter's neighbour, the L1.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MK_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MK_DONE;\n"
+        "bra MK_WAIT;\n"
+        "MK_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+
+template <int ENC, int U, int T, bool B32>
+__global__ void __launch_bounds__(T, 1) mk_scan_d16_tma(const __grid_constant__ ScanParams P) {
+    constexpr int kWarps = T / 32;
+    constexpr uint32_t kTileBytes = U * 512;
+    extern __shared__ __align__(128) uint32_t s_dyn[];  // [filter | kWarps x 2 stages x kTileBytes]
+    __shared__ uint2 s_queue[kWarps][kQueueCap];
+    __shared__ uint32_t s_qcount[kWarps];
+    __shared__ __align__(8) uint64_t s_bar[kWarps][2];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t lb = P.filter_blocks;
+    const uint32_t filter_bytes = (P.filter_blocks * 8u + 127u) & ~127u;
+    uint8_t* stage0 = reinterpret_cast<uint8_t*>(s_dyn) + filter_bytes + (size_t)w * 2 * kTileBytes;
+    const uint64_t pol = make_evict_first_policy();
+    const uint32_t nwarps = gridDim.x * kWarps;
+    const uint32_t full_tiles = P.n_vec / (U * 32);
+    WarpQueue wq{s_queue[w], 0, &s_qcount[w]};
+    if (lane == 0) {
+        *wq.cnt = 0;
+        mbar_init(&s_bar[w][0], 1);
+        mbar_init(&s_bar[w][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t t = blockIdx.x * kWarps + w;
+    const uint32_t warp0 = t;
+    const uint8_t* text = reinterpret_cast<const uint8_t*>(P.text);
+    auto issue = [&](uint32_t tile, uint32_t st) {  // lane 0: one bulk copy of the tile into stage st
+        mbar_expect_tx(&s_bar[w][st], kTileBytes);
+        bulk_g2s(stage0 + st * kTileBytes, text + (size_t)tile * kTileBytes, kTileBytes, &s_bar[w][st], pol);
+    };
+    if (lane == 0) {
+        if (t < full_tiles) issue(t, 0);
+        if (t + nwarps < full_tiles) issue(t + nwarps, 1);
+    }
+    stage_filter<kFilterSmem>(P, s_dyn);
+    const uint32_t* __restrict__ filt = s_dyn;
+
+    uint32_t st = 0, phase = 0;
+    uint4 a[U];
+    while (t < full_tiles) {
+        mbar_wait(&s_bar[w][st], phase);
+        const uint4* sv = reinterpret_cast<const uint4*>(stage0 + st * kTileBytes) + lane;
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = sv[u * 32];
+        __syncwarp();  // every lane has its vectors: the stage may be refilled
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            const uint32_t tn2 = t + 2 * nwarps;
+            if (tn2 < full_tiles) issue(tn2, st);
+        }
+        process_tile<ENC, kFilterSmem, U, false, B32>(P, filt, lb, a, t * (U * 32) + lane, wq, lane);
+        t += nwarps;
+        st ^= 1;
+        if (st == 0) phase ^= 1;
+    }
+    // ragged last tile (16-byte loads with bounds checks)
+    if (P.n_vec % (U * 32) != 0 && warp0 == full_tiles % nwarps) {
+        const uint32_t v0 = full_tiles * (U * 32) + lane;
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = (v0 + u * 32 < P.n_vec) ? ld_stream(P.text + v0 + u * 32, pol) : make_uint4(0, 0, 0, 0);
+        process_tile<ENC, kFilterSmem, U, false, B32>(P, filt, lb, a, v0, wq, lane);
     }
     queue_flush(P, wq, lane);
 }

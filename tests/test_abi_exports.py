@@ -72,3 +72,44 @@ def test_table_builder_output_is_unchanged(tmp_path):
     assert len(got) == len(want) == 18
     for g, w in zip(got, want):
         assert g == w
+
+
+def test_struct_layout_matches_the_binding_tables(tmp_path):
+    """The sizes and offsets INTEGRATION.md lists for the #[repr(C)] structs of a Rust binding, checked from a C
+    translation unit (the header's own _Static_asserts fire at compile time; the numbers are printed and compared
+    with the documented table as well)."""
+    import re
+    import subprocess
+    src = tmp_path / "layout.c"
+    fields = {
+        "mk_patterns": ["off", "n"], "mk_config": ["n_slots", "max_batch_records", "max_batch_bytes", "hit_capacity"],
+        "mk_hit": ["start", "pattern", "len"],
+        "mk_result": ["n_records", "hits", "n_hits", "bases_scanned", "device_ns", "scan_ns", "verify_ns", "n_candidates", "n_rescans", "d_record_flags", "d_hits"],
+        "mk_engine_info": ["seed_q", "seed_d", "n_seeds", "filter_log2_bits", "filter_hashes", "filter_bytes", "filter_in_smem", "table_bytes", "sm_count", "features"],
+    }
+    body = "".join(f'printf("{s} %zu", sizeof({s}));' + "".join(f'printf(" {f} %zu", offsetof({s}, {f}));' for f in fs) + 'printf("\\n");' for s, fs in fields.items())
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "merkurio_cuda.h"\nint main(void){' + body + "return 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-I", str(ROOT / "include"), "-o", str(exe), str(src)], check=True)
+    got = {ln.split()[0]: ln.split()[1:] for ln in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines()}
+    doc = (ROOT / "INTEGRATION.md").read_text()
+    for s, fs in fields.items():
+        row = next(ln for ln in doc.splitlines() if ln.startswith(f"| `{s}` |"))
+        cells = [c.strip() for c in row.strip("|").split("|")]
+        assert got[s][0] == cells[1], (s, got[s][0], cells[1])
+        documented = dict(re.findall(r"`(\w+)` (\d+)", cells[2]))
+        for f, off in zip(got[s][1::2], got[s][2::2]):
+            assert documented[f] == off, (s, f, off, documented[f])
+
+
+def test_exports_cover_the_header():
+    """Every function the header declares is exported by the built library (and listed in capi.EXPORTS)."""
+    import re
+    import subprocess
+    from merkurio_b200 import capi
+    hdr = (ROOT / "include" / "merkurio_cuda.h").read_text()
+    declared = set(re.findall(r"\b(mk_[a-z_0-9]+)\s*\(", hdr)) - {"mk_hit"}
+    syms = subprocess.run(["nm", "-D", "--defined-only", str(capi.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (mk_[a-z_0-9]+)", syms))
+    assert declared <= exported, declared - exported
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)

@@ -522,3 +522,28 @@ def test_dual8_alphabet_gate_edges(monkeypatch, kmin, foreign):
         with capi.Engine(pats, case_insensitive=True, max_batch_bytes=len(text) + 64, max_batch_records=len(recs)) as e:
             r2 = check_batch(pats, recs, case_insensitive=True, engine=e)
             assert r2.n_hits >= r.n_hits
+
+
+def test_candidate_index_range_is_refused_not_wrapped():
+    """candidate positions are 32-bit grid indices; a batch whose last index would not fit is refused
+    with MK_ERR_CAPACITY before anything is allocated or launched (it used to be scanned at wrapped positions). The
+    device buffer here is tiny: the sizes are only claimed."""
+    import torch
+    rng = np.random.default_rng(1)
+    d = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    off = torch.zeros(2, dtype=torch.int64, device="cuda")
+    cases = [
+        # (patterns, encoding, bases that must be refused, bases just below the limit of that geometry)
+        ([rand_seq(rng, 31) for _ in range(50)], capi.MK_ENC_BAM4, (1 << 36) + 64, None),       # stride 16 BAM4: 2 candidates per vector
+        ([rand_seq(rng, 27) for _ in range(50)], capi.MK_ENC_ASCII, (1 << 35) + 64, None),      # window scan, stride 8: 2 per vector
+        ([rand_seq(rng, 16) for _ in range(50)], capi.MK_ENC_ASCII, (1 << 34) + 64, None),      # window scan, stride 4: 4 per vector
+        ([rand_seq(rng, 12) for _ in range(50)], capi.MK_ENC_ASCII, (1 << 32) + 64, None),      # ordered scan: base positions
+    ]
+    for pats, enc, too_many, _ in cases:
+        with capi.Engine(sorted(set(pats)), n_slots=0) as e:
+            with pytest.raises(capi.MkError) as ei:
+                e.scan_device(d.data_ptr(), off.data_ptr(), 1, too_many, capi.MK_MODE_FLAG, enc)
+            assert ei.value.code == -6 and ("candidate index" in ei.value.message or "2^32 bases" in ei.value.message), ei.value.message
+            # the engine is still usable
+            small = e.scan_device(d.data_ptr(), off.data_ptr(), 1, 0, capi.MK_MODE_FLAG, enc, fetch=True)
+            assert small.n_hits == 0
