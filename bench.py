@@ -300,7 +300,9 @@ def bench_e2e_file(args):
     from merkurio_b200.synth import Synth
     from oracle import refmodel as rm
     n = args.file_reads
-    shm = Path("/dev/shm") if Path("/dev/shm").is_dir() else Path("/tmp")
+    import shutil
+    need = n * 340 * 1.2  # the FASTQ (~320 bytes per read) plus what is extracted
+    shm = next((Path(c) for c in ("/dev/shm", "/tmp", str(ROOT / "gpurun_out")) if Path(c).is_dir() and shutil.disk_usage(c).free > need), Path("/tmp"))
     d = shm / f"mk_bench_file_{os.getpid()}"
     out_json = d / "cli.json"
     try:
@@ -311,7 +313,6 @@ def bench_e2e_file(args):
             return {"error": pr.stderr[-400:]}
         res = json.loads(out_json.read_text())
     finally:
-        import shutil
         shutil.rmtree(d, ignore_errors=True)
     # the reference's matcher on the same reads, one thread, no parsing and no output (it can only be faster than the reference)
     m = min(n, args.file_ref_reads)
