@@ -278,9 +278,28 @@ ScanLaunch pick_tma() {
     }
 }
 
+// Strides 1 and 2, ASCII, direct prefix bitmap in shared memory (shortest pattern below 15 bases). MK_SHORT_SHAPE picks
+// another launch shape (tuning runs only).
+ScanLaunch pick_short(uint32_t d) {
+    static const int shape = std::getenv("MK_SHORT_SHAPE") ? std::atoi(std::getenv("MK_SHORT_SHAPE")) : 0;
+    if (d == 1) {
+        switch (shape) {
+            case 1: return {mk::mk_scan_short<1, 4, 512>, 512, 4 * 32};
+            case 3: return {mk::mk_scan_short<1, 2, 1024>, 1024, 2 * 32};  // (spills at 64 registers)
+            default: return {mk::mk_scan_short<1, 2, 768>, 768, 2 * 32};
+        }
+    }
+    switch (shape) {
+        case 1: return {mk::mk_scan_short<2, 4, 512>, 512, 4 * 32};
+        case 2: return {mk::mk_scan_short<2, 2, 768>, 768, 2 * 32};
+        default: return {mk::mk_scan_short<2, 2, 1024>, 1024, 2 * 32};
+    }
+}
+
 // The scan kernel of a table set
 ScanLaunch pick_kernel(int enc, uint32_t d, bool smemf, bool win = false, bool f32 = false);
 ScanLaunch pick_kernel(const mk::Tables& t) {
+    if (t.filter_direct) return pick_short(t.d);
     if (t.dual_perm) return pick_dual8(t.gate_mask != 0);
     if (use_tma(t)) {
         if (t.enc == MK_ENC_ASCII) return t.filter32 ? pick_tma<MK_ENC_ASCII, true>() : pick_tma<MK_ENC_ASCII, false>();
@@ -484,6 +503,8 @@ int enqueue(mk_engine* e, Workspace& ws) {
     P.case_insensitive = e->tab->ps.case_insensitive ? 1 : 0;
     P.short_mask = t.dual_perm ? t.win_mask0 : 0xFFFFFFFFu;
     P.pos_flags2 = t.dual_perm ? 1u : 0u;
+    P.direct_shift = t.filter_direct ? 32u - 2u * t.direct_q1 : 0u;
+    P.direct_words = t.filter_direct ? (uint32_t)t.filter.size() : 0u;
     P.gate_mask = t.gate_mask;
     P.gate_val = t.gate_val;
     P.cand = ws.cand.p;
@@ -830,7 +851,9 @@ const char* mk_engine_scan_kernel(mk_engine* e, mk_encoding enc) {
     const mk::Tables& t = *e->tables[enc].host;
     const char* en = enc == MK_ENC_ASCII ? "ASCII" : "BAM4";
     char buf[160];
-    if (use_tma(t))
+    if (t.filter_direct)
+        std::snprintf(buf, sizeof buf, "mk_scan_short<%s, stride %u, direct %u-base prefix bitmap>", en, t.d, t.direct_q1);
+    else if (use_tma(t))
         std::snprintf(buf, sizeof buf, "mk_scan_d16_tma<%s, bulk-copy staged tiles, shape %d>", en, tma_shape());
     else if (t.dual_perm)
         std::snprintf(buf, sizeof buf, "mk_scan_dual8<%s, stride 8, L2 dual-key filter%s>", en, t.gate_mask ? ", alphabet gate" : "");

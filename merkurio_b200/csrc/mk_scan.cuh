@@ -64,6 +64,7 @@ struct ScanParams {
     int case_insensitive;
     uint32_t short_mask;            // candidate code -> short seed code: (code >> short_shift) & short_mask
     uint32_t pos_flags2;            // 1: bit 1 of a candidate position says "only the short key passed" (mk_scan_dual8)
+    uint32_t direct_shift, direct_words;  // mk_scan_short: 32 - 2 * q1 and the size of the direct bitmap in 32-bit words
     uint32_t gate_mask, gate_val;   // alphabet gate (mk_scan_dual8): byte b with (b ^ gate_val) & gate_mask != 0 occurs in no pattern (per byte lane)
     // candidates: seeds that passed both filters, handed from the scan to the verify kernel
     uint2* cand;                    // {seed position / pos_mul, seed code}
@@ -1006,6 +1007,119 @@ __global__ void __launch_bounds__(T, 1) mk_scan_dual8(const __grid_constant__ Sc
 #pragma unroll
         for (int u = 0; u < U; ++u) a[u] = (v0 + u * 32 < P.n_vec) ? ld_stream(P.text + v0 + u * 32, pol) : zero;
         process_tile_dual8<U, GATE>(P, a, zero, v0, wq, lane);
+    }
+    queue_flush(P, wq, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// D == 1 or 2, ASCII, small query sets (shortest pattern below 15 bases: every or every second base starts a seed).
+// With 8-16 probes per 16 bases the scan is bound by its instructions and by shared-memory probes, not by HBM, so the
+// first level is the cheapest test there is: a DIRECT bitmap over the first q1 = min(q, 10) bases of a seed (4^10 bits
+// = 128 KiB at most), indexed by the ordered 2-bit code itself — one shift, one LDS.32 and a bit test per position,
+// no hashing (the blocked Bloom filter of mk_scan_ord costs about 16 instructions per probe). For q <= 10 that is
+// exact set membership of the seed classes; for q = 11..13 the full seed is tested by the second-level (L2-resident)
+// bitmap on the way out of the candidate queue, which only the ~1 % of positions that pass the prefix test reach
+// (the builder keeps the Bloom filter when more than 1 % of the prefixes are occupied). Same double-buffered tile
+// loop and batched queue insertion as the other scans (mk_scan_ord loads, probes and votes one probe at a time).
+// ---------------------------------------------------------------------------------------------
+template <int D, int U>
+__device__ __forceinline__ void process_tile_short(const ScanParams& P, const uint32_t* __restrict__ bitmap, const uint4 (&v)[U],
+                                                   const uint4& halo, uint32_t v0, WarpQueue& wq, uint32_t lane) {
+    constexpr int PPV = 16 / D;  // probes per vector
+    const uint32_t pshift = P.direct_shift;  // 32 - 2 * q1: window code -> index of its q1-base prefix
+    uint32_t c[U + 1];
+#pragma unroll
+    for (int u = 0; u < U; ++u) c[u] = mk_pack_ascii_ord(v[u].x, v[u].y, v[u].z, v[u].w);
+    c[U] = mk_pack_ascii_ord(halo.x, halo.y, halo.z, halo.w);  // meaningful in lane 31 only
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint32_t from_next_lane = __shfl_down_sync(0xFFFFFFFFu, c[u], 1);
+        const uint32_t from_next_row = (u + 1 < U) ? __shfl_sync(0xFFFFFFFFu, c[u + 1], 0) : c[U];
+        const uint32_t succ = (lane == 31) ? from_next_row : from_next_lane;
+        uint32_t pass = 0;
+#pragma unroll
+        for (int k = 0; k < PPV; ++k) {
+            const uint32_t idx = __funnelshift_l(succ, c[u], 2 * k * D) >> pshift;  // (k == 0: c[u] itself)
+            pass += (__funnelshift_r(bitmap[idx >> 5], 0u, idx) & 1u) * (1u << k);
+        }
+        const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, __popc(pass));
+        if (total == 0) continue;
+        // candidate = {base position, 16-base window at that position}
+        const uint32_t pos0 = (v0 + u * 32) * 16u;
+        if (wq.count + total <= kQueueCap) {
+            if (pass) {
+                uint32_t idx = atomicAdd(wq.cnt, __popc(pass));
+                MK_ASSERT(idx + __popc(pass) <= kQueueCap);
+#pragma unroll
+                for (int k = 0; k < PPV; ++k)
+                    if ((pass >> k) & 1u) wq.slot[idx++] = make_uint2(pos0 + k * D, __funnelshift_l(succ, c[u], 2 * k * D));
+            }
+            __syncwarp();
+            wq.count += total;
+            if (wq.count >= 32) {
+                do queue_drain32(P, wq, lane); while (wq.count >= 32);
+                if (lane == 0) *wq.cnt = wq.count;
+                __syncwarp();
+            }
+        } else {  // a burst (poly-A text against a poly-A pattern, ...): probe by probe, draining on the way
+#pragma unroll
+            for (int k = 0; k < PPV; ++k)
+                queue_push(P, wq, lane, (pass >> k) & 1u, pos0 + k * D, __funnelshift_l(succ, c[u], 2 * k * D));
+            if (lane == 0) *wq.cnt = wq.count;
+            __syncwarp();
+        }
+    }
+}
+
+template <int D, int U, int T>
+__global__ void __launch_bounds__(T, 1) mk_scan_short(const __grid_constant__ ScanParams P) {
+    constexpr int kWarps = T / 32;
+    extern __shared__ __align__(16) uint32_t s_bitmap[];
+    __shared__ uint2 s_queue[kWarps][kQueueCap];
+    __shared__ uint32_t s_qcount[kWarps];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t pol = make_evict_first_policy();
+    const uint32_t nwarps = gridDim.x * kWarps;
+    const uint32_t full_tiles = P.n_vec / (U * 32);
+    WarpQueue wq{s_queue[threadIdx.x >> 5], 0, &s_qcount[threadIdx.x >> 5]};
+    if (lane == 0) *wq.cnt = 0;
+    __syncwarp();
+    uint32_t t = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const uint32_t warp0 = t;
+    const size_t stride = (size_t)nwarps * (U * 32);
+    const uint4* p = P.text + (size_t)t * (U * 32) + lane;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    auto load_halo = [&](uint32_t tt) {  // first vector of the tile after tile `tt` (lane 31 only; zero past the end of the text)
+        const uint64_t hv = ((uint64_t)tt + 1) * (U * 32);
+        return (lane == 31 && hv < P.n_vec) ? ld_stream(P.text + hv, pol) : zero;
+    };
+    uint4 a[U], b[U], ha = zero, hb = zero;
+    if (t < full_tiles) { load_rows<U, false>(p, pol, a); ha = load_halo(t); }
+    {   // in flight meanwhile: the bitmap into shared memory (direct_words is a multiple of 4)
+        const uint4* src = reinterpret_cast<const uint4*>(P.filter);
+        uint4* dst = reinterpret_cast<uint4*>(s_bitmap);
+        for (uint32_t i = threadIdx.x; i < P.direct_words / 4; i += T) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    while (t < full_tiles) {
+        uint32_t tn = t + nwarps;
+        if (tn < full_tiles) { load_rows<U, false>(p + stride, pol, b); hb = load_halo(tn); }
+        process_tile_short<D, U>(P, s_bitmap, a, ha, t * (U * 32) + lane, wq, lane);
+        t = tn;
+        p += stride;
+        if (t >= full_tiles) break;
+        tn = t + nwarps;
+        if (tn < full_tiles) { load_rows<U, false>(p + stride, pol, a); ha = load_halo(tn); }
+        process_tile_short<D, U>(P, s_bitmap, b, hb, t * (U * 32) + lane, wq, lane);
+        t = tn;
+        p += stride;
+    }
+    // ragged last tile (bounds-checked loads; nothing follows it)
+    if (P.n_vec % (U * 32) != 0 && warp0 == full_tiles % nwarps) {
+        const uint32_t v0 = full_tiles * (U * 32) + lane;
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = (v0 + u * 32 < P.n_vec) ? ld_stream(P.text + v0 + u * 32, pol) : zero;
+        process_tile_short<D, U>(P, s_bitmap, a, zero, v0, wq, lane);
     }
     queue_flush(P, wq, lane);
 }

@@ -54,6 +54,8 @@ struct Tables {
     bool win = false;   // D == 8 / 4 with the shared-memory filter: seeds are masked 16-base windows in the permuted packing
     uint32_t win_mask0 = 0xFFFFFFFFu, win_mask1 = 0xFFFFFFFFu;
     bool filter_dual = false;  // L2-resident 64-bit blocked filter probed with both keys (stride < 16)
+    bool filter_direct = false;  // mk_scan_short (ASCII, stride 1 / 2): `filter` is a direct bitmap over the first direct_q1 bases of a seed
+    uint32_t direct_q1 = 0;
     bool dual_perm = false;    // dual-key flavour for mk_scan_dual8 (ASCII, stride 8): keys in the permuted window layout, 3-bit filter entries
     // Alphabet gate: a text byte b with (b ^ gate_val) & gate_mask != 0 occurs in no pattern (after -I folding),
     // so a seed window that holds one inside its first q bytes cannot belong to a match. 0: no such bit exists.
@@ -498,7 +500,44 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
 
     TBT("cuckoo");
     const double nn = (double)t.n_seeds;
-    if (want_smem) {
+    // Strides 1 and 2 (shortest pattern below 15 bases), ASCII: a direct bitmap over the first q1 = min(q, 10) bases of
+    // every seed instead of the hashed filter (mk_scan_short) — while it stays selective: at most 1 % of the 4^q1
+    // prefixes occupied, or q <= 10 (then it is exact and a Bloom filter could only pass more). The second-level bitmap
+    // on the full seed code is built as usual.
+    if (want_smem && enc == 0 && t.d <= 2 && !t.win && !std::getenv("MK_NO_DIRECT")) {
+        const uint32_t q1 = std::min<uint32_t>(t.q, 10);
+        const uint32_t words = std::max<uint32_t>(4u, (uint32_t)(((uint64_t)1 << (2 * q1)) / 32));
+        std::vector<uint32_t> bm(words, 0);
+        size_t occupied = 0;
+        for (auto& kv : keys) {
+            const uint32_t idx = kv.code >> (2 * (t.q - q1));
+            uint32_t& w = bm[idx >> 5];
+            if (!((w >> (idx & 31)) & 1u)) { w |= 1u << (idx & 31); ++occupied; }
+        }
+        if (t.q <= 10 || (double)occupied <= 0.01 * std::ldexp(1.0, 2 * (int)q1)) {
+            t.filter_direct = true;
+            t.direct_q1 = q1;
+        }
+        if (t.filter_direct) {
+            t.filter_in_smem = true;
+            t.filter32 = false;
+            t.filter_blocks = 0;
+            t.filter_log2_bits = 0;
+            t.filter_hashes = 1;
+            t.filter = std::move(bm);
+            uint32_t b2 = 16;
+            while (b2 < 30 && std::ldexp(1.0, b2) < nn * 64.0) ++b2;
+            t.filter2_log2_bits = b2;
+            t.filter2.assign((size_t)1 << (b2 - 5), 0);
+            for (auto& kv : keys) {
+                uint32_t h = mk_hash_f2(kv.code, b2);
+                t.filter2[h >> 5] |= 1u << (h & 31);
+            }
+        }
+    }
+    if (t.filter_direct) {
+        // (tables done above)
+    } else if (want_smem) {
         t.filter_in_smem = true;
         // small seed sets: 32-bit blocks are as selective and cost half the shared-memory traffic per probe
         // (k = 19..30, 2 000 patterns: 6.4 -> 7.0 TB/s); larger sets need the 64-bit blocks' lower false-positive rate

@@ -26,9 +26,9 @@ int main(int argc,char**argv){
       double t0=now();
       mk::Tables t = mk::build_tables(ps, enc);
       double dt=now()-t0;
-      printf("case %d enc %d: q=%u d=%u q2=%u lml=%u perm=%d win=%d wm=%x/%x dual=%d seeds=%u flb=%u fh=%u fb=%u smem=%d f32=%d f2lb=%u bm=%u dperm=%d gate=%x/%x | filter %016llx filter2 %016llx slots %016llx post %016llx pb %016llx po %016llx pl %016llx",
+      printf("case %d enc %d: q=%u d=%u q2=%u lml=%u perm=%d win=%d wm=%x/%x dual=%d seeds=%u flb=%u fh=%u fb=%u smem=%d f32=%d f2lb=%u bm=%u dperm=%d direct=%d/%u gate=%x/%x | filter %016llx filter2 %016llx slots %016llx post %016llx pb %016llx po %016llx pl %016llx",
         ci, enc, t.q,t.d,t.q2,t.long_min_len,t.perm,t.win,t.win_mask0,t.win_mask1,t.filter_dual,t.n_seeds,t.filter_log2_bits,t.filter_hashes,t.filter_blocks,t.filter_in_smem,t.filter32,t.filter2_log2_bits,t.bucket_mask,
-        t.dual_perm,t.gate_mask,t.gate_val,
+        t.dual_perm,t.filter_direct,t.direct_q1,t.gate_mask,t.gate_val,
         (unsigned long long)hv(t.filter),(unsigned long long)hv(t.filter2),(unsigned long long)hv(t.slots),(unsigned long long)hv(t.postings),(unsigned long long)hv(t.pat_bytes),(unsigned long long)hv(t.pat_off),(unsigned long long)hv(t.pat_live));
       fprintf(stderr,"case %d enc %d: %.3f s\n",ci,enc,dt);
       printf("\n");

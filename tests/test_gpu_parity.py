@@ -547,3 +547,19 @@ def test_candidate_index_range_is_refused_not_wrapped():
             # the engine is still usable
             small = e.scan_device(d.data_ptr(), off.data_ptr(), 1, 0, capi.MK_MODE_FLAG, enc, fetch=True)
             assert small.n_hits == 0
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 7, 9, 10, 11, 12, 13, 14])
+def test_short_patterns_direct_bitmap(k):
+    """mk_scan_short (strides 1 and 2, direct prefix bitmap): every pattern length below 15, dense hits (short patterns
+    occur everywhere), bursts that overflow the per-warp queue (poly-A), N and lower case next to occurrences, records
+    of every length, and a pattern set mixing the shortest length with much longer ones."""
+    rng = np.random.default_rng(200 + k)
+    pats = sorted({rand_seq(rng, k) for _ in range(6)} | {rand_seq(rng, int(x)) for x in rng.integers(k, k + 40, size=30)} | {b"A" * k})
+    recs = planted_records(rng, pats, 300, 0, 400, plant_p=0.6)
+    recs += [b"A" * 3000, b"", b"ACGT"[:k], rand_seq(rng, 20000), (b"acgtn" * 50) + pats[0] + b"N" + pats[-1] + b"n" + pats[1]]
+    with capi.Engine(pats, max_batch_bytes=sum(map(len, recs)) + 64, max_batch_records=len(recs), hit_capacity=1 << 12) as e:
+        check_batch(pats, recs, engine=e)
+        assert "mk_scan_short" in e.scan_kernel(capi.MK_ENC_ASCII), e.scan_kernel(capi.MK_ENC_ASCII)
+    if k >= 3:  # -I through the same path
+        check_batch(pats[:12], recs[:100] + [recs[-1]], case_insensitive=True)
