@@ -148,21 +148,51 @@ class ScanResult:
         return np.nonzero(bits)[0]
 
 
-class Engine:
-    """One engine per GPU (mk_engine_create). `patterns` is the sorted unique query list."""
+def _pattern_blob(patterns: Sequence[bytes]):
+    pats = [bytes(p) for p in patterns]
+    blob = np.frombuffer(b"".join(pats), dtype=np.uint8).copy() if sum(map(len, pats)) else np.zeros(1, np.uint8)
+    off = np.zeros(len(pats) + 1, dtype=np.uint32)
+    if pats:
+        off[1:] = np.cumsum([len(p) for p in pats])
+    return pats, blob, off
 
-    def __init__(self, patterns: Sequence[bytes], device: int = 0, case_insensitive: bool = False, n_slots: int = 2,
+
+class Tables:
+    """Host side of a query set (mk_tables_create): built once, shared by the engines created from it."""
+
+    def __init__(self, patterns: Sequence[bytes], case_insensitive: bool = False):
+        self.patterns, blob, off = _pattern_blob(patterns)
+        self.case_insensitive = case_insensitive
+        mp = MkPatterns(blob.ctypes.data, off.ctypes.data, len(self.patterns))
+        h = C.c_void_p()
+        _check(load().mk_tables_create(C.byref(mp), int(case_insensitive), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().mk_tables_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class Engine:
+    """One engine per GPU (mk_engine_create). `patterns` is the sorted unique query list, or a `Tables` object
+    (mk_engine_create_shared)."""
+
+    def __init__(self, patterns, device: int = 0, case_insensitive: bool = False, n_slots: int = 2,
                  max_batch_bytes: int = 64 << 20, max_batch_records: int = 1 << 20, hit_capacity: int = 0):
         L = load()
-        pats = [bytes(p) for p in patterns]
-        self._blob = np.frombuffer(b"".join(pats), dtype=np.uint8).copy() if sum(map(len, pats)) else np.zeros(1, np.uint8)
-        self._off = np.zeros(len(pats) + 1, dtype=np.uint32)
-        if pats:
-            self._off[1:] = np.cumsum([len(p) for p in pats])
-        mp = MkPatterns(self._blob.ctypes.data, self._off.ctypes.data, len(pats))
-        cfg = MkConfig(device, int(case_insensitive), n_slots, max_batch_records, max_batch_bytes, hit_capacity)
         h = C.c_void_p()
-        _check(L.mk_engine_create(C.byref(mp), C.byref(cfg), C.byref(h)))
+        if isinstance(patterns, Tables):
+            pats = patterns.patterns
+            cfg = MkConfig(device, int(patterns.case_insensitive), n_slots, max_batch_records, max_batch_bytes, hit_capacity)
+            _check(L.mk_engine_create_shared(patterns._h, C.byref(cfg), C.byref(h)))
+        else:
+            pats, self._blob, self._off = _pattern_blob(patterns)
+            mp = MkPatterns(self._blob.ctypes.data, self._off.ctypes.data, len(pats))
+            cfg = MkConfig(device, int(case_insensitive), n_slots, max_batch_records, max_batch_bytes, hit_capacity)
+            _check(L.mk_engine_create(C.byref(mp), C.byref(cfg), C.byref(h)))
         self._h = h
         self.n_slots = n_slots
         self.max_batch_bytes = max_batch_bytes

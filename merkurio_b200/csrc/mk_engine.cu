@@ -2,6 +2,7 @@
 // streams, kernel dispatch, overflow handling. No CPU matching path exists in this library.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <chrono>
 #include <cstdio>
@@ -97,6 +98,7 @@ struct Workspace {
     DevBuf<uint32_t> buckets;                // bucket sort: counts [kBuckets], starts [kBuckets + 1], cursors [kBuckets]
     DevBuf<uint2> cand;                      // candidate list handed from the scan to the verify kernel
     uint64_t cand_cap = 0;
+    DevBuf<unsigned long long> cta_clock;    // MK_CTA_CLOCKS=1: per-CTA start / end times of the scan kernel (diagnostics)
     DevBuf<unsigned long long> counters;     // [0] hits appended, [1] distinct pairs, [2] candidates
     PinBuf<unsigned long long> h_counters;
     PinBuf<uint64_t> h_flags;
@@ -222,6 +224,12 @@ ScanKernel pick_d16_u(int u, bool v8) {
 }
 #endif
 
+// MK_D16_SHAPE (tuning): launch shape of the stride-16 scan, see pick_by_d
+int d16_shape() {
+    const char* v = std::getenv("MK_D16_SHAPE");  // read per batch: a tuning process sweeps the shapes
+    return v ? std::atoi(v) : 0;
+}
+
 template <int ENC, int FMODE>
 ScanLaunch pick_by_d(uint32_t d) {
     if (d == 16) {
@@ -237,7 +245,10 @@ ScanLaunch pick_by_d(uint32_t d) {
             default: return {pick_d16_u<ENC, FMODE, 1024>(u, v8), 1024, u * 32};
         }
 #else
-        // measured best shape: 4 vectors per lane and tile, 896 threads, 16-byte loads
+        // measured best shapes. ASCII: 4 vectors per lane and tile, 896 threads, 16-byte loads. BAM4 (bound by its shared-memory probes, not by
+        // HBM): 768 threads, 2.8 % faster on BASELINE cfg4 (0.631 -> 0.607 ms). MK_D16_SHAPE=1 / 2 force 768 / 896.
+        const int shape = d16_shape();
+        if (shape == 1 || (shape == 0 && ENC == MK_ENC_BAM4)) return {mk::mk_scan_d16<ENC, FMODE, 4, 768, false>, 768, 4 * 32};
         return {mk::mk_scan_d16<ENC, FMODE, 4, 896, false>, 896, 4 * 32};
 #endif
     }
@@ -253,7 +264,7 @@ ScanLaunch pick_by_d(uint32_t d) {
 // (tuning runs only).
 ScanLaunch pick_dual8(bool gate) {
     // measured (cfg5, upper-case queries, scan ms): U=2 T=1024: 1.06, U=4 T=768: 1.08, U=4 T=512: 1.14
-    static const int shape = std::getenv("MK_DUAL_SHAPE") ? std::atoi(std::getenv("MK_DUAL_SHAPE")) : 1;
+    const int shape = std::getenv("MK_DUAL_SHAPE") ? std::atoi(std::getenv("MK_DUAL_SHAPE")) : 1;
     switch (shape) {
         case 0: return gate ? ScanLaunch{mk::mk_scan_dual8<4, 512, true>, 512, 4 * 32} : ScanLaunch{mk::mk_scan_dual8<4, 512, false>, 512, 4 * 32};
         case 2: return gate ? ScanLaunch{mk::mk_scan_dual8<4, 768, true>, 768, 4 * 32} : ScanLaunch{mk::mk_scan_dual8<4, 768, false>, 768, 4 * 32};
@@ -469,6 +480,20 @@ int check_position_range(const mk::Tables& t, mk_encoding enc, uint64_t n_units)
     return MK_OK;
 }
 
+// One candidate per thread; CTAs of 128 threads (MK_VERIFY_THREADS=256: 256; same speed when the kernel runs alone, and
+// the smaller CTAs find room earlier while the last CTAs of a scan kernel on another stream are still running).
+void launch_verify(mk_engine* e, Workspace& ws, const mk::ScanParams& P) {
+    const int vt = std::getenv("MK_VERIFY_THREADS") ? std::atoi(std::getenv("MK_VERIFY_THREADS")) : 128;
+    const int ctas = e->sm_count * 8 * 256 / (vt == 256 ? 256 : 128);
+    if (vt == 256) {
+        if (ws.enc == MK_ENC_ASCII) mk::mk_verify_candidates<MK_ENC_ASCII, 256><<<ctas, 256, 0, ws.stream>>>(P);
+        else mk::mk_verify_candidates<MK_ENC_BAM4, 256><<<ctas, 256, 0, ws.stream>>>(P);
+    } else {
+        if (ws.enc == MK_ENC_ASCII) mk::mk_verify_candidates<MK_ENC_ASCII, 128><<<ctas, 128, 0, ws.stream>>>(P);
+        else mk::mk_verify_candidates<MK_ENC_BAM4, 128><<<ctas, 128, 0, ws.stream>>>(P);
+    }
+}
+
 // Enqueue the device work of one batch on ws.stream (no host synchronisation).
 int enqueue(mk_engine* e, Workspace& ws) {
     DeviceTables& dt = e->tables[ws.enc];
@@ -522,6 +547,12 @@ int enqueue(mk_engine* e, Workspace& ws) {
     P.max_len = e->tab->ps.max_len;
     P.n_patterns = e->tab->ps.n;
     P.n_postings = (uint32_t)t.postings.size();
+    P.cta_clock = nullptr;
+    if (std::getenv("MK_CTA_CLOCKS")) {
+        CU(ws.cta_clock.ensure(2 * (size_t)e->sm_count));
+        CU(cudaMemsetAsync(ws.cta_clock.p, 0, 2 * (size_t)e->sm_count * sizeof(unsigned long long), ws.stream));
+        P.cta_clock = ws.cta_clock.p;
+    }
 
     uint32_t key_bits;
     if (ws.mode == MK_MODE_ALL_HITS) key_bits = mk::bits_for(ws.n_units) + P.len_bits + P.tie_bits;
@@ -543,8 +574,7 @@ int enqueue(mk_engine* e, Workspace& ws) {
         int grid = (int)std::min<uint64_t>((uint64_t)e->sm_count, std::max<uint64_t>(want, 1));
         k.fn<<<grid, k.threads, scan_smem_bytes(t), ws.stream>>>(P);
         CU(cudaEventRecord(ws.ev_scan, ws.stream));
-        if (ws.enc == MK_ENC_ASCII) mk::mk_verify_candidates<MK_ENC_ASCII><<<e->sm_count * 8, 256, 0, ws.stream>>>(P);
-        else mk::mk_verify_candidates<MK_ENC_BAM4><<<e->sm_count * 8, 256, 0, ws.stream>>>(P);
+        launch_verify(e, ws, P);
         CU(cudaGetLastError());
     } else {
         CU(cudaEventRecord(ws.ev_scan, ws.stream));
@@ -607,6 +637,24 @@ int finish_batch(mk_engine* e, Workspace& ws, mk_result* out) {
         CU(cudaEventElapsedTime(&b, ws.ev_begin, ws.ev_scan));
         CU(cudaEventElapsedTime(&c, ws.ev_scan, ws.ev_verify));
         ms_total += a; ms_scan += b; ms_verify += c;
+        if (ws.cta_clock.p && std::getenv("MK_CTA_CLOCKS")) {  // diagnostics: when did the scan CTAs start and end?
+            std::vector<unsigned long long> h(2 * (size_t)e->sm_count);
+            CU(cudaMemcpy(h.data(), ws.cta_clock.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            unsigned long long s0 = ~0ull, s1 = 0, e0 = ~0ull, e1 = 0;
+            std::vector<unsigned long long> ends;
+            for (int i = 0; i < e->sm_count; ++i) {
+                if (!h[2 * i] || !h[2 * i + 1]) continue;
+                s0 = std::min(s0, h[2 * i]); s1 = std::max(s1, h[2 * i]);
+                e0 = std::min(e0, h[2 * i + 1]); e1 = std::max(e1, h[2 * i + 1]);
+                ends.push_back(h[2 * i + 1]);
+            }
+            if (!ends.empty()) {
+                std::sort(ends.begin(), ends.end());
+                std::fprintf(stderr, "[merkurio] scan CTAs: %zu, start spread %.1f us, kernel %.1f us, ends before the last CTA's: first %.1f, median %.1f, 90th percentile %.1f us\n",
+                             ends.size(), (s1 - s0) / 1e3, (e1 - s0) / 1e3, (e1 - e0) / 1e3, (e1 - ends[ends.size() / 2]) / 1e3,
+                             (e1 - ends[ends.size() * 9 / 10]) / 1e3);
+            }
+        }
         const bool cand_over = ws.h_counters.p[2] > ws.cand_cap;
         const bool hits_over = ws.mode != MK_MODE_FLAG && ws.h_counters.p[0] > ws.hit_cap;
         if (!cand_over && !hits_over && ws.used_buckets && ws.h_counters.p[3]) {
@@ -956,9 +1004,13 @@ int mk_scan_device_submit(mk_engine* e, uint32_t slot, const void* d_seq, const 
     if ((!d_seq && n_units) || !d_off) return fail(MK_ERR_INVALID, "null device buffers");
     if (reinterpret_cast<uintptr_t>(d_seq) % 16) return fail(MK_ERR_INVALID, "d_seq must be 16-byte aligned");
     CU(cudaSetDevice(e->device));
-    // device-resident batches run in submission order: they would only compete for the same SMs, and the
-    // per-batch CUDA-event times stay those of the batch alone
-    if (e->last_device_submit && e->last_device_submit != s->ws.ev_end) CU(cudaStreamWaitEvent(s->ws.stream, e->last_device_submit, 0));
+    // Device-resident batches run in submission order: they would only compete for the same SMs, and the per-batch
+    // CUDA-event times stay those of the batch alone. Measured alternatives (scripts/bench_overlap.py, DESIGN.md section 4,
+    // profiles/r2_overlap_experiment/): the slots' streams left to run freely (MK_FREE=1), or all scans on one
+    // high-priority stream with the post-processing of the batch before beside them — 2-12 % more throughput for a
+    // stream of stride-16 batches, a loss of 17-60 % for the L2-filter scans, and no clean per-kernel times.
+    if (!std::getenv("MK_FREE") && e->last_device_submit && e->last_device_submit != s->ws.ev_end)
+        CU(cudaStreamWaitEvent(s->ws.stream, e->last_device_submit, 0));
     rc = begin_batch(e, s->ws, d_seq, reinterpret_cast<const unsigned long long*>(d_off), d_lens, n_records, n_units, enc, mode,
                      fetch != 0);
     if (rc == MK_OK) e->last_device_submit = s->ws.ev_end;

@@ -79,7 +79,16 @@ struct ScanParams {
     int mode;
     uint32_t len_bits, tie_bits, pat_bits, max_len;
     uint32_t n_patterns, n_postings;  // bounds for the debug checks
+    unsigned long long* cta_clock;    // MK_CTA_CLOCKS=1 (diagnostics): [2 * blockIdx.x] = globaltimer at CTA start, [+1] at its end
 };
+
+__device__ __forceinline__ void cta_clock_mark(const ScanParams& P, int which) {
+    if (P.cta_clock && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.cta_clock[2 * blockIdx.x + which] = t;
+    }
+}
 
 constexpr int kScanThreads = 1024;
 constexpr int kScanWarps = kScanThreads / 32;
@@ -512,6 +521,7 @@ __global__ void __launch_bounds__(T, 1) mk_scan_d16(const __grid_constant__ Scan
     const uint64_t pol = V8 ? 0 : make_evict_first_policy();
     const uint32_t nwarps = gridDim.x * kScanWarps;
     const uint32_t full_tiles = P.n_vec / (U * 32);
+    cta_clock_mark(P, 0);
     WarpQueue wq{s_queue[threadIdx.x >> 5], 0, &s_qcount[threadIdx.x >> 5]};
     if (lane == 0) *wq.cnt = 0;
     __syncwarp();
@@ -547,6 +557,7 @@ __global__ void __launch_bounds__(T, 1) mk_scan_d16(const __grid_constant__ Scan
         process_tile<ENC, FMODE, U, false, B32>(P, filt, lb, a, v0, wq, lane);
     }
     queue_flush(P, wq, lane);
+    if (P.cta_clock) { __syncthreads(); cta_clock_mark(P, 1); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -969,6 +980,7 @@ __global__ void __launch_bounds__(T, 1) mk_scan_dual8(const __grid_constant__ Sc
     constexpr int kWarps = T / 32;
     __shared__ uint2 s_queue[kWarps][kQueueCap];
     __shared__ uint32_t s_qcount[kWarps];
+    cta_clock_mark(P, 0);
     const uint32_t lane = threadIdx.x & 31;
     const uint64_t pol = make_evict_first_policy();
     const uint32_t nwarps = gridDim.x * kWarps;
@@ -976,7 +988,10 @@ __global__ void __launch_bounds__(T, 1) mk_scan_dual8(const __grid_constant__ Sc
     WarpQueue wq{s_queue[threadIdx.x >> 5], 0, &s_qcount[threadIdx.x >> 5]};
     if (lane == 0) *wq.cnt = 0;
     __syncwarp();
-    uint32_t t = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    // Adjacent tiles go to different CTAs (tile t -> CTA t mod grid): the gate makes soft-masked and N spans (kilobases =
+    // tens to hundreds of tiles) nearly free, and spread over the CTAs they leave the SMs evenly loaded; with adjacent
+    // tiles in one CTA the median CTA ended 50 us (5 %) before the last one on BASELINE cfg5.
+    uint32_t t = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
     const uint32_t warp0 = t;
     const size_t stride = (size_t)nwarps * (U * 32);
     const uint4* p = P.text + (size_t)t * (U * 32) + lane;
@@ -1009,6 +1024,7 @@ __global__ void __launch_bounds__(T, 1) mk_scan_dual8(const __grid_constant__ Sc
         process_tile_dual8<U, GATE>(P, a, zero, v0, wq, lane);
     }
     queue_flush(P, wq, lane);
+    if (P.cta_clock) { __syncthreads(); cta_clock_mark(P, 1); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1129,8 +1145,7 @@ __global__ void __launch_bounds__(T, 1) mk_scan_short(const __grid_constant__ Sc
 // bucket, postings, pattern bytes, record offsets) of thousands of candidates are in flight together
 // instead of stalling a streaming warp. The list length is read from device memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int kVerifyThreads = 256;
-template <int ENC>
+template <int ENC, int kVerifyThreads>
 __global__ void __launch_bounds__(kVerifyThreads) mk_verify_candidates(const __grid_constant__ ScanParams P) {
     __shared__ RawHit s_hits[kVerifyThreads / 32][kHitStage];
     __shared__ uint32_t s_cnt[kVerifyThreads / 32];
