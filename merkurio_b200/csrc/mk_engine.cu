@@ -335,6 +335,7 @@ ScanLaunch pick_kernel(int enc, uint32_t d, bool smemf, bool win, bool f32) {
             return {mk::mk_scan_win<MK_ENC_BAM4, 8, 4, 768, true>, 768, 4 * 32};
         }
         if (enc == MK_ENC_ASCII) return {mk::mk_scan_d16<MK_ENC_ASCII, mk::kFilterSmem, 4, 896, false, true>, 896, 4 * 32};
+        if (d16_shape() != 2) return {mk::mk_scan_d16<MK_ENC_BAM4, mk::kFilterSmem, 4, 768, false, true>, 768, 4 * 32};
         return {mk::mk_scan_d16<MK_ENC_BAM4, mk::kFilterSmem, 4, 896, false, true>, 896, 4 * 32};
     }
     if (win) {  // stride 8 / 4, shared-memory filter, window seeds in the permuted packing
@@ -404,6 +405,8 @@ int ensure_tables(mk_engine* e, int enc) {
     ScanLaunch k = pick_kernel(*dt.host);
     if (scan_smem_bytes(*dt.host))
         CU(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem_bytes(*dt.host)));
+    if (const char* co = std::getenv("MK_CARVEOUT"))  // tuning: shared-memory carve-out of the scan kernel in per cent
+        CU(cudaFuncSetAttribute(k.fn, cudaFuncAttributePreferredSharedMemoryCarveout, std::atoi(co)));
     dt.built = true;
     return MK_OK;
 }
@@ -549,8 +552,8 @@ int enqueue(mk_engine* e, Workspace& ws) {
     P.n_postings = (uint32_t)t.postings.size();
     P.cta_clock = nullptr;
     if (std::getenv("MK_CTA_CLOCKS")) {
-        CU(ws.cta_clock.ensure(2 * (size_t)e->sm_count));
-        CU(cudaMemsetAsync(ws.cta_clock.p, 0, 2 * (size_t)e->sm_count * sizeof(unsigned long long), ws.stream));
+        CU(ws.cta_clock.ensure(3 * (size_t)e->sm_count));
+        CU(cudaMemsetAsync(ws.cta_clock.p, 0, 3 * (size_t)e->sm_count * sizeof(unsigned long long), ws.stream));
         P.cta_clock = ws.cta_clock.p;
     }
 
@@ -638,7 +641,7 @@ int finish_batch(mk_engine* e, Workspace& ws, mk_result* out) {
         CU(cudaEventElapsedTime(&c, ws.ev_scan, ws.ev_verify));
         ms_total += a; ms_scan += b; ms_verify += c;
         if (ws.cta_clock.p && std::getenv("MK_CTA_CLOCKS")) {  // diagnostics: when did the scan CTAs start and end?
-            std::vector<unsigned long long> h(2 * (size_t)e->sm_count);
+            std::vector<unsigned long long> h(3 * (size_t)e->sm_count);
             CU(cudaMemcpy(h.data(), ws.cta_clock.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
             unsigned long long s0 = ~0ull, s1 = 0, e0 = ~0ull, e1 = 0;
             std::vector<unsigned long long> ends;
@@ -647,6 +650,12 @@ int finish_batch(mk_engine* e, Workspace& ws, mk_result* out) {
                 s0 = std::min(s0, h[2 * i]); s1 = std::max(s1, h[2 * i]);
                 e0 = std::min(e0, h[2 * i + 1]); e1 = std::max(e1, h[2 * i + 1]);
                 ends.push_back(h[2 * i + 1]);
+            }
+            if (std::getenv("MK_CTA_CLOCKS")[0] == '2') {  // per CTA: SM id and duration
+                std::fprintf(stderr, "[merkurio] scan CTA us by smid:");
+                for (int i = 0; i < e->sm_count; ++i)
+                    if (h[2 * i] && h[2 * i + 1]) std::fprintf(stderr, " %llu:%.0f", h[2 * (size_t)e->sm_count + i], (h[2 * i + 1] - h[2 * i]) / 1e3);
+                std::fprintf(stderr, "\n");
             }
             if (!ends.empty()) {
                 std::sort(ends.begin(), ends.end());

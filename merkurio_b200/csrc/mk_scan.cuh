@@ -87,6 +87,11 @@ __device__ __forceinline__ void cta_clock_mark(const ScanParams& P, int which) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         P.cta_clock[2 * blockIdx.x + which] = t;
+        if (which == 0) {
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            P.cta_clock[2 * gridDim.x + blockIdx.x] = smid;
+        }
     }
 }
 
