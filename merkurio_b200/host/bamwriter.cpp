@@ -1,4 +1,5 @@
 #include "bamwriter.h"
+#include "inflate.h"
 
 #include <atomic>
 #include <mutex>
@@ -126,7 +127,7 @@ static void bgzf_compress_block(const std::vector<uint8_t>& in, std::vector<uint
     size_t clen = zs.total_out, total = 18 + clen + 8;
     const uint8_t head[18] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 'B', 'C', 2, 0, (uint8_t)((total - 1) & 0xFF), (uint8_t)((total - 1) >> 8)};
     std::memcpy(out->data(), head, 18);
-    uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), in.data(), (uInt)in.size()), isize = (uint32_t)in.size();
+    uint32_t crc = crc32_fast(0, reinterpret_cast<const uint8_t*>(in.data()), in.size()), isize = (uint32_t)in.size();
     std::memcpy(out->data() + 18 + clen, &crc, 4);
     std::memcpy(out->data() + 18 + clen + 4, &isize, 4);
     out->resize(total);

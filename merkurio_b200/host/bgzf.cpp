@@ -5,9 +5,11 @@
 
 #include <algorithm>
 #include <cerrno>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
+#include "inflate.h"
 
 namespace mkh {
 
@@ -58,19 +60,25 @@ void BgzfReader::inflate_block(const Block& b) {
     const size_t hdr = 12 + xlen;
     if (b.in_len < hdr + 8) throw Error("corrupt BGZF block");
     if (b.out_len == 0) return;
-    z_stream zs;
-    std::memset(&zs, 0, sizeof zs);
-    if (inflateInit2(&zs, -15) != Z_OK) throw Error("inflateInit2 failed");
-    zs.next_in = const_cast<unsigned char*>(p + hdr);
-    zs.avail_in = (unsigned)(b.in_len - hdr - 8);
-    zs.next_out = reinterpret_cast<unsigned char*>(out_.data() + b.out_off);
-    zs.avail_out = (unsigned)b.out_len;
-    const int rc = inflate(&zs, Z_FINISH);
-    inflateEnd(&zs);
-    if (rc != Z_STREAM_END || zs.avail_out != 0) throw Error("Error while decompressing the input");
+    static const bool use_zlib = std::getenv("MERKURIO_ZLIB_INFLATE") != nullptr;  // the round-1 path, kept for comparison
+    if (use_zlib) {
+        z_stream zs;
+        std::memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) throw Error("inflateInit2 failed");
+        zs.next_in = const_cast<unsigned char*>(p + hdr);
+        zs.avail_in = (unsigned)(b.in_len - hdr - 8);
+        zs.next_out = reinterpret_cast<unsigned char*>(out_.data() + b.out_off);
+        zs.avail_out = (unsigned)b.out_len;
+        const int rc = inflate(&zs, Z_FINISH);
+        inflateEnd(&zs);
+        if (rc != Z_STREAM_END || zs.avail_out != 0) throw Error("Error while decompressing the input");
+    } else if (!inflate_exact(p + hdr, b.in_len - hdr - 8, reinterpret_cast<uint8_t*>(out_.data() + b.out_off), b.out_len)) {
+        // (the 8 trailer bytes and the next block, or the padding of in_, follow the payload: readable)
+        throw Error("Error while decompressing the input");
+    }
     const unsigned char* t = p + b.in_len - 8;
     const uint32_t want = t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
-    const uint32_t got = (uint32_t)crc32(crc32(0L, Z_NULL, 0), reinterpret_cast<const unsigned char*>(out_.data() + b.out_off), (unsigned)b.out_len);
+    const uint32_t got = crc32_fast(0, reinterpret_cast<const uint8_t*>(out_.data() + b.out_off), b.out_len);
     if (want != got) throw Error("Error while decompressing the input (CRC mismatch)");
 }
 

@@ -9,12 +9,15 @@
 #include <cerrno>
 #include <cstdint>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <string>
 #include <thread>
 #include <vector>
 
 #include "bgzf.h"
 #include "common.h"
+#include "inflate.h"
 #include "io.h"
 
 namespace mkh {
@@ -84,17 +87,178 @@ private:
     uint64_t pos_ = 0;
 };
 
-// gzip (also concatenated members, as `cat a.gz b.gz` and bgzip produce) through zlib's inflate. Not gzread: that
-// function reports an incomplete stream only from gzclose() (Z_BUF_ERROR), so a file cut short — a FASTA cut anywhere,
-// a FASTQ cut on a record boundary — would be taken for a complete, shorter input. Here the end of the file inside a
-// member is an error, like in the bzip2 / xz / zstd streams below.
+// gzip (RFC 1952; also concatenated members, as `cat a.gz b.gz` and bgzip produce) through the decoder of inflate.h
+// (MERKURIO_ZLIB_INFLATE=1: through zlib's inflate, the round-1 path, kept for comparison). The end of the file
+// inside a member is an error wherever it falls, like in the bzip2 / xz / zstd streams below, and so is a member
+// whose CRC-32 or length does not match its trailer. What was decoded in front of a damaged spot is handed out first.
 class GzipStream : public InputStream {
 public:
-    explicit GzipStream(int fd) : fd_(fd), in_(1 << 20) {
+    explicit GzipStream(int fd) : fd_(fd), in_((1 << 20) + 64), win_(kHistory + kChunk + Inflater::kOutputMargin + 64) {}
+    ~GzipStream() override { ::close(fd_); }
+    size_t read(char* dst, size_t n) override {
+        if (n == 0) return 0;
+        while (pend_begin_ == pend_end_) {
+            if (failed_) throw Error(error_);
+            if (state_ == kFinished) return 0;
+            try {
+                decode_some();
+            } catch (const Error& e) {
+                failed_ = true;
+                error_ = e.what();
+            }
+        }
+        const size_t k = std::min(n, pend_end_ - pend_begin_);
+        std::memcpy(dst, win_.data() + pend_begin_, k);
+        pend_begin_ += k;
+        return k;
+    }
+
+private:
+    enum State { kHeader, kBody, kTrailer, kFinished };
+    static constexpr size_t kHistory = 32u << 10, kChunk = 1u << 20;
+
+    // more compressed bytes behind the unconsumed ones; false at the end of the file
+    bool fill() {
+        if (eof_) return false;
+        if (in_pos_ > 0) {
+            std::memmove(in_.data(), in_.data() + in_pos_, in_len_ - in_pos_);
+            in_len_ -= in_pos_;
+            in_pos_ = 0;
+        }
+        const size_t cap = in_.size() - 64;
+        bool any = false;
+        while (in_len_ < cap) {
+            const size_t got = read_fd(fd_, in_.data() + in_len_, cap - in_len_);
+            if (got == 0) { eof_ = true; break; }
+            in_len_ += got;
+            any = true;
+        }
+        return any;
+    }
+    size_t avail() const { return in_len_ - in_pos_; }
+
+    // Parses the member header at in_pos_: 1 = done, 0 = more input needed.
+    int parse_header() {
+        const uint8_t* p = in_.data() + in_pos_;
+        const size_t n = avail();
+        if (n < 10) return 0;
+        if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || (p[3] & 0xE0)) throw Error("Error while decompressing the input (gzip)");
+        const unsigned flg = p[3];
+        size_t q = 10;
+        if (flg & 4) {  // FEXTRA
+            if (n < q + 2) return 0;
+            const size_t xlen = p[q] | ((size_t)p[q + 1] << 8);
+            q += 2;
+            if (n < q + xlen) return 0;
+            q += xlen;
+        }
+        for (unsigned bit : {8u, 16u}) {  // FNAME, FCOMMENT: zero-terminated
+            if (!(flg & bit)) continue;
+            const void* z = std::memchr(p + q, 0, n - q);
+            if (!z) return 0;
+            q = (size_t)(static_cast<const uint8_t*>(z) - p) + 1;
+        }
+        if (flg & 2) {  // FHCRC: the low 16 bits of the CRC-32 of the header so far (checked, as zlib and flate2 do)
+            if (n < q + 2) return 0;
+            const uint32_t want = p[q] | ((uint32_t)p[q + 1] << 8);
+            if ((crc32_fast(0, p, q) & 0xFFFFu) != want) throw Error("Error while decompressing the input (gzip)");
+            q += 2;
+        }
+        in_pos_ += q;
+        return 1;
+    }
+
+    // One step: a header, up to kChunk bytes of a member's data, or a trailer.
+    void decode_some() {
+        if (state_ == kHeader) {
+            if (avail() == 0 && !fill()) {
+                if (!first_member_) { state_ = kFinished; return; }  // clean end of the file behind a member
+                throw Error("Error while decompressing the input (truncated gzip stream)");
+            }
+            while (!parse_header()) {
+                if (avail() >= in_.size() - 64) throw Error("Error while decompressing the input (gzip)");  // a header of a megabyte
+                if (!fill()) throw Error("Error while decompressing the input (truncated gzip stream)");
+            }
+            first_member_ = false;
+            inf_.reset();
+            crc_ = (uint32_t)crc32(0L, Z_NULL, 0);
+            isize_ = 0;
+            hist_ = 0;
+            out_ = 0;
+            state_ = kBody;
+            return;
+        }
+        if (state_ == kBody) {
+            // slide: keep the last 32 KiB in front of the place the next chunk is decoded to
+            if (out_ > kHistory) {
+                std::memmove(win_.data(), win_.data() + out_ - kHistory, kHistory);
+                out_ = kHistory;
+                hist_ = kHistory;
+            }
+            const size_t begin = out_;
+            uint8_t* const out_end = win_.data() + begin + kChunk + Inflater::kOutputMargin;
+            for (;;) {
+                const uint8_t* ip = in_.data() + in_pos_;
+                uint8_t* op = win_.data() + out_;
+                const Inflater::Status rc = inf_.run(&ip, in_.data() + in_len_, eof_, win_.data(), &op, out_end);
+                in_pos_ = (size_t)(ip - in_.data());
+                out_ = (size_t)(op - win_.data());
+                if (rc == Inflater::kNeedInput) {
+                    fill();  // (at the end of the file the next call runs with in_final)
+                    continue;
+                }
+                if (rc == Inflater::kError) {
+                    deliver(begin);
+                    throw Error(eof_ && in_pos_ + 16 >= in_len_ ? "Error while decompressing the input (truncated gzip stream)"
+                                                                 : "Error while decompressing the input (gzip)");
+                }
+                if (rc == Inflater::kStreamEnd) state_ = kTrailer;
+                break;
+            }
+            deliver(begin);
+            return;
+        }
+        if (state_ == kTrailer) {
+            while (avail() < 8)
+                if (!fill()) throw Error("Error while decompressing the input (truncated gzip stream)");
+            const uint8_t* t = in_.data() + in_pos_;
+            const uint32_t want_crc = t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+            const uint32_t want_len = t[4] | ((uint32_t)t[5] << 8) | ((uint32_t)t[6] << 16) | ((uint32_t)t[7] << 24);
+            if (want_crc != crc_ || want_len != isize_) throw Error("Error while decompressing the input (gzip)");
+            in_pos_ += 8;
+            state_ = kHeader;
+        }
+    }
+    // [begin, out_) of the window was decoded by this step
+    void deliver(size_t begin) {
+        if (out_ == begin) return;
+        crc_ = crc32_fast(crc_, win_.data() + begin, out_ - begin);
+        isize_ += (uint32_t)(out_ - begin);
+        pend_begin_ = begin;
+        pend_end_ = out_;
+    }
+
+    int fd_;
+    std::vector<uint8_t> in_, win_;
+    size_t in_pos_ = 0, in_len_ = 0;
+    bool eof_ = false, first_member_ = true, failed_ = false;
+    std::string error_;
+    State state_ = kHeader;
+    Inflater inf_;
+    size_t hist_ = 0, out_ = 0;  // window: [0, out_) holds the latest output of the member, at least its last 32 KiB
+    size_t pend_begin_ = 0, pend_end_ = 0;  // decoded, not handed out yet
+    uint32_t crc_ = 0, isize_ = 0;
+};
+
+// The same through zlib (MERKURIO_ZLIB_INFLATE=1). Not gzread: that function reports an incomplete stream only from
+// gzclose() (Z_BUF_ERROR), so a file cut short would be taken for a complete, shorter input.
+class ZlibGzipStream : public InputStream {
+public:
+    explicit ZlibGzipStream(int fd) : fd_(fd), in_(1 << 20) {
         std::memset(&z_, 0, sizeof z_);
         if (inflateInit2(&z_, 15 + 16) != Z_OK) { ::close(fd_); throw Error("cannot open the gzip stream"); }
     }
-    ~GzipStream() override {
+    ~ZlibGzipStream() override {
         inflateEnd(&z_);
         ::close(fd_);
     }
@@ -328,6 +492,7 @@ std::unique_ptr<InputStream> InputStream::open(const std::string& path) {
     ssize_t n = ::pread(fd, m, sizeof m, 0);
     if (n >= 2 && m[0] == 0x1f && m[1] == 0x8b) {
         if (decompression_threads() > 1 && is_bgzf(fd)) return std::unique_ptr<InputStream>(new BgzfStream(fd, decompression_threads()));
+        if (std::getenv("MERKURIO_ZLIB_INFLATE")) return std::unique_ptr<InputStream>(new ZlibGzipStream(fd));
         return std::unique_ptr<InputStream>(new GzipStream(fd));
     }
     if (n >= 3 && m[0] == 'B' && m[1] == 'Z' && m[2] == 'h') return std::unique_ptr<InputStream>(new Bzip2Stream(fd));

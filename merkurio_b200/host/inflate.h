@@ -1,0 +1,67 @@
+// Raw DEFLATE (RFC 1951) decoder for the ingest path: gzip members and BGZF blocks of FASTA / FASTQ / BAM inputs
+// (the reference reads them through needletail / the bam crate, i.e. flate2). zlib's inflate decodes one symbol
+// per table walk through a 32-bit bit buffer; on sequencing data (mostly literals and short matches) that is the
+// slowest stage of the whole pipeline once the matching runs on the GPU. This decoder keeps 56-63 bits in a
+// 64-bit buffer (one unaligned load per refill), resolves literal / length codes through an 11-bit first-level
+// table, and copies matches eight bytes at a time. It can stop and resume at any symbol boundary, so a stream
+// is decoded in pieces of bounded size from an input buffer that is refilled in between.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace mkh {
+
+class Inflater {
+public:
+    enum Status {
+        kNeedInput,   // fewer than kInputMargin bytes left and `in_final` is false: call again with more input
+        kOutputFull,  // fewer than kOutputMargin bytes of room left: hand out what was produced and call again
+        kStreamEnd,   // the final block ended; `in` points behind the last byte the stream used
+        kError        // invalid or (with in_final) truncated stream
+    };
+    // A call makes progress unless it returns kNeedInput / kOutputFull with margins as below.
+    static constexpr size_t kInputMargin = 1200;  // a dynamic block header is parsed only when it is there in full
+    static constexpr size_t kOutputMargin = 320;  // a match of 258 bytes + the overshoot of the wide copies
+
+    Inflater() { reset(); }
+    void reset();
+    // With in_final: the output buffer is exactly as large as the stream's output, so decode up to its last byte
+    // (byte-wise copies near the end) instead of stopping kOutputMargin bytes short of it.
+    void set_exact_tail(bool on) { exact_tail_ = on; }
+    // Decodes from [*in, in_end) into [*out, out_end). Bytes from out_base on are the history matches may refer to
+    // (at least the last 32 KiB produced so far, or everything if less). The 16 bytes behind in_end must be
+    // readable (their value does not matter). Nothing is written at or behind out_end.
+    Status run(const uint8_t** in, const uint8_t* in_end, bool in_final, const uint8_t* out_base, uint8_t** out, uint8_t* out_end);
+
+private:
+    enum State { kBlockHeader, kStored, kHuffman, kDone };
+    static constexpr int kLitlenBits = 11, kDistBits = 8;
+    static constexpr int kLitlenEntries = (1 << kLitlenBits) + 1400, kDistEntries = (1 << kDistBits) + 700;
+
+    Status run_impl(const uint8_t** in, const uint8_t* in_end, bool in_final, const uint8_t* out_base, uint8_t** out, uint8_t* out_end);
+    Status run_generic(const uint8_t** in, const uint8_t* in_end, bool in_final, const uint8_t* out_base, uint8_t** out, uint8_t* out_end);
+    Status run_bmi2(const uint8_t** in, const uint8_t* in_end, bool in_final, const uint8_t* out_base, uint8_t** out, uint8_t* out_end);
+    bool read_dynamic_header(const uint8_t*& in, const uint8_t* in_end, bool in_final);
+    void use_fixed_codes();
+    static bool build_table(uint32_t* table, int table_bits, int table_cap, const uint8_t* lens, int n_syms, int kind);
+
+    uint64_t bitbuf_;
+    unsigned bitcnt_;
+    State state_;
+    bool last_block_;
+    uint32_t stored_left_;
+    bool fixed_loaded_;
+    bool exact_tail_ = false;
+    uint8_t tail_[2 * 1200 + 64];  // the last bytes of the input, zero padded: a (truncated) block header is parsed from here
+    uint32_t litlen_[kLitlenEntries];
+    uint32_t dist_[kDistEntries];
+};
+
+// CRC-32 as zlib's crc32() computes it (same running value in and out), by carry-less multiplication where the CPU has
+// it (PCLMULQDQ: four 128-bit lanes folded over 64 bytes per step), else through zlib.
+uint32_t crc32_fast(uint32_t crc, const uint8_t* p, size_t len);
+
+// One-shot helper (BGZF blocks): the whole stream is in [in, in + in_len), the output has exactly out_len bytes.
+bool inflate_exact(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len);
+
+}  // namespace mkh

@@ -264,7 +264,7 @@ int run(int argc, char** argv) {
         return 0;
     }
     if (cmd == "records") {
-        // diagnostic (not in the reference): merkurio records <file> <generic|chunked> [chunk_bytes]
+        // diagnostic (not in the reference): merkurio records <file> <generic|chunked|count|count-generic|cat> [chunk_bytes]
         // dumps what the record readers hand to the matcher and to the writer — the ingest half of the
         // extract path, testable without a GPU. One block per record: id, sequence, then the bytes the
         // FASTA/FASTQ writer would emit; a parse error ends the dump with "#error".
@@ -275,6 +275,18 @@ int run(int argc, char** argv) {
             out += "#id\t" + id + "\n#seq\t" + seq + "\n";
             r.write(&out);
         };
+        if (how == "cat") {  // the decompressed byte stream (codecs.cpp), as the readers see it
+            std::vector<char> buf(argc > 4 ? (size_t)std::strtoull(argv[4], nullptr, 10) : (size_t)8 << 20);
+            try {
+                std::unique_ptr<InputStream> in = InputStream::open(path);
+                while (size_t got = in->read(buf.data(), buf.size())) std::fwrite(buf.data(), 1, got, stdout);
+            } catch (const Error& e) {
+                std::fflush(stdout);
+                std::fprintf(stderr, "#error\t%s\n", e.what());
+                return 1;
+            }
+            return 0;
+        }
         if (how == "count" || how == "count-generic") {  // reader throughput: records and bases only
             uint64_t n = 0, bases = 0;
             if (how == "count") {
