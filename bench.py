@@ -15,7 +15,8 @@ Beside the headline the line carries (N = 1 only, each can be switched off):
   configs     cfg3 / cfg4 / cfg5 at BASELINE size: device time, dominant kernel, fraction of the HBM peak,
               and parity with the oracle on a sample of the same data
   e2e_file    file -> file: the host binary `merkurio extract` on a FASTQ on tmpfs, wall clock, with the
-              single-threaded oracle matcher timed on the same reads
+              single-threaded oracle matcher timed on the same reads; `gzip_input`: the same on a gzip-compressed
+              FASTQ through the host's own DEFLATE decoder and through zlib
 """
 from __future__ import annotations
 
@@ -312,6 +313,20 @@ def bench_e2e_file(args):
         if pr.returncode != 0:
             return {"error": pr.stderr[-400:]}
         res = json.loads(out_json.read_text())
+        # the same command on gzip-compressed input (how reads are stored in practice): the host's own DEFLATE decoder
+        # (host/inflate.cpp), and zlib's inflate (MERKURIO_ZLIB_INFLATE=1, the round-1 path) beside it
+        gz = {}
+        if args.file_gz_reads > 0:
+            for key, extra in (("own_decoder", {}), ("zlib", {"MERKURIO_ZLIB_INFLATE": "1"})):
+                pg = subprocess.run([sys.executable, str(ROOT / "scripts" / "bench_cli.py"), "--config", "cfg2", "--gz", "--reads", str(args.file_gz_reads),
+                                     "--dir", str(d), "--out", str(out_json)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600,
+                                    env={**os.environ, **extra})
+                if pg.returncode != 0:
+                    gz[key] = {"error": pg.stderr[-300:]}
+                    continue
+                rg = json.loads(out_json.read_text())
+                gz[key] = {"records_per_s": rg["records_per_s"], "records_per_s_after_cuda_startup": rg["records_per_s_after_setup"],
+                           "wall_s": rg["wall_s"], "input_bytes": rg["input_bytes"], "reads": rg["reads"]}
     finally:
         shutil.rmtree(d, ignore_errors=True)
     # the reference's matcher on the same reads, one thread, no parsing and no output (it can only be faster than the reference)
@@ -331,7 +346,7 @@ def bench_e2e_file(args):
             "extracted_set_equals_oracle": True, "host_cores": res["host_cores"],
             "reference_matcher_single_thread": {"records_per_s": m / t_ref, "gbases_per_s": m * 150 / t_ref / 1e9, "reads": m, "kind": "port",
                                                 "what": "oracle Aho-Corasick any-hit scan of the same reads in memory: no parsing, no output"},
-            "speedup_vs_reference_matcher": (n / wall) / (m / t_ref), "stages_last_run": res.get("stages_last_run", [])}
+            "speedup_vs_reference_matcher": (n / wall) / (m / t_ref), "gzip_input": gz, "stages_last_run": res.get("stages_last_run", [])}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -632,6 +647,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--no-e2e-file", action="store_true")
     ap.add_argument("--file-reads", type=int, default=12_000_000, help="reads of the FASTQ of the file -> file run")
+    ap.add_argument("--file-gz-reads", type=int, default=3_000_000, help="reads of the gzip-compressed FASTQ of the file -> file run (0: skip)")
     ap.add_argument("--file-ref-reads", type=int, default=4_000_000, help="reads the single-threaded oracle matcher is timed on")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -17,10 +17,10 @@ KERNELS = {
     # file stem: (substring of the mangled name, note)
     "mk_scan_d16_ascii": ("mk_scan_d16ILi0ELi0ELi4ELi896ELb0ELb1E", "cfg2: ASCII, stride 16, shared-memory filter with 32-bit blocks, U=4, T=896"),
     "mk_scan_d16_ascii_f64": ("mk_scan_d16ILi0ELi0ELi4ELi896ELb0ELb0E", "cfg3: ASCII, stride 16, shared-memory filter with 64-bit blocks"),
-    "mk_scan_d16_bam4": ("mk_scan_d16ILi1ELi0ELi4ELi896ELb0ELb0E", "cfg4: BAM 4-bit, stride 16, two seeds per 16-byte vector"),
+    "mk_scan_d16_bam4": ("mk_scan_d16ILi1ELi0ELi4ELi768ELb0ELb0E", "cfg4: BAM 4-bit, stride 16, two seeds per 16-byte vector, T=768"),
     "mk_scan_win_ascii_d8": ("mk_scan_winILi0ELi8ELi4ELi896ELb1E", "k = 19..30, small query sets: window seeds, stride 8"),
     "mk_scan_dual8_gate": ("mk_scan_dual8ILi2ELi1024ELb1E", "cfg5: stride 8, L2-resident dual-key filter, alphabet gate, U=2, T=1024"),
-    "mk_verify_candidates_ascii": ("mk_verify_candidatesILi0E", "candidate verification, one candidate per thread"),
+    "mk_verify_candidates_ascii": ("mk_verify_candidatesILi0ELi128E", "candidate verification, one candidate per thread, CTAs of 128 threads"),
 }
 
 
