@@ -22,6 +22,8 @@
 
 namespace mkh {
 
+std::unique_ptr<InputStream> open_parallel_gzip(int fd);  // pgzip.cpp
+
 namespace {
 
 size_t read_fd(int fd, void* dst, size_t n) {
@@ -139,33 +141,11 @@ private:
 
     // Parses the member header at in_pos_: 1 = done, 0 = more input needed.
     int parse_header() {
-        const uint8_t* p = in_.data() + in_pos_;
-        const size_t n = avail();
-        if (n < 10) return 0;
-        if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || (p[3] & 0xE0)) throw Error("Error while decompressing the input (gzip)");
-        const unsigned flg = p[3];
-        size_t q = 10;
-        if (flg & 4) {  // FEXTRA
-            if (n < q + 2) return 0;
-            const size_t xlen = p[q] | ((size_t)p[q + 1] << 8);
-            q += 2;
-            if (n < q + xlen) return 0;
-            q += xlen;
-        }
-        for (unsigned bit : {8u, 16u}) {  // FNAME, FCOMMENT: zero-terminated
-            if (!(flg & bit)) continue;
-            const void* z = std::memchr(p + q, 0, n - q);
-            if (!z) return 0;
-            q = (size_t)(static_cast<const uint8_t*>(z) - p) + 1;
-        }
-        if (flg & 2) {  // FHCRC: the low 16 bits of the CRC-32 of the header so far (checked, as zlib and flate2 do)
-            if (n < q + 2) return 0;
-            const uint32_t want = p[q] | ((uint32_t)p[q + 1] << 8);
-            if ((crc32_fast(0, p, q) & 0xFFFFu) != want) throw Error("Error while decompressing the input (gzip)");
-            q += 2;
-        }
-        in_pos_ += q;
-        return 1;
+        size_t len = 0;
+        const int rc = parse_gzip_header(in_.data() + in_pos_, avail(), &len);
+        if (rc < 0) throw Error("Error while decompressing the input (gzip)");
+        if (rc) in_pos_ += len;
+        return rc;
     }
 
     // One step: a header, up to kChunk bytes of a member's data, or a trailer.
@@ -493,6 +473,7 @@ std::unique_ptr<InputStream> InputStream::open(const std::string& path) {
     if (n >= 2 && m[0] == 0x1f && m[1] == 0x8b) {
         if (decompression_threads() > 1 && is_bgzf(fd)) return std::unique_ptr<InputStream>(new BgzfStream(fd, decompression_threads()));
         if (std::getenv("MERKURIO_ZLIB_INFLATE")) return std::unique_ptr<InputStream>(new ZlibGzipStream(fd));
+        if (std::unique_ptr<InputStream> par = open_parallel_gzip(fd)) return par;  // large regular files: several threads (pgzip.cpp)
         return std::unique_ptr<InputStream>(new GzipStream(fd));
     }
     if (n >= 3 && m[0] == 'B' && m[1] == 'Z' && m[2] == 'h') return std::unique_ptr<InputStream>(new Bzip2Stream(fd));

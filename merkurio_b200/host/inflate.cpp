@@ -2,6 +2,7 @@
 
 #include <zlib.h>
 
+#include <algorithm>
 #include <cstddef>
 #include <cstring>
 #if defined(__x86_64__)
@@ -329,6 +330,7 @@ __attribute__((always_inline)) inline Inflater::Status Inflater::run_impl(const 
                 stored_left_ -= (uint32_t)n;
             }
             state_ = last_block_ ? kDone : kBlockHeader;
+            if (stop_at_block_end_ && !last_block_) MK_LEAVE(kBlockEnd);
             continue;
         }
         // state_ == kHuffman
@@ -464,6 +466,7 @@ __attribute__((always_inline)) inline Inflater::Status Inflater::run_impl(const 
             state_ = kDone;
         } else {
             state_ = kBlockHeader;
+            if (stop_at_block_end_) MK_LEAVE(kBlockEnd);
         }
     }
 
@@ -507,6 +510,242 @@ __attribute__((target("bmi2")))
 Inflater::Status Inflater::run_bmi2(const uint8_t** in_p, const uint8_t* in_end, bool in_final, const uint8_t* out_base,
                                     uint8_t** out_p, uint8_t* out_end) {
     return run_impl(in_p, in_end, in_final, out_base, out_p, out_end);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// A stream taken apart at block boundaries
+// ---------------------------------------------------------------------------------------------------------------
+#define MK_REFILL()                                  \
+    do {                                             \
+        bitbuf |= load64(in) << bitcnt;              \
+        in += (63 - bitcnt) >> 3;                    \
+        bitcnt |= 56;                                \
+    } while (0)
+#define MK_BITS(n) ((uint32_t)bitbuf & ((1u << (n)) - 1u))
+#define MK_DROP(n) (bitbuf >>= (n), bitcnt -= (n))
+
+const uint8_t* Inflater::seek_bits(const uint8_t* base, uint64_t bitpos) {
+    const uint8_t* in = base + (bitpos >> 3);
+    const unsigned sub = (unsigned)(bitpos & 7);
+    bitbuf_ = 0;
+    bitcnt_ = 0;
+    if (sub) {
+        bitbuf_ = (uint64_t)(*in >> sub);
+        bitcnt_ = 8 - sub;
+        ++in;
+    }
+    state_ = kBlockHeader;
+    last_block_ = false;
+    stored_left_ = 0;
+    return in;
+}
+
+bool Inflater::probe_dynamic_header(const uint8_t* base, const uint8_t* end, uint64_t bitpos) {
+    const uint8_t* p = base + (bitpos >> 3);
+    if (end - p < 8) return false;
+    const unsigned sub = (unsigned)(bitpos & 7);
+    const uint64_t v = load64(p) >> sub;  // >= 57 bits
+    // BFINAL = 0, BTYPE = 2 (bits 1..2, least significant first), HLIT <= 29, HDIST <= 29
+    if ((v & 7) != 4 || ((v >> 3) & 31) > 29 || ((v >> 8) & 31) > 29) return false;
+    // the code-length code must be complete (Kraft sum 1): what zlib and every other deflate writes
+    const unsigned hclen = (unsigned)((v >> 13) & 15) + 4;
+    uint64_t w = v >> 17;  // 40 bits = 13 lengths; the rest from a second load
+    unsigned kraft = 0;
+    for (unsigned i = 0; i < hclen; ++i) {
+        if (i == 13) w = load64(base + ((bitpos + 17 + 39) >> 3)) >> ((bitpos + 17 + 39) & 7);
+        const unsigned len = (unsigned)(w & 7);
+        w >>= 3;
+        if (len) kraft += 128u >> len;
+    }
+    if (kraft != 128) return false;
+    // the whole header: both codes built (complete, not over-subscribed, end-of-block code present)
+    const uint8_t* in = seek_bits(base, bitpos);
+    uint64_t bitbuf = bitbuf_;
+    unsigned bitcnt = bitcnt_;
+    MK_REFILL();
+    MK_DROP(3);
+    bitbuf_ = bitbuf;
+    bitcnt_ = bitcnt;
+    return read_dynamic_header(in, end, true);
+}
+
+Inflater::MarkerRun Inflater::run_markers(const uint8_t* base, const uint8_t* end, uint64_t start_bit, uint64_t stop_bit,
+                                          std::vector<uint16_t>* outv, size_t max_symbols) {
+    MarkerRun res;
+    constexpr size_t kWin = 32768;
+    constexpr uint32_t kLMask = (1u << kLitlenBits) - 1, kDMask = (1u << kDistBits) - 1;
+    std::vector<uint16_t>& out = *outv;
+    if (out.size() < kWin + (1u << 20)) out.resize(kWin + (1u << 20));
+    for (size_t j = 0; j < kWin; ++j) out[j] = (uint16_t)(256 + j);
+    size_t n = kWin;
+    const uint8_t* in = seek_bits(base, start_bit);
+    uint64_t bitbuf = bitbuf_;
+    unsigned bitcnt = bitcnt_;
+    for (;;) {
+        if (in - (bitcnt >> 3) > end) return res;
+        MK_REFILL();
+        const bool last = MK_BITS(1); MK_DROP(1);
+        const unsigned type = MK_BITS(2); MK_DROP(2);
+        if (type == 0) {
+            MK_DROP(bitcnt & 7);
+            in -= bitcnt >> 3;
+            bitbuf = 0;
+            bitcnt = 0;
+            if (end - in < 4) return res;
+            const uint32_t len = in[0] | ((uint32_t)in[1] << 8), nlen = in[2] | ((uint32_t)in[3] << 8);
+            if ((len ^ nlen) != 0xFFFFu) return res;
+            in += 4;
+            if ((size_t)(end - in) < len) return res;
+            if (n - kWin + len > max_symbols) return res;
+            if (out.size() < n + len) out.resize(std::max(out.size() * 2, n + len));
+            for (uint32_t i = 0; i < len; ++i) out[n + i] = in[i];
+            n += len;
+            in += len;
+        } else if (type == 3) {
+            return res;
+        } else {
+            if (type == 1) {
+                use_fixed_codes();
+            } else {
+                bitbuf_ = bitbuf;
+                bitcnt_ = bitcnt;
+                if (!read_dynamic_header(in, end, true)) return res;
+                bitbuf = bitbuf_;
+                bitcnt = bitcnt_;
+            }
+            for (;;) {
+                if (in - (bitcnt >> 3) > end) return res;
+                if (out.size() < n + 260) {
+                    if (n - kWin > max_symbols) return res;
+                    out.resize(out.size() * 2);
+                }
+                uint16_t* o = out.data() + n;
+                MK_REFILL();
+                uint32_t e = litlen_[bitbuf & kLMask];
+                if (e & kLit) {
+                    // up to three first-level entries = six literals without another refill (as in the byte decoder)
+                    for (int k = 0; k < 3 && (e & kLit); ++k) {
+                        MK_DROP(e & 0xFF);
+                        o[0] = (uint16_t)((e >> 16) & 0xFF);
+                        o[1] = (uint16_t)(e >> 24);
+                        o += 1 + ((e >> 15) & 1);
+                        e = litlen_[bitbuf & kLMask];
+                    }
+                    n = (size_t)(o - out.data());
+                    continue;
+                }
+                if (e & kPtr) {
+                    MK_DROP(kLitlenBits);
+                    e = litlen_[(e >> 16) + MK_BITS((e >> 8) & 15)];
+                }
+                unsigned nb = e & 0xFF;
+                if (!nb) return res;
+                MK_DROP(nb);
+                if (e & kLit) {
+                    out[n++] = (uint16_t)((e >> 16) & 0xFF);
+                    continue;
+                }
+                if (e & kEob) break;
+                const unsigned xl = (e >> 8) & 15;
+                const size_t len = (e >> 16) + MK_BITS(xl);
+                MK_DROP(xl);
+                uint32_t d = dist_[bitbuf & kDMask];
+                if (d & kPtr) {
+                    MK_DROP(kDistBits);
+                    d = dist_[(d >> 16) + MK_BITS((d >> 8) & 15)];
+                }
+                nb = d & 0xFF;
+                if (!nb) return res;
+                MK_DROP(nb);
+                const unsigned xd = (d >> 8) & 15;
+                const size_t dist = (d >> 16) + MK_BITS(xd);
+                MK_DROP(xd);
+                // (dist <= 32768 <= n always: what lies in front of the start is the window of place holders)
+                const uint16_t* src = o - dist;
+                if (dist >= 4) {
+                    size_t k = 0;
+                    do {
+                        std::memcpy(o + k, src + k, 8);  // four symbols; the room behind n + len is there (260)
+                        k += 4;
+                    } while (k < len);
+                } else {
+                    for (size_t k = 0; k < len; ++k) o[k] = src[k];
+                }
+                n += len;
+            }
+        }
+        if (in - (bitcnt >> 3) > end) return res;
+        const uint64_t pos = (uint64_t)(in - base) * 8 - bitcnt;
+        if (last || pos >= stop_bit) {
+            out.resize(n);
+            res.ok = true;
+            res.ended_final = last;
+            res.end_bit = pos;
+            return res;
+        }
+    }
+}
+
+#undef MK_REFILL
+#undef MK_BITS
+#undef MK_DROP
+
+int parse_gzip_header(const uint8_t* p, size_t n, size_t* len) {
+    if (n < 10) return 0;
+    if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || (p[3] & 0xE0)) return -1;
+    const unsigned flg = p[3];
+    size_t q = 10;
+    if (flg & 4) {  // FEXTRA
+        if (n < q + 2) return 0;
+        const size_t xlen = p[q] | ((size_t)p[q + 1] << 8);
+        q += 2;
+        if (n < q + xlen) return 0;
+        q += xlen;
+    }
+    for (unsigned bit : {8u, 16u}) {  // FNAME, FCOMMENT: zero-terminated
+        if (!(flg & bit)) continue;
+        const void* z = std::memchr(p + q, 0, n - q);
+        if (!z) return 0;
+        q = (size_t)(static_cast<const uint8_t*>(z) - p) + 1;
+    }
+    if (flg & 2) {  // FHCRC: the low 16 bits of the CRC-32 of the header so far (checked, as zlib and flate2 do)
+        if (n < q + 2) return 0;
+        const uint32_t want = p[q] | ((uint32_t)p[q + 1] << 8);
+        if ((crc32_fast(0, p, q) & 0xFFFFu) != want) return -1;
+        q += 2;
+    }
+    *len = q;
+    return 1;
+}
+
+bool resolve_markers(const uint16_t* src, size_t n, const uint8_t* window, size_t window_valid, uint8_t* dst) {
+    const size_t first_valid = 32768 - window_valid;
+    bool ok = true;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t a, b;
+        std::memcpy(&a, src + i, 8);
+        std::memcpy(&b, src + i + 4, 8);
+        if (((a | b) & 0xFF00FF00FF00FF00ull) == 0) {  // eight plain bytes
+            for (int k = 0; k < 8; ++k) dst[i + k] = (uint8_t)src[i + k];
+            continue;
+        }
+        for (int k = 0; k < 8; ++k) {
+            const uint16_t v = src[i + k];
+            if (v < 256) { dst[i + k] = (uint8_t)v; continue; }
+            const size_t j = (size_t)v - 256;
+            ok &= j >= first_valid;
+            dst[i + k] = window[j];
+        }
+    }
+    for (; i < n; ++i) {
+        const uint16_t v = src[i];
+        if (v < 256) { dst[i] = (uint8_t)v; continue; }
+        const size_t j = (size_t)v - 256;
+        ok &= j >= first_valid;
+        dst[i] = window[j];
+    }
+    return ok;
 }
 
 #if defined(__x86_64__) && defined(__GNUC__)

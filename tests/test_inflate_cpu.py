@@ -170,3 +170,111 @@ def test_large_stream_in_pieces(exe, tmp_path):
         rc, out, err = cat(exe, p)
         assert rc == 0, err
         assert out == raw
+
+
+# ------------------------------------------------------------------------------------------------
+# One gzip member on several threads (merkurio_b200/host/pgzip.cpp): pieces of the compressed file are decoded without
+# their 32 KiB of history and stitched where the real decode arrives at their first bit. Small pieces here, so that a
+# megabyte of input is dozens of tasks; the result must be what zlib returns, whatever the tasks find.
+PAR = {"MERKURIO_GZIP_THREADS": "4", "MERKURIO_GZIP_PIECE_KB": "16", "MERKURIO_TIMING": "1"}
+
+
+def _stats(err: bytes):
+    """(pieces, used, not used, sequential blocks) from the MERKURIO_TIMING line of the parallel reader."""
+    import re
+    m = re.search(rb"gzip on (\d+) threads: (\d+) pieces of the file, (\d+) continued the decode where it stood, (\d+) not used; (\d+) blocks", err)
+    assert m, err
+    return tuple(int(x) for x in m.groups()[1:])
+
+
+@pytest.mark.parametrize("name", ["fastq_level6", "fastq_level1", "fastq_level9", "stored_blocks", "fixed_codes", "huffman_only", "run_length",
+                                  "small_blocks", "incompressible", "zeros", "period_25", "short_periods", "members"])
+def test_parallel_gzip_equals_zlib(exe, tmp_path, name):
+    raw, comp = CASES[name]
+    p = tmp_path / "x.gz"
+    p.write_bytes(comp)
+    for env in (PAR, {**PAR, "MERKURIO_GZIP_PIECE_KB": "5", "MERKURIO_GZIP_THREADS": "7"}, {**PAR, "MERKURIO_GZIP_PIECE_KB": "200", "MERKURIO_GZIP_THREADS": "2"}):
+        if len(comp) < 3 * 1024 * int(env["MERKURIO_GZIP_PIECE_KB"]):
+            continue  # (too small for this piece size: the sequential reader takes it)
+        rc, out, err = cat(exe, p, None, env)
+        assert rc == 0, (name, err)
+        assert out == raw, name
+        pieces, used, unused, seq = _stats(err)
+        assert used + unused <= pieces  # (pieces behind the end of the last member's data are never looked at)
+        if name.startswith("fastq_level"):
+            assert used >= 2, (pieces, used, unused, seq)  # (pieces smaller than a block find the same block start: one of them is used)
+        if name == "stored_blocks":
+            assert used <= 1 and seq > 0  # nothing the search accepts: the sequential decoder does the work, correctly
+        if name == "fixed_codes":
+            assert used == 1 and seq == 0  # one block from the first bit to the last: the first task decodes all of it
+
+
+def test_parallel_gzip_pieces_line_up(exe, tmp_path):
+    """Pieces larger than a block, dynamic blocks all along (what a FASTQ from gzip looks like): every piece finds a block
+    start and the real decode arrives exactly there, so the sequential decoder has nothing to do."""
+    raw = fastq(30_000, 31)
+    p = tmp_path / "x.gz"
+    p.write_bytes(gz(raw))
+    rc, out, err = cat(exe, p, None, {**PAR, "MERKURIO_GZIP_PIECE_KB": "200"})
+    assert rc == 0 and out == raw
+    pieces, used, unused, seq = _stats(err)
+    assert pieces >= 8 and used == pieces and seq == 0, (pieces, used, unused, seq)
+
+
+def test_parallel_gzip_reads_in_pieces_of_any_size(exe, tmp_path):
+    raw, comp = CASES["fastq_level6"]
+    p = tmp_path / "x.gz"
+    p.write_bytes(comp)
+    for chunk in (1000, 65536, 3_000_000):
+        rc, out, err = cat(exe, p, chunk, PAR)
+        assert rc == 0 and out == raw, chunk
+
+
+def test_parallel_gzip_errors_are_the_sequential_reader_s(exe, tmp_path):
+    """Cut or damaged files: the same exit status, the same message, and a prefix of the data in front of it."""
+    rng = random.Random(8)
+    raw = fastq(4000, 21)
+    comp = gz(raw)
+    p = tmp_path / "bad.gz"
+    seq_env = {"MERKURIO_GZIP_THREADS": "1"}
+    for cut in [len(comp) - 1, len(comp) - 4, len(comp) - 8, len(comp) - 9, len(comp) // 2, len(comp) // 3 + 1, 70_000, 50_001]:
+        p.write_bytes(comp[:cut])
+        rc, out, err = cat(exe, p, None, PAR)
+        rc1, out1, err1 = cat(exe, p, None, seq_env)
+        assert rc != 0 and rc1 != 0
+        assert [l for l in err.splitlines() if l.startswith(b"#error")] == [l for l in err1.splitlines() if l.startswith(b"#error")], cut
+        assert raw.startswith(out), cut
+    for _ in range(40):
+        c = bytearray(comp)
+        c[rng.randrange(10, len(comp))] ^= 1 << rng.randrange(8)
+        p.write_bytes(bytes(c))
+        rc, out, err = cat(exe, p, None, PAR)
+        try:
+            ref = gzip.decompress(bytes(c))
+        except Exception:
+            ref = None
+        if ref is None:
+            assert rc != 0
+        else:
+            assert rc == 0 and out == ref
+    p.write_bytes(comp + b"\0" * 16)  # bytes that are no member behind the last one
+    rc, out, err = cat(exe, p, None, PAR)
+    assert rc != 0 and out == raw
+    c = bytearray(comp)
+    c[-6] ^= 0x40  # the CRC-32 of the trailer
+    p.write_bytes(bytes(c))
+    rc, out, err = cat(exe, p, None, PAR)
+    assert rc != 0 and out == raw and b"Error while decompressing the input (gzip)" in err
+
+
+def test_parallel_gzip_through_the_fastq_reader(exe, tmp_path):
+    """The chunked FASTQ reader on top of the parallel stream hands over the same records as from the plain file."""
+    raw = fastq(8000, 5)
+    plain = tmp_path / "r.fastq"
+    plain.write_bytes(raw)
+    zipped = tmp_path / "r.fastq.gz"
+    zipped.write_bytes(gz(raw))
+    want = subprocess.run([exe, "records", str(plain), "chunked"], capture_output=True)
+    got = subprocess.run([exe, "records", str(zipped), "chunked"], capture_output=True, env={**os.environ, **PAR})
+    assert want.returncode == 0 and got.returncode == 0
+    assert got.stdout == want.stdout and want.stdout.count(b"#id\t") == 8000
