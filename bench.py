@@ -16,7 +16,7 @@ Beside the headline the line carries (N = 1 only, each can be switched off):
               and parity with the oracle on a sample of the same data
   e2e_file    file -> file: the host binary `merkurio extract` on a FASTQ on tmpfs, wall clock, with the
               single-threaded oracle matcher timed on the same reads; `gzip_input`: the same on a gzip-compressed
-              FASTQ through the host's own DEFLATE decoder and through zlib
+              FASTQ through the host's own DEFLATE decoder (several threads / one thread) and through zlib
 """
 from __future__ import annotations
 
@@ -313,12 +313,13 @@ def bench_e2e_file(args):
         if pr.returncode != 0:
             return {"error": pr.stderr[-400:]}
         res = json.loads(out_json.read_text())
-        # the same command on gzip-compressed input (how reads are stored in practice): the host's own DEFLATE decoder
-        # (host/inflate.cpp), and zlib's inflate (MERKURIO_ZLIB_INFLATE=1, the round-1 path) beside it
+        # the same command on gzip-compressed input (how reads are stored in practice; binned random qualities, level 1):
+        # the host's own DEFLATE decoder on several threads (host/pgzip.cpp), on one thread (host/inflate.cpp), and
+        # zlib's inflate (MERKURIO_ZLIB_INFLATE=1, the round-1 path) beside it
         gz = {}
         if args.file_gz_reads > 0:
-            for key, extra in (("own_decoder", {}), ("zlib", {"MERKURIO_ZLIB_INFLATE": "1"})):
-                pg = subprocess.run([sys.executable, str(ROOT / "scripts" / "bench_cli.py"), "--config", "cfg2", "--gz", "--reads", str(args.file_gz_reads),
+            for key, extra in (("own_decoder_parallel", {}), ("own_decoder_one_thread", {"MERKURIO_GZIP_THREADS": "1"}), ("zlib", {"MERKURIO_ZLIB_INFLATE": "1"})):
+                pg = subprocess.run([sys.executable, str(ROOT / "scripts" / "bench_cli.py"), "--config", "cfg2", "--gz", "--reuse", "--reads", str(args.file_gz_reads),
                                      "--dir", str(d), "--out", str(out_json)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600,
                                     env={**os.environ, **extra})
                 if pg.returncode != 0:
@@ -647,7 +648,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true")
     ap.add_argument("--no-e2e-file", action="store_true")
     ap.add_argument("--file-reads", type=int, default=12_000_000, help="reads of the FASTQ of the file -> file run")
-    ap.add_argument("--file-gz-reads", type=int, default=3_000_000, help="reads of the gzip-compressed FASTQ of the file -> file run (0: skip)")
+    ap.add_argument("--file-gz-reads", type=int, default=2_000_000, help="reads of the gzip-compressed FASTQ of the file -> file run (0: skip)")
     ap.add_argument("--file-ref-reads", type=int, default=4_000_000, help="reads the single-threaded oracle matcher is timed on")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

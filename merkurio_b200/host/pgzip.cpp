@@ -463,7 +463,8 @@ private:
 std::unique_ptr<InputStream> open_parallel_gzip(int fd) {
     struct stat st;
     if (::fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) return nullptr;
-    int threads = (int)std::min(16u, std::max(2u, std::thread::hardware_concurrency() / 2));
+    const unsigned hw = std::thread::hardware_concurrency();
+    int threads = (int)std::min(16u, std::max(2u, hw > 2 ? hw - 2 : 2u));  // (the stages behind the decoder mostly wait for it)
     if (const char* e = std::getenv("MERKURIO_GZIP_THREADS")) threads = std::atoi(e);
     if (threads < 2) return nullptr;
     size_t piece = (size_t)2 << 20;

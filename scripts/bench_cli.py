@@ -39,6 +39,7 @@ ap.add_argument("--keep-all", action="store_true", help="cfg4: tag every record 
 ap.add_argument("--check-reads", type=int, default=200_000)
 ap.add_argument("--gpus", type=int, default=1)
 ap.add_argument("--dir", default=None)
+ap.add_argument("--reuse", action="store_true", help="cfg2 / cfg3: keep the input files a previous run with the same arguments left in --dir")
 ap.add_argument("--out", default=None)
 args = ap.parse_args()
 EXE = ROOT / "merkurio_b200" / "lib" / "merkurio"
@@ -57,7 +58,13 @@ def fastq_bytes(seq: np.ndarray, n: int, r0: int, mate: str = "") -> bytes:
     rec[:, w + 1 + L] = 10
     rec[:, w + 2 + L] = ord("+")
     rec[:, w + 3 + L] = 10
-    rec[:, w + 4 + L:w + 4 + 2 * L] = ord("I")
+    if args.gz:
+        # binned qualities of a present-day sequencer (mostly 'F', some ':', ',', '#'): with a constant quality line the
+        # file would compress five-fold and decode far faster than real reads do
+        q = np.frombuffer(b"FFFFFFFFFFFF::,#", dtype=np.uint8)[np.random.default_rng(r0).integers(0, 16, size=(n, L), dtype=np.uint8)]
+        rec[:, w + 4 + L:w + 4 + 2 * L] = q
+    else:
+        rec[:, w + 4 + L:w + 4 + 2 * L] = ord("I")
     rec[:, -1] = 10
     flat = rec.reshape(-1)
     return flat[flat != 0].tobytes()  # names are NUL padded to a common width
@@ -160,13 +167,10 @@ if args.config in ("cfg2", "cfg3"):
     ext = ".fastq.gz" if args.gz else ".fastq"
     opener = (lambda p: gzip.open(p, "wb", compresslevel=1)) if args.gz else (lambda p: open(p, "wb"))
     p1 = tmp / ("reads_1" + ext)
-    files = [opener(p1)]
-    inputs = [p1]
-    if args.config == "cfg3":
-        p2 = tmp / ("reads_2" + ext)
-        files.append(opener(p2))
-        inputs.append(p2)
-    for r0 in range(0, n, CH):
+    inputs = [p1] + ([tmp / ("reads_2" + ext)] if args.config == "cfg3" else [])
+    reuse = args.reuse and all(p.exists() for p in inputs)  # (the caller ran the same --config / --reads / --gz in this --dir before)
+    files = [] if reuse else [opener(p) for p in inputs]
+    for r0 in range(0, 0 if reuse else n, CH):
         r1 = min(n, r0 + CH)
         seq, _ = syn.host_reads(r0, r1, 0)
         files[0].write(fastq_bytes(seq, r1 - r0, r0, "/1" if args.config == "cfg3" else ""))
