@@ -677,7 +677,7 @@ Inflater::MarkerRun Inflater::run_markers(const uint8_t* base, const uint8_t* en
         if (in - (bitcnt >> 3) > end) return res;
         const uint64_t pos = (uint64_t)(in - base) * 8 - bitcnt;
         if (last || pos >= stop_bit) {
-            out.resize(n);
+            res.n_out = n;
             res.ok = true;
             res.ended_final = last;
             res.end_bit = pos;

@@ -45,11 +45,13 @@ public:
         bool ok = false;           // the data decoded without an error up to end_bit
         bool ended_final = false;  // end_bit is the end of the final block of a member
         uint64_t end_bit = 0;      // a block boundary: the first one at or behind stop_bit, or the end of the final block
+        size_t n_out = 0;          // entries of `out` in use: 32768 place holders of the window + the symbols decoded
     };
     // Decodes from the block header at start_bit, block after block, WITHOUT knowing the 32 KiB in front of it: the
     // output is 16-bit, a value below 256 is a byte, 256 + j stands for byte j of the unknown window (j = 32767: the
-    // byte just before the start). out->size() on return = 32768 (the window's place holders) + the symbols decoded.
-    // Fails (ok = false) on invalid data, at the end of the input inside a block, or beyond max_symbols.
+    // byte just before the start). `out` only ever grows (a buffer that goes round is not filled with zeros again);
+    // n_out of the result says how much of it is in use. Fails (ok = false) on invalid data, at the end of the input
+    // inside a block, or beyond max_symbols.
     MarkerRun run_markers(const uint8_t* base, const uint8_t* end, uint64_t start_bit, uint64_t stop_bit, std::vector<uint16_t>* out,
                           size_t max_symbols);
     // Decodes from [*in, in_end) into [*out, out_end). Bytes from out_base on are the history matches may refer to

@@ -56,18 +56,21 @@ struct Task {  // one piece of the compressed file, decoded with an unknown wind
     bool ok = false;           // a start was found and the data decoded up to end_bit
     bool ended_final = false;
     uint64_t start_bit = 0, end_bit = 0;
-    std::vector<uint16_t> sym;  // kWin place holders + the decoded symbols
+    std::vector<uint16_t> sym;  // kWin place holders + the decoded symbols (n_sym entries in use)
+    size_t n_sym = 0;
 };
 
 struct Piece {  // one stretch of output, in the order of the stream
     enum Kind { kData, kMemberEnd, kError, kEnd } kind = kData;
     bool ready = false;
-    std::vector<uint8_t> bytes;
-    uint32_t crc = 0;              // kData: of `bytes`; kMemberEnd: the trailer's
+    std::vector<uint8_t> bytes;    // (a buffer that goes round: n_bytes of it are the data)
+    size_t n_bytes = 0;
+    uint32_t crc = 0;              // kData: of the data; kMemberEnd: the trailer's
     uint32_t isize = 0;            // kMemberEnd: the trailer's
     std::string error;             // kError
     // kData that still has place holders to replace (a job for the pool):
     std::vector<uint16_t> sym;
+    size_t n_sym = 0;
     std::vector<uint8_t> window;   // the 32 KiB in front of it
     size_t window_valid = 0;
     bool bad_distance = false;
@@ -128,8 +131,8 @@ public:
     size_t read(char* dst, size_t n) override {
         if (n == 0) return 0;
         for (;;) {
-            if (cur_ && cur_pos_ < cur_->bytes.size()) {
-                const size_t k = std::min(n, cur_->bytes.size() - cur_pos_);
+            if (cur_ && cur_pos_ < cur_->n_bytes) {
+                const size_t k = std::min(n, cur_->n_bytes - cur_pos_);
                 std::memcpy(dst, cur_->bytes.data() + cur_pos_, k);
                 cur_pos_ += k;
                 return k;
@@ -147,13 +150,14 @@ public:
                 pieces_.pop_front();
             }
             cv_piece_.notify_all();  // (room for the stitcher)
+            if (cur_) give_bytes(std::move(cur_->bytes));
             cur_.reset();
             cur_pos_ = 0;
             switch (p->kind) {
                 case Piece::kData:
                     if (p->bad_distance) fail("Error while decompressing the input (gzip)");
-                    crc_ = p->bytes.empty() ? crc_ : (uint32_t)crc32_combine(crc_, p->crc, (z_off_t)p->bytes.size());
-                    isize_ += (uint32_t)p->bytes.size();
+                    crc_ = p->n_bytes == 0 ? crc_ : (uint32_t)crc32_combine(crc_, p->crc, (z_off_t)p->n_bytes);
+                    isize_ += (uint32_t)p->n_bytes;
                     cur_ = p;
                     break;
                 case Piece::kMemberEnd:
@@ -180,6 +184,32 @@ private:
         throw Error(msg);
     }
 
+    // Buffers go round (tasks' symbols, pieces' bytes): a fresh 30 MB vector per task is thousands of page faults, and
+    // page faults of a dozen threads hold up the CUDA start-up that runs beside the first seconds of a decode
+    // (both want the process's address-space lock).
+    std::vector<uint16_t> take_sym() {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (free_sym_.empty()) return {};
+        std::vector<uint16_t> v = std::move(free_sym_.back());
+        free_sym_.pop_back();
+        return v;
+    }
+    std::vector<uint8_t> take_bytes() {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (free_bytes_.empty()) return {};
+        std::vector<uint8_t> v = std::move(free_bytes_.back());
+        free_bytes_.pop_back();
+        return v;
+    }
+    void give_sym_locked(std::vector<uint16_t>&& v) {
+        if (v.capacity() && free_sym_.size() < lookahead_ + max_pieces_) free_sym_.push_back(std::move(v));
+        else std::vector<uint16_t>().swap(v);
+    }
+    void give_bytes(std::vector<uint8_t>&& v) {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (v.capacity() && free_bytes_.size() < max_pieces_ + 2) free_bytes_.push_back(std::move(v));
+    }
+
     // ---- the pool: replacing place holders first (the reader waits for those), decoding pieces of the file otherwise --------
     void worker() {
         Inflater inf;
@@ -199,15 +229,17 @@ private:
             }
             if (job) {
                 const double t0 = now_s();
-                const size_t n = job->sym.size() - kWin;
-                job->bytes.resize(n);
+                const size_t n = job->n_sym - kWin;
+                job->bytes = take_bytes();
+                if (job->bytes.size() < n) job->bytes.resize(n);
+                job->n_bytes = n;
                 job->bad_distance = !resolve_markers(job->sym.data() + kWin, n, job->window.data(), job->window_valid, job->bytes.data());
                 job->crc = crc32_fast(0, job->bytes.data(), n);
-                std::vector<uint16_t>().swap(job->sym);
                 std::vector<uint8_t>().swap(job->window);
                 const double dt = now_s() - t0;
                 {
                     std::lock_guard<std::mutex> lk(mu_);
+                    give_sym_locked(std::move(job->sym));
                     job->ready = true;
                     t_resolve_ += dt;
                 }
@@ -216,6 +248,7 @@ private:
             }
             Task& t = tasks_[i];
             double t_search = 0, t_decode = 0;
+            t.sym = take_sym();
             run_task(inf, i, t, &t_search, &t_decode);
             {
                 std::lock_guard<std::mutex> lk(mu_);
@@ -244,10 +277,10 @@ private:
         *t_search = t1 - t0;
         *t_decode = now_s() - t1;
         t.ok = r.ok;
+        t.n_sym = r.n_out;
         t.ended_final = r.ended_final;
         t.start_bit = start;
         t.end_bit = r.end_bit;
-        if (!r.ok) std::vector<uint16_t>().swap(t.sym);
     }
 
     // ---- the stitcher ----------------------------------------------------------------------------------------------
@@ -263,7 +296,8 @@ private:
     void drop_oldest_task() {
         {
             std::lock_guard<std::mutex> lk(mu_);
-            std::vector<uint16_t>().swap(tasks_[consumed_].sym);
+            give_sym_locked(std::move(tasks_[consumed_].sym));
+            tasks_[consumed_].sym = std::vector<uint16_t>();
             ++consumed_;
         }
         cv_work_.notify_all();
@@ -331,9 +365,10 @@ private:
                     // the real decode stands at the first bit of this task: its symbols are the continuation
                     auto p = std::make_shared<Piece>();
                     p->sym.swap(t->sym);
+                    p->n_sym = t->n_sym;
                     p->window = window_;
                     p->window_valid = window_valid_;
-                    const size_t n = p->sym.size() - kWin;
+                    const size_t n = p->n_sym - kWin;
                     // the next window: the last 32 KiB of this piece, resolved here (the rest is a job for the pool; a
                     // distance that reaches in front of the member shows there as well and is reported in order)
                     const size_t tail = std::min(n, kWin);
@@ -373,7 +408,10 @@ private:
         const size_t n = (size_t)(op - area);
         if (n) {
             auto p = std::make_shared<Piece>();
-            p->bytes.assign(area, area + n);
+            p->bytes = take_bytes();
+            if (p->bytes.size() < n) p->bytes.resize(n);
+            std::memcpy(p->bytes.data(), area, n);
+            p->n_bytes = n;
             p->crc = crc32_fast(0, area, n);
             p->ready = true;
             slide_window(area, n);
@@ -432,6 +470,8 @@ private:
     std::condition_variable cv_work_, cv_done_, cv_piece_;
     std::vector<Task> tasks_;
     std::deque<std::shared_ptr<Piece>> pieces_, jobs_;  // pieces_: in stream order, for the reader; jobs_: place holders to replace
+    std::vector<std::vector<uint16_t>> free_sym_;
+    std::vector<std::vector<uint8_t>> free_bytes_;
     std::vector<std::thread> pool_;
     std::thread stitcher_;
     size_t next_task_ = 0, consumed_ = 0, lookahead_ = 4, max_pieces_ = 4;

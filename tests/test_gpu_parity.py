@@ -563,3 +563,37 @@ def test_short_patterns_direct_bitmap(k):
         assert "mk_scan_short" in e.scan_kernel(capi.MK_ENC_ASCII), e.scan_kernel(capi.MK_ENC_ASCII)
     if k >= 3:  # -I through the same path
         check_batch(pats[:12], recs[:100] + [recs[-1]], case_insensitive=True)
+
+
+def test_engines_on_shared_tables_and_free_running_slots(monkeypatch):
+    """mk_tables_create / mk_engine_create_shared through capi.Tables: two engines on one table object give the oracle's
+    hits, also after the Python handle of the tables is closed (the engines hold their own reference); and with
+    MK_FREE=1 (the slots' streams not ordered among each other) batches in flight still come back complete."""
+    import torch
+    rng = np.random.default_rng(91)
+    pats = sorted({rand_seq(rng, int(rng.integers(31, 50))) for _ in range(300)})
+    recs = planted_records(rng, pats, 3000, 100, 200, plant_p=0.2)
+    want = oracle_hits(pats, recs)
+    tables = capi.Tables(pats)
+    e1 = capi.Engine(tables, n_slots=2, max_batch_bytes=1 << 20, max_batch_records=1 << 12)
+    e2 = capi.Engine(tables, n_slots=2, max_batch_bytes=1 << 20, max_batch_records=1 << 12)
+    tables.close()
+    seq, off = pack_records(recs)
+    for e in (e1, e2):
+        r = e.scan(seq, off)
+        for name, w in zip(("record", "start", "pattern"), want):
+            np.testing.assert_array_equal(r.hits[name], w)
+    e2.close()
+    monkeypatch.setenv("MK_FREE", "1")
+    d_seq = torch.from_numpy(np.concatenate([seq, np.zeros(64, np.uint8)])).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    for i in range(6):
+        if i >= 2:
+            r = e1.wait(i % 2)
+            for name, w in zip(("record", "start", "pattern"), want):
+                np.testing.assert_array_equal(r.hits[name], w)
+        e1.scan_device_submit(i % 2, d_seq.data_ptr(), d_off.data_ptr(), len(recs), int(seq.size), capi.MK_MODE_ALL_HITS, fetch=True)
+    for s in (0, 1):
+        r = e1.wait(s)
+        np.testing.assert_array_equal(r.hits["start"], want[1])
+    e1.close()
