@@ -205,8 +205,9 @@ def test_extract_random_single(tmp_path, mode):
     assert (tmp_path / "nolog" / "o.fastq").read_bytes() == (tmp_path / "ora" / "o.fastq").read_bytes()
 
 
-@pytest.mark.parametrize("n_pat", [4, 40])
-def test_extract_random_paired_gz(tmp_path, n_pat):
+@pytest.mark.parametrize("n_pat,gz_threads", [(4, 1), (40, 1), (40, 3)])
+def test_extract_random_paired_gz(tmp_path, n_pat, gz_threads):
+    """gz_threads = 3: both files through the parallel gzip reader (host/pgzip.cpp), in pieces of 8 KiB."""
     rng = np.random.default_rng(n_pat)
     pats = sorted({rng.choice(np.frombuffer(b"ACGT", np.uint8), size=31).tobytes() for _ in range(n_pat)})
     r1 = _rand_reads(rng, 2500, 150, 150, pats, plant=0.05)
@@ -224,7 +225,8 @@ def test_extract_random_paired_gz(tmp_path, n_pat):
 
     _compare_with_oracle(tmp_path, ["extract", "-i", tmp_path / "a_1.fastq.gz", "-2", tmp_path / "a_2.fastq.gz", "-f", kf, "-r", "-o", "@OUT@/x",
                                     "-l", "@OUT@/x.log", "-j", "@OUT@/x.json"], oracle,
-                         [("x_1.fastq", "raw"), ("x_2.fastq", "raw"), ("x.log", "log"), ("x.json", "json")], env={"MERKURIO_BATCH_BYTES": "200000"})
+                         [("x_1.fastq", "raw"), ("x_2.fastq", "raw"), ("x.log", "log"), ("x.json", "json")],
+                         env={"MERKURIO_BATCH_BYTES": "200000", "MERKURIO_GZIP_THREADS": str(gz_threads), "MERKURIO_GZIP_PIECE_KB": "8"})
 
 
 def test_extract_long_fasta_records_in_pieces(tmp_path):

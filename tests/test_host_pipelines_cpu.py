@@ -101,9 +101,11 @@ def test_fastq_pipeline_equals_record_path(exe, stub, tmp_path, flavour):
     p1, p2 = tmp_path / "r1.fq", tmp_path / "r2.fq"
     p1.write_bytes(gzip.compress(d1) if flavour == "gz" else d1)
     p2.write_bytes(gzip.compress(d2) if flavour == "gz" else d2)
+    # gz: also with both files through the parallel gzip reader (host/pgzip.cpp), in pieces of 8 KiB
+    par_gz = [{"MERKURIO_GZIP_THREADS": "3", "MERKURIO_GZIP_PIECE_KB": "8", "MERKURIO_BATCH_BYTES": "20000", "MERKURIO_CHUNK_BYTES": "5000"}] if flavour == "gz" else []
     for paired in (False, True):
         results = []
-        for env in [{"MERKURIO_NO_FASTQ_PIPELINE": "1"}] + SIZES:
+        for env in [{"MERKURIO_NO_FASTQ_PIPELINE": "1"}] + SIZES + par_gz:
             d = tmp_path / ("out%d%d" % (paired, len(results)))
             d.mkdir()
             args = ["extract", "-i", p1, "-s", QUERY, "-v", "-o", d / "x.fastq", "-l", d / "x.log"] + (["-2", p2] if paired else [])
@@ -227,9 +229,11 @@ def test_fastq_paths_agree_on_flagged_records(exe, stub, tmp_path, flavour, extr
     p1, p2 = tmp_path / "r1.fq", tmp_path / "r2.fq"
     p1.write_bytes(d1)
     p2.write_bytes(d2)
+    # gz: also with both files through the parallel gzip reader (host/pgzip.cpp), in pieces of 8 KiB
+    par_gz = [{"MERKURIO_GZIP_THREADS": "3", "MERKURIO_GZIP_PIECE_KB": "8", "MERKURIO_BATCH_BYTES": "20000", "MERKURIO_CHUNK_BYTES": "5000"}] if flavour == "gz" else []
     for paired in (False, True):
         results = []
-        for env in [{"MERKURIO_NO_FASTQ_PIPELINE": "1"}] + SIZES:
+        for env in [{"MERKURIO_NO_FASTQ_PIPELINE": "1"}] + SIZES + par_gz:
             d = tmp_path / ("out%d%d" % (paired, len(results)))
             d.mkdir()
             args = ["extract", "-i", p1, "-s", QUERY[:25], "-o", d / "x.fastq"] + [a.replace("@", str(d)) for a in extra] + (["-2", p2] if paired else [])
