@@ -276,6 +276,11 @@ __attribute__((always_inline)) inline Inflater::Status Inflater::run_impl(const 
         if (state_ == kBlockHeader) {
             if (in_end - in < (ptrdiff_t)kInputMargin) {
                 if (!in_final) MK_LEAVE(kNeedInput);
+                // whole bytes still in the bit buffer go back first: `in` must be the true position for the check and
+                // the copy below (a stored block gives its bytes back as well, and must not step in front of the copy)
+                in -= bitcnt >> 3;
+                bitcnt &= 7;
+                bitbuf &= (1ull << bitcnt) - 1;
                 if (in > in_end) MK_LEAVE(kError);
                 if (!in_tail) {
                     // the input ends within a header's length: go on in a zero-padded copy, so that nothing is read

@@ -66,6 +66,19 @@ def stream_cases():
     }
     raw, _ = cases["short_periods"]
     cases["short_periods"] = (raw, gz(raw, 9))
+    # Z_SYNC_FLUSH / Z_FULL_FLUSH in the middle (empty stored blocks between the others), also within the last kilobyte of
+    # the stream, where the decoder works on a padded copy of the input's tail
+    def flushed(data, cuts, level=6):
+        c = zlib.compressobj(level, zlib.DEFLATED, 31)
+        out, pos = b"", 0
+        for cut, how in cuts:
+            out += c.compress(data[pos:cut]) + c.flush(how)
+            pos = cut
+        return out + c.compress(data[pos:]) + c.flush()
+    n = len(fq)
+    cases["flushes"] = (fq, flushed(fq, [(n // 5, zlib.Z_SYNC_FLUSH), (n // 2, zlib.Z_FULL_FLUSH), (n // 2 + 1, zlib.Z_SYNC_FLUSH), (n - 300, zlib.Z_SYNC_FLUSH), (n - 7, zlib.Z_FULL_FLUSH), (n, zlib.Z_SYNC_FLUSH)]))
+    rep = b"A" * 1_500_000
+    cases["flushes_in_a_short_stream"] = (rep, flushed(rep, [(700_000, zlib.Z_SYNC_FLUSH), (1_400_000, zlib.Z_FULL_FLUSH), (1_499_999, zlib.Z_SYNC_FLUSH)]))
     # a header with every optional field
     b = io.BytesIO()
     with gzip.GzipFile(filename="some_name.fq", mode="wb", fileobj=b, mtime=5) as f:
@@ -188,7 +201,7 @@ def _stats(err: bytes):
 
 
 @pytest.mark.parametrize("name", ["fastq_level6", "fastq_level1", "fastq_level9", "stored_blocks", "fixed_codes", "huffman_only", "run_length",
-                                  "small_blocks", "incompressible", "zeros", "period_25", "short_periods", "members"])
+                                  "small_blocks", "incompressible", "zeros", "period_25", "short_periods", "members", "flushes"])
 def test_parallel_gzip_equals_zlib(exe, tmp_path, name):
     raw, comp = CASES[name]
     p = tmp_path / "x.gz"
