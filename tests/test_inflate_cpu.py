@@ -291,3 +291,19 @@ def test_parallel_gzip_through_the_fastq_reader(exe, tmp_path):
     got = subprocess.run([exe, "records", str(zipped), "chunked"], capture_output=True, env={**os.environ, **PAR})
     assert want.returncode == 0 and got.returncode == 0
     assert got.stdout == want.stdout and want.stdout.count(b"#id\t") == 8000
+
+
+def test_decoder_under_address_and_undefined_behaviour_sanitizers(tmp_path):
+    """tests/stub/inflate_fuzz.cpp: valid, cut and bit-flipped streams of five kinds of data through every entry point of
+    the decoder (run in pieces, inflate_exact, probe_dynamic_header, run_markers) with exactly the padding behind the
+    input that inflate.h promises — built with -fsanitize=address,undefined, so one byte read or written outside the
+    buffers ends the run; valid streams must decode to the original bytes."""
+    exe = tmp_path / "inflate_fuzz"
+    cc = subprocess.run(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-std=c++17",
+                         "-I", str(ROOT / "merkurio_b200" / "host"), "-o", str(exe), str(ROOT / "tests" / "stub" / "inflate_fuzz.cpp"),
+                         str(ROOT / "merkurio_b200" / "host" / "inflate.cpp"), "-lz"], capture_output=True, text=True)
+    if cc.returncode != 0 and "sanitize" in cc.stderr:
+        pytest.skip("the sanitizer runtimes are not installed")
+    assert cc.returncode == 0, cc.stderr
+    r = subprocess.run([str(exe), "20", "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "done:" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
