@@ -576,6 +576,21 @@ bool Inflater::probe_dynamic_header(const uint8_t* base, const uint8_t* end, uin
 
 Inflater::MarkerRun Inflater::run_markers(const uint8_t* base, const uint8_t* end, uint64_t start_bit, uint64_t stop_bit,
                                           std::vector<uint16_t>* outv, size_t max_symbols) {
+#if defined(__x86_64__) && defined(__GNUC__)
+    static const bool bmi2 = __builtin_cpu_supports("bmi2");
+    if (bmi2) return run_markers_bmi2(base, end, start_bit, stop_bit, outv, max_symbols);
+#endif
+    return run_markers_impl(base, end, start_bit, stop_bit, outv, max_symbols);
+}
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("bmi2")))
+#endif
+Inflater::MarkerRun Inflater::run_markers_bmi2(const uint8_t* base, const uint8_t* end, uint64_t start_bit, uint64_t stop_bit,
+                                               std::vector<uint16_t>* outv, size_t max_symbols) {
+    return run_markers_impl(base, end, start_bit, stop_bit, outv, max_symbols);
+}
+__attribute__((always_inline)) inline Inflater::MarkerRun Inflater::run_markers_impl(const uint8_t* base, const uint8_t* end, uint64_t start_bit,
+                                                                                uint64_t stop_bit, std::vector<uint16_t>* outv, size_t max_symbols) {
     MarkerRun res;
     constexpr size_t kWin = 32768;
     constexpr uint32_t kLMask = (1u << kLitlenBits) - 1, kDMask = (1u << kDistBits) - 1;
@@ -618,65 +633,126 @@ Inflater::MarkerRun Inflater::run_markers(const uint8_t* base, const uint8_t* en
                 bitbuf = bitbuf_;
                 bitcnt = bitcnt_;
             }
-            for (;;) {
+            bool block_done = false;
+            while (!block_done) {
                 if (in - (bitcnt >> 3) > end) return res;
-                if (out.size() < n + 260) {
+                if (out.size() < n + 4096) {
                     if (n - kWin > max_symbols) return res;
                     out.resize(out.size() * 2);
                 }
+                // as long as 32 input bytes and 600 output symbols are at hand: no checks per symbol; the entry of the
+                // next symbol is looked up before the current match is copied
                 uint16_t* o = out.data() + n;
+                uint16_t* const o_stop = out.data() + out.size() - 600;
                 MK_REFILL();
                 uint32_t e = litlen_[bitbuf & kLMask];
-                if (e & kLit) {
-                    // up to three first-level entries = six literals without another refill (as in the byte decoder)
-                    for (int k = 0; k < 3 && (e & kLit); ++k) {
-                        MK_DROP(e & 0xFF);
-                        o[0] = (uint16_t)((e >> 16) & 0xFF);
-                        o[1] = (uint16_t)(e >> 24);
-                        o += 1 + ((e >> 15) & 1);
-                        e = litlen_[bitbuf & kLMask];
+                while (end - in >= 32 && o < o_stop) {
+                    if (e & kLit) {
+                        // up to three first-level entries = six literals without another refill (as in the byte decoder)
+#define MK_EMIT_LITERALS()                                   \
+    do {                                                     \
+        MK_DROP(e & 0xFF);                                   \
+        o[0] = (uint16_t)((e >> 16) & 0xFF);                 \
+        o[1] = (uint16_t)(e >> 24);                          \
+        o += 1 + ((e >> 15) & 1);                            \
+        e = litlen_[bitbuf & kLMask];                        \
+    } while (0)
+                        MK_EMIT_LITERALS();
+                        if (e & kLit) {
+                            MK_EMIT_LITERALS();
+                            if (e & kLit) MK_EMIT_LITERALS();
+                        }
+#undef MK_EMIT_LITERALS
+                        MK_REFILL();
+                        continue;
                     }
-                    n = (size_t)(o - out.data());
-                    continue;
+                    if (e & kPtr) {
+                        MK_DROP(kLitlenBits);
+                        e = litlen_[(e >> 16) + MK_BITS((e >> 8) & 15)];
+                    }
+                    unsigned nb = e & 0xFF;
+                    if (!nb) return res;
+                    MK_DROP(nb);
+                    if (e & kLit) {
+                        *o++ = (uint16_t)((e >> 16) & 0xFF);
+                        MK_REFILL();
+                        e = litlen_[bitbuf & kLMask];
+                        continue;
+                    }
+                    if (e & kEob) { block_done = true; break; }
+                    const unsigned xl = (e >> 8) & 15;
+                    const size_t len = (e >> 16) + MK_BITS(xl);
+                    MK_DROP(xl);
+                    uint32_t d = dist_[bitbuf & kDMask];
+                    if (d & kPtr) {
+                        MK_DROP(kDistBits);
+                        d = dist_[(d >> 16) + MK_BITS((d >> 8) & 15)];
+                    }
+                    nb = d & 0xFF;
+                    if (!nb) return res;
+                    MK_DROP(nb);
+                    const unsigned xd = (d >> 8) & 15;
+                    const size_t dist = (d >> 16) + MK_BITS(xd);
+                    MK_DROP(xd);
+                    MK_REFILL();
+                    e = litlen_[bitbuf & kLMask];
+                    // (dist <= 32768 <= o - out.data() always: in front of the start lies the window of place holders)
+                    const uint16_t* src = o - dist;
+                    if (dist >= 8) {
+                        std::memcpy(o, src, 16);  // eight symbols at a time; 600 symbols of room behind o
+                        if (len > 8) {
+                            size_t k = 8;
+                            do {
+                                std::memcpy(o + k, src + k, 16);
+                                k += 8;
+                            } while (k < len);
+                        }
+                    } else {
+                        for (size_t k = 0; k < len; ++k) o[k] = src[k];
+                    }
+                    o += len;
                 }
-                if (e & kPtr) {
-                    MK_DROP(kLitlenBits);
-                    e = litlen_[(e >> 16) + MK_BITS((e >> 8) & 15)];
+                n = (size_t)(o - out.data());
+                if (block_done) break;
+                if (end - in >= 32) continue;  // the output buffer was the reason: grow it
+                // the last bytes of the input: one symbol at a time, with every check (`e` is looked up again: none of
+                // its bits were consumed)
+                for (;;) {
+                    if (in - (bitcnt >> 3) > end) return res;
+                    if (out.size() < n + 600) break;
+                    MK_REFILL();
+                    e = litlen_[bitbuf & kLMask];
+                    if (e & kPtr) {
+                        MK_DROP(kLitlenBits);
+                        e = litlen_[(e >> 16) + MK_BITS((e >> 8) & 15)];
+                    }
+                    unsigned nb = e & 0xFF;
+                    if (!nb) return res;
+                    if (e & kLit2) nb = (e >> 8) & 15;  // one literal at a time here
+                    MK_DROP(nb);
+                    if (e & kLit) {
+                        out[n++] = (uint16_t)((e >> 16) & 0xFF);
+                        continue;
+                    }
+                    if (e & kEob) { block_done = true; break; }
+                    const unsigned xl = (e >> 8) & 15;
+                    const size_t len = (e >> 16) + MK_BITS(xl);
+                    MK_DROP(xl);
+                    uint32_t d = dist_[bitbuf & kDMask];
+                    if (d & kPtr) {
+                        MK_DROP(kDistBits);
+                        d = dist_[(d >> 16) + MK_BITS((d >> 8) & 15)];
+                    }
+                    nb = d & 0xFF;
+                    if (!nb) return res;
+                    MK_DROP(nb);
+                    const unsigned xd = (d >> 8) & 15;
+                    if (bitcnt < xd) MK_REFILL();
+                    const size_t dist = (d >> 16) + MK_BITS(xd);
+                    MK_DROP(xd);
+                    for (size_t k = 0; k < len; ++k) out[n + k] = out[n + k - dist];
+                    n += len;
                 }
-                unsigned nb = e & 0xFF;
-                if (!nb) return res;
-                MK_DROP(nb);
-                if (e & kLit) {
-                    out[n++] = (uint16_t)((e >> 16) & 0xFF);
-                    continue;
-                }
-                if (e & kEob) break;
-                const unsigned xl = (e >> 8) & 15;
-                const size_t len = (e >> 16) + MK_BITS(xl);
-                MK_DROP(xl);
-                uint32_t d = dist_[bitbuf & kDMask];
-                if (d & kPtr) {
-                    MK_DROP(kDistBits);
-                    d = dist_[(d >> 16) + MK_BITS((d >> 8) & 15)];
-                }
-                nb = d & 0xFF;
-                if (!nb) return res;
-                MK_DROP(nb);
-                const unsigned xd = (d >> 8) & 15;
-                const size_t dist = (d >> 16) + MK_BITS(xd);
-                MK_DROP(xd);
-                // (dist <= 32768 <= n always: what lies in front of the start is the window of place holders)
-                const uint16_t* src = o - dist;
-                if (dist >= 4) {
-                    size_t k = 0;
-                    do {
-                        std::memcpy(o + k, src + k, 8);  // four symbols; the room behind n + len is there (260)
-                        k += 4;
-                    } while (k < len);
-                } else {
-                    for (size_t k = 0; k < len; ++k) o[k] = src[k];
-                }
-                n += len;
             }
         }
         if (in - (bitcnt >> 3) > end) return res;
@@ -723,34 +799,55 @@ int parse_gzip_header(const uint8_t* p, size_t n, size_t* len) {
     return 1;
 }
 
-bool resolve_markers(const uint16_t* src, size_t n, const uint8_t* window, size_t window_valid, uint8_t* dst) {
-    const size_t first_valid = 32768 - window_valid;
-    bool ok = true;
+// Symbols -> bytes through one table: entries 0..255 are the bytes themselves, entry 256 + j is byte j of the window, so a
+// symbol is one load whatever it is (no branch on "is it a place holder": they make up a tenth of sequencing data,
+// spread evenly).
+#if defined(__x86_64__) && defined(__GNUC__)
+// sixteen symbols per step where none of them is a place holder
+__attribute__((target("avx2")))
+static size_t resolve_markers_avx2(const uint16_t* src, size_t n, const uint8_t* lut, uint32_t first_valid_symbol, uint8_t* dst, uint32_t* bad) {
     size_t i = 0;
-    for (; i + 8 <= n; i += 8) {
-        uint64_t a, b;
-        std::memcpy(&a, src + i, 8);
-        std::memcpy(&b, src + i + 4, 8);
-        if (((a | b) & 0xFF00FF00FF00FF00ull) == 0) {  // eight plain bytes
-            for (int k = 0; k < 8; ++k) dst[i + k] = (uint8_t)src[i + k];
+    const __m256i high = _mm256_set1_epi16((short)0xFF00);
+    uint32_t b = 0;
+    for (; i + 16 <= n; i += 16) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+        if (_mm256_testz_si256(v, high)) {
+            const __m256i p = _mm256_permute4x64_epi64(_mm256_packus_epi16(v, v), 0x08);  // lanes 0 and 2 hold the 16 bytes
+            _mm_storeu_si128(reinterpret_cast<__m128i*>(dst + i), _mm256_castsi256_si128(p));
             continue;
         }
-        for (int k = 0; k < 8; ++k) {
-            const uint16_t v = src[i + k];
-            if (v < 256) { dst[i + k] = (uint8_t)v; continue; }
-            const size_t j = (size_t)v - 256;
-            ok &= j >= first_valid;
-            dst[i + k] = window[j];
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t x = src[i + k];
+            dst[i + k] = lut[x];
+            b |= (uint32_t)(x >= 256) & (uint32_t)(x < first_valid_symbol);
         }
     }
-    for (; i < n; ++i) {
-        const uint16_t v = src[i];
-        if (v < 256) { dst[i] = (uint8_t)v; continue; }
-        const size_t j = (size_t)v - 256;
-        ok &= j >= first_valid;
-        dst[i] = window[j];
+    *bad |= b;
+    return i;
+}
+#endif
+
+bool resolve_markers(const uint16_t* src, size_t n, const uint8_t* window, size_t window_valid, uint8_t* dst) {
+    static thread_local uint8_t lut[256 + 32768];
+    static thread_local bool lut_ready = false;
+    if (!lut_ready) {
+        for (int v = 0; v < 256; ++v) lut[v] = (uint8_t)v;
+        lut_ready = true;
     }
-    return ok;
+    std::memcpy(lut + 256, window, 32768);
+    const uint32_t first_valid_symbol = 256 + (uint32_t)(32768 - window_valid);  // place holders below it point in front of the data
+    uint32_t bad = 0;
+    size_t i = 0;
+#if defined(__x86_64__) && defined(__GNUC__)
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) i = resolve_markers_avx2(src, n, lut, first_valid_symbol, dst, &bad);
+#endif
+    for (; i < n; ++i) {
+        const uint32_t x = src[i];
+        dst[i] = lut[x];
+        bad |= (uint32_t)(x >= 256) & (uint32_t)(x < first_valid_symbol);
+    }
+    return bad == 0;
 }
 
 #if defined(__x86_64__) && defined(__GNUC__)

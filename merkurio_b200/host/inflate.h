@@ -67,6 +67,10 @@ private:
     Status run_impl(const uint8_t** in, const uint8_t* in_end, bool in_final, const uint8_t* out_base, uint8_t** out, uint8_t* out_end);
     Status run_generic(const uint8_t** in, const uint8_t* in_end, bool in_final, const uint8_t* out_base, uint8_t** out, uint8_t* out_end);
     Status run_bmi2(const uint8_t** in, const uint8_t* in_end, bool in_final, const uint8_t* out_base, uint8_t** out, uint8_t* out_end);
+    MarkerRun run_markers_impl(const uint8_t* base, const uint8_t* end, uint64_t start_bit, uint64_t stop_bit, std::vector<uint16_t>* out,
+                               size_t max_symbols);
+    MarkerRun run_markers_bmi2(const uint8_t* base, const uint8_t* end, uint64_t start_bit, uint64_t stop_bit, std::vector<uint16_t>* out,
+                               size_t max_symbols);
     bool read_dynamic_header(const uint8_t*& in, const uint8_t* in_end, bool in_final);
     void use_fixed_codes();
     static bool build_table(uint32_t* table, int table_bits, int table_cap, const uint8_t* lens, int n_syms, int kind);
