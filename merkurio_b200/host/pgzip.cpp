@@ -272,8 +272,9 @@ private:
         }
         const double t1 = now_s();
         const uint64_t stop = (i + 1 == tasks_.size()) ? ~0ull : hi;
-        // at most 48 Mi symbols (96 MB) per task: data that expand further than that is left to the sequential decoder
-        Inflater::MarkerRun r = inf.run_markers(base_, end_, start, stop, &t.sym, (size_t)48 << 20);
+        // at most 24 Mi symbols per task (12 times the piece; the buffer doubles, so 64 MB at most): data that expands
+        // further than that is left to the sequential decoder
+        Inflater::MarkerRun r = inf.run_markers(base_, end_, start, stop, &t.sym, (size_t)12 * piece_);
         *t_search = t1 - t0;
         *t_decode = now_s() - t1;
         t.ok = r.ok;

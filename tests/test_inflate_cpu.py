@@ -307,3 +307,15 @@ def test_decoder_under_address_and_undefined_behaviour_sanitizers(tmp_path):
     assert cc.returncode == 0, cc.stderr
     r = subprocess.run([str(exe), "20", "3"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "done:" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])
+
+
+def test_parallel_gzip_leaves_data_that_expands_a_thousandfold_to_the_sequential_decoder(exe, tmp_path):
+    """A task holds 16-bit symbols for at most 12 times its piece of the file; 40 MB of zeros in 39 KB exceed that in every
+    piece, so every task gives up and the sequential decoder produces the output (bounded memory, same bytes)."""
+    raw = b"\0" * 40_000_000
+    p = tmp_path / "z.gz"
+    p.write_bytes(gz(raw))
+    rc, out, err = cat(exe, p, None, {**PAR, "MERKURIO_GZIP_PIECE_KB": "5"})
+    assert rc == 0 and out == raw
+    pieces, used, unused, seq = _stats(err)
+    assert used == 0 and seq > 0, (pieces, used, unused, seq)
