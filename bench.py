@@ -226,7 +226,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def bench_config(name: str, steps: int, peak: float, oracle_check: bool = True):
+def bench_config(name: str, steps: int, peak: float, oracle_check: bool = True, sampler=None):
     """One of cfg3 / cfg4 / cfg5 at BASELINE size: device-timed passes over the resident batch, the dominant (scan)
     kernel against the HBM peak, and parity: oracle on a sample of the same data + size-independent properties."""
     import torch
@@ -258,11 +258,16 @@ def bench_config(name: str, steps: int, peak: float, oracle_check: bool = True):
             n_warm += 1
         entry["warmup_passes"] = n_warm
         scan, dev, ver = [], [], []
+        t_steps0 = time.perf_counter()
         for _ in range(steps):
             r = wl.scan(eng)
             scan.append(r.scan_ns / 1e6)
             dev.append(r.device_ns / 1e6)
             ver.append(r.verify_ns / 1e6)
+        if sampler is not None:  # the clocks seen from the start of the warm-up to the last timed pass
+            entry["clocks"] = sampler.window(t_warm - 0.5, time.perf_counter())
+        entry["kernel_ms_per_step"] = [round(x, 4) for x in scan]
+        entry["timed_steps_wall_s"] = time.perf_counter() - t_steps0
         full = wl.scan(eng, fetch=True)
         info = eng.info()
         enc = wl.enc
@@ -601,7 +606,7 @@ def run_ours(args):
             for name in args.configs.split(","):
                 t0c = time.perf_counter()
                 try:
-                    configs.append(bench_config(name.strip(), args.config_steps, peak))
+                    configs.append(bench_config(name.strip(), args.config_steps, peak, sampler=sampler))
                 except Exception as ex:  # reported, never hidden: a failed parity check must show in the line
                     configs.append({"config": name, "error": repr(ex)[:300], "oracle_sample_equal": False})
                 log(f"[bench] {name}: {time.perf_counter() - t0c:.1f} s  {json.dumps({k: v for k, v in configs[-1].items() if k in ('kernel_ms', 'device_ms', 'frac', 'n_hits', 'oracle_sample_equal', 'error')})}")
