@@ -248,10 +248,12 @@ def bench_config(name: str, steps: int, peak: float, oracle_check: bool = True, 
         t0 = time.perf_counter()
         wl.scan(eng)  # first pass: waits for the seed tables (built on host threads while the engine starts)
         entry["table_build_and_first_pass_s"] = time.perf_counter() - t0
-        # warm-up: at least 3 passes and half a second of them — the legs in front of this one (the CPU baseline, the
-        # generators) leave the GPU idle for seconds, and the first passes after that run at clocks that are still
-        # ramping up (cfg3, the first config, measured 2.39 ms that way against 2.09 ms a moment later)
-        t_warm = time.perf_counter() + 0.5
+        # warm-up: at least 3 passes and 0.1 s of them. The legs in front of this one (the CPU baseline, the generators)
+        # leave the GPU idle for seconds, and the first passes after that run at clocks that are still ramping up (cfg3, the
+        # first config, measured 2.39 ms that way against 2.09 ms a moment later); half a second of passes, on the other
+        # hand, runs a 1 kW part into its software power cap (SM clock 1.65-1.87 GHz: cfg3 2.64 ms, cfg4 0.66-0.70 ms), which
+        # is the sustained regime, not that of 10 timed passes. `clocks` of the entry says which regime a run saw.
+        t_warm = time.perf_counter() + 0.1
         n_warm = 0
         while n_warm < 3 or time.perf_counter() < t_warm:
             wl.scan(eng)
@@ -265,7 +267,7 @@ def bench_config(name: str, steps: int, peak: float, oracle_check: bool = True, 
             dev.append(r.device_ns / 1e6)
             ver.append(r.verify_ns / 1e6)
         if sampler is not None:  # the clocks seen from the start of the warm-up to the last timed pass
-            entry["clocks"] = sampler.window(t_warm - 0.5, time.perf_counter())
+            entry["clocks"] = sampler.window(t_warm - 0.1, time.perf_counter())
         entry["kernel_ms_per_step"] = [round(x, 4) for x in scan]
         entry["timed_steps_wall_s"] = time.perf_counter() - t_steps0
         full = wl.scan(eng, fetch=True)
