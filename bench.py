@@ -477,6 +477,23 @@ def run_ours(args):
     scan_ms = float(np.mean(scan_ns)) / 1e6
     dev_ms_max = max_over_ranks(float(np.mean(dev_ns)) / 1e6)
 
+    # ---- the other BASELINE configs (rank 0, N == 1) ----------------------------------------------------------------
+    # Before the sustained run and the end-to-end legs, not after them: seconds at 1 kW leave the part in its software
+    # power cap for a while, and the kernels that are not HBM-bound (cfg3's and cfg4's scans) then measure 10-15 % slower
+    # than in a process of their own (cfg4: 0.66-0.74 ms after those legs, 0.606-0.608 ms in four separate processes).
+    peak, peak_src = measured_peak_gbs()
+    configs = None
+    if rank == 0 and world == 1:
+        if not args.no_configs:
+            configs = []
+            for name in args.configs.split(","):
+                t0c = time.perf_counter()
+                try:
+                    configs.append(bench_config(name.strip(), args.config_steps, peak, sampler=sampler))
+                except Exception as ex:  # reported, never hidden: a failed parity check must show in the line
+                    configs.append({"config": name, "error": repr(ex)[:300], "oracle_sample_equal": False})
+                log(f"[bench] {name}: {time.perf_counter() - t0c:.1f} s  {json.dumps({k: v for k, v in configs[-1].items() if k in ('kernel_ms', 'device_ms', 'frac', 'n_hits', 'oracle_sample_equal', 'error')})}")
+
     # ---- sustained: seconds of back-to-back passes (thermal / power evidence for the burst figure) -------
     sustained = None
     if args.sustained_s > 0:
@@ -595,23 +612,9 @@ def run_ours(args):
         del h, ac
 
     total_flagged = sum_over_ranks(float(flagged_resident))
-    peak, peak_src = measured_peak_gbs()
     eng.close()
     del d_seq, d_off
     torch.cuda.empty_cache()
-
-    # ---- the other BASELINE configs and the file -> file run (rank 0, N == 1) ------------------------
-    configs = None
-    if rank == 0 and world == 1:
-        if not args.no_configs:
-            configs = []
-            for name in args.configs.split(","):
-                t0c = time.perf_counter()
-                try:
-                    configs.append(bench_config(name.strip(), args.config_steps, peak, sampler=sampler))
-                except Exception as ex:  # reported, never hidden: a failed parity check must show in the line
-                    configs.append({"config": name, "error": repr(ex)[:300], "oracle_sample_equal": False})
-                log(f"[bench] {name}: {time.perf_counter() - t0c:.1f} s  {json.dumps({k: v for k, v in configs[-1].items() if k in ('kernel_ms', 'device_ms', 'frac', 'n_hits', 'oracle_sample_equal', 'error')})}")
 
     if rank == 0:
         algo_bytes = n_bytes + (n_reads + 7) // 8  # sequence bytes + flag bitmap; offsets are only read for hits
