@@ -100,13 +100,13 @@ public:
         const int hrc = parse_gzip_header(base_, size_, &hdr);
         if (hrc != 1) {  // (the caller has seen the magic bytes: a broken or cut header)
             push_error(hrc == 0 ? "Error while decompressing the input (truncated gzip stream)" : "Error while decompressing the input (gzip)");
+            started_ = true;  // (nothing to start: the reader finds the error)
             return;
         }
         pos_ = (uint64_t)hdr * 8;
         data_begin_ = hdr;
         tasks_.resize(std::max<size_t>((size_ - hdr + piece_ - 1) / piece_, 1));
-        for (int t = 0; t < threads; ++t) pool_.emplace_back([this] { worker(); });
-        stitcher_ = std::thread([this] { stitch(); });
+        n_threads_ = threads;  // (started by the first read that goes beyond the head of the data: see read())
     }
     ~ParallelGzipStream() override {
         {
@@ -118,7 +118,7 @@ public:
         cv_piece_.notify_all();
         if (stitcher_.joinable()) stitcher_.join();
         for (auto& t : pool_) t.join();
-        if (timing_) {
+        if (timing_ && !pool_.empty()) {
             std::fprintf(stderr, "[merkurio] gzip on %zu threads: %zu pieces of the file, %zu continued the decode where it stood, %zu not used; %zu blocks by the sequential decoder\n",
                          pool_.size(), tasks_.size(), n_used_, n_dropped_, n_seq_blocks_);
             std::fprintf(stderr, "[merkurio] gzip stitcher: waited %.3f s for tasks, %.3f s for the reader; pool: %.3f s searching, %.3f s decoding, %.3f s replacing place holders (sums over threads)\n",
@@ -130,6 +130,32 @@ public:
 
     size_t read(char* dst, size_t n) override {
         if (n == 0) return 0;
+        if (!started_) {
+            // The first 64 KiB come from a sequential decode of the head of the file, and the threads are only started
+            // by a read that goes beyond it: the callers open every input a few times just to look at its first bytes
+            // (is it there? FASTA or FASTQ?), and a pool that starts on a dozen pieces for each of those looks costs
+            // tens of milliseconds of work that is thrown away.
+            if (!head_tried_) {
+                head_tried_ = true;
+                head_.resize(kHead + Inflater::kOutputMargin + 64);
+                Inflater h;
+                const uint8_t* ip = base_ + data_begin_;
+                uint8_t* op = head_.data();
+                const Inflater::Status rc = h.run(&ip, end_, true, head_.data(), &op, head_.data() + head_.size() - 8);
+                head_len_ = rc == Inflater::kError ? 0 : (size_t)(op - head_.data());  // (an error: reported by the full decode, in order)
+            }
+            if (head_pos_ < head_len_) {
+                const size_t k = std::min(n, head_len_ - head_pos_);
+                std::memcpy(dst, head_.data() + head_pos_, k);
+                head_pos_ += k;
+                return k;
+            }
+            std::vector<uint8_t>().swap(head_);
+            skip_ = head_len_;  // the full decode starts at the first byte again: what was handed out already is dropped
+            started_ = true;
+            for (int t = 0; t < n_threads_; ++t) pool_.emplace_back([this] { worker(); });
+            stitcher_ = std::thread([this] { stitch(); });
+        }
         for (;;) {
             if (cur_ && cur_pos_ < cur_->n_bytes) {
                 const size_t k = std::min(n, cur_->n_bytes - cur_pos_);
@@ -159,6 +185,10 @@ public:
                     crc_ = p->n_bytes == 0 ? crc_ : (uint32_t)crc32_combine(crc_, p->crc, (z_off_t)p->n_bytes);
                     isize_ += (uint32_t)p->n_bytes;
                     cur_ = p;
+                    if (skip_) {
+                        cur_pos_ = std::min(skip_, p->n_bytes);
+                        skip_ -= cur_pos_;
+                    }
                     break;
                 case Piece::kMemberEnd:
                     if (p->crc != crc_ || p->isize != isize_) fail("Error while decompressing the input (gzip)");
@@ -176,7 +206,7 @@ public:
     }
 
 private:
-    static constexpr size_t kSeqArea = 4u << 20;
+    static constexpr size_t kSeqArea = 4u << 20, kHead = 64u << 10;
 
     [[noreturn]] void fail(const std::string& msg) {
         ended_ = true;
@@ -490,6 +520,10 @@ private:
     double t_wait_tasks_ = 0, t_wait_reader_ = 0, t_search_ = 0, t_decode_ = 0, t_resolve_ = 0;
 
     // reader state
+    bool started_ = false, head_tried_ = false;
+    int n_threads_ = 0;
+    std::vector<uint8_t> head_;
+    size_t head_len_ = 0, head_pos_ = 0, skip_ = 0;
     std::shared_ptr<Piece> cur_;
     size_t cur_pos_ = 0;
     bool ended_ = false;
