@@ -93,6 +93,17 @@ def build_host(force: bool = False, verbose: bool = False) -> Path:
     return out
 
 
+def build_io(force: bool = False, verbose: bool = False) -> Path:
+    """libmerkurio_io.so: the host's input streams behind a C ABI (include/merkurio_io.h); no CUDA."""
+    LIBDIR.mkdir(exist_ok=True)
+    out = LIBDIR / "libmerkurio_io.so"
+    srcs = [HOST / n for n in ("io_capi.cpp", "codecs.cpp", "inflate.cpp", "pgzip.cpp", "bgzf.cpp", "io.cpp")]
+    if force or _stale(out, srcs + sorted(HOST.glob("*.h")) + [ROOT / "include" / "merkurio_io.h"]):
+        _run(["g++", "-O2", "-std=c++17", "-Wall", "-fPIC", "-shared", "-pthread", "-I", ROOT / "include", "-o", out, *srcs,
+              "-lz", "-ldl", "-Wl,--no-undefined"], verbose)
+    return out
+
+
 def build_oracle(force: bool = False, verbose: bool = False) -> Path:
     """oracle/_build/libmk_oracle.so: CPU restatement of the reference matchers (checker only)."""
     outdir = ORACLE / "_build"
@@ -111,6 +122,7 @@ def build_all(force: bool = False, verbose: bool = False):
         "cuda": build_cuda(force, verbose),
         "synth": build_synth(force, verbose),
         "host": build_host(force, verbose),
+        "io": build_io(force, verbose),
         "oracle": build_oracle(force, verbose),
     }
 

@@ -113,3 +113,58 @@ def test_exports_cover_the_header():
     exported = set(re.findall(r"\bT (mk_[a-z_0-9]+)", syms))
     assert declared <= exported, declared - exported
     assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+
+
+# ------------------------------------------------------------------------------------------------
+# include/merkurio_io.h: the host's input streams behind a C ABI (libmerkurio_io.so, no CUDA)
+def test_io_library_exports_its_header_and_reads_like_gzip(tmp_path):
+    import gzip
+    import random
+    from merkurio_b200.build import build_io
+    text = (ROOT / "include" / "merkurio_io.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(mk_input_[a-z_]+)\s*\(", text)))
+    assert declared == ["mk_input_close", "mk_input_error", "mk_input_open", "mk_input_read"]
+    lib = ctypes.CDLL(str(build_io()))
+    for n in declared:
+        assert hasattr(lib, n), n
+    lib.mk_input_open.restype = ctypes.c_void_p
+    lib.mk_input_open.argtypes = [ctypes.c_char_p]
+    lib.mk_input_read.restype = ctypes.c_longlong
+    lib.mk_input_read.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_ulonglong]
+    lib.mk_input_error.restype = ctypes.c_char_p
+    lib.mk_input_error.argtypes = [ctypes.c_void_p]
+    lib.mk_input_close.argtypes = [ctypes.c_void_p]
+
+    def slurp(path, piece=1 << 16):
+        h = lib.mk_input_open(str(path).encode())
+        assert h, lib.mk_input_error(None)
+        buf = ctypes.create_string_buffer(piece)
+        out = bytearray()
+        while True:
+            n = lib.mk_input_read(h, buf, piece)
+            if n <= 0:
+                break
+            out += buf.raw[:n]
+        err = lib.mk_input_error(h).decode()
+        lib.mk_input_close(h)
+        return n, bytes(out), err
+
+    rng = random.Random(2)
+    raw = "".join("@r%d\n%s\n+\n%s\n" % (i, "".join(rng.choices("ACGT", k=120)), "".join(rng.choices("FF:,#", k=120))) for i in range(40000)).encode()
+    plain, zipped = tmp_path / "r.fastq", tmp_path / "r.fastq.gz"
+    plain.write_bytes(raw)
+    zipped.write_bytes(gzip.compress(raw, 6))
+    assert slurp(plain) == (0, raw, "")
+    assert slurp(zipped, 12345) == (0, raw, "")
+    os.environ["MERKURIO_GZIP_PIECE_KB"] = "64"  # the same file on several threads
+    try:
+        assert slurp(zipped) == (0, raw, "")
+    finally:
+        del os.environ["MERKURIO_GZIP_PIECE_KB"]
+    cut = tmp_path / "cut.fastq.gz"
+    cut.write_bytes(zipped.read_bytes()[:100000])
+    rc, out, err = slurp(cut)
+    assert rc == -1 and raw.startswith(out) and len(out) > 0 and "truncated gzip stream" in err
+    assert not lib.mk_input_open(str(tmp_path / "missing.fq").encode())
+    assert b"No such file" in lib.mk_input_error(None)
