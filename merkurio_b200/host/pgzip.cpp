@@ -259,12 +259,17 @@ private:
             }
             if (job) {
                 const double t0 = now_s();
-                const size_t n = job->n_sym - kWin;
-                job->bytes = take_bytes();
-                if (job->bytes.size() < n) job->bytes.resize(n);
-                job->n_bytes = n;
-                job->bad_distance = !resolve_markers(job->sym.data() + kWin, n, job->window.data(), job->window_valid, job->bytes.data());
-                job->crc = crc32_fast(0, job->bytes.data(), n);
+                try {
+                    const size_t n = job->n_sym - kWin;
+                    job->bytes = take_bytes();
+                    if (job->bytes.size() < n) job->bytes.resize(n);
+                    job->n_bytes = n;
+                    job->bad_distance = !resolve_markers(job->sym.data() + kWin, n, job->window.data(), job->window_valid, job->bytes.data());
+                    job->crc = crc32_fast(0, job->bytes.data(), n);
+                } catch (const std::exception&) {  // (no memory for the piece's bytes)
+                    job->kind = Piece::kError;
+                    job->error = "Error while decompressing the input (out of memory)";
+                }
                 std::vector<uint8_t>().swap(job->window);
                 const double dt = now_s() - t0;
                 {
@@ -278,8 +283,13 @@ private:
             }
             Task& t = tasks_[i];
             double t_search = 0, t_decode = 0;
-            t.sym = take_sym();
-            run_task(inf, i, t, &t_search, &t_decode);
+            try {
+                t.sym = take_sym();
+                run_task(inf, i, t, &t_search, &t_decode);
+            } catch (const std::exception&) {  // (no memory for the symbols: this piece is left to the sequential decoder)
+                t.ok = false;
+                std::vector<uint16_t>().swap(t.sym);
+            }
             {
                 std::lock_guard<std::mutex> lk(mu_);
                 t.done = true;
