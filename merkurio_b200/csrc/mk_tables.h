@@ -469,6 +469,8 @@ inline Tables build_tables(const PatternSet& ps, int enc) {
         win_layout = false;
         if (!long_seeds && !t.dual_perm) index_seeds(0);  // (with dual_perm the codes of the first pass are already right)
         TBT("index2");
+    } else if (t.dual_perm && !long_seeds) {
+        index_seeds(0);  // MK_NO_WIN_SCAN (a test switch): the first pass packed ordered codes, mk_scan_dual8 wants window codes
     }
     t.win = win_layout;
 

@@ -597,3 +597,20 @@ def test_engines_on_shared_tables_and_free_running_slots(monkeypatch):
         r = e1.wait(s)
         np.testing.assert_array_equal(r.hits["start"], want[1])
     e1.close()
+
+
+@pytest.mark.parametrize("knobs", [{"MK_NO_WIN_SCAN": "1"}, {"MK_NO_WIN_SCAN": "1", "MK_NO_LONG_SEEDS": "1"}, {"MK_NO_WIN_SCAN": "1", "MK_NO_GATE": "1"}])
+def test_l2_filter_stride_8_without_the_window_layout_of_the_first_index_pass(monkeypatch, knobs):
+    """Found by scripts/gpu_fuzz.py: with MK_NO_WIN_SCAN the first index pass packs ordered seed codes, and the stride-8
+    scan with the L2-resident filter (mk_scan_dual8, which takes window codes) found nothing. The builder now indexes
+    again for it. Amino-acid alphabet, k = 19..35, every switch combination that reached the bug."""
+    rng = np.random.default_rng(77)
+    alpha = b"ACDEFGHIKLMNPQRSTVWY"
+    monkeypatch.setenv("MK_FILTER_MODE", "l2")
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    for kmin, kmax, n_pat in ((25, 35, 7), (21, 31, 1), (19, 20, 300)):
+        pats = sorted({rand_seq(rng, int(rng.integers(kmin, kmax + 1)), alpha) for _ in range(n_pat)})
+        recs = planted_records(rng, pats, 400, 0, 300, alpha, plant_p=0.5)
+        r = check_batch(pats, recs)
+        assert r.n_hits > 50
