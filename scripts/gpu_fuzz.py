@@ -1,6 +1,6 @@
 """Randomised parity runs of the device path against the oracle (needs a GPU): query sets and texts drawn with random
 lengths, alphabets, case modes, record shapes and filter flavours, each checked in ALL_HITS, PATTERN_SET and FLAG mode
-with tests/test_gpu_parity.check_batch (bit-exact hit lists). A soak test beside the fixed-seed cases of the suite.
+with tests/test_gpu_parity.check_batch / check_bam4 (bit-exact hit lists; a third of the ACGT(N) cases as BAM 4-bit text). A soak test beside the fixed-seed cases of the suite.
 
     python scripts/gpu_fuzz.py [--seconds 120] [--seed 1]
 """
@@ -13,7 +13,7 @@ from pathlib import Path
 import numpy as np
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-from tests.test_gpu_parity import check_batch, planted_records, rand_seq  # noqa: E402
+from tests.test_gpu_parity import check_bam4, check_batch, planted_records, rand_seq  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--seconds", type=float, default=120)
@@ -52,10 +52,14 @@ while time.time() - t0 < args.seconds:
     os.environ.update(knobs)
     if kmin <= 3 and shape in (1, 3):
         recs = [r[:20000] for r in recs[:3]]  # (millions of hits otherwise)
+    bam = (not ci) and alpha in (b"ACGT", b"ACGTN") and rng.random() < 0.35  # BAM 4-bit text (upper-case IUPAC only)
     try:
-        check_batch(pats, recs, case_insensitive=ci)
+        if bam:
+            check_bam4(pats, [r for r in recs] or [b""])
+        else:
+            check_batch(pats, recs, case_insensitive=ci)
     except Exception as ex:
-        print(f"FAILED case {n}: seed {args.seed} kmin {kmin} kmax {kmax} alphabet {alpha} patterns {len(pats)} ci {ci} shape {shape} knobs {knobs}: {repr(ex)[:500]}", flush=True)
+        print(f"FAILED case {n}: seed {args.seed} kmin {kmin} kmax {kmax} alphabet {alpha} patterns {len(pats)} ci {ci} bam {bam} shape {shape} knobs {knobs}: {repr(ex)[:500]}", flush=True)
         raise
     n += 1
 print(f"{n} random cases in {time.time() - t0:.0f} s: all equal to the oracle")
