@@ -55,3 +55,6 @@ while time.time() - t0 < (float(sys.argv[2]) if len(sys.argv) > 2 else 300):
     if r.returncode!=0 or r.stdout!=raw:
         bad+=1; print('MISMATCH',it,len(raw),len(data),env['MERKURIO_GZIP_THREADS'],env['MERKURIO_GZIP_PIECE_KB'],r.returncode,r.stderr[:200]); open(os.path.join(TMP, f'fail{it}.gz'), 'wb').write(data)
 print('iterations', it, 'bad', bad, '(failing files, if any, are kept in ' + TMP + ')')
+if bad == 0:
+    import shutil
+    shutil.rmtree(TMP, ignore_errors=True)
