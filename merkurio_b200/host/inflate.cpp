@@ -249,9 +249,9 @@ bool Inflater::read_dynamic_header(const uint8_t*& in_ref, const uint8_t* in_end
     if (n != total) return false;       // a repeat ran over the end
     if (lens[256] == 0) return false;   // no end-of-block code
     if (in_final && in - (bitcnt >> 3) > in_end) return false;  // the header runs past the end of the input
+    fixed_loaded_ = false;  // (before the tables are touched: a header that fails half way must not leave them marked as the fixed ones)
     if (!build_table(litlen_, kLitlenBits, kLitlenEntries, lens, (int)hlit, 0)) return false;
     if (!build_table(dist_, kDistBits, kDistEntries, lens + hlit, (int)hdist, 1)) return false;
-    fixed_loaded_ = false;
     in_ref = in;
     bitbuf_ = bitbuf;
     bitcnt_ = bitcnt;
