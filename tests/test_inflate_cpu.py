@@ -77,6 +77,18 @@ def stream_cases():
         return out + c.compress(data[pos:]) + c.flush()
     n = len(fq)
     cases["flushes"] = (fq, flushed(fq, [(n // 5, zlib.Z_SYNC_FLUSH), (n // 2, zlib.Z_FULL_FLUSH), (n // 2 + 1, zlib.Z_SYNC_FLUSH), (n - 300, zlib.Z_SYNC_FLUSH), (n - 7, zlib.Z_FULL_FLUSH), (n, zlib.Z_SYNC_FLUSH)]))
+    # dynamic, fixed and stored blocks alternating in one member: raw deflate pieces of independent compressors, each ended
+    # with Z_FULL_FLUSH (byte aligned, not final), behind one gzip header — the decoder's tables change kind from block
+    # to block, also in the tasks of the parallel reader that start in the middle
+    def mixed(parts):
+        out, raw_all = b"", b""
+        for i, (data, level, strategy) in enumerate(parts):
+            c = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+            out += c.compress(data) + (c.flush() if i + 1 == len(parts) else c.flush(zlib.Z_FULL_FLUSH))
+            raw_all += data
+        return raw_all, b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03" + out + struct.pack("<II", zlib.crc32(raw_all), len(raw_all) & 0xFFFFFFFF)
+    kinds = [(6, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED), (0, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_FIXED)]
+    cases["mixed_block_types"] = mixed([(fastq(rng.randint(100, 700), 100 + i),) + kinds[i % len(kinds)] for i in range(40)])
     rep = b"A" * 1_500_000
     cases["flushes_in_a_short_stream"] = (rep, flushed(rep, [(700_000, zlib.Z_SYNC_FLUSH), (1_400_000, zlib.Z_FULL_FLUSH), (1_499_999, zlib.Z_SYNC_FLUSH)]))
     # a header with every optional field
@@ -201,7 +213,8 @@ def _stats(err: bytes):
 
 
 @pytest.mark.parametrize("name", ["fastq_level6", "fastq_level1", "fastq_level9", "stored_blocks", "fixed_codes", "huffman_only", "run_length",
-                                  "small_blocks", "incompressible", "zeros", "period_25", "short_periods", "members", "flushes"])
+                                  "small_blocks", "incompressible", "zeros", "period_25", "short_periods", "members", "flushes",
+                                  "mixed_block_types"])
 def test_parallel_gzip_equals_zlib(exe, tmp_path, name):
     raw, comp = CASES[name]
     p = tmp_path / "x.gz"
