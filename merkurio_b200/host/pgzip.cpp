@@ -240,6 +240,11 @@ private:
         if (v.capacity() && free_bytes_.size() < max_pieces_ + 2) free_bytes_.push_back(std::move(v));
     }
 
+    static void huge_pages(void* p, size_t bytes) {
+        const uintptr_t lo = ((uintptr_t)p + ((size_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1), hi = ((uintptr_t)p + bytes) & ~(((uintptr_t)2 << 20) - 1);
+        if (hi > lo) ::madvise((void*)lo, hi - lo, MADV_HUGEPAGE);
+    }
+
     // ---- the pool: replacing place holders first (the reader waits for those), decoding pieces of the file otherwise --------
     void worker() {
         Inflater inf;
@@ -262,6 +267,10 @@ private:
                 try {
                     const size_t n = job->n_sym - kWin;
                     job->bytes = take_bytes();
+                    if (job->bytes.capacity() < n) {
+                        job->bytes.reserve(n + n / 4);
+                        huge_pages(job->bytes.data(), job->bytes.capacity());
+                    }
                     if (job->bytes.size() < n) job->bytes.resize(n);
                     job->n_bytes = n;
                     job->bad_distance = !resolve_markers(job->sym.data() + kWin, n, job->window.data(), job->window_valid, job->bytes.data());
@@ -314,6 +323,12 @@ private:
         const uint64_t stop = (i + 1 == tasks_.size()) ? ~0ull : hi;
         // at most 24 Mi symbols per task (12 times the piece; the buffer doubles, so 64 MB at most): data that expands
         // further than that is left to the sequential decoder
+        // (sized for a five-fold expansion at once: growing by doubling copies the symbols five times over)
+        if (t.sym.capacity() < kWin + 5 * piece_ + 4096) {
+            t.sym.reserve(kWin + 5 * piece_ + 4096);
+            huge_pages(t.sym.data(), t.sym.capacity() * sizeof(uint16_t));  // (a sixth of the page faults where THP is on "madvise")
+        }
+        if (t.sym.size() < kWin + 5 * piece_ + 4096) t.sym.resize(kWin + 5 * piece_ + 4096);
         Inflater::MarkerRun r = inf.run_markers(base_, end_, start, stop, &t.sym, (size_t)12 * piece_);
         *t_search = t1 - t0;
         *t_decode = now_s() - t1;
