@@ -78,20 +78,24 @@ struct Piece {  // one stretch of output, in the order of the stream
 
 class ParallelGzipStream : public InputStream {
 public:
-    ParallelGzipStream(int fd, size_t file_size, int threads, size_t piece_bytes)
-        : fd_(fd), size_(file_size), piece_(piece_bytes), window_(kWin), seqbuf_(kWin + kSeqArea + Inflater::kOutputMargin + 64) {
-        // the file, and one zero page behind it: the decoders read up to 600 bytes past the end of the data
+    // The file, and one zero page behind it (the decoders read up to 600 bytes past the end of the data); nullptr if the
+    // file cannot be mapped (the caller then reads it with the sequential reader).
+    static const uint8_t* map_file(int fd, size_t size, size_t* map_len) {
         const size_t page = (size_t)sysconf(_SC_PAGESIZE);
-        map_len_ = (size_ + page - 1) / page * page + page;
-        void* m = ::mmap(nullptr, map_len_, PROT_READ, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-        if (m == MAP_FAILED) { ::close(fd_); throw Error("cannot map the input"); }
-        if (::mmap(m, size_, PROT_READ, MAP_PRIVATE | MAP_FIXED, fd_, 0) == MAP_FAILED) {
-            ::munmap(m, map_len_);
-            ::close(fd_);
-            throw Error("cannot map the input");
+        *map_len = (size + page - 1) / page * page + page;
+        void* m = ::mmap(nullptr, *map_len, PROT_READ, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (m == MAP_FAILED) return nullptr;
+        if (::mmap(m, size, PROT_READ, MAP_PRIVATE | MAP_FIXED, fd, 0) == MAP_FAILED) {
+            ::munmap(m, *map_len);
+            return nullptr;
         }
-        ::madvise(m, size_, MADV_SEQUENTIAL);
-        base_ = static_cast<const uint8_t*>(m);
+        ::madvise(m, size, MADV_SEQUENTIAL);
+        return static_cast<const uint8_t*>(m);
+    }
+
+    ParallelGzipStream(int fd, const uint8_t* mapped, size_t map_len, size_t file_size, int threads, size_t piece_bytes)
+        : fd_(fd), size_(file_size), piece_(piece_bytes), map_len_(map_len), base_(mapped), window_(kWin),
+          seqbuf_(kWin + kSeqArea + Inflater::kOutputMargin + 64) {
         end_ = base_ + size_;
         timing_ = std::getenv("MERKURIO_TIMING") != nullptr;
         max_pieces_ = (size_t)threads + 2;
@@ -570,7 +574,10 @@ std::unique_ptr<InputStream> open_parallel_gzip(int fd) {
     size_t piece = (size_t)2 << 20;
     if (const char* e = std::getenv("MERKURIO_GZIP_PIECE_KB")) piece = std::max<size_t>(4, (size_t)std::atoll(e)) << 10;  // (tests: many small pieces)
     if ((size_t)st.st_size < 3 * piece) return nullptr;
-    return std::unique_ptr<InputStream>(new ParallelGzipStream(fd, (size_t)st.st_size, threads, piece));
+    size_t map_len = 0;
+    const uint8_t* mapped = ParallelGzipStream::map_file(fd, (size_t)st.st_size, &map_len);
+    if (!mapped) return nullptr;  // (a file system without mmap: the sequential reader)
+    return std::unique_ptr<InputStream>(new ParallelGzipStream(fd, mapped, map_len, (size_t)st.st_size, threads, piece));
 }
 
 }  // namespace mkh
