@@ -293,13 +293,14 @@ void extract_records(CmdExtract args) {
             chunks1 = FastqPipeline::open_reader(in1, paired ? 2 : 1);
             if (paired) chunks2 = FastqPipeline::open_reader(in2, 2);
         }
-        // single-file FASTA has its own pipeline (fasta_pipeline.h): records of any length, cut into pieces
-        const bool fasta_pipelined = !pipelined && !paired && !std::getenv("MERKURIO_NO_FASTA_PIPELINE") && looks_like_fasta(in1);
-        std::unique_ptr<FastaChunkReader> fa_chunks;
+        // FASTA (one file, or two files of mates) has its own pipeline (fasta_pipeline.h): records of any length, cut
+        // into pieces
+        const bool fasta_pipelined = !pipelined && !std::getenv("MERKURIO_NO_FASTA_PIPELINE") && looks_like_fasta(in1) &&
+                                     (!paired || looks_like_fasta(in2));
+        std::unique_ptr<FastaChunkReader> fa_chunks, fa_chunks2;
         if (fasta_pipelined) {
-            const size_t chunk_bytes = std::getenv("MERKURIO_CHUNK_BYTES") ? (size_t)std::strtoull(std::getenv("MERKURIO_CHUNK_BYTES"), nullptr, 10)
-                                                                           : (size_t)8 << 20;
-            fa_chunks.reset(new FastaChunkReader(in1, chunk_bytes, prefetch_depth(chunk_bytes, 1)));
+            fa_chunks = FastaPipeline::open_reader(in1, paired ? 2 : 1);
+            if (paired) fa_chunks2 = FastaPipeline::open_reader(in2, 2);
         }
         // the record-by-record path (FASTA, and whatever the FASTQ pipeline does not take) reads ahead on its own
         // threads, also started before the engines
@@ -404,6 +405,8 @@ void extract_records(CmdExtract args) {
                 RecMeta m;
                 m.kind = 2;
                 m.chunk = &rec;
+                m.keep = pc.rec;  // a first mate waits for the second one, which may end in a later batch
+                m.file = rec.file;
                 m.a = rec.id;
                 m.len = (uint32_t)rec.len;
                 m.crlf = rec.crlf;
@@ -414,7 +417,8 @@ void extract_records(CmdExtract args) {
         try {
             if (fasta_pipelined) {
                 reader.reset();
-                FastaPipeline pipe(engines, std::move(fa_chunks), mode, keep_text, consume_fasta);
+                reader2.reset();
+                FastaPipeline pipe(engines, std::move(fa_chunks), std::move(fa_chunks2), mode, keep_text, consume_fasta);
                 pipe.run();
             } else if (pipelined) {
                 reader.reset();

@@ -28,6 +28,7 @@ struct RecMeta {
     // FASTQ pipeline (fastq_pipeline.h): the record is span `idx` of `chunk` and a, b, c stay empty; the
     // batch being delivered keeps the chunk alive
     const void* chunk = nullptr;
+    std::shared_ptr<const void> keep;  // FASTA records: owner of `chunk` for a meta that outlives its batch (the first mate of a pair)
     uint32_t idx = 0;
     uint8_t kind = 0;  // 0: strings a / b / c; 1: FASTQ span (chunk = Chunk, idx); 2: FASTA record (chunk = FaRecord); 3: alignment span
 };

@@ -48,8 +48,8 @@ std::shared_ptr<FaChunk> FastaChunkReader::next() {
 // line is carried over to the front of the next block.
 void FastaChunkReader::run() {
     double t_index = 0, t_starved = 0, t_blocked = 0;
+    std::vector<char> carry;
     try {
-        std::vector<char> carry;
         std::shared_ptr<Shared> pool = pool_;
         BlockReader::Block rb;
         OffsetList nl;
@@ -128,7 +128,19 @@ void FastaChunkReader::run() {
             cv_.notify_all();
         }
     } catch (const std::exception& e) {
+        // The input cannot be read any further. If the bytes in front of that spot end in an unfinished header line,
+        // the record before it is complete — a line-by-line reader has seen the '>' — so that line is still handed
+        // out; the error follows it.
+        std::shared_ptr<FaChunk> tail;
+        if (!carry.empty() && carry[0] == '>' && carry.size() < ((size_t)1 << 30)) {
+            tail.reset(new FaChunk);
+            ByteBuf d(kHead + carry.size());
+            std::memcpy(d.data() + kHead, carry.data(), carry.size());
+            tail->data.swap(d);
+            tail->lines.push_back(FaLine{(uint32_t)kHead, (uint32_t)carry.size(), 1});
+        }
         std::lock_guard<std::mutex> lk(mu_);
+        if (tail && !stop_) ready_.push_back(std::move(tail));
         io_error_ = e.what();
     }
     if (std::getenv("MERKURIO_TIMING"))
@@ -159,20 +171,47 @@ bool looks_like_fasta(const std::string& path) {
 }
 
 // ------------------------------------------------------------------------------------------------
-FastaPipeline::FastaPipeline(EngineSet& engines, std::unique_ptr<FastaChunkReader> reader, mk_mode mode, bool keep_text, BatchConsumer consumer)
-    : SlotPipeline(engines, MK_ENC_ASCII, mode, std::move(consumer)), rd_(std::move(reader)), keep_text_(keep_text) {
+namespace {
+const char* kParseError = "Error during FASTQ/A record parsing.";
+const char* kFirstCtx = "Error during FASTQ record parsing of first file.";
+const char* kSecondCtx = "Error during FASTQ record parsing of second file. Do the two input files contain the same number of records?";
+const char* kUnequal = "The two input files have a different number of records. Please provide valid paired-end read files.";
+}  // namespace
+
+std::unique_ptr<FastaChunkReader> FastaPipeline::open_reader(const std::string& path, int n_files) {
+    const size_t chunk_bytes = std::getenv("MERKURIO_CHUNK_BYTES") ? (size_t)std::strtoull(std::getenv("MERKURIO_CHUNK_BYTES"), nullptr, 10)
+                                                                   : (size_t)8 << 20;
+    return std::unique_ptr<FastaChunkReader>(new FastaChunkReader(path, chunk_bytes, prefetch_depth(chunk_bytes, n_files)));
+}
+
+FastaPipeline::FastaPipeline(EngineSet& engines, std::unique_ptr<FastaChunkReader> reader, std::unique_ptr<FastaChunkReader> reader2,
+                             mk_mode mode, bool keep_text, BatchConsumer consumer)
+    : SlotPipeline(engines, MK_ENC_ASCII, mode, std::move(consumer)), paired_((bool)reader2), keep_text_(keep_text) {
+    src_[0].rd = std::move(reader);
+    src_[1].rd = std::move(reader2);
     overlap_ = es_.max_pattern_len ? es_.max_pattern_len - 1 : 0;
 }
 
 FastaPipeline::~FastaPipeline() { stop_packer(); }
 
-void FastaPipeline::begin() { cur_ = rd_->next(); }
-
-void FastaPipeline::flush_range() {
-    if (range_open_ && rec_ && keep_text_) rec_->raw.push_back(FaRecord::Range{cur_, range_off_, range_end_ - range_off_});
-    range_open_ = false;
+void FastaPipeline::begin() {
+    for (int f = 0; f < (paired_ ? 2 : 1); ++f) {
+        try {
+            src_[f].cur = src_[f].rd->next();
+        } catch (const Error& e) {  // surfaces in fill(), where it gets the record path's context
+            src_[f].read_error = e.what();
+        }
+    }
 }
 
+void FastaPipeline::flush_range(Src& s) {
+    if (s.range_open && s.rec && keep_text_) s.rec->raw.push_back(FaRecord::Range{s.cur, s.range_off, s.range_end - s.range_off});
+    s.range_open = false;
+}
+
+// Fill one slot. One record is packed at a time — with two files the records of the first and the second file in
+// turn (record 2i of the consumer's sequence = record i of file 1, record 2i + 1 = its mate) — and a record that does
+// not fit goes on in the next batch, whichever file it is from.
 bool FastaPipeline::fill(PackedBatch& b) {
     b.n_records = 0;
     b.n_units = b.n_bytes = b.total_bases = 0;
@@ -184,93 +223,128 @@ bool FastaPipeline::fill(PackedBatch& b) {
     if (input_done_) return false;
     const uint64_t cap = es_.max_bytes;
     const uint32_t max_rec = es_.max_records;
-    // open a piece of rec_ in this batch; false if the batch has no record slot left
-    auto open_piece = [&](bool first) {
+    auto fail = [&](std::vector<std::string> chain) {
+        b.error_chain = std::move(chain);
+        input_done_ = true;
+    };
+    // step s to its next line; false if the file cannot be read any further (*why: what the record-by-record
+    // reader would have thrown there). At the end of the file s.cur is null.
+    auto advance = [&](Src& s, std::string* why) {
+        if (!s.read_error.empty()) { *why = s.read_error; return false; }
+        while (s.cur && s.line == s.cur->lines.size()) {
+            flush_range(s);
+            try {
+                s.cur = s.rd->next();
+            } catch (const Error& e) {
+                s.cur = nullptr;
+                s.read_error = e.what();
+                *why = s.read_error;
+                return false;
+            }
+            s.line = 0;
+            s.line_pos = 0;
+        }
+        return true;
+    };
+    // open a piece of s.rec in this batch; false if the batch has no record slot left
+    auto open_piece = [&](Src& s, bool first) {
         if (b.n_records >= max_rec) return false;
-        uint64_t lead = first ? 0 : std::min<uint64_t>(overlap_, rec_->len);
+        uint64_t lead = first ? 0 : std::min<uint64_t>(overlap_, s.rec->len);
         if (lead) {  // the record's last bases again: they are the tail of the slot filled before this one
             std::memmove(b.seq + b.n_bytes, prev_seq_ + prev_bytes_ - lead, lead);
         }
         b.off[b.n_records] = b.n_bytes;
-        info->pieces.push_back(FaPiece{rec_, first, false, rec_->len - lead, (uint32_t)lead});
+        info->pieces.push_back(FaPiece{s.rec, first, false, s.rec->len - lead, (uint32_t)lead});
         b.n_bytes += lead;
         b.n_records += 1;
-        rec_open_piece_ = true;
+        s.rec_open_piece = true;
         return true;
     };
-    auto end_record = [&] {  // rec_'s piece is the last one of this batch
-        flush_range();
+    auto end_record = [&](Src& s) {  // s.rec's piece is the last one of this batch; the other file is next
+        flush_range(s);
         info->pieces.back().last = true;
-        rec_.reset();
-        rec_open_piece_ = false;
+        s.rec.reset();
+        s.rec_open_piece = false;
+        if (paired_) turn_ ^= 1;
     };
     for (;;) {
-        while (cur_ && line_ == cur_->lines.size()) {
-            flush_range();
-            cur_ = rd_->next();
-            line_ = 0;
-            line_pos_ = 0;
+        Src& s = src_[turn_];
+        std::string why;
+        if (!advance(s, &why)) {
+            fail(paired_ ? std::vector<std::string>{turn_ == 0 ? kFirstCtx : kSecondCtx, why} : std::vector<std::string>{kParseError, why});
+            break;
         }
-        if (!cur_) {  // end of input
-            if (rec_) {
-                if (!rec_open_piece_ && !open_piece(false)) break;
-                end_record();
+        if (!s.cur) {  // end of this file
+            if (s.rec) {
+                if (!s.rec_open_piece && !open_piece(s, false)) break;
+                end_record(s);
+                if (paired_) continue;
+            } else if (paired_) {
+                if (turn_ == 1) {  // file 1 had one more record
+                    fail({kSecondCtx});
+                    break;
+                }
+                Src& o = src_[1];  // file 1 is exhausted: file 2 must be, too
+                if (!advance(o, &why)) fail({why});
+                else if (o.cur) fail({kUnequal});
             }
             input_done_ = true;
             break;
         }
-        const FaLine& ln = cur_->lines[line_];
-        const char* text = cur_->data.data() + ln.off;
+        const FaLine& ln = s.cur->lines[s.line];
+        const char* text = s.cur->data.data() + ln.off;
         const bool cr = ln.len && text[ln.len - 1] == '\r';
-        if (!started_) {
-            if (ln.len == (cr ? 1u : 0u)) { ++line_; continue; }  // blank lines before the first record
-            started_ = true;
+        if (!s.started) {
+            if (ln.len == (cr ? 1u : 0u)) { ++s.line; continue; }  // blank lines before the first record
+            s.started = true;
         }
         if (ln.header) {
-            if (rec_) {  // the previous record ends here
-                if (!rec_open_piece_ && !open_piece(false)) break;
-                end_record();
+            if (s.rec) {  // the previous record ends here
+                if (!s.rec_open_piece && !open_piece(s, false)) break;
+                end_record(s);
+                continue;  // (with two files: to the other file's record; this header waits)
             }
             if (b.n_records >= max_rec) break;  // the header opens the next batch
-            rec_.reset(new FaRecord);
-            rec_->id.assign(text + 1, ln.len - 1 - (cr ? 1 : 0));
-            rec_->crlf = cr;
-            open_piece(true);
-            ++line_;
+            s.rec.reset(new FaRecord);
+            s.rec->id.assign(text + 1, ln.len - 1 - (cr ? 1 : 0));
+            s.rec->file = (uint8_t)turn_;
+            s.rec->crlf = cr;
+            open_piece(s, true);
+            ++s.line;
             continue;
         }
-        // a sequence line of rec_
-        if (!rec_open_piece_) {
-            if (b.n_bytes + std::min<uint64_t>(overlap_, rec_->len) >= cap && b.n_records > 0) break;
-            if (!open_piece(false)) break;
+        // a sequence line of s.rec
+        if (!s.rec_open_piece) {
+            if (b.n_bytes + std::min<uint64_t>(overlap_, s.rec->len) >= cap && b.n_records > 0) break;
+            if (!open_piece(s, false)) break;
         }
-        if (line_pos_ == 0) {
-            if (!range_open_) { range_open_ = true; range_off_ = ln.off; }
-            range_end_ = ln.off + ln.len;
+        if (s.line_pos == 0) {
+            if (!s.range_open) { s.range_open = true; s.range_off = ln.off; }
+            s.range_end = ln.off + ln.len;
         }
         const uint32_t bases = ln.len - (cr ? 1 : 0);
         const uint64_t room = cap - b.n_bytes;
-        const uint64_t take = std::min<uint64_t>(bases - line_pos_, room);
+        const uint64_t take = std::min<uint64_t>(bases - s.line_pos, room);
         if (take) {
-            std::memcpy(b.seq + b.n_bytes, text + line_pos_, take);
+            std::memcpy(b.seq + b.n_bytes, text + s.line_pos, take);
             b.n_bytes += take;
-            rec_->len += take;
-            line_pos_ += (uint32_t)take;
+            s.rec->len += take;
+            s.line_pos += (uint32_t)take;
         }
-        if (line_pos_ == bases) {
-            ++line_;
-            line_pos_ = 0;
+        if (s.line_pos == bases) {
+            ++s.line;
+            s.line_pos = 0;
             continue;
         }
         // the slot is full in the middle of the record: it goes on in the next batch
-        rec_open_piece_ = false;
+        s.rec_open_piece = false;
         break;
     }
     b.off[b.n_records] = b.n_bytes;
     b.n_units = b.total_bases = b.n_bytes;
     prev_seq_ = b.seq;
     prev_bytes_ = b.n_bytes;
-    return b.n_records > 0;
+    return b.n_records > 0 || !b.error_chain.empty();
 }
 
 }  // namespace mkh

@@ -6,6 +6,8 @@
 // starts with the last (longest pattern - 1) bases again, so that every occurrence lies inside one
 // piece; a hit that ends inside that overlap belongs to the piece before. The record's wrapped text
 // is never copied: the batch keeps (chunk, offset, length) ranges for the writer.
+// Two FASTA files (paired reads, src/cmd_extract.rs:412-418, :463-607) go through the same packer: record i of the
+// first file, then record i of the second, so the consumer sees the mates alternate in input order.
 #pragma once
 #include "fastq_stream.h"
 #include "slot_pipeline.h"
@@ -52,6 +54,7 @@ bool looks_like_fasta(const std::string& path);
 // One FASTA record while its pieces travel through the batches.
 struct FaRecord {
     std::string id;       // header without '>' and line break
+    uint8_t file = 0;     // 0 / 1: which input file (mate)
     bool crlf = false;    // header ended in "\r\n"
     uint64_t len = 0;     // bases
     struct Range { std::shared_ptr<FaChunk> chunk; uint32_t off, len; };
@@ -74,8 +77,13 @@ struct FaBatchInfo {
 
 class FastaPipeline : public SlotPipeline {
 public:
-    FastaPipeline(EngineSet& engines, std::unique_ptr<FastaChunkReader> reader, mk_mode mode, bool keep_text, BatchConsumer consumer);
+    // `reader2` (may be null): the second file of a pair. The input's errors (a file that cannot be read any
+    // further, files with different numbers of records) are raised by run() after everything in front of them has
+    // been delivered, with the record-by-record path's messages.
+    FastaPipeline(EngineSet& engines, std::unique_ptr<FastaChunkReader> reader, std::unique_ptr<FastaChunkReader> reader2, mk_mode mode,
+                  bool keep_text, BatchConsumer consumer);
     ~FastaPipeline() override;
+    static std::unique_ptr<FastaChunkReader> open_reader(const std::string& path, int n_files);
     // the pieces of a batch handed to the consumer
     static const FaBatchInfo& info(const PackedBatch& b) { return *static_cast<const FaBatchInfo*>(b.extra.get()); }
 
@@ -84,22 +92,28 @@ protected:
     bool fill(PackedBatch& b) override;
 
 private:
-    void close_record();
-    std::unique_ptr<FastaChunkReader> rd_;
+    // where the packer stands in one input file
+    struct Src {
+        std::unique_ptr<FastaChunkReader> rd;
+        std::shared_ptr<FaChunk> cur;
+        size_t line = 0;
+        uint32_t line_pos = 0;  // bytes of the current sequence line already packed
+        bool started = false;
+        std::shared_ptr<FaRecord> rec;  // record being packed
+        bool rec_open_piece = false;    // its current piece sits in the batch being filled
+        // raw-text range of the record inside the current chunk
+        bool range_open = false;
+        uint32_t range_off = 0, range_end = 0;
+        std::string read_error;  // what next() threw: the file ends there
+    };
+    void flush_range(Src& s);
+    Src src_[2];
+    bool paired_;
+    int turn_ = 0;  // the file whose record is being packed
     bool keep_text_;
-    std::shared_ptr<FaChunk> cur_;
-    size_t line_ = 0;
-    uint32_t line_pos_ = 0;  // bytes of the current sequence line already packed
-    bool started_ = false;
-    std::shared_ptr<FaRecord> rec_;  // record being packed
-    bool rec_open_piece_ = false;    // its current piece sits in the batch being filled
     uint64_t overlap_ = 0;
     const uint8_t* prev_seq_ = nullptr;  // the slot filled before this one (source of the overlap)
     uint64_t prev_bytes_ = 0;
-    // raw-text range of the record inside the current chunk
-    bool range_open_ = false;
-    uint32_t range_off_ = 0, range_end_ = 0;
-    void flush_range();
 };
 
 }  // namespace mkh

@@ -577,3 +577,51 @@ def test_fasta_pipeline_equals_record_path_and_oracle(tmp_path, logs):
     if logs:
         assert_log_equal(files["x.log"], (tmp_path / "ora" / "x.log").read_bytes())
         assert_json_equal(files["x.json"], (tmp_path / "ora" / "x.json").read_bytes())
+
+
+@pytest.mark.parametrize("mode", ["ac_logs", "bndmq_logs", "no_logs", "unequal"])
+def test_paired_fasta_pipeline_equals_record_path_and_oracle(tmp_path, mode):
+    """Two FASTA files of mates (src/cmd_extract.rs:412-418, :463-607) through the chunked FASTA pipeline: batches far
+    smaller than the long records, so mates end in different batches and occurrences straddle pieces in either file. Same
+    pair files, logs, exit status and error text as the record-by-record path, and the oracle's outputs."""
+    rng = np.random.default_rng(321)
+    n_pat = 3 if mode == "bndmq_logs" else 25
+    pats = sorted({rng.choice(np.frombuffer(b"ACGT", np.uint8), size=int(k)).tobytes() for k in rng.integers(21, 50, size=n_pat)})
+    files_in = []
+    for f in range(2):
+        recs = []
+        for i in range(120):
+            n = int(rng.integers(0, 500)) if (i + 7 * f) % 40 else int(rng.integers(40000, 90000))
+            r = bytearray(rng.choice(np.frombuffer(b"ACGTNacgt", np.uint8), size=n).tobytes())
+            pos = int(rng.integers(0, 900))
+            while pos + 70 < n:
+                p = pats[int(rng.integers(len(pats)))]
+                r[pos:pos + len(p)] = p
+                pos += int(rng.integers(700, 1400))
+            recs.append(bytes(r))
+        if mode == "unequal" and f == 1:
+            recs = recs[:90]
+        fa = tmp_path / ("m_%d.fa" % (f + 1))
+        _write_fasta(fa, recs, width=70)
+        files_in.append(fa)
+    kf = tmp_path / "k.txt"
+    kf.write_bytes(b"\n".join(pats) + b"\n")
+    logs = mode != "no_logs"
+    log_args = ["-l", "@OUT@/x.log", "-j", "@OUT@/x.json"] if logs else []
+    env = {"MERKURIO_BATCH_BYTES": "30000", "MERKURIO_CHUNK_BYTES": "8000"}
+    args = ["extract", "-i", files_in[0], "-2", files_in[1], "-f", kf, "-o", "@OUT@/x.fa", *log_args]
+    rc, err, files = _same_both_ways(tmp_path, args, "MERKURIO_NO_FASTA_PIPELINE", env)
+    if mode == "unequal":
+        assert rc != 0 and b"Do the two input files contain the same number of records?" in err
+        assert files["x_1.fa"].count(b">chr") >= 10
+        return
+    assert rc == 0, err
+    (tmp_path / "ora").mkdir()
+    rm.extract_records(rm.CmdExtract(in_fastx=str(files_in[0]), in_fastq_2=str(files_in[1]), kmer_file=str(kf), out_fastx=str(tmp_path / "ora" / "x.fa"),
+                                     out_log=str(tmp_path / "ora" / "x.log") if logs else None, json_log=str(tmp_path / "ora" / "x.json") if logs else None))
+    for name in ("x_1.fa", "x_2.fa"):
+        assert files[name] == (tmp_path / "ora" / name).read_bytes(), name
+    assert files["x_1.fa"].count(b">chr") >= 20
+    if logs:
+        assert_log_equal(files["x.log"], (tmp_path / "ora" / "x.log").read_bytes())
+        assert_json_equal(files["x.json"], (tmp_path / "ora" / "x.json").read_bytes())

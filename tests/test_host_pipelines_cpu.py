@@ -78,6 +78,73 @@ def test_fasta_pipeline_equals_record_path(exe, stub, tmp_path, kw):
         assert other == results[0]
 
 
+def paired_fasta_text(rng, n, tag, crlf=False, width=60, long_every=0):
+    out = bytearray()
+    le = b"\r\n" if crlf else b"\n"
+    for i in range(n):
+        m = int(rng.integers(0, 400)) if not long_every or i % long_every else int(rng.integers(30000, 70000))
+        s = bytes(rng.choice(np.frombuffer(b"ACGTNacgt", dtype=np.uint8), size=m).tobytes())
+        out += b">pair%d/%s" % (i, tag) + le
+        for k in range(0, m, width):
+            out += s[k:k + width] + le
+    return bytes(out)
+
+
+@pytest.mark.parametrize("kw", [{}, {"crlf": True}, {"width": 10 ** 6}, {"long_every": 50}], ids=lambda k: "-".join(k) or "plain")
+def test_paired_fasta_pipeline_equals_record_path(exe, stub, tmp_path, kw):
+    """Two FASTA files of mates (src/cmd_extract.rs:412-418, :463-607) go through the chunked FASTA pipeline as well: the
+    same two output files and the same log as the record-by-record path, whatever the chunk and batch sizes, with records
+    that span batches (`long_every`) in either file."""
+    rng = np.random.default_rng(5)
+    a, b = tmp_path / "m_1.fa", tmp_path / "m_2.fa"
+    a.write_bytes(paired_fasta_text(rng, 600, b"1", **kw))
+    b.write_bytes(b"\n\n" + paired_fasta_text(rng, 600, b"2", **kw))  # (blank lines in front of the first record)
+    results = []
+    for env in [{"MERKURIO_NO_FASTA_PIPELINE": "1"}] + SIZES:
+        d = tmp_path / ("r%d" % len(results))
+        d.mkdir()
+        r = run(exe, stub, ["extract", "-i", a, "-2", b, "-s", QUERY, "-v", "-o", d / "o.fa", "-l", d / "l.log"], env)
+        assert r.returncode == 0, r.stderr
+        results.append(((d / "o_1.fa").read_bytes(), (d / "o_2.fa").read_bytes(), log_body(d / "l.log")))
+    assert results[0][0].count(b">pair") == 600 and results[0][1].count(b">pair") == 600
+    assert b"records searched: 1200" in results[0][2]
+    for other in results[1:]:
+        assert other == results[0]
+
+
+@pytest.mark.parametrize("case", ["second_shorter", "second_longer", "second_cut_gz", "first_cut_gz"])
+def test_paired_fasta_pipeline_fails_like_the_record_path(exe, stub, tmp_path, case):
+    """Files with different numbers of records and inputs that cannot be read to their end stop the paired FASTA pipeline
+    with the messages and the output of the record-by-record path (everything in front of the error is written)."""
+    rng = np.random.default_rng(6)
+    t1, t2 = paired_fasta_text(rng, 3000, b"1"), paired_fasta_text(rng, 3000, b"2")
+    a, b = tmp_path / "m_1.fa", tmp_path / "m_2.fa"
+    if case == "second_shorter":
+        t2 = t2[: t2.index(b">pair2000/")]
+    elif case == "second_longer":
+        t1 = t1[: t1.index(b">pair2000/")]
+    if case == "second_cut_gz":
+        z = gzip.compress(t2)
+        b = tmp_path / "m_2.fa.gz"
+        t2 = z[: len(z) // 2]
+    if case == "first_cut_gz":
+        z = gzip.compress(t1)
+        a = tmp_path / "m_1.fa.gz"
+        t1 = z[: len(z) // 2]
+    a.write_bytes(t1)
+    b.write_bytes(t2)
+    results = []
+    for env in [{"MERKURIO_NO_FASTA_PIPELINE": "1"}, {}, {"MERKURIO_BATCH_BYTES": "20000", "MERKURIO_CHUNK_BYTES": "5000"}]:
+        d = tmp_path / ("r%d" % len(results))
+        d.mkdir()
+        r = run(exe, stub, ["extract", "-i", a, "-2", b, "-s", QUERY, "-v", "-o", d / "o.fa"], env)
+        assert r.returncode != 0
+        results.append((r.returncode, r.stderr, (d / "o_1.fa").read_bytes(), (d / "o_2.fa").read_bytes()))
+    assert results[0][2].count(b">pair") >= 1000, results[0][1]
+    for other in results[1:]:
+        assert other == results[0]
+
+
 def fastq_text(rng, n, prefix, crlf=False, odd=False):
     out = bytearray()
     le = b"\r\n" if crlf else b"\n"
@@ -308,9 +375,12 @@ def test_truncated_gzip_fasta_and_write_errors_end_the_run(exe, stub, tmp_path):
     z = gzip.compress(fasta_text(rng))
     cut = tmp_path / "cut.fa.gz"
     cut.write_bytes(z[: len(z) * 2 // 3])
-    for env in ({}, {"MERKURIO_NO_FASTA_PIPELINE": "1"}):
+    seen = []
+    for env in ({}, {"MERKURIO_NO_FASTA_PIPELINE": "1"}, {"MERKURIO_BATCH_BYTES": "20000", "MERKURIO_CHUNK_BYTES": "5000"}):
         r = run(exe, stub, ["extract", "-i", cut, "-s", QUERY, "-v", "-o", tmp_path / "o.fa"], env)
         assert r.returncode != 0 and b"decompress" in r.stderr, (env, r.stderr)
+        seen.append((r.stderr, (tmp_path / "o.fa").read_bytes()))
+    assert seen[0][1].count(b">rec") >= 10 and seen[1] == seen[0] and seen[2] == seen[0]  # the records in front of the cut are written
     ok = tmp_path / "ok.fa.gz"
     ok.write_bytes(z)
     assert run(exe, stub, ["extract", "-i", ok, "-s", QUERY, "-v", "-o", tmp_path / "o2.fa"]).returncode == 0
