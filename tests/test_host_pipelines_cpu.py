@@ -78,7 +78,7 @@ def test_fasta_pipeline_equals_record_path(exe, stub, tmp_path, kw):
         assert other == results[0]
 
 
-def paired_fasta_text(rng, n, tag, crlf=False, width=60, long_every=0):
+def paired_fasta_text(rng, n, tag, crlf=False, width=60, long_every=0, blanks=False, final_nl=True):
     out = bytearray()
     le = b"\r\n" if crlf else b"\n"
     for i in range(n):
@@ -87,10 +87,15 @@ def paired_fasta_text(rng, n, tag, crlf=False, width=60, long_every=0):
         out += b">pair%d/%s" % (i, tag) + le
         for k in range(0, m, width):
             out += s[k:k + width] + le
-    return bytes(out)
+            if blanks and rng.random() < 0.05:
+                out += le
+        if blanks and i % 9 == 0:
+            out += le + le
+    return bytes(out) if final_nl else bytes(out).rstrip(b"\r\n")
 
 
-@pytest.mark.parametrize("kw", [{}, {"crlf": True}, {"width": 10 ** 6}, {"long_every": 50}], ids=lambda k: "-".join(k) or "plain")
+@pytest.mark.parametrize("kw", [{}, {"crlf": True}, {"width": 10 ** 6}, {"long_every": 50}, {"blanks": True, "final_nl": False},
+                                {"crlf": True, "blanks": True, "final_nl": False, "long_every": 70, "width": 7}], ids=lambda k: "-".join(k) or "plain")
 def test_paired_fasta_pipeline_equals_record_path(exe, stub, tmp_path, kw):
     """Two FASTA files of mates (src/cmd_extract.rs:412-418, :463-607) go through the chunked FASTA pipeline as well: the
     same two output files and the same log as the record-by-record path, whatever the chunk and batch sizes, with records
