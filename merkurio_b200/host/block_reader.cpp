@@ -38,7 +38,7 @@ void find_line_breaks(const char* d, size_t from, size_t to, OffsetList& out);
 BlockReader::BlockReader(const std::string& path, size_t block_bytes, size_t head, size_t depth, bool scan_lines)
     : path_(path), block_bytes_(std::max<size_t>(block_bytes, 4096)), head_(head), depth_(std::max<size_t>(depth, 1)), scan_lines_(scan_lines) {
     helpers_ = std::getenv("MERKURIO_READ_THREADS") ? std::max(1, std::atoi(std::getenv("MERKURIO_READ_THREADS")))
-                                                    : (int)std::max(1u, std::min(4u, std::thread::hardware_concurrency() / 4));
+                                                    : (int)std::max(1u, std::min(6u, std::thread::hardware_concurrency() * 3 / 8));
     // open here so that a missing file fails in the caller's thread, with the caller's context
     { std::unique_ptr<InputStream> probe = InputStream::open(path_); }
     thread_ = std::thread([this] { run(); });
@@ -108,21 +108,55 @@ void BlockReader::run() {
             }
             b.last = eof && error.empty();
             b.nl.clear();
+            b.nl_ctx.clear();
             b.has_nl = false;
             if (scan_lines_ && b.n > 0 && head_ + b.n < ((size_t)1 << 32)) {
                 // line breaks of the block, a slice per helper thread, concatenated in order
                 const int K = (b.n >= ((size_t)1 << 20)) ? helpers_ : 1;
                 const char* d = b.data.data();
+                const size_t lo = head_, hi = head_ + b.n;
+                // the neighbours of the breaks list[i0...) (the whole block has been read: a slice may look beyond its end)
+                auto context = [d, lo, hi](const OffsetList& list, size_t i0, uint8_t* out) {
+                    for (size_t i = i0; i < list.n; ++i) {
+                        const size_t e = list.p[i];
+                        uint8_t c = 0;
+                        if (e > lo) c |= d[e - 1] == '\r' ? kNlCr : 0;
+                        else c |= kNlNoPrev;
+                        if (e + 1 < hi) c |= d[e + 1] == '@' ? kNlAt : (d[e + 1] == '+' ? kNlPlus : 0);
+                        else c |= kNlNoNext;
+                        out[i - i0] = c;
+                    }
+                };
                 if (K == 1) {
-                    find_line_breaks(d, head_, head_ + b.n, b.nl);
+                    // a stretch at a time, so that the neighbours are looked at while the stretch is in the cache
+                    for (size_t at = lo; at < hi;) {
+                        const size_t upto = std::min(hi, at + ((size_t)128 << 10)), i0 = b.nl.n;
+                        find_line_breaks(d, at, upto, b.nl);
+                        b.nl_ctx.resize(b.nl.n);
+                        context(b.nl, i0, b.nl_ctx.data() + i0);
+                        at = upto;
+                    }
                 } else {
                     std::vector<OffsetList> part((size_t)K);
-                    auto job = [&](int t) { find_line_breaks(d, head_ + b.n * (size_t)t / (size_t)K, head_ + b.n * (size_t)(t + 1) / (size_t)K, part[(size_t)t]); };
+                    std::vector<std::vector<uint8_t>> part_ctx((size_t)K);
+                    auto job = [&](int t) {
+                        OffsetList& list = part[(size_t)t];
+                        std::vector<uint8_t>& cx = part_ctx[(size_t)t];
+                        const size_t from = lo + b.n * (size_t)t / (size_t)K, to = lo + b.n * (size_t)(t + 1) / (size_t)K;
+                        for (size_t at = from; at < to;) {
+                            const size_t upto = std::min(to, at + ((size_t)128 << 10)), i0 = list.n;
+                            find_line_breaks(d, at, upto, list);
+                            cx.resize(list.n);
+                            context(list, i0, cx.data() + i0);
+                            at = upto;
+                        }
+                    };
                     std::vector<std::thread> th;
                     for (int t = 1; t < K; ++t) th.emplace_back(job, t);
                     job(0);
                     for (auto& x : th) x.join();
                     for (auto& pl : part) b.nl.append(pl);
+                    for (auto& cx : part_ctx) b.nl_ctx.insert(b.nl_ctx.end(), cx.begin(), cx.end());
                 }
                 b.has_nl = true;
             }

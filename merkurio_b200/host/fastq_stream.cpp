@@ -146,8 +146,10 @@ void FastqChunkReader::run() {
             const OffsetList& nl = c->nl;
             size_t p = begin, k = 0;  // nl[k]: the first line break at or after p
             bool stuck = false;       // malformed or truncated: nothing more to parse in this block
+            size_t n_head_breaks = 0;  // line breaks of the bytes carried over: c->nl[n_head_breaks + i] == rb.nl[i]
             if (pre) {
                 find_line_breaks(d, begin, kHead, c->nl);
+                n_head_breaks = c->nl.size();
                 c->nl.append(rb.nl);
             }
             for (size_t scanned = begin; !stuck && (scanned < have || (eof && p < have));) {
@@ -156,6 +158,35 @@ void FastqChunkReader::run() {
                 scanned = upto;
                 const bool last = eof && scanned == have;  // only then a line without '\n' is complete
                 for (;;) {
+                    // The common record — "@id\nseq\n+\nqual\n", no '\r' — is recognised from the offsets of its line
+                    // breaks and from what the reading stage noted beside them (BlockReader::kNl*), without touching
+                    // the block's bytes: they have left this core's caches, and pulling them through once more was
+                    // the whole cost of indexing. Everything else takes the general rules below, which give such a
+                    // record the same span.
+                    if (pre) {
+                        using BR = BlockReader;
+                        const uint8_t* cx = rb.nl_ctx.data();
+                        while (k > n_head_breaks && k + 4 <= nl.size()) {
+                            const size_t j = k - n_head_breaks;  // cx[j] belongs to nl[k]; nl[k - 1] + 1 == p
+                            const size_t e0 = nl[k], e1 = nl[k + 1], e2 = nl[k + 2], e3 = nl[k + 3];
+                            if ((cx[j - 1] & (BR::kNlAt | BR::kNlNoNext)) != BR::kNlAt || (cx[j] & (BR::kNlCr | BR::kNlNoPrev)) ||
+                                (cx[j + 1] & (BR::kNlCr | BR::kNlNoPrev | BR::kNlPlus | BR::kNlNoNext)) != BR::kNlPlus || e2 != e1 + 2 ||
+                                (cx[j + 3] & (BR::kNlCr | BR::kNlNoPrev)) || e1 - e0 != e3 - e2)
+                                break;
+                            RecSpan r;
+                            r.start = (uint32_t)p;
+                            r.id_len = (uint32_t)(e0 - p - 1);
+                            r.seq_off = (uint32_t)(e0 + 1);
+                            r.seq_len = (uint32_t)(e1 - e0 - 1);
+                            r.qual_off = (uint32_t)(e2 + 1);
+                            r.end = (uint32_t)(e3 + 1);
+                            r.crlf = 0;
+                            r.plain = 1;
+                            c->recs.push_back(r);
+                            p = e3 + 1;
+                            k += 4;
+                        }
+                    }
                     Line h;
                     const size_t kp = k;
                     size_t q = p, kh = k;

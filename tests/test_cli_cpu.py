@@ -452,6 +452,40 @@ def test_chunked_fastq_reader_fuzz(exe, tmp_path):
             assert got.stdout == want.stdout, (trial, kind, chunk)
 
 
+def test_chunked_fastq_reader_with_several_read_helpers(exe, tmp_path):
+    """Blocks of 1 MiB and more have their line breaks — and what stands either side of each (BlockReader::kNl*) — located
+    by several helper threads, a slice each; the indexer recognises ordinary records from those notes alone. Messy
+    records (CRLF islands, '+id' lines, blank lines, qualities that start with '@' or '+', damage) at every slice and
+    block boundary must still come out as the line reader has them."""
+    import numpy as np
+    rng = np.random.default_rng(77)
+    for trial in range(6):
+        recs = []
+        for i in range(30000):
+            n = int(rng.integers(0, 90))
+            s = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=n).tobytes())
+            le = b"\r\n" if rng.random() < 0.01 else b"\n"
+            plus = b"+" + (b"x%d" % i if rng.random() < 0.02 else b"")
+            q = bytes(rng.choice(np.frombuffer(b"@+IF#", dtype=np.uint8), size=n).tobytes())
+            recs.append(b"@q%d/%d" % (trial, i) + le + s + le + plus + le + q + le + (b"\n" if rng.random() < 0.01 else b""))
+        data = bytearray(b"".join(recs))
+        if trial % 3 == 1:
+            a = int(rng.integers(len(data) // 2, len(data) - 100))
+            del data[a:a + int(rng.integers(1, 60))]
+        elif trial % 3 == 2:
+            while data and data[-1] in b"\r\n":
+                data.pop()
+        p = tmp_path / ("h%d.fastq" % trial)
+        p.write_bytes(bytes(data))
+        want = subprocess.run([exe, "records", str(p), "generic"], capture_output=True)
+        assert want.returncode == 0 and want.stdout.count(b"#id\t") > 10000, want.stderr
+        for threads, chunk in ((3, 1 << 20), (5, (1 << 20) + 4097), (2, 3 << 20)):
+            env = dict(os.environ, MERKURIO_READ_THREADS=str(threads))
+            got = subprocess.run([exe, "records", str(p), "chunked", str(chunk)], capture_output=True, env=env)
+            assert got.returncode == 0, got.stderr
+            assert got.stdout == want.stdout, (trial, threads, chunk)
+
+
 def test_chunked_sam_reader_fuzz(exe, tmp_path):
     """Damaged SAM text: both alignment readers stop at the same record with the same message."""
     import numpy as np
