@@ -70,11 +70,11 @@ FastxRecord to_record(const RecMeta& m) {
 }
 
 // Records of the chunked FASTQ ingest carry a (chunk, span) reference instead of strings.
-std::string record_id(const RecMeta& m) {
+std::string_view record_id(const RecMeta& m) {
     if (m.kind != 1) return m.a;
     const Chunk* ch = static_cast<const Chunk*>(m.chunk);
     const RecSpan& r = ch->recs[m.idx];
-    return std::string(ch->id(r), r.id_len);
+    return std::string_view(ch->id(r), r.id_len);
 }
 
 void write_record(OutFile& w, const RecMeta& m) {
@@ -185,7 +185,7 @@ void extract_records(CmdExtract args) {
     }
 
     auto emit = [&](const std::string& fname, const RecMeta& m, const RecHit& h) {
-        const std::string id = record_id(m);
+        const std::string_view id = record_id(m);
         logger.log_fields(fname, id, pattern_list[h.pattern], h.start);
         if (jl) jl->log_fields(fname, id, pattern_list[h.pattern], h.start);
     };

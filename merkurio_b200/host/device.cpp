@@ -118,8 +118,8 @@ EngineSet::~EngineSet() {
     const double t_destroy = now_s() - t_d0;
     if (std::getenv("MERKURIO_TIMING"))
         std::fprintf(stderr, "[merkurio] engine setup %.3f s, %llu batches, %llu records, %.3f Gbases, waited %.3f s for the GPU, "
-                     "device time %.3f s, delivering results %.3f s, packer %.3f s busy (incl. waiting for input) + %.3f s waiting for a slot, pipeline %.3f s, engine teardown %.3f s, total %.3f s\n", t_setup, (unsigned long long)n_batches,
-                     (unsigned long long)n_records, (double)n_bases / 1e9, t_wait, (double)device_ns / 1e9, t_deliver, t_pack, t_pack_wait, t_run, t_destroy, now_s() - t_start);
+                     "device time %.3f s, delivering results %.3f s, packer %.3f s busy (incl. waiting for input) + %.3f s waiting for a slot, pipeline %.3f s (submitting %.3f s, idle %.3f s), engine teardown %.3f s, total %.3f s\n", t_setup, (unsigned long long)n_batches,
+                     (unsigned long long)n_records, (double)n_bases / 1e9, t_wait, (double)device_ns / 1e9, t_deliver, t_pack, t_pack_wait, t_run, t_submit, t_idle, t_destroy, now_s() - t_start);
 }
 
 void EngineSet::wait(int engine, uint32_t slot, mk_result* out) {

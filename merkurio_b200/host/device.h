@@ -57,6 +57,7 @@ struct EngineSet {
     uint64_t max_bytes = 0;
     double t_start = 0, t_setup = 0, t_wait = 0, t_deliver = 0;
     double t_run = 0;  // SlotPipeline::run from its first to its last statement
+    double t_submit = 0, t_idle = 0;  // ... of which: inside mk_scan_submit / waiting for the packer with nothing in flight
     double t_pack = 0, t_pack_wait = 0;  // packer thread: filling slots / waiting for a free slot
     uint64_t device_ns = 0, n_records = 0, n_bases = 0, n_batches = 0;
 };

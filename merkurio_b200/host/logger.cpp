@@ -70,11 +70,15 @@ Sink::~Sink() {
     if (f_ && owned_) std::fclose(f_);
 }
 
-void BufferedLogger::log_fields(const std::string& prefix, const std::string& record, const std::string& pattern, uint64_t index) {
+void BufferedLogger::log_fields(const std::string& prefix, std::string_view record, const std::string& pattern, uint64_t index) {
+    if (!sink_) return;  // no text log asked for (the JSON log alone, or none)
     buf_ += prefix; buf_ += '\t';
     buf_ += record; buf_ += '\t';
     buf_ += pattern; buf_ += '\t';
-    buf_ += std::to_string(index); buf_ += '\n';
+    char digits[24];
+    auto r = std::to_chars(digits, digits + sizeof digits, index);
+    buf_.append(digits, r.ptr);
+    buf_ += '\n';
     if (buf_.size() >= cap_) flush();
 }
 void BufferedLogger::flush() {
@@ -85,16 +89,36 @@ void BufferedLogger::flush() {
 JsonLogger::JsonLogger(std::unique_ptr<Sink> sink, size_t buffer_size) : sink_(std::move(sink)), cap_(buffer_size) {
     if (sink_) sink_->write("{\n  \"matching_records\": [\n");
 }
-void JsonLogger::log_fields(const std::string& file, const std::string& record, const std::string& pattern, uint64_t index) {
+namespace {
+// s as a JSON string at the end of out; ordinary text (nothing to escape) is appended in one piece
+void append_json_string(std::string& out, std::string_view s) {
+    bool plain = true;
+    for (unsigned char c : s) plain &= (c >= 0x20 && c != '"' && c != '\\');
+    if (plain) {
+        out += '"';
+        out += s;
+        out += '"';
+    } else {
+        out += json_escape(std::string(s));
+    }
+}
+}  // namespace
+
+void JsonLogger::log_fields(const std::string& file, std::string_view record, const std::string& pattern, uint64_t index) {
     if (!first_) buf_ += ",\n";
     first_ = false;
     // keys in sorted order, 2-space pretty print, every line prefixed with 4 spaces
-    buf_ += "    {\n";
-    buf_ += "      \"file\": " + json_escape(file) + ",\n";
-    buf_ += "      \"pattern\": " + json_escape(pattern) + ",\n";
-    buf_ += "      \"position\": \"" + std::to_string(index) + "\",\n";
-    buf_ += "      \"record_id\": " + json_escape(record) + "\n";
-    buf_ += "    }\n";
+    buf_ += "    {\n      \"file\": ";
+    append_json_string(buf_, file);
+    buf_ += ",\n      \"pattern\": ";
+    append_json_string(buf_, pattern);
+    buf_ += ",\n      \"position\": \"";
+    char digits[24];
+    auto r = std::to_chars(digits, digits + sizeof digits, index);
+    buf_.append(digits, r.ptr);
+    buf_ += "\",\n      \"record_id\": ";
+    append_json_string(buf_, record);
+    buf_ += "\n    }\n";
     if (buf_.size() >= cap_) flush();
 }
 void JsonLogger::flush() {

@@ -6,6 +6,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <string_view>
 #include <vector>
 
 namespace mkh {
@@ -48,7 +49,7 @@ class BufferedLogger {
 public:
     BufferedLogger(std::unique_ptr<Sink> sink, size_t buffer_size) : sink_(std::move(sink)), cap_(buffer_size) { buf_.reserve(buffer_size + 256); }
     bool active() const { return (bool)sink_; }
-    void log_fields(const std::string& prefix, const std::string& record, const std::string& pattern, uint64_t index);
+    void log_fields(const std::string& prefix, std::string_view record, const std::string& pattern, uint64_t index);
     void write_header(const std::string& header) { if (sink_) sink_->write(header); }
     void flush();
 private:
@@ -61,7 +62,7 @@ private:
 class JsonLogger {
 public:
     JsonLogger(std::unique_ptr<Sink> sink, size_t buffer_size);
-    void log_fields(const std::string& file, const std::string& record, const std::string& pattern, uint64_t index);
+    void log_fields(const std::string& file, std::string_view record, const std::string& pattern, uint64_t index);
     void flush();
     // patterns: the sorted unique query list (= the key order serde_json's sorted map gives), counts[i] its hits
     void finalize(const Json& meta_information, const std::vector<std::string>& patterns, const std::vector<uint64_t>& counts,

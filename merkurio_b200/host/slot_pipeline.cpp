@@ -157,7 +157,11 @@ void SlotPipeline::run() {
         {
             std::unique_lock<std::mutex> lk(mu_);
             // with batches in flight do not block on the packer: consuming them is what frees its slots
-            if (inflight.empty()) cv_.wait(lk, [this] { return !packed_.empty() || packer_done_; });
+            if (inflight.empty()) {
+                const double t0 = now_s();
+                cv_.wait(lk, [this] { return !packed_.empty() || packer_done_; });
+                es_.t_idle += now_s() - t0;
+            }
             if (!packed_.empty()) {
                 b = std::move(packed_.front());
                 packed_.pop_front();
@@ -167,8 +171,10 @@ void SlotPipeline::run() {
         }
         if (b) {
             if (b->n_records > 0) {
-                if (mk_scan_submit(es_.engines[(size_t)b->engine], b->slot, b->n_records, b->n_units, enc_ == MK_ENC_BAM4 ? 1 : 0, enc_, mode_) != 0)
-                    throw Error(std::string("GPU matching engine: ") + mk_last_error());
+                const double t0 = now_s();
+                const int rc_submit = mk_scan_submit(es_.engines[(size_t)b->engine], b->slot, b->n_records, b->n_units, enc_ == MK_ENC_BAM4 ? 1 : 0, enc_, mode_);
+                es_.t_submit += now_s() - t0;
+                if (rc_submit != 0) throw Error(std::string("GPU matching engine: ") + mk_last_error());
                 inflight.push_back(std::move(b));
             } else {
                 // nothing but the input's error
