@@ -122,7 +122,7 @@ void BlockReader::run() {
                         uint8_t c = 0;
                         if (e > lo) c |= d[e - 1] == '\r' ? kNlCr : 0;
                         else c |= kNlNoPrev;
-                        if (e + 1 < hi) c |= d[e + 1] == '@' ? kNlAt : (d[e + 1] == '+' ? kNlPlus : 0);
+                        if (e + 1 < hi) c |= d[e + 1] == '@' ? kNlAt : (d[e + 1] == '+' ? kNlPlus : (d[e + 1] == '>' ? kNlGt : 0));
                         else c |= kNlNoNext;
                         out[i - i0] = c;
                     }

@@ -100,8 +100,9 @@ public:
     static constexpr uint8_t kNlCr = 1;        // data[e - 1] == '\r'
     static constexpr uint8_t kNlAt = 2;        // data[e + 1] == '@'
     static constexpr uint8_t kNlPlus = 4;      // data[e + 1] == '+'
+    static constexpr uint8_t kNlGt = 8;        // data[e + 1] == '>'
     static constexpr uint8_t kNlNoPrev = 64;   // e is the first byte of the block: bit kNlCr unknown
-    static constexpr uint8_t kNlNoNext = 128;  // e is the last byte of the block: bits kNlAt / kNlPlus unknown
+    static constexpr uint8_t kNlNoNext = 128;  // e is the last byte of the block: bits kNlAt / kNlPlus / kNlGt unknown
     BlockReader(const std::string& path, size_t block_bytes, size_t head, size_t depth = 3, bool scan_lines = false);
     // The same over an input that is already open: read(dst, n) returns up to n bytes, 0 at the end.
     using ReadFn = std::function<size_t(char*, size_t)>;

@@ -16,7 +16,7 @@ struct FastaChunkReader::Shared {
 
 FastaChunkReader::FastaChunkReader(const std::string& path, size_t chunk_bytes, size_t depth)
     : path_(path), chunk_bytes_(std::max<size_t>(chunk_bytes, 4096)), depth_(std::max<size_t>(depth, 1)), pool_(new Shared) {
-    blocks_.reset(new BlockReader(path_, chunk_bytes_, kHead));  // a missing file fails here, in the caller's thread
+    blocks_.reset(new BlockReader(path_, chunk_bytes_, kHead, 3, true));  // a missing file fails here, in the caller's thread
     thread_ = std::thread([this] { run(); });
 }
 
@@ -83,11 +83,38 @@ void FastaChunkReader::run() {
                 begin = kHead;
                 have = kHead + carry.size() + rb.n;
             }
+            const size_t carry_len = carry.size();
             carry.clear();
             // line breaks are located a stretch at a time, the lines noted while the stretch is still in the cache
             const char* d = c->data.data();
             size_t p = begin;
-            for (size_t scanned = begin; scanned < have;) {
+            size_t scan_from = begin;
+            if (rb.has_nl && carry_len <= kHead && rb.nl_ctx.size() == rb.nl.size()) {
+                // the reading stage has located the block's line breaks and noted whether a '>' follows each
+                // (BlockReader::kNlGt): the lines are listed without touching the block's bytes again. Only the bytes
+                // carried over are scanned here.
+                nl.clear();
+                find_line_breaks(d, begin, kHead, nl);
+                const size_t n0 = nl.n, n1 = rb.nl.size(), base = c->lines.size();
+                c->lines.resize(base + n0 + n1);
+                FaLine* w = c->lines.data() + base;
+                for (size_t i = 0; i < n0; ++i) {
+                    const size_t e = nl.p[i];
+                    w[i] = FaLine{(uint32_t)p, (uint32_t)(e - p), (uint8_t)(e > p && d[p] == '>')};
+                    p = e + 1;
+                }
+                w += n0;
+                const uint8_t* cx = rb.nl_ctx.data();
+                for (size_t i = 0; i < n1; ++i) {
+                    const size_t e = rb.nl[i];
+                    // the line starts behind the block's previous break (what follows it was noted), or in front of the block
+                    const bool gt = (i > 0 && p == (size_t)rb.nl[i - 1] + 1) ? (cx[i - 1] & BlockReader::kNlGt) != 0 : (e > p && d[p] == '>');
+                    w[i] = FaLine{(uint32_t)p, (uint32_t)(e - p), (uint8_t)gt};
+                    p = e + 1;
+                }
+                scan_from = have;
+            }
+            for (size_t scanned = scan_from; scanned < have;) {
                 const size_t upto = std::min(have, scanned + kStretch);
                 nl.clear();
                 find_line_breaks(d, scanned, upto, nl);

@@ -11,6 +11,7 @@
  * tagged and logged, flagged and unflagged ones mixed. */
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "merkurio_cuda.h"
 
@@ -31,6 +32,10 @@ struct mk_engine {
 
 int mk_engine_create(const mk_patterns* p, const mk_config* c, mk_engine** out) {
     (void)p;
+    /* MK_STUB_STARTUP_MS: the time a CUDA context takes to come up (scripts/bench_host_stub.py: the readers run ahead
+       meanwhile, as they do in front of the real engine) */
+    const char* ms = getenv("MK_STUB_STARTUP_MS");
+    if (ms && *ms) usleep((useconds_t)atoi(ms) * 1000);
     mk_engine* e = calloc(1, sizeof *e);
     e->cfg = *c;
     for (uint32_t s = 0; s < c->n_slots && s < 16; ++s) {
