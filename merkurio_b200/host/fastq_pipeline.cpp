@@ -48,6 +48,11 @@ bool FastqPipeline::fill(PackedBatch& b) {
     const uint64_t cap = es_.max_bytes;
     const uint32_t max_rec = es_.max_records;
     uint32_t nrec[2] = {0, 0};
+    // the copies are carried out by the pool while this thread goes on choosing records; the list must not move
+    copies_.clear();
+    copies_.reserve((size_t)max_rec + 2);
+    copy_pool_.begin(b.seq, copies_.data());
+    size_t published = 0;
     auto fail = [&](std::vector<std::string> chain) {
         b.error_chain = std::move(chain);
         input_done_ = true;
@@ -114,10 +119,14 @@ bool FastqPipeline::fill(PackedBatch& b) {
         if (b.n_records + (uint32_t)F > max_rec || b.n_units + need > cap) break;  // full: the record opens the next batch
         add(0);
         if (paired_) add(1);
+        if (copies_.size() >= published + 4096) {
+            published = copies_.size();
+            copy_pool_.publish(published);
+        }
     }
     b.off[b.n_records] = b.n_units;
     b.n_bytes = b.total_bases = b.n_units;
-    copy_pool_.run(b.seq, copies_);  // the chunks the copies read from are held by b.seg
+    copy_pool_.finish(copies_.size());  // the chunks the copies read from are held by b.seg
     copies_.clear();
     return b.n_records > 0 || !b.error_chain.empty();
 }

@@ -18,7 +18,7 @@ static int pack_threads() {
 }
 
 CopyPool::CopyPool(int threads) {
-    for (int t = 1; t < threads; ++t) workers_.emplace_back([this, t] { work((size_t)t); });
+    for (int t = 1; t < threads; ++t) workers_.emplace_back([this] { work(); });
 }
 
 CopyPool::~CopyPool() {
@@ -34,42 +34,64 @@ void CopyPool::copy_range(uint8_t* base, const Copy* c, size_t lo, size_t hi) {
     for (size_t i = lo; i < hi; ++i) std::memcpy(base + c[i].dst, c[i].src, c[i].len);
 }
 
-void CopyPool::work(size_t me) {
-    uint64_t seen = 0;
+bool CopyPool::take(std::unique_lock<std::mutex>&, size_t* lo, size_t* hi) {
+    if (next_ >= ready_) return false;
+    *lo = next_;
+    *hi = std::min(ready_, next_ + kBlock);
+    next_ = *hi;
+    return true;
+}
+
+void CopyPool::work() {
+    std::unique_lock<std::mutex> lk(mu_);
     for (;;) {
-        uint8_t* base;
-        const Copy* list;
-        size_t n;
-        {
-            std::unique_lock<std::mutex> lk(mu_);
-            cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
-            if (stop_) return;
-            seen = generation_;
-            base = base_; list = list_; n = n_;
+        cv_.wait(lk, [&] { return stop_ || next_ < ready_; });
+        if (stop_) return;
+        size_t lo, hi;
+        while (take(lk, &lo, &hi)) {
+            uint8_t* base = base_;
+            const Copy* list = list_;
+            lk.unlock();
+            copy_range(base, list, lo, hi);
+            lk.lock();
+            done_ += hi - lo;
+            if (done_ == ready_) done_cv_.notify_all();
         }
-        const size_t parts = workers_.size() + 1;
-        copy_range(base, list, n * me / parts, n * (me + 1) / parts);
-        std::lock_guard<std::mutex> lk(mu_);
-        if (--pending_ == 0) done_cv_.notify_one();
     }
 }
 
-void CopyPool::run(uint8_t* base, const std::vector<Copy>& list) {
-    const size_t n = list.size(), parts = workers_.size() + 1;
-    if (workers_.empty() || n < 4096) {  // not worth a hand-over
-        copy_range(base, list.data(), 0, n);
-        return;
-    }
+void CopyPool::begin(uint8_t* base, const Copy* list) {
+    std::lock_guard<std::mutex> lk(mu_);
+    base_ = base;
+    list_ = list;
+    ready_ = next_ = done_ = 0;
+}
+
+void CopyPool::publish(size_t n) {
+    if (workers_.empty()) return;  // the packer does them all in finish()
     {
         std::lock_guard<std::mutex> lk(mu_);
-        base_ = base; list_ = list.data(); n_ = n;
-        pending_ = workers_.size();
-        ++generation_;
+        ready_ = n;
     }
     cv_.notify_all();
-    copy_range(base, list.data(), 0, n / parts);  // the packer thread takes the first range itself
+}
+
+void CopyPool::finish(size_t n) {
     std::unique_lock<std::mutex> lk(mu_);
-    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    ready_ = n;
+    if (!workers_.empty() && next_ < ready_) {
+        lk.unlock();
+        cv_.notify_all();
+        lk.lock();
+    }
+    size_t lo, hi;
+    while (take(lk, &lo, &hi)) {  // the packer thread takes its share of what is left
+        lk.unlock();
+        copy_range(base_, list_, lo, hi);
+        lk.lock();
+        done_ += hi - lo;
+    }
+    done_cv_.wait(lk, [&] { return done_ == ready_; });
 }
 
 SlotPipeline::SlotPipeline(EngineSet& engines, mk_encoding enc, mk_mode mode, BatchConsumer consumer)

@@ -64,10 +64,11 @@ struct PackedBatch {
 
 using BatchConsumer = std::function<void(const PackedBatch&, const mk_result&)>;
 
-// Helper threads of the packer. Deciding which records go into a batch, and where, is one cheap sequential pass
-// over the record index (it has to be: a batch closes when the slot is full); copying the sequence bytes — most of
-// the packer's time — is not, so fill() notes the copies and the pool carries them out on MERKURIO_PACK_THREADS
-// threads (default: 4 or a quarter of the cores, the packer thread included), each a contiguous range of the list.
+// Helper threads of the packer. Deciding which records go into a batch, and where, is one sequential pass over
+// the record index (it has to be: a batch closes when the slot is full); copying the sequence bytes — most of the
+// packer's time — is not. fill() notes the copies in a list and publishes the list's length every few thousand
+// records; MERKURIO_PACK_THREADS - 1 workers (default: 4 threads or a quarter of the cores, the packer thread included)
+// carry out blocks of the published part while the packer goes on deciding, and the packer joins them at the end.
 class CopyPool {
 public:
     struct Copy {
@@ -78,21 +79,25 @@ public:
     explicit CopyPool(int threads);
     ~CopyPool();
     CopyPool(const CopyPool&) = delete;
-    void run(uint8_t* base, const std::vector<Copy>& list);  // returns when every copy is done
+    // A batch: begin(), any number of publish() calls with growing counts, finish(). `list` must not move in between
+    // (the caller reserves it), and the sources must stay readable until finish() returns.
+    void begin(uint8_t* base, const Copy* list);
+    void publish(size_t n);  // list[0, n) is final
+    void finish(size_t n);   // ... and n is all there is; returns when every copy is done
     int threads() const { return (int)workers_.size() + 1; }
 
 private:
-    void work(size_t me);
+    static constexpr size_t kBlock = 2048;  // copies a thread takes at a time
+    void work();
+    bool take(std::unique_lock<std::mutex>& lk, size_t* lo, size_t* hi);  // a block of the published part, if any is left
     static void copy_range(uint8_t* base, const Copy* c, size_t lo, size_t hi);
     std::vector<std::thread> workers_;
     std::mutex mu_;
     std::condition_variable cv_, done_cv_;
-    uint64_t generation_ = 0;
-    size_t pending_ = 0;
     bool stop_ = false;
     uint8_t* base_ = nullptr;
     const Copy* list_ = nullptr;
-    size_t n_ = 0;
+    size_t ready_ = 0, next_ = 0, done_ = 0;  // published / handed out / carried out
 };
 
 class SlotPipeline {

@@ -9,6 +9,7 @@
  * "hit" of the first query at position 0. Nothing is compared with the queries — the point is only that
  * the host's paths (which cut their batches differently) must then agree on which records are written,
  * tagged and logged, flagged and unflagged ones mixed. */
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
@@ -87,8 +88,31 @@ int mk_scan_submit(mk_engine* e, uint32_t s, uint32_t n, uint64_t u, int l, mk_e
     e->mode[s] = m;
     return 0;
 }
+/* MK_STUB_DIGEST_FILE: after every batch, "<records> <bases> <digest>\n" of everything scanned so far is written there;
+   the digest is the sum over the records (ASCII batches) of an FNV-1a hash of their bases, so it depends on what the
+   packer put into the slots, not on how the records were dealt into batches. FASTA pieces that repeat bases change
+   it: meant for inputs whose records are not cut. */
+static uint64_t g_records, g_bases, g_digest;
+static void stub_digest(mk_engine* e, uint32_t s) {
+    const char* path = getenv("MK_STUB_DIGEST_FILE");
+    if (!path || !*path || e->enc[s] != MK_ENC_ASCII) return;
+    for (uint32_t i = 0; i < e->n_records[s]; ++i) {
+        uint64_t h = 1469598103934665603ull;
+        for (uint64_t p = e->off[s][i]; p < e->off[s][i + 1]; ++p) h = (h ^ e->seq[s][p]) * 1099511628211ull;
+        g_digest += h;
+        g_bases += e->off[s][i + 1] - e->off[s][i];
+    }
+    g_records += e->n_records[s];
+    FILE* f = fopen(path, "w");
+    if (f) {
+        fprintf(f, "%llu %llu %016llx\n", (unsigned long long)g_records, (unsigned long long)g_bases, (unsigned long long)g_digest);
+        fclose(f);
+    }
+}
+
 int mk_scan_wait(mk_engine* e, uint32_t s, mk_result* r) {
     memset(r, 0, sizeof *r);
+    stub_digest(e, s);
     r->record_flags = e->flags;  /* all zero: no record has a hit */
     r->n_records = e->n_records[s];
     r->bases_scanned = e->n_units[s];

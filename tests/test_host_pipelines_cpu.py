@@ -191,6 +191,38 @@ def test_fastq_pipeline_equals_record_path(exe, stub, tmp_path, flavour):
             assert other == results[0]
 
 
+@pytest.mark.parametrize("paired", [False, True])
+def test_fastq_packer_puts_the_same_bases_into_the_slots(exe, stub, tmp_path, paired):
+    """The packer's copies run on a pool of threads while it goes on choosing records (CopyPool: begin / publish / finish).
+    What arrives in the engine's slots — the test double sums a hash of every record's bases (MK_STUB_DIGEST_FILE) — must
+    be the same with one thread, with several, and on the record-by-record path, and equal the hash computed here."""
+    rng = np.random.default_rng(12)
+    n = 30000
+    reads = [bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=int(rng.integers(0, 250))).tobytes()) for _ in range(n * (2 if paired else 1))]
+
+    def fnv(b):
+        h = 1469598103934665603
+        for c in b:
+            h = ((h ^ c) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    want = "%d %d %016x" % (len(reads), sum(map(len, reads)), sum(map(fnv, reads)) & 0xFFFFFFFFFFFFFFFF)
+    files = []
+    for f in range(2 if paired else 1):
+        p = tmp_path / ("r_%d.fastq" % (f + 1))
+        mine = reads[f::2] if paired else reads
+        p.write_bytes(b"".join(b"@r%d\n%s\n+\n%s\n" % (i, r, b"I" * len(r)) for i, r in enumerate(mine)))
+        files.append(p)
+    args = ["extract", "-i", files[0]] + (["-2", files[1]] if paired else []) + ["-s", QUERY, "-o", tmp_path / "o.fastq"]
+    for env in ({"MERKURIO_PACK_THREADS": "1"}, {"MERKURIO_PACK_THREADS": "4"}, {"MERKURIO_PACK_THREADS": "7", "MERKURIO_BATCH_BYTES": "3000000"},
+                {"MERKURIO_PACK_THREADS": "3", "MERKURIO_BATCH_BYTES": "50000", "MERKURIO_CHUNK_BYTES": "20000"}, {"MERKURIO_NO_FASTQ_PIPELINE": "1"}):
+        dg = tmp_path / "digest.txt"
+        dg.unlink(missing_ok=True)
+        r = run(exe, stub, args, dict(env, MK_STUB_DIGEST_FILE=str(dg)))
+        assert r.returncode == 0, r.stderr
+        assert dg.read_text().strip() == want, env
+
+
 @pytest.mark.parametrize("n_reads,level", [(3000, 9), (40000, 1)])
 def test_fastq_pipeline_reports_read_errors_like_the_record_path(exe, stub, tmp_path, n_reads, level):
     """A gzip stream that breaks half way (flipped bytes): both paths stop with the same status and the same
