@@ -114,8 +114,10 @@ bool FastqPipeline::fill(PackedBatch& b) {
             }
             need += cur_[1]->recs[idx_[1]].seq_len;
         }
-        if (need > cap)
+        if (need > cap) {
+            copy_pool_.finish(copies_.size());  // no copy is left running behind the exception
             throw Error("a record of " + std::to_string(need) + " bases does not fit a batch (raise MERKURIO_BATCH_MB)");
+        }
         if (b.n_records + (uint32_t)F > max_rec || b.n_units + need > cap) break;  // full: the record opens the next batch
         add(0);
         if (paired_) add(1);

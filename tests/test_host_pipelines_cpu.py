@@ -223,6 +223,19 @@ def test_fastq_packer_puts_the_same_bases_into_the_slots(exe, stub, tmp_path, pa
         assert dg.read_text().strip() == want, env
 
 
+def test_fastq_record_larger_than_a_batch_ends_the_run(exe, stub, tmp_path):
+    """A read that does not fit a slot stops the FASTQ pipeline with a message that names the remedy — after the copies of
+    the records in front of it have been carried out (the pool is not left running behind the exception), no hang."""
+    rng = np.random.default_rng(8)
+    recs = [b"@r%d\n%s\n+\n%s\n" % (i, b"ACGT" * 25, b"I" * 100) for i in range(9000)]
+    big = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=300000).tobytes())
+    recs.insert(7000, b"@big\n" + big + b"\n+\n" + b"I" * len(big) + b"\n")
+    p = tmp_path / "r.fastq"
+    p.write_bytes(b"".join(recs))
+    r = run(exe, stub, ["extract", "-i", p, "-s", QUERY, "-v", "-o", tmp_path / "o.fastq"], {"MERKURIO_BATCH_BYTES": "200000", "MERKURIO_PACK_THREADS": "4"})
+    assert r.returncode != 0 and b"does not fit a batch (raise MERKURIO_BATCH_MB)" in r.stderr, r.stderr
+
+
 @pytest.mark.parametrize("n_reads,level", [(3000, 9), (40000, 1)])
 def test_fastq_pipeline_reports_read_errors_like_the_record_path(exe, stub, tmp_path, n_reads, level):
     """A gzip stream that breaks half way (flipped bytes): both paths stop with the same status and the same
