@@ -150,6 +150,44 @@ def test_paired_fasta_pipeline_fails_like_the_record_path(exe, stub, tmp_path, c
         assert other == results[0]
 
 
+@pytest.mark.parametrize("kw", [{}, {"crlf": True, "blanks": True, "final_nl": False}, {"width": 7}, {"width": 300}], ids=lambda k: "-".join(k) or "plain")
+def test_fasta_packer_puts_the_same_bases_into_the_slots(exe, stub, tmp_path, kw):
+    """What the FASTA packer (single file and two files of mates) copies into the engine's slots — sequence lines without
+    their line breaks, whole lines in a tight loop, the rest by the general rules — hashed by the test double
+    (MK_STUB_DIGEST_FILE) and compared with the hash of the records computed here. Records are not cut in these runs
+    (a cut record repeats bases in its next piece); chunks are small, so runs of lines end everywhere."""
+    rng = np.random.default_rng(31)
+    texts = [paired_fasta_text(rng, 800, b"1", **kw), paired_fasta_text(rng, 800, b"2", **kw)]
+
+    def fnv(b):
+        h = 1469598103934665603
+        for c in b:
+            h = ((h ^ c) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    def records(text):
+        out = []
+        for block in text.replace(b"\r", b"").split(b">")[1:]:
+            out.append(b"".join(block.split(b"\n")[1:]))
+        return out
+
+    files = []
+    for f, t in enumerate(texts):
+        p = tmp_path / ("m_%d.fa" % (f + 1))
+        p.write_bytes(t)
+        files.append(p)
+    for paired in (False, True):
+        recs = records(texts[0]) + (records(texts[1]) if paired else [])
+        want = "%d %d %016x" % (len(recs), sum(map(len, recs)), sum(map(fnv, recs)) & 0xFFFFFFFFFFFFFFFF)
+        args = ["extract", "-i", files[0]] + (["-2", files[1]] if paired else []) + ["-s", QUERY, "-o", tmp_path / "o.fa"]
+        for env in ({}, {"MERKURIO_CHUNK_BYTES": "4096"}, {"MERKURIO_CHUNK_BYTES": "5000", "MERKURIO_GPUS": "2"}):
+            dg = tmp_path / "digest.txt"
+            dg.unlink(missing_ok=True)
+            r = run(exe, stub, args, dict(env, MK_STUB_DIGEST_FILE=str(dg)))
+            assert r.returncode == 0, r.stderr
+            assert dg.read_text().strip() == want, (paired, env)
+
+
 def fastq_text(rng, n, prefix, crlf=False, odd=False):
     out = bytearray()
     le = b"\r\n" if crlf else b"\n"
